@@ -1,0 +1,92 @@
+"""ctypes binding of libdcgp.so (the C ABI declared in include/dcgp.h).
+
+There is no CPU fallback: importing the ops without the built library raises.
+torch is used only to obtain device pointers and the current CUDA stream.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_double, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdcgp.so")
+
+F64, F32 = 0, 1
+KIND_RBF, KIND_MATERN32, KIND_MATERN12, KIND_MATERN52 = 0, 1, 2, 3
+MAX_COMPONENTS, MAX_DIMS = 4, 8
+GRAM_SAME, GRAM_OUT_F64 = 1, 2
+GEMM_LOWER, GEMM_NO_SPLITK = 1, 2
+
+
+class Component(Structure):
+    _fields_ = [("kind", c_int32), ("ndims", c_int32), ("dims", c_int32 * MAX_DIMS),
+                ("lengthscale", c_void_p), ("outputscale", c_void_p)]
+
+
+class KernelSpec(Structure):
+    _fields_ = [("n_components", c_int32), ("reserved", c_int32), ("comp", Component * MAX_COMPONENTS)]
+
+
+class DcgpError(RuntimeError):
+    pass
+
+
+_SIGNATURES = {
+    "dcgp_version": (c_int, []),
+    "dcgp_arch": (c_int, []),
+    "dcgp_gram": (c_int, [POINTER(KernelSpec), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
+                          c_int64, c_void_p, c_double, c_int, c_int, c_void_p]),
+    "dcgp_gram_bwd": (c_int, [POINTER(KernelSpec), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
+                              c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "dcgp_gemm": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_double, c_void_p, c_int64, c_void_p, c_int64,
+                          c_double, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "dcgp_potrf_workspace": (c_size_t, [c_int64, c_int]),
+    "dcgp_potrf": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "dcgp_trsm_workspace": (c_size_t, [c_int64, c_int64, c_int]),
+    "dcgp_trsm": (c_int, [c_int, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_int,
+                          c_int, c_void_p]),
+    "dcgp_potrs": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_int, c_int,
+                           c_void_p]),
+    "dcgp_logdet_chol": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
+    "dcgp_bag_sum": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]),
+    "dcgp_gram_bagsum": (c_int, [POINTER(KernelSpec), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p,
+                                 c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "dcgp_gram_bagsum_bwd": (c_int, [POINTER(KernelSpec), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p,
+                                     c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
+                                     c_void_p]),
+    "dcgp_gram_bag_blocksum": (c_int, [POINTER(KernelSpec), c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int,
+                                       c_int, c_void_p]),
+    "dcgp_gram_bag_blocksum_bwd": (c_int, [POINTER(KernelSpec), c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                           c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "dcgp_whitened_kl": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                 c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load():
+    """Loads libdcgp.so once; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DcgpError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or python deconditional_downscaling_b200/build.py). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    if rc <= -1000:
+        raise DcgpError(f"{what}: CUDA error {-rc - 1000}")
+    raise DcgpError(f"{what}: invalid argument #{-rc}")

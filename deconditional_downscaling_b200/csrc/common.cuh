@@ -1,0 +1,165 @@
+// Shared device/host helpers for libdcgp (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/dcgp.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libdcgp is written for sm_100a (B200) only"
+#endif
+
+#define DCGP_CUDA_ERR(e) (-(1000 + (int)(e)))
+#define DCGP_CHECK_LAUNCH()                                 \
+    do {                                                    \
+        cudaError_t _e = cudaGetLastError();                \
+        if (_e != cudaSuccess) return DCGP_CUDA_ERR(_e);    \
+    } while (0)
+
+constexpr int kMaxTotalDims = 16;  // sum of active dims over the additive components
+
+// Flattened kernel description passed by value to kernels (__grid_constant__).
+// Slot layout: component c owns slots [c*dpc, (c+1)*dpc); unused slots read input column 0
+// with inverse lengthscale 0 (so they contribute exactly 0 to the squared distance) and
+// unused components carry outputscale 0.  (ncb, dpc) are template buckets, so every inner
+// loop is fully unrolled with no runtime predicates.
+struct DevSpec {
+    int n_comp;
+    int ncb;  // component bucket: 1, 2 or 4
+    int dpc;  // dims-per-component bucket: 2, 4 or 8   (ncb * dpc <= kMaxTotalDims)
+    int kind[DCGP_MAX_COMPONENTS];
+    int ndims[DCGP_MAX_COMPONENTS];
+    int col[kMaxTotalDims];
+    const void* ls[DCGP_MAX_COMPONENTS];
+    const void* os[DCGP_MAX_COMPONENTS];
+};
+
+inline int make_dev_spec(const dcgp_kernel_spec* s, DevSpec* d) {
+    if (!s || s->n_components < 1 || s->n_components > DCGP_MAX_COMPONENTS) return -1;
+    d->n_comp = s->n_components;
+    d->ncb = s->n_components == 1 ? 1 : (s->n_components == 2 ? 2 : 4);
+    int maxd = 1;
+    for (int c = 0; c < s->n_components; ++c) {
+        const dcgp_component& k = s->comp[c];
+        if (k.kind < 0 || k.kind > DCGP_KIND_MATERN52) return -1;
+        if (k.ndims < 1 || k.ndims > DCGP_MAX_DIMS || !k.lengthscale || !k.outputscale) return -1;
+        if (k.ndims > maxd) maxd = k.ndims;
+    }
+    d->dpc = maxd <= 2 ? 2 : (maxd <= 4 ? 4 : 8);
+    if (d->ncb * d->dpc > kMaxTotalDims) return -1;
+    for (int i = 0; i < kMaxTotalDims; ++i) d->col[i] = 0;
+    for (int c = 0; c < DCGP_MAX_COMPONENTS; ++c) {
+        d->kind[c] = DCGP_KIND_RBF;
+        d->ndims[c] = 0;
+        d->ls[c] = nullptr;
+        d->os[c] = nullptr;
+    }
+    for (int c = 0; c < s->n_components; ++c) {
+        const dcgp_component& k = s->comp[c];
+        d->kind[c] = k.kind;
+        d->ndims[c] = k.ndims;
+        for (int j = 0; j < k.ndims; ++j) {
+            if (k.dims[j] < 0) return -1;
+            d->col[c * d->dpc + j] = k.dims[j];
+        }
+        d->ls[c] = k.lengthscale;
+        d->os[c] = k.outputscale;
+    }
+    return 0;
+}
+
+// per-CTA copy of the (device-resident) hyper-parameters, padded to the slot layout
+template <typename T>
+struct SpecVals {
+    T inv_ls[kMaxTotalDims];
+    T os[DCGP_MAX_COMPONENTS];
+};
+
+template <typename T>
+__device__ __forceinline__ void load_spec_vals(const DevSpec& sp, SpecVals<T>* sv) {
+    for (int c = threadIdx.x; c < DCGP_MAX_COMPONENTS; c += blockDim.x)
+        sv->os[c] = (c < sp.n_comp) ? ((const T*)sp.os[c])[0] : T(0);
+    for (int s = threadIdx.x; s < kMaxTotalDims; s += blockDim.x) {
+        int c = s / sp.dpc, j = s % sp.dpc;
+        sv->inv_ls[s] = (c < sp.n_comp && j < sp.ndims[c]) ? T(1) / ((const T*)sp.ls[c])[j] : T(0);
+    }
+}
+
+#define DCGP_DISPATCH_LAYOUT(sp, CALL)                 \
+    do {                                               \
+        if ((sp).ncb == 1 && (sp).dpc == 2) CALL(1, 2) \
+        else if ((sp).ncb == 1 && (sp).dpc == 4) CALL(1, 4) \
+        else if ((sp).ncb == 1) CALL(1, 8)             \
+        else if ((sp).ncb == 2 && (sp).dpc == 2) CALL(2, 2) \
+        else if ((sp).ncb == 2 && (sp).dpc == 4) CALL(2, 4) \
+        else if ((sp).ncb == 2) CALL(2, 8)             \
+        else if ((sp).dpc == 2) CALL(4, 2)             \
+        else CALL(4, 4)                                \
+    } while (0)
+
+template <typename T> __device__ __forceinline__ T t_exp(T x);
+template <> __device__ __forceinline__ double t_exp<double>(double x) { return exp(x); }
+template <> __device__ __forceinline__ float t_exp<float>(float x) { return __expf(x); }
+template <typename T> __device__ __forceinline__ T t_sqrt(T x);
+template <> __device__ __forceinline__ double t_sqrt<double>(double x) { return sqrt(x); }
+template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqrtf(x); }
+template <typename T> __device__ __forceinline__ T t_log(T x);
+template <> __device__ __forceinline__ double t_log<double>(double x) { return log(x); }
+template <> __device__ __forceinline__ float t_log<float>(float x) { return logf(x); }
+
+// phi(r^2) for one base kernel and w(r^2) with  d phi / d u_k = -w * u_k  (u = scaled difference).
+template <typename T>
+__device__ __forceinline__ T kernel_phi(int kind, T r2) {
+    if (kind == DCGP_KIND_RBF) return t_exp<T>(T(-0.5) * r2);
+    T r = t_sqrt<T>(r2 > T(1e-30) ? r2 : T(1e-30));
+    if (kind == DCGP_KIND_MATERN32) {
+        T s = T(1.7320508075688772) * r;
+        return (T(1) + s) * t_exp<T>(-s);
+    }
+    if (kind == DCGP_KIND_MATERN12) return t_exp<T>(-r);
+    T s = T(2.23606797749979) * r;
+    return (T(1) + s + T(5.0 / 3.0) * r2) * t_exp<T>(-s);
+}
+
+template <typename T>
+__device__ __forceinline__ void kernel_phi_w(int kind, T r2, T& phi, T& w) {
+    if (kind == DCGP_KIND_RBF) {
+        phi = t_exp<T>(T(-0.5) * r2);
+        w = phi;
+        return;
+    }
+    T r = t_sqrt<T>(r2 > T(1e-30) ? r2 : T(1e-30));
+    if (kind == DCGP_KIND_MATERN32) {
+        T s = T(1.7320508075688772) * r;
+        T e = t_exp<T>(-s);
+        phi = (T(1) + s) * e;
+        w = T(3) * e;
+    } else if (kind == DCGP_KIND_MATERN12) {
+        T e = t_exp<T>(-r);
+        phi = e;
+        w = (r2 > T(1e-30)) ? e / r : T(0);
+    } else {
+        T s = T(2.23606797749979) * r;
+        T e = t_exp<T>(-s);
+        phi = (T(1) + s + T(5.0 / 3.0) * r2) * e;
+        w = T(5.0 / 3.0) * (T(1) + s) * e;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+inline int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}

@@ -1,0 +1,619 @@
+// Gram assembly kernels (RBF / Matern, ARD lengthscales, additive over active_dims).
+//
+// Forward: one pass, HBM-write bound.  Each CTA produces a 64 x (32*VEC) tile; every thread
+// keeps the scaled coordinates of its VEC columns in registers, walks 8 rows whose scaled
+// coordinates are broadcast from shared memory, and issues one 16-byte store per row
+// (a warp writes 512 contiguous bytes).  The squared distance is formed from coordinate
+// differences, not from the |x|^2+|y|^2-2xy expansion: with an inner dimension of d<=8 the
+// tensor pipe could not be fed anyway (the kernel is bound by the N1*N2 output bytes and, in
+// FP64, by exp), and the difference form has no cancellation, so the diagonal is exact and
+// K stays positive definite in FP32/TF32 builds.
+//
+// Backward (dense upstream gradient): a warp owns RW rows and strides the columns of a
+// column chunk; hyper-parameter and input-coordinate adjoints are accumulated in registers,
+// reduced with warp shuffles and committed with one atomicAdd per warp and output value.
+#include "common.cuh"
+
+namespace {
+
+// value of the additive kernel for one pair; a[] and b[] already scaled by 1/l
+template <typename T, int NC, int DPC>
+__device__ __forceinline__ T eval_pair(const DevSpec& sp, const T* os, const T (&a)[NC * DPC],
+                                       const T (&b)[NC * DPC]) {
+    T val = T(0);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        T acc = T(0);
+#pragma unroll
+        for (int j = 0; j < DPC; ++j) {
+            T d = a[c * DPC + j] - b[c * DPC + j];
+            acc = fma(d, d, acc);
+        }
+        val = fma(os[c], kernel_phi<T>(sp.kind[c], acc), val);
+    }
+    return val;
+}
+
+// accumulate the adjoints of one pair: g multiplies dK/dtheta, gs multiplies dK/da
+template <typename T, int NC, int DPC>
+__device__ __forceinline__ void accum_pair(const DevSpec& sp, const T* os, const T (&a)[NC * DPC],
+                                           const T (&b)[NC * DPC], T g, T gs, T (&gl)[NC * DPC], T (&go)[NC],
+                                           T (&ga)[NC * DPC]) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        T acc = T(0);
+        T u[DPC];
+#pragma unroll
+        for (int j = 0; j < DPC; ++j) {
+            u[j] = a[c * DPC + j] - b[c * DPC + j];
+            acc = fma(u[j], u[j], acc);
+        }
+        T phi, w;
+        kernel_phi_w<T>(sp.kind[c], acc, phi, w);
+        go[c] = fma(g, phi, go[c]);
+        const T ow = os[c] * w;
+        const T gow = g * ow, gsow = -gs * ow;
+#pragma unroll
+        for (int j = 0; j < DPC; ++j) {
+            gl[c * DPC + j] = fma(gow * u[j], u[j], gl[c * DPC + j]);
+            ga[c * DPC + j] = fma(gsow, u[j], ga[c * DPC + j]);
+        }
+    }
+}
+
+// commit warp-reduced hyper-parameter adjoints: d/dl_k = sum g*os*w*u_k^2 / l_k
+template <typename T, int NC, int DPC>
+__device__ __forceinline__ void commit_theta(const DevSpec& sp, const SpecVals<T>& sv, T (&gl)[NC * DPC], T (&go)[NC],
+                                             T* dls, T* dos, int lane) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+#pragma unroll
+        for (int j = 0; j < DPC; ++j) {
+            T v = warp_sum(gl[c * DPC + j]);
+            if (lane == 0 && dls && c < sp.n_comp && j < sp.ndims[c])
+                atomicAdd(&dls[c * DCGP_MAX_DIMS + j], v * sv.inv_ls[c * DPC + j]);
+        }
+        T v = warp_sum(go[c]);
+        if (lane == 0 && dos && c < sp.n_comp) atomicAdd(&dos[c], v);
+    }
+}
+
+template <typename T, typename TO, int NC, int DPC>
+__global__ void __launch_bounds__(256) gram_fwd_kernel(const __grid_constant__ DevSpec sp, const T* __restrict__ x1,
+                                                       int64_t n1, int64_t ldx1, const T* __restrict__ x2, int64_t n2,
+                                                       int64_t ldx2, TO* __restrict__ K, int64_t ldk,
+                                                       const T* __restrict__ diag_dev, T diag_const, int same,
+                                                       int vec_ok) {
+    constexpr int TD = NC * DPC;
+    constexpr int VEC = 16 / sizeof(TO);
+    constexpr int TCOLS = 32 * VEC;
+    constexpr int TROWS = 64;
+    __shared__ SpecVals<T> sv;
+    __shared__ T s1[TROWS][TD];
+    load_spec_vals<T>(sp, &sv);
+    __syncthreads();
+    const int64_t row0 = (int64_t)blockIdx.y * TROWS;
+    const int64_t col0 = (int64_t)blockIdx.x * TCOLS;
+    for (int e = threadIdx.x; e < TROWS * TD; e += 256) {
+        int r = e / TD, k = e % TD;
+        s1[r][k] = (row0 + r < n1) ? x1[(row0 + r) * ldx1 + sp.col[k]] * sv.inv_ls[k] : T(0);
+    }
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    T b[VEC][TD];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        int64_t c = col0 + tx * VEC + v;
+#pragma unroll
+        for (int k = 0; k < TD; ++k) b[v][k] = (c < n2) ? x2[c * ldx2 + sp.col[k]] * sv.inv_ls[k] : T(0);
+    }
+    T dadd = T(0);
+    if (same) dadd = diag_const + (diag_dev ? diag_dev[0] : T(0));
+    __syncthreads();
+#pragma unroll 2
+    for (int rr = 0; rr < TROWS / 8; ++rr) {
+        const int r = rr * 8 + ty;
+        const int64_t row = row0 + r;
+        if (row >= n1) break;
+        T a[TD];
+#pragma unroll
+        for (int k = 0; k < TD; ++k) a[k] = s1[r][k];
+        TO out[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            T val = eval_pair<T, NC, DPC>(sp, sv.os, a, b[v]);
+            if (same && row == col0 + tx * VEC + v) val += dadd;
+            out[v] = (TO)val;
+        }
+        const int64_t c = col0 + tx * VEC;
+        TO* dst = K + row * ldk + c;
+        if (vec_ok && c + VEC <= n2) {
+            if constexpr (sizeof(TO) == 8) {
+                *reinterpret_cast<double2*>(dst) = make_double2((double)out[0], (double)out[1]);
+            } else {
+                *reinterpret_cast<float4*>(dst) =
+                    make_float4((float)out[0], (float)out[1], (float)out[2], (float)out[3]);
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                if (c + v < n2) dst[v] = out[v];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// backward, dense upstream gradient G (n1 x n2)
+// ---------------------------------------------------------------------------------------
+template <typename T, int NC, int DPC, int RW>
+__global__ void __launch_bounds__(256) gram_bwd_kernel(const __grid_constant__ DevSpec sp, const T* __restrict__ x1,
+                                                       int64_t n1, int64_t ldx1, const T* __restrict__ x2, int64_t n2,
+                                                       int64_t ldx2, const T* __restrict__ G, int64_t ldg,
+                                                       T* __restrict__ dls, T* __restrict__ dos, T* __restrict__ dx1,
+                                                       int64_t lddx1, int same, int cblk) {
+    constexpr int TD = NC * DPC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* s2 = reinterpret_cast<T*>(smem_raw);  // [TD][cblk]
+    __shared__ SpecVals<T> sv;
+    load_spec_vals<T>(sp, &sv);
+    __syncthreads();
+    const int64_t col0 = (int64_t)blockIdx.x * cblk;
+    const int ncols = (int)min((int64_t)cblk, n2 - col0);
+    for (int e = threadIdx.x; e < TD * cblk; e += 256) {
+        int k = e / cblk, c = e % cblk;
+        s2[e] = (c < ncols) ? x2[(col0 + c) * ldx2 + sp.col[k]] * sv.inv_ls[k] : T(0);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row0 = ((int64_t)blockIdx.y * 8 + warp) * RW;
+    if (row0 >= n1) return;
+    T a[RW][TD], gx[RW][TD], gl[TD], go[NC];
+#pragma unroll
+    for (int r = 0; r < RW; ++r)
+#pragma unroll
+        for (int k = 0; k < TD; ++k) {
+            a[r][k] = (row0 + r < n1) ? x1[(row0 + r) * ldx1 + sp.col[k]] * sv.inv_ls[k] : T(0);
+            gx[r][k] = T(0);
+        }
+#pragma unroll
+    for (int k = 0; k < TD; ++k) gl[k] = T(0);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) go[c] = T(0);
+
+    for (int cc = lane; cc < ncols; cc += 32) {
+        const int64_t col = col0 + cc;
+        T b[TD];
+#pragma unroll
+        for (int k = 0; k < TD; ++k) b[k] = s2[k * cblk + cc];
+#pragma unroll
+        for (int r = 0; r < RW; ++r) {
+            const int64_t row = row0 + r;
+            if (row < n1) {
+                const T g = G[row * ldg + col];
+                const T gs = same ? g + G[col * ldg + row] : g;  // both argument slots for d/dx
+                accum_pair<T, NC, DPC>(sp, sv.os, a[r], b, g, gs, gl, go, gx[r]);
+            }
+        }
+    }
+    commit_theta<T, NC, DPC>(sp, sv, gl, go, dls, dos, lane);
+    if (dx1) {
+#pragma unroll
+        for (int r = 0; r < RW; ++r)
+#pragma unroll
+            for (int k = 0; k < TD; ++k) {
+                T v = warp_sum(gx[r][k]);
+                if (lane == 0 && row0 + r < n1 && (k / DPC) < sp.n_comp && (k % DPC) < sp.ndims[k / DPC])
+                    atomicAdd(&dx1[(row0 + r) * lddx1 + sp.col[k]], v * sv.inv_ls[k]);
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// bag-summed cross Gram: out[a, i] = sum_{j in bag a} k(z_i, x_j)   (n_bags x M)
+// A CTA owns 128 rows of z (one per thread, coordinates in registers) and BCH consecutive
+// bags; the bags' scaled coordinates stream through shared memory and are read as warp
+// broadcasts.  K_Zx (M x N) is never written.
+// ---------------------------------------------------------------------------------------
+constexpr int kBagChunk = 16;
+constexpr int kXTile = 256;
+
+template <typename T, int NC, int DPC>
+__global__ void __launch_bounds__(128) gram_bagsum_kernel(const __grid_constant__ DevSpec sp, const T* __restrict__ z,
+                                                          int64_t M, int64_t ldz, const T* __restrict__ x, int64_t ldx,
+                                                          const int64_t* __restrict__ offsets, int64_t n_bags,
+                                                          T* __restrict__ out, int64_t ldo) {
+    constexpr int TD = NC * DPC;
+    __shared__ SpecVals<T> sv;
+    __shared__ T sx[kXTile][TD];
+    load_spec_vals<T>(sp, &sv);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    T a[TD];
+#pragma unroll
+    for (int k = 0; k < TD; ++k) a[k] = (i < M) ? z[i * ldz + sp.col[k]] * sv.inv_ls[k] : T(0);
+    const int64_t bag0 = (int64_t)blockIdx.y * kBagChunk;
+    const int64_t bag1 = min(bag0 + kBagChunk, n_bags);
+    for (int64_t bag = bag0; bag < bag1; ++bag) {
+        const int64_t j0 = offsets[bag], j1 = offsets[bag + 1];
+        T sum = T(0);
+        for (int64_t jt = j0; jt < j1; jt += kXTile) {
+            const int nt = (int)min((int64_t)kXTile, j1 - jt);
+            __syncthreads();
+            for (int e = threadIdx.x; e < nt * TD; e += 128) {
+                int r = e / TD, k = e % TD;
+                sx[r][k] = x[(jt + r) * ldx + sp.col[k]] * sv.inv_ls[k];
+            }
+            __syncthreads();
+            for (int r = 0; r < nt; ++r) {
+                T b[TD];
+#pragma unroll
+                for (int k = 0; k < TD; ++k) b[k] = sx[r][k];
+                sum += eval_pair<T, NC, DPC>(sp, sv.os, a, b);
+            }
+        }
+        if (i < M) out[bag * ldo + i] = sum;
+    }
+}
+
+template <typename T, int NC, int DPC>
+__global__ void __launch_bounds__(128) gram_bagsum_bwd_kernel(const __grid_constant__ DevSpec sp,
+                                                              const T* __restrict__ z, int64_t M, int64_t ldz,
+                                                              const T* __restrict__ x, int64_t ldx,
+                                                              const int64_t* __restrict__ offsets, int64_t n_bags,
+                                                              const T* __restrict__ G, int64_t ldg, T* __restrict__ dls,
+                                                              T* __restrict__ dos, T* __restrict__ dz, int64_t lddz) {
+    constexpr int TD = NC * DPC;
+    __shared__ SpecVals<T> sv;
+    __shared__ T sx[kXTile][TD];
+    load_spec_vals<T>(sp, &sv);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    T a[TD], ga[TD], gl[TD], go[NC];
+#pragma unroll
+    for (int k = 0; k < TD; ++k) {
+        a[k] = (i < M) ? z[i * ldz + sp.col[k]] * sv.inv_ls[k] : T(0);
+        ga[k] = T(0);
+        gl[k] = T(0);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) go[c] = T(0);
+    const int64_t bag0 = (int64_t)blockIdx.y * kBagChunk;
+    const int64_t bag1 = min(bag0 + kBagChunk, n_bags);
+    for (int64_t bag = bag0; bag < bag1; ++bag) {
+        const int64_t j0 = offsets[bag], j1 = offsets[bag + 1];
+        const T g = (i < M) ? G[bag * ldg + i] : T(0);
+        for (int64_t jt = j0; jt < j1; jt += kXTile) {
+            const int nt = (int)min((int64_t)kXTile, j1 - jt);
+            __syncthreads();
+            for (int e = threadIdx.x; e < nt * TD; e += 128) {
+                int r = e / TD, k = e % TD;
+                sx[r][k] = x[(jt + r) * ldx + sp.col[k]] * sv.inv_ls[k];
+            }
+            __syncthreads();
+            for (int r = 0; r < nt; ++r) {
+                T b[TD];
+#pragma unroll
+                for (int k = 0; k < TD; ++k) b[k] = sx[r][k];
+                accum_pair<T, NC, DPC>(sp, sv.os, a, b, g, g, gl, go, ga);
+            }
+        }
+    }
+    commit_theta<T, NC, DPC>(sp, sv, gl, go, dls, dos, threadIdx.x & 31);
+    if (dz && i < M) {
+#pragma unroll
+        for (int k = 0; k < TD; ++k)
+            if ((k / DPC) < sp.n_comp && (k % DPC) < sp.ndims[k / DPC])
+                atomicAdd(&dz[i * lddz + sp.col[k]], ga[k] * sv.inv_ls[k]);
+    }
+}
+
+// within-bag block sums: out[a] = sum_{i,j in bag a} k(x_i, x_j); one CTA per bag.
+template <typename T, int NC, int DPC, bool BWD>
+__global__ void __launch_bounds__(256) gram_bag_blocksum_kernel(const __grid_constant__ DevSpec sp,
+                                                                const T* __restrict__ x, int64_t ldx,
+                                                                const int64_t* __restrict__ offsets,
+                                                                const T* __restrict__ g_in, T* __restrict__ out,
+                                                                T* __restrict__ dls, T* __restrict__ dos) {
+    constexpr int TD = NC * DPC;
+    __shared__ SpecVals<T> sv;
+    __shared__ T red[8];
+    load_spec_vals<T>(sp, &sv);
+    __syncthreads();
+    const int64_t bag = blockIdx.x;
+    const int64_t j0 = offsets[bag];
+    const int64_t na = offsets[bag + 1] - j0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T sum = T(0);
+    T gl[TD], go[NC], ga[TD];
+#pragma unroll
+    for (int k = 0; k < TD; ++k) gl[k] = ga[k] = T(0);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) go[c] = T(0);
+    const T g = BWD ? g_in[bag] : T(0);
+    // a warp takes rows i = warp, warp+8, ...; lanes stride the columns
+    for (int64_t i = warp; i < na; i += 8) {
+        T a[TD];
+#pragma unroll
+        for (int k = 0; k < TD; ++k) a[k] = x[(j0 + i) * ldx + sp.col[k]] * sv.inv_ls[k];
+        for (int64_t j = lane; j < na; j += 32) {
+            T b[TD];
+#pragma unroll
+            for (int k = 0; k < TD; ++k) b[k] = x[(j0 + j) * ldx + sp.col[k]] * sv.inv_ls[k];
+            if constexpr (BWD) accum_pair<T, NC, DPC>(sp, sv.os, a, b, g, g, gl, go, ga);
+            else sum += eval_pair<T, NC, DPC>(sp, sv.os, a, b);
+        }
+    }
+    if constexpr (BWD) {
+        commit_theta<T, NC, DPC>(sp, sv, gl, go, dls, dos, lane);
+    } else {
+        sum = warp_sum(sum);
+        if (lane == 0) red[warp] = sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            T t = T(0);
+            for (int w = 0; w < 8; ++w) t += red[w];
+            out[bag] = t;
+        }
+    }
+}
+
+template <typename T>
+__global__ void bag_sum_kernel(const T* __restrict__ X, int64_t ldx, int64_t m, const int64_t* __restrict__ offsets,
+                               T* __restrict__ out, int64_t ldo) {
+    const int64_t bag = blockIdx.x;
+    const int64_t j0 = offsets[bag], j1 = offsets[bag + 1];
+    for (int64_t c = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; c < m; c += (int64_t)gridDim.y * blockDim.x) {
+        T s = T(0);
+        for (int64_t j = j0; j < j1; ++j) s += X[j * ldx + c];
+        out[bag * ldo + c] = s;
+    }
+}
+
+// whitened KL, one pass over Ls
+template <typename T>
+__global__ void __launch_bounds__(256) whitened_kl_kernel(const T* __restrict__ m, const T* __restrict__ Ls, int64_t M,
+                                                          int64_t ldls, T* __restrict__ out, T* __restrict__ dm,
+                                                          T* __restrict__ dLs, int64_t lddls) {
+    __shared__ T red[8];
+    T acc = T(0);
+    const int64_t total = M * M;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+        const int64_t i = e / M, j = e % M;
+        T g = T(0);
+        if (j <= i) {
+            const T v = Ls[i * ldls + j];
+            acc = fma(v, v, acc);
+            g = v;
+            if (i == j) {
+                acc -= t_log<T>(v * v) + T(1);
+                g -= T(1) / v;
+                const T mi = m[i];
+                acc = fma(mi, mi, acc);
+                if (dm) dm[i] = mi;
+            }
+        }
+        if (dLs) dLs[i * lddls + j] = g;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T t = T(0);
+        for (int w = 0; w < 8; ++w) t += red[w];
+        atomicAdd(out, T(0.5) * t);
+    }
+}
+
+// ------------------------------------------------------------------------- launchers
+template <typename T, typename TO>
+int launch_gram_fwd(const DevSpec& sp, const void* x1, int64_t n1, int64_t ldx1, const void* x2, int64_t n2,
+                    int64_t ldx2, void* K, int64_t ldk, const void* diag_dev, double diag_const, int same,
+                    cudaStream_t st) {
+    constexpr int VEC = 16 / sizeof(TO);
+    dim3 grid((unsigned)((n2 + 32 * VEC - 1) / (32 * VEC)), (unsigned)((n1 + 63) / 64));
+    int vec_ok = ((reinterpret_cast<uintptr_t>(K) % 16) == 0) && ((ldk * sizeof(TO)) % 16 == 0);
+#define CALL(NCV, DPCV)                                                                                      \
+    gram_fwd_kernel<T, TO, NCV, DPCV><<<grid, 256, 0, st>>>(sp, (const T*)x1, n1, ldx1, (const T*)x2, n2, ldx2, \
+                                                            (TO*)K, ldk, (const T*)diag_dev, (T)diag_const, same, \
+                                                            vec_ok);
+    DCGP_DISPATCH_LAYOUT(sp, CALL);
+#undef CALL
+    DCGP_CHECK_LAUNCH();
+    return 0;
+}
+
+template <typename T, int NC, int DPC, int RW>
+void launch_gram_bwd_one(const DevSpec& sp, const void* x1, int64_t n1, int64_t ldx1, const void* x2, int64_t n2,
+                         int64_t ldx2, const void* G, int64_t ldg, void* dls, void* dos, void* dx1, int64_t lddx1,
+                         int same, cudaStream_t st) {
+    const int cblk = 512;
+    size_t smem = (size_t)NC * DPC * cblk * sizeof(T);
+    dim3 grid((unsigned)((n2 + cblk - 1) / cblk), (unsigned)((n1 + 8 * RW - 1) / (8 * RW)));
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(gram_bwd_kernel<T, NC, DPC, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gram_bwd_kernel<T, NC, DPC, RW><<<grid, 256, smem, st>>>(sp, (const T*)x1, n1, ldx1, (const T*)x2, n2, ldx2,
+                                                             (const T*)G, ldg, (T*)dls, (T*)dos, (T*)dx1, lddx1, same,
+                                                             cblk);
+}
+
+template <typename T>
+int launch_gram_bwd(const DevSpec& sp, const void* x1, int64_t n1, int64_t ldx1, const void* x2, int64_t n2,
+                    int64_t ldx2, const void* G, int64_t ldg, void* dls, void* dos, void* dx1, int64_t lddx1,
+                    int same, cudaStream_t st) {
+#define CALL(NCV, DPCV)                                                                                             \
+    launch_gram_bwd_one<T, NCV, DPCV, (NCV * DPCV <= 4 ? 4 : (NCV * DPCV <= 8 ? 2 : 1))>(sp, x1, n1, ldx1, x2, n2,  \
+                                                                                         ldx2, G, ldg, dls, dos,   \
+                                                                                         dx1, lddx1, same, st);
+    DCGP_DISPATCH_LAYOUT(sp, CALL);
+#undef CALL
+    DCGP_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int dcgp_gram(const dcgp_kernel_spec* spec, const void* x1, int64_t n1, int64_t ldx1, const void* x2,
+                         int64_t n2, int64_t ldx2, void* K, int64_t ldk, const void* diag_dev, double diag_const,
+                         int dtype, int flags, void* stream) {
+    DevSpec sp;
+    if (make_dev_spec(spec, &sp)) return -1;
+    if (!x1 || n1 < 0) return -2;
+    if (!x2 || n2 < 0) return -5;
+    if (!K || ldk < n2) return -8;
+    if (n1 == 0 || n2 == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int same = (flags & DCGP_GRAM_SAME) ? 1 : 0;
+    if (dtype == DCGP_F64)
+        return launch_gram_fwd<double, double>(sp, x1, n1, ldx1, x2, n2, ldx2, K, ldk, diag_dev, diag_const, same, st);
+    if (dtype == DCGP_F32) {
+        if (flags & DCGP_GRAM_OUT_F64)
+            return launch_gram_fwd<float, double>(sp, x1, n1, ldx1, x2, n2, ldx2, K, ldk, diag_dev, diag_const, same,
+                                                  st);
+        return launch_gram_fwd<float, float>(sp, x1, n1, ldx1, x2, n2, ldx2, K, ldk, diag_dev, diag_const, same, st);
+    }
+    return -12;
+}
+
+extern "C" int dcgp_gram_bwd(const dcgp_kernel_spec* spec, const void* x1, int64_t n1, int64_t ldx1, const void* x2,
+                             int64_t n2, int64_t ldx2, const void* G, int64_t ldg, void* dls, void* dos, void* dx1,
+                             int64_t lddx1, int dtype, int flags, void* stream) {
+    DevSpec sp;
+    if (make_dev_spec(spec, &sp)) return -1;
+    if (!x1 || n1 < 0) return -2;
+    if (!x2 || n2 < 0) return -5;
+    if (!G || ldg < n2) return -8;
+    const int same = (flags & DCGP_GRAM_SAME) ? 1 : 0;
+    if (same && n1 != n2) return -15;
+    if (n1 == 0 || n2 == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == DCGP_F64)
+        return launch_gram_bwd<double>(sp, x1, n1, ldx1, x2, n2, ldx2, G, ldg, dls, dos, dx1, lddx1, same, st);
+    if (dtype == DCGP_F32)
+        return launch_gram_bwd<float>(sp, x1, n1, ldx1, x2, n2, ldx2, G, ldg, dls, dos, dx1, lddx1, same, st);
+    return -14;
+}
+
+extern "C" int dcgp_bag_sum(const void* X, int64_t ldx, int64_t m, const int64_t* offsets, int64_t n_bags, void* out,
+                            int64_t ldo, int dtype, void* stream) {
+    if (!X || !offsets || !out) return -1;
+    if (n_bags <= 0 || m <= 0) return 0;
+    dim3 grid((unsigned)n_bags, (unsigned)((m + 127) / 128));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == DCGP_F64)
+        bag_sum_kernel<double><<<grid, 128, 0, st>>>((const double*)X, ldx, m, offsets, (double*)out, ldo);
+    else if (dtype == DCGP_F32)
+        bag_sum_kernel<float><<<grid, 128, 0, st>>>((const float*)X, ldx, m, offsets, (float*)out, ldo);
+    else
+        return -8;
+    DCGP_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dcgp_gram_bagsum(const dcgp_kernel_spec* spec, const void* z, int64_t M, int64_t ldz, const void* x,
+                                int64_t ldx, const int64_t* offsets, int64_t n_bags, void* out, int64_t ldo, int dtype,
+                                int flags, void* stream) {
+    DevSpec sp;
+    if (make_dev_spec(spec, &sp)) return -1;
+    if (!z || !x || !offsets || !out) return -2;
+    if (M <= 0 || n_bags <= 0) return 0;
+    dim3 grid((unsigned)((M + 127) / 128), (unsigned)((n_bags + kBagChunk - 1) / kBagChunk));
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(NCV, DPCV)                                                                                              \
+    if (dtype == DCGP_F64)                                                                                           \
+        gram_bagsum_kernel<double, NCV, DPCV><<<grid, 128, 0, st>>>(sp, (const double*)z, M, ldz, (const double*)x,  \
+                                                                    ldx, offsets, n_bags, (double*)out, ldo);        \
+    else                                                                                                             \
+        gram_bagsum_kernel<float, NCV, DPCV><<<grid, 128, 0, st>>>(sp, (const float*)z, M, ldz, (const float*)x, ldx, \
+                                                                   offsets, n_bags, (float*)out, ldo);
+    if (dtype != DCGP_F64 && dtype != DCGP_F32) return -11;
+    DCGP_DISPATCH_LAYOUT(sp, CALL);
+#undef CALL
+    DCGP_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dcgp_gram_bagsum_bwd(const dcgp_kernel_spec* spec, const void* z, int64_t M, int64_t ldz, const void* x,
+                                    int64_t ldx, const int64_t* offsets, int64_t n_bags, const void* G, int64_t ldg,
+                                    void* dls, void* dos, void* dz, int64_t lddz, int dtype, int flags, void* stream) {
+    DevSpec sp;
+    if (make_dev_spec(spec, &sp)) return -1;
+    if (!z || !x || !offsets || !G) return -2;
+    if (M <= 0 || n_bags <= 0) return 0;
+    dim3 grid((unsigned)((M + 127) / 128), (unsigned)((n_bags + kBagChunk - 1) / kBagChunk));
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(NCV, DPCV)                                                                                        \
+    if (dtype == DCGP_F64)                                                                                     \
+        gram_bagsum_bwd_kernel<double, NCV, DPCV><<<grid, 128, 0, st>>>(                                       \
+            sp, (const double*)z, M, ldz, (const double*)x, ldx, offsets, n_bags, (const double*)G, ldg,       \
+            (double*)dls, (double*)dos, (double*)dz, lddz);                                                    \
+    else                                                                                                       \
+        gram_bagsum_bwd_kernel<float, NCV, DPCV><<<grid, 128, 0, st>>>(                                        \
+            sp, (const float*)z, M, ldz, (const float*)x, ldx, offsets, n_bags, (const float*)G, ldg,          \
+            (float*)dls, (float*)dos, (float*)dz, lddz);
+    if (dtype != DCGP_F64 && dtype != DCGP_F32) return -15;
+    DCGP_DISPATCH_LAYOUT(sp, CALL);
+#undef CALL
+    DCGP_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dcgp_gram_bag_blocksum(const dcgp_kernel_spec* spec, const void* x, int64_t ldx, const int64_t* offsets,
+                                      int64_t n_bags, void* out, int dtype, int flags, void* stream) {
+    DevSpec sp;
+    if (make_dev_spec(spec, &sp)) return -1;
+    if (!x || !offsets || !out) return -2;
+    if (n_bags <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(NCV, DPCV)                                                                                            \
+    if (dtype == DCGP_F64)                                                                                         \
+        gram_bag_blocksum_kernel<double, NCV, DPCV, false><<<(unsigned)n_bags, 256, 0, st>>>(                      \
+            sp, (const double*)x, ldx, offsets, nullptr, (double*)out, nullptr, nullptr);                          \
+    else                                                                                                           \
+        gram_bag_blocksum_kernel<float, NCV, DPCV, false><<<(unsigned)n_bags, 256, 0, st>>>(                       \
+            sp, (const float*)x, ldx, offsets, nullptr, (float*)out, nullptr, nullptr);
+    if (dtype != DCGP_F64 && dtype != DCGP_F32) return -7;
+    DCGP_DISPATCH_LAYOUT(sp, CALL);
+#undef CALL
+    DCGP_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dcgp_gram_bag_blocksum_bwd(const dcgp_kernel_spec* spec, const void* x, int64_t ldx,
+                                          const int64_t* offsets, int64_t n_bags, const void* g, void* dls, void* dos,
+                                          int dtype, int flags, void* stream) {
+    DevSpec sp;
+    if (make_dev_spec(spec, &sp)) return -1;
+    if (!x || !offsets || !g) return -2;
+    if (n_bags <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(NCV, DPCV)                                                                                            \
+    if (dtype == DCGP_F64)                                                                                         \
+        gram_bag_blocksum_kernel<double, NCV, DPCV, true><<<(unsigned)n_bags, 256, 0, st>>>(                       \
+            sp, (const double*)x, ldx, offsets, (const double*)g, nullptr, (double*)dls, (double*)dos);            \
+    else                                                                                                           \
+        gram_bag_blocksum_kernel<float, NCV, DPCV, true><<<(unsigned)n_bags, 256, 0, st>>>(                        \
+            sp, (const float*)x, ldx, offsets, (const float*)g, nullptr, (float*)dls, (float*)dos);
+    if (dtype != DCGP_F64 && dtype != DCGP_F32) return -9;
+    DCGP_DISPATCH_LAYOUT(sp, CALL);
+#undef CALL
+    DCGP_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dcgp_whitened_kl(const void* m, const void* Ls, int64_t M, int64_t ldls, void* out, void* dm, void* dLs,
+                                int64_t lddls, int dtype, void* stream) {
+    if (!m || !Ls || !out) return -1;
+    if (M <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t total = M * M;
+    unsigned grid = (unsigned)min((int64_t)(num_sms() * 4), (total + 255) / 256);
+    if (dtype == DCGP_F64)
+        whitened_kl_kernel<double><<<grid, 256, 0, st>>>((const double*)m, (const double*)Ls, M, ldls, (double*)out,
+                                                         (double*)dm, (double*)dLs, lddls);
+    else if (dtype == DCGP_F32)
+        whitened_kl_kernel<float><<<grid, 256, 0, st>>>((const float*)m, (const float*)Ls, M, ldls, (float*)out,
+                                                        (float*)dm, (float*)dLs, lddls);
+    else
+        return -9;
+    DCGP_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,263 @@
+"""Thin Python launchers over the C ABI (include/dcgp.h) and the
+torch.autograd.Function wrappers with hand-written backward passes.
+
+torch is plumbing here: it owns device memory and the current stream; every
+O(N^2)/O(N^3) operation is a libdcgp kernel.  No function in this module has a
+CPU or pure-torch fallback: non-CUDA tensors raise.
+"""
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import F32, F64, GEMM_LOWER, GRAM_SAME, KernelSpec, MAX_DIMS, check
+
+KINDS = {"rbf": _lib.KIND_RBF, "matern32": _lib.KIND_MATERN32, "matern12": _lib.KIND_MATERN12,
+         "matern52": _lib.KIND_MATERN52}
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float64:
+        return F64
+    if t.dtype == torch.float32:
+        return F32
+    raise TypeError(f"libdcgp supports float64 and float32, got {t.dtype}")
+
+
+def _req(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.DcgpError("libdcgp ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _rowmajor(t: torch.Tensor) -> torch.Tensor:
+    """2-D tensor whose last dim is contiguous (row stride arbitrary)."""
+    if t.dim() == 1:
+        t = t.unsqueeze(-1)
+    if t.stride(-1) != 1 or (t.size(0) > 1 and t.stride(0) < t.size(1)):
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.size(0) > 1 else max(t.size(1), 1)
+
+
+class FlatSpec:
+    """Additive kernel = list of (kind, dims, lengthscale[nd], outputscale[]) with the
+    hyper-parameters as device tensors (already softplus-transformed)."""
+
+    def __init__(self, kinds: Sequence[str], dims: Sequence[Sequence[int]], lengthscales: Sequence[torch.Tensor],
+                 outputscales: Sequence[torch.Tensor]):
+        self.kinds, self.dims = list(kinds), [list(d) for d in dims]
+        self.lengthscales = [l.reshape(-1).contiguous() for l in lengthscales]
+        self.outputscales = [o.reshape(1).contiguous() for o in outputscales]
+        if not (1 <= len(self.kinds) <= _lib.MAX_COMPONENTS):
+            raise ValueError("1..4 additive components supported")
+
+    def cast(self, dtype):
+        return FlatSpec(self.kinds, self.dims, [l.to(dtype) for l in self.lengthscales],
+                        [o.to(dtype) for o in self.outputscales])
+
+    def detach(self):
+        return FlatSpec(self.kinds, self.dims, [l.detach() for l in self.lengthscales],
+                        [o.detach() for o in self.outputscales])
+
+    def c_spec(self) -> KernelSpec:
+        s = KernelSpec()
+        s.n_components = len(self.kinds)
+        for c, (kind, dims, ls, os_) in enumerate(zip(self.kinds, self.dims, self.lengthscales, self.outputscales)):
+            _req(ls, os_)
+            if ls.numel() != len(dims):
+                raise ValueError("lengthscale size must match active dims")
+            s.comp[c].kind = KINDS[kind]
+            s.comp[c].ndims = len(dims)
+            for j, d in enumerate(dims):
+                s.comp[c].dims[j] = int(d)
+            s.comp[c].lengthscale = ls.data_ptr()
+            s.comp[c].outputscale = os_.data_ptr()
+        return s
+
+
+# --------------------------------------------------------------------------------------
+# raw launchers (no autograd)
+# --------------------------------------------------------------------------------------
+def gram(spec: FlatSpec, x1, x2=None, diag_dev=None, diag_const=0.0, out=None):
+    same = x2 is None
+    x1 = _rowmajor(x1)
+    x2 = x1 if same else _rowmajor(x2)
+    _req(x1, x2, diag_dev)
+    n1, n2 = x1.size(0), x2.size(0)
+    K = out if out is not None else torch.empty(n1, n2, dtype=x1.dtype, device=x1.device)
+    cs = spec.c_spec()
+    rc = _lib.load().dcgp_gram(ctypes.byref(cs), _ptr(x1), n1, _ld(x1), _ptr(x2), n2, _ld(x2), _ptr(K), _ld(K),
+                               _ptr(diag_dev), float(diag_const), _dt(x1), GRAM_SAME if same else 0, _stream())
+    check(rc, "dcgp_gram")
+    return K
+
+
+def gram_bwd(spec: FlatSpec, x1, x2, G, need_dx1=False):
+    """Returns (dls [ncomp, MAX_DIMS], dos [ncomp], dx1 or None)."""
+    same = x2 is None
+    x1 = _rowmajor(x1)
+    x2 = x1 if same else _rowmajor(x2)
+    G = _rowmajor(G)
+    _req(x1, x2, G)
+    nc = len(spec.kinds)
+    dls = torch.zeros(nc, MAX_DIMS, dtype=x1.dtype, device=x1.device)
+    dos = torch.zeros(nc, dtype=x1.dtype, device=x1.device)
+    dx1 = torch.zeros_like(x1) if need_dx1 else None
+    cs = spec.c_spec()
+    rc = _lib.load().dcgp_gram_bwd(ctypes.byref(cs), _ptr(x1), x1.size(0), _ld(x1), _ptr(x2), x2.size(0), _ld(x2),
+                                   _ptr(G), _ld(G), _ptr(dls), _ptr(dos), _ptr(dx1), _ld(dx1) if need_dx1 else 0,
+                                   _dt(x1), GRAM_SAME if same else 0, _stream())
+    check(rc, "dcgp_gram_bwd")
+    return dls, dos, dx1
+
+
+def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, C=None, lower=False, no_splitk=False):
+    """C = alpha * op(A) @ op(B) + beta * C."""
+    A, B = _rowmajor(A), _rowmajor(B)
+    _req(A, B, C)
+    m, k = (A.size(1), A.size(0)) if transa else (A.size(0), A.size(1))
+    k2, n = (B.size(1), B.size(0)) if transb else (B.size(0), B.size(1))
+    if k != k2:
+        raise ValueError(f"gemm inner dims differ: {k} vs {k2}")
+    if C is None:
+        C = torch.empty(m, n, dtype=A.dtype, device=A.device)
+        beta = 0.0
+    flags = (GEMM_LOWER if lower else 0) | (_lib.GEMM_NO_SPLITK if no_splitk else 0)
+    rc = _lib.load().dcgp_gemm(int(transa), int(transb), m, n, k, float(alpha), _ptr(A), _ld(A), _ptr(B), _ld(B),
+                               float(beta), _ptr(C), _ld(C), _dt(A), flags, _stream())
+    check(rc, "dcgp_gemm")
+    return C
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def potrf_(A, info=None):
+    """In-place lower Cholesky of the (row-major) square matrix A.  Returns the device info tensor."""
+    _req(A)
+    n = A.size(0)
+    if info is None:
+        info = torch.zeros(1, dtype=torch.int32, device=A.device)
+    lib = _lib.load()
+    ws = _workspace(lib.dcgp_potrf_workspace(n, _dt(A)), A.device)
+    rc = lib.dcgp_potrf(_ptr(A), n, _ld(A), _ptr(info), _ptr(ws), ws.numel(), _dt(A), 0, _stream())
+    check(rc, "dcgp_potrf")
+    return info
+
+
+def trsm_(L, B, trans=False):
+    """In-place solve op(L) X = B, B is (n, m) row-major."""
+    _req(L, B)
+    n, m = B.size(0), B.size(1)
+    lib = _lib.load()
+    ws = _workspace(lib.dcgp_trsm_workspace(n, m, _dt(L)), L.device)
+    rc = lib.dcgp_trsm(int(trans), _ptr(L), n, _ld(L), _ptr(B), m, _ld(B), _ptr(ws), ws.numel(), _dt(L), 0, _stream())
+    check(rc, "dcgp_trsm")
+    return B
+
+
+def potrs_(L, B):
+    _req(L, B)
+    n, m = B.size(0), B.size(1)
+    lib = _lib.load()
+    ws = _workspace(lib.dcgp_trsm_workspace(n, m, _dt(L)), L.device)
+    rc = lib.dcgp_potrs(_ptr(L), n, _ld(L), _ptr(B), m, _ld(B), _ptr(ws), ws.numel(), _dt(L), 0, _stream())
+    check(rc, "dcgp_potrs")
+    return B
+
+
+def logdet_chol(L):
+    _req(L)
+    out = torch.empty(1, dtype=L.dtype, device=L.device)
+    check(_lib.load().dcgp_logdet_chol(_ptr(L), L.size(0), _ld(L), _ptr(out), _dt(L), _stream()), "dcgp_logdet_chol")
+    return out[0]
+
+
+def bag_sum(X, offsets):
+    X = _rowmajor(X)
+    _req(X, offsets)
+    nb = offsets.numel() - 1
+    out = torch.empty(nb, X.size(1), dtype=X.dtype, device=X.device)
+    check(_lib.load().dcgp_bag_sum(_ptr(X), _ld(X), X.size(1), _ptr(offsets), nb, _ptr(out), _ld(out), _dt(X),
+                                   _stream()), "dcgp_bag_sum")
+    return out
+
+
+def gram_bagsum(spec, z, x, offsets):
+    z, x = _rowmajor(z), _rowmajor(x)
+    _req(z, x, offsets)
+    nb = offsets.numel() - 1
+    out = torch.empty(nb, z.size(0), dtype=z.dtype, device=z.device)
+    cs = spec.c_spec()
+    check(_lib.load().dcgp_gram_bagsum(ctypes.byref(cs), _ptr(z), z.size(0), _ld(z), _ptr(x), _ld(x), _ptr(offsets),
+                                       nb, _ptr(out), _ld(out), _dt(z), 0, _stream()), "dcgp_gram_bagsum")
+    return out
+
+
+def gram_bagsum_bwd(spec, z, x, offsets, G, need_dz=True):
+    z, x, G = _rowmajor(z), _rowmajor(x), _rowmajor(G)
+    _req(z, x, offsets, G)
+    nb = offsets.numel() - 1
+    nc = len(spec.kinds)
+    dls = torch.zeros(nc, MAX_DIMS, dtype=z.dtype, device=z.device)
+    dos = torch.zeros(nc, dtype=z.dtype, device=z.device)
+    dz = torch.zeros_like(z) if need_dz else None
+    cs = spec.c_spec()
+    check(_lib.load().dcgp_gram_bagsum_bwd(ctypes.byref(cs), _ptr(z), z.size(0), _ld(z), _ptr(x), _ld(x),
+                                           _ptr(offsets), nb, _ptr(G), _ld(G), _ptr(dls), _ptr(dos), _ptr(dz),
+                                           _ld(dz) if need_dz else 0, _dt(z), 0, _stream()), "dcgp_gram_bagsum_bwd")
+    return dls, dos, dz
+
+
+def gram_bag_blocksum(spec, x, offsets):
+    x = _rowmajor(x)
+    _req(x, offsets)
+    nb = offsets.numel() - 1
+    out = torch.empty(nb, dtype=x.dtype, device=x.device)
+    cs = spec.c_spec()
+    check(_lib.load().dcgp_gram_bag_blocksum(ctypes.byref(cs), _ptr(x), _ld(x), _ptr(offsets), nb, _ptr(out), _dt(x),
+                                             0, _stream()), "dcgp_gram_bag_blocksum")
+    return out
+
+
+def gram_bag_blocksum_bwd(spec, x, offsets, g):
+    x = _rowmajor(x)
+    g = g.contiguous()
+    _req(x, offsets, g)
+    nb = offsets.numel() - 1
+    nc = len(spec.kinds)
+    dls = torch.zeros(nc, MAX_DIMS, dtype=x.dtype, device=x.device)
+    dos = torch.zeros(nc, dtype=x.dtype, device=x.device)
+    cs = spec.c_spec()
+    check(_lib.load().dcgp_gram_bag_blocksum_bwd(ctypes.byref(cs), _ptr(x), _ld(x), _ptr(offsets), nb, _ptr(g),
+                                                 _ptr(dls), _ptr(dos), _dt(x), 0, _stream()),
+          "dcgp_gram_bag_blocksum_bwd")
+    return dls, dos
+
+
+def whitened_kl(m, Ls, need_grad=False):
+    m = m.contiguous()
+    Ls = _rowmajor(Ls)
+    _req(m, Ls)
+    out = torch.zeros(1, dtype=m.dtype, device=m.device)
+    dm = torch.empty_like(m) if need_grad else None
+    dLs = torch.empty(Ls.size(0), Ls.size(1), dtype=m.dtype, device=m.device) if need_grad else None
+    check(_lib.load().dcgp_whitened_kl(_ptr(m), _ptr(Ls), m.numel(), _ld(Ls), _ptr(out), _ptr(dm), _ptr(dLs),
+                                       _ld(dLs) if need_grad else 0, _dt(m), _stream()), "dcgp_whitened_kl")
+    return out[0], dm, dLs

@@ -1,0 +1,171 @@
+/*
+ * dcgp.h — C ABI of libdcgp.so: the B200 (sm_100a) hot path of the
+ * deconditional-GP framework (Gram assembly -> Cholesky / solves -> bag ELBO).
+ *
+ * The reference (shahineb/deconditional-downscaling) has no FFI of its own:
+ * every dense operation on this path is issued through gpytorch 1.4.0
+ * LazyTensor algebra into ATen/cuBLAS/cuSOLVER.  Each entry point below
+ * replaces the library call sequence triggered at the cited reference line;
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the
+ * reference side.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types.  All data pointers are
+ *     DEVICE pointers unless stated; the caller owns every buffer (inputs,
+ *     outputs, workspace); the library never allocates device memory, never
+ *     synchronises the stream and keeps no mutable global state.
+ *   - matrices are ROW-MAJOR with an explicit leading dimension (elements
+ *     between consecutive rows).
+ *   - dtype: DCGP_F64 computes and stores in double (FP64 tensor/vector
+ *     pipes); DCGP_F32 stores float and contracts on TF32 tensor cores.
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - return value: 0 = success; -k = argument k (1-based) invalid;
+ *     <= -1000 = -(1000 + cudaError_t).  Factorisation failures are reported
+ *     LAPACK-style through a device `int* info` (0 ok, i>0: leading minor i
+ *     not positive definite) so no host synchronisation is forced.
+ */
+#ifndef DCGP_H_
+#define DCGP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DCGP_API __attribute__((visibility("default")))
+#else
+#define DCGP_API
+#endif
+
+#define DCGP_F64 0
+#define DCGP_F32 1
+
+#define DCGP_KIND_RBF 0      /* os * exp(-r^2/2)                       gpytorch RBFKernel     */
+#define DCGP_KIND_MATERN32 1 /* os * (1+sqrt3 r) exp(-sqrt3 r)         gpytorch MaternKernel(nu=1.5) */
+#define DCGP_KIND_MATERN12 2 /* os * exp(-r)                           MaternKernel(nu=0.5)   */
+#define DCGP_KIND_MATERN52 3 /* os * (1+sqrt5 r+5/3 r^2) exp(-sqrt5 r) MaternKernel(nu=2.5)   */
+
+#define DCGP_MAX_COMPONENTS 4
+#define DCGP_MAX_DIMS 8 /* active dims per component; total over components <= 16 */
+
+/* flags */
+#define DCGP_GRAM_SAME 1        /* x2 is x1 (enables +diag and the symmetric fast path)  */
+#define DCGP_GRAM_OUT_F64 2     /* dtype F32 inputs/math, store K as double (fp64 island) */
+#define DCGP_GEMM_LOWER 1       /* only tiles touching the lower triangle of C are computed/written */
+#define DCGP_GEMM_NO_SPLITK 2   /* C aliases an input (in-place): the K loop is never split across CTAs */
+
+/* One ScaleKernel(base kernel with ARD lengthscales, active_dims) term of an
+ * additive kernel.  lengthscale / outputscale are DEVICE pointers to the
+ * already-transformed (softplus) values in the compute dtype. */
+typedef struct dcgp_component {
+    int32_t kind;
+    int32_t ndims;
+    int32_t dims[DCGP_MAX_DIMS];
+    const void* lengthscale; /* [ndims] */
+    const void* outputscale; /* [1]     */
+} dcgp_component;
+
+typedef struct dcgp_kernel_spec {
+    int32_t n_components;
+    int32_t reserved;
+    dcgp_component comp[DCGP_MAX_COMPONENTS];
+} dcgp_kernel_spec;
+
+DCGP_API int dcgp_version(void);
+/* compiled SM architecture * 10 (1000 for sm_100a) */
+DCGP_API int dcgp_arch(void);
+
+/* ---- Gram assembly ---------------------------------------------------
+ * K[i,j] = sum_c os_c * phi_c(|| (x1_i - x2_j)[dims_c] / l_c ||)  (+ diag on i==j if SAME)
+ * Replaces gpytorch Kernel.__call__ -> covar_dist -> exp/matern post-processing
+ * (reference call sites src/models/cmp.py:60,65,98,99; src/models/variational_cmp.py:79,99,103;
+ *  src/kernels/cme_aggregate_kernel.py:38-39; src/means/cme_aggregate_mean.py:36).
+ * diag_dev: optional device scalar added to the diagonal (e.g. sigma_ind^2),
+ * diag_const: host constant added to the diagonal (lbda*N, jitter). */
+DCGP_API int dcgp_gram(const dcgp_kernel_spec* spec, const void* x1, int64_t n1, int64_t ldx1, const void* x2, int64_t n2,
+              int64_t ldx2, void* K, int64_t ldk, const void* diag_dev, double diag_const, int dtype, int flags,
+              void* stream);
+
+/* Backward of dcgp_gram for a dense upstream gradient G (n1 x n2):
+ *   dls[c*DCGP_MAX_DIMS + k] += sum_ij G_ij dK_ij/dl_{c,k}
+ *   dos[c]                   += sum_ij G_ij dK_ij/dos_c
+ *   dx1[i, col]              += sum_j  G_ij dK_ij/dx1_{i,col}      (optional, may be NULL)
+ * With DCGP_GRAM_SAME, x2 is x1 and dx1 receives both argument slots
+ * (G_ij + G_ji), i.e. the gradient w.r.t. the shared input.
+ * Outputs are ACCUMULATED into (caller zeroes them).  Replaces autograd through the
+ * same gpytorch ops (hyper-parameter leaves listed in SURVEY.md §8a). */
+DCGP_API int dcgp_gram_bwd(const dcgp_kernel_spec* spec, const void* x1, int64_t n1, int64_t ldx1, const void* x2, int64_t n2,
+                  int64_t ldx2, const void* G, int64_t ldg, void* dls, void* dos, void* dx1, int64_t lddx1, int dtype,
+                  int flags, void* stream);
+
+/* ---- dense contraction --------------------------------------------------
+ * C = alpha * op(A) op(B) + beta * C ; op(X) = X or X^T ; C is m x n, inner dim k.
+ * F64: DMMA (mma.sync m8n8k4 f64); F32: TF32 tensor cores.  With DCGP_GEMM_LOWER only
+ * tiles intersecting the lower triangle are touched (SYRK trailing update).
+ * Replaces the MatmulLazyTensor / torch.matmul products of
+ * src/kernels/cme_aggregate_kernel.py:63-70, src/likelihoods/cmp_likelihood.py:61-73,
+ * src/variational/variational_strategy.py:44-65. */
+DCGP_API int dcgp_gemm(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
+              const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype, int flags, void* stream);
+
+/* ---- Cholesky and triangular solves -----------------------------------------
+ * dcgp_potrf: A (n x n, lower triangle read) is overwritten by L (A = L L^T) in its lower
+ * triangle; blocked right-looking, panel on CUDA cores, TRSM + SYRK trailing update on
+ * tensor cores.  *info (device) = 0 or the 1-based index of the first non-positive pivot.
+ * Replaces psd_safe_cholesky / root_inv_decomposition / inv_quad_logdet Cholesky
+ * (src/models/cmp.py:66-67, src/models/variational_cmp.py:99-100,
+ *  src/variational/variational_strategy.py:35, src/likelihoods/cmp_likelihood.py:58,69,73). */
+DCGP_API size_t dcgp_potrf_workspace(int64_t n, int dtype);
+DCGP_API int dcgp_potrf(void* A, int64_t n, int64_t lda, int* info, void* workspace, size_t workspace_bytes, int dtype,
+               int flags, void* stream);
+
+/* dcgp_trsm: solves op(L) X = B in place (B is n x m row-major), L lower triangular,
+ * trans = 0: L X = B, trans = 1: L^T X = B.  Replaces TriangularLazyTensor.inv_matmul /
+ * torch.triangular_solve (src/variational/variational_strategy.py:44) and, chained,
+ * cholesky_solve behind LazyTensor.inv_matmul (cmp_prediction_strategy.py:60,164). */
+DCGP_API size_t dcgp_trsm_workspace(int64_t n, int64_t m, int dtype);
+DCGP_API int dcgp_trsm(int trans, const void* L, int64_t n, int64_t ldl, void* B, int64_t m, int64_t ldb, void* workspace,
+              size_t workspace_bytes, int dtype, int flags, void* stream);
+/* dcgp_potrs: X = (L L^T)^{-1} B in place = trsm(0) then trsm(1). */
+DCGP_API int dcgp_potrs(const void* L, int64_t n, int64_t ldl, void* B, int64_t m, int64_t ldb, void* workspace,
+               size_t workspace_bytes, int dtype, int flags, void* stream);
+/* out[0] = 2 * sum_i log L_ii   (log det of L L^T) */
+DCGP_API int dcgp_logdet_chol(const void* L, int64_t n, int64_t ldl, void* out, int dtype, void* stream);
+
+/* ---- bag aggregation ------------------------------------------------------------
+ * Bags are contiguous row ranges: bag a = rows [offsets[a], offsets[a+1]) (int64 device array
+ * of n_bags+1 entries).  Replaces the python loops over bags of
+ * src/likelihoods/vbagg_gaussian_likelihood.py:75,99-101. */
+/* out[a, :] = sum_{i in bag a} X[i, :]            (X is N x m) */
+DCGP_API int dcgp_bag_sum(const void* X, int64_t ldx, int64_t m, const int64_t* offsets, int64_t n_bags, void* out,
+                 int64_t ldo, int dtype, void* stream);
+/* out[a, i] = sum_{j in bag a} k(z_i, x_j)        (n_bags x M) — bag-summed cross Gram, K_Zx never stored */
+DCGP_API int dcgp_gram_bagsum(const dcgp_kernel_spec* spec, const void* z, int64_t M, int64_t ldz, const void* x, int64_t ldx,
+                     const int64_t* offsets, int64_t n_bags, void* out, int64_t ldo, int dtype, int flags,
+                     void* stream);
+/* backward of dcgp_gram_bagsum for upstream G (n_bags x M): accumulates dls, dos, dz */
+DCGP_API int dcgp_gram_bagsum_bwd(const dcgp_kernel_spec* spec, const void* z, int64_t M, int64_t ldz, const void* x,
+                         int64_t ldx, const int64_t* offsets, int64_t n_bags, const void* G, int64_t ldg, void* dls,
+                         void* dos, void* dz, int64_t lddz, int dtype, int flags, void* stream);
+/* out[a] = sum_{i,j in bag a} k(x_i, x_j)         within-bag block sums 1_a^T K_xx 1_a */
+DCGP_API int dcgp_gram_bag_blocksum(const dcgp_kernel_spec* spec, const void* x, int64_t ldx, const int64_t* offsets,
+                           int64_t n_bags, void* out, int dtype, int flags, void* stream);
+/* backward of dcgp_gram_bag_blocksum for upstream g (n_bags): accumulates dls, dos */
+DCGP_API int dcgp_gram_bag_blocksum_bwd(const dcgp_kernel_spec* spec, const void* x, int64_t ldx, const int64_t* offsets,
+                               int64_t n_bags, const void* g, void* dls, void* dos, int dtype, int flags,
+                               void* stream);
+
+/* ---- whitened KL ---------------------------------------------------------------
+ * out[0] = 0.5 * (||tril(Ls)||_F^2 + ||m||^2 - M - sum_i log Ls_ii^2) in one pass over Ls
+ * (src/mlls/bag_variational_elbo.py:49 -> variational_strategy.kl_divergence()).
+ * dLs (M x M, optional) = tril(Ls) - diag(1/Ls_ii), dm (optional) = m. */
+DCGP_API int dcgp_whitened_kl(const void* m, const void* Ls, int64_t M, int64_t ldls, void* out, void* dm, void* dLs,
+                     int64_t lddls, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCGP_H_ */

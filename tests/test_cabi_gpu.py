@@ -1,0 +1,267 @@
+"""GPU parity tests of the C-ABI kernels (through the ctypes launchers in
+deconditional_downscaling_b200.ops) against the CPU oracle (oracle/restate.py)
+and the golden vectors produced by the reference's own src/ code.
+
+Tolerances: FP64 path 1e-6 relative (north_star), stated per assert; the
+FP32/TF32 path 1e-3 relative against the same FP64 oracle values.
+"""
+import math
+
+import pytest
+import torch
+from torch.nn.functional import softplus
+
+import golden_util as G
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def ops():
+    from deconditional_downscaling_b200 import ops as o
+    return o
+
+
+def dev(t, dtype):
+    return t.to(device=DEV, dtype=dtype)
+
+
+def flat(spec, dtype):
+    o = ops()
+    return o.FlatSpec([c.kind for c in spec.components],
+                      [list(c.dims) if c.dims is not None else list(range(c.raw_lengthscale.numel())) for c in spec.components],
+                      [dev(c.lengthscale.detach(), dtype) for c in spec.components],
+                      [dev(c.outputscale.detach(), dtype) for c in spec.components])
+
+
+def comp(kind, ls, os_, dims=None):
+    return R.Component(kind, torch.as_tensor(ls, dtype=torch.float64), torch.as_tensor(os_, dtype=torch.float64), dims)
+
+
+def relerr(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-300)).item()
+
+
+TOLS = {torch.float64: 1e-6, torch.float32: 1e-3}
+
+
+# ------------------------------------------------------------------ Gram forward
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_gram_matches_reference_golden(dtype):
+    g = G.load("gram")
+    rbf = R.KernelSpec([comp("rbf", g["rbf_raw_lengthscale"], g["rbf_raw_outputscale"])])
+    mat = R.KernelSpec([comp("matern32", g["mat_raw_lengthscale"], g["mat_raw_outputscale"], dims=[0, 1])])
+    add = R.KernelSpec(mat.components + [comp("rbf", g["add_rbf_raw_lengthscale"], g["add_rbf_raw_outputscale"], dims=[2])])
+    for name, s in (("rbf", rbf), ("mat", mat), ("add", add)):
+        K12 = ops().gram(flat(s, dtype), dev(g["x1"], dtype), dev(g["x2"], dtype))
+        K11 = ops().gram(flat(s, dtype), dev(g["x1"], dtype))
+        tol = 1e-10 if dtype == torch.float64 else 2e-5   # fp32 here is plain FFMA + __expf, not TF32
+        assert relerr(K12, g[name + "_x1x2"]) < tol
+        assert relerr(K11, g[name + "_x1x1"]) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("n1,n2,d", [(1, 1, 1), (63, 65, 3), (257, 130, 5), (1000, 777, 8)])
+def test_gram_ragged_shapes_vs_oracle(dtype, n1, n2, d):
+    torch.manual_seed(n1 * 7 + n2)
+    x1, x2 = torch.randn(n1, d, dtype=torch.float64), torch.randn(n2, d, dtype=torch.float64)
+    s = R.KernelSpec([comp("matern32", torch.randn(d) * 0.3, 0.1)]) if d % 2 else R.KernelSpec([comp("rbf", torch.randn(d) * 0.3, -0.2)])
+    ref = R.gram(s, x1, x2)
+    K = ops().gram(flat(s, dtype), dev(x1, dtype), dev(x2, dtype))
+    assert relerr(K, ref) < (1e-10 if dtype == torch.float64 else 3e-5)
+
+
+def test_gram_diag_add_and_exact_diagonal():
+    torch.manual_seed(0)
+    x = torch.randn(300, 3, dtype=torch.float64)
+    s = R.KernelSpec([comp("rbf", [0.1, 0.2, 0.3], 0.4)])
+    extra = torch.tensor([0.25], dtype=torch.float64, device=DEV)
+    K = ops().gram(flat(s, torch.float64), dev(x, torch.float64), None, diag_dev=extra, diag_const=1.5)
+    ref = R.gram(s, x) + (1.5 + 0.25) * torch.eye(300, dtype=torch.float64)
+    assert relerr(K, ref) < 1e-12
+    # difference form => the diagonal is exactly outputscale + diag (the reference zero-fills it, Appendix A)
+    os_ = softplus(torch.tensor(0.4, dtype=torch.float64)).item()
+    assert torch.equal(K.diagonal().cpu(), torch.full((300,), os_ + 1.75, dtype=torch.float64))
+
+
+# ------------------------------------------------------------------ Gram backward
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("case", ["rbf3", "additive", "same"])
+def test_gram_bwd_vs_oracle_autograd(dtype, case):
+    torch.manual_seed(5)
+    n1, n2 = 150, 97
+    if case == "additive":
+        d = 5
+        raw = [torch.randn(2, dtype=torch.float64).requires_grad_(), torch.randn(3, dtype=torch.float64).requires_grad_()]
+        ros = [torch.tensor(0.3, dtype=torch.float64, requires_grad=True), torch.tensor(-0.2, dtype=torch.float64, requires_grad=True)]
+        s = R.KernelSpec([R.Component("matern32", raw[0], ros[0], [0, 1]), R.Component("rbf", raw[1], ros[1], [2, 3, 4])])
+    else:
+        d = 3
+        raw = [torch.randn(3, dtype=torch.float64).requires_grad_()]
+        ros = [torch.tensor(0.3, dtype=torch.float64, requires_grad=True)]
+        s = R.KernelSpec([R.Component("rbf", raw[0], ros[0], None)])
+    x1 = torch.randn(n1, d, dtype=torch.float64, requires_grad=True)
+    same = case == "same"
+    x2 = None if same else torch.randn(n2, d, dtype=torch.float64)
+    Gup = torch.randn(n1, n1 if same else n2, dtype=torch.float64)
+    # oracle: gradient w.r.t. the *transformed* hypers (lengthscale, outputscale) and x1
+    ls = [softplus(r).detach().requires_grad_() for r in raw]
+    os_ = [softplus(r).detach().requires_grad_() for r in ros]
+
+    def k_of(a, b):
+        out = 0
+        for c, l, o in zip(s.components, ls, os_):
+            aa, bb = R._select(a, c.dims), R._select(b, c.dims)
+            dist2 = ((aa.unsqueeze(1) - bb.unsqueeze(0)) / l).pow(2).sum(-1)
+            if c.kind == "rbf":
+                out = out + o * torch.exp(-0.5 * dist2)
+            else:
+                r = dist2.clamp_min(1e-30).sqrt()
+                out = out + o * (1 + math.sqrt(3) * r) * torch.exp(-math.sqrt(3) * r)
+        return out
+
+    K = k_of(x1, x1 if same else x2)
+    (K * Gup).sum().backward()
+    fs = flat(s, dtype)
+    dls, dos, dx1 = ops().gram_bwd(fs, dev(x1.detach(), dtype), None if same else dev(x2, dtype), dev(Gup, dtype), need_dx1=True)
+    tol = 1e-9 if dtype == torch.float64 else 2e-4
+    for c in range(len(ls)):
+        nd = ls[c].numel()
+        assert relerr(dls[c, :nd], ls[c].grad) < tol
+        assert relerr(dos[c], os_[c].grad) < tol
+    assert relerr(dx1, x1.grad) < tol
+
+
+# ------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (130, 70, 33), (257, 300, 515), (64, 1000, 128)])
+def test_gemm_all_layouts(dtype, ta, tb, m, n, k):
+    torch.manual_seed(m + n + k)
+    A = torch.randn((k, m) if ta else (m, k), dtype=torch.float64)
+    B = torch.randn((n, k) if tb else (k, n), dtype=torch.float64)
+    C0 = torch.randn(m, n, dtype=torch.float64)
+    ref = 0.7 * (A.t() if ta else A) @ (B.t() if tb else B) - 0.3 * C0
+    C = dev(C0, dtype).clone()
+    ops().gemm(dev(A, dtype), dev(B, dtype), transa=ta, transb=tb, alpha=0.7, beta=-0.3, C=C)
+    assert relerr(C, ref) < (1e-13 if dtype == torch.float64 else 2e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_gemm_split_k_and_lower(dtype):
+    torch.manual_seed(1)
+    A = torch.randn(200, 4096, dtype=torch.float64)
+    ref = A @ A.t()
+    C = ops().gemm(dev(A, dtype), dev(A, dtype), transb=True)     # 2x2 tiles, deep K => split-K path
+    assert relerr(C, ref) < (1e-13 if dtype == torch.float64 else 2e-3)
+    P = torch.randn(700, 128, dtype=torch.float64)
+    S0 = torch.randn(700, 700, dtype=torch.float64)
+    S = dev(S0, dtype).clone()
+    ops().gemm(dev(P, dtype), dev(P, dtype), transb=True, alpha=-1.0, beta=1.0, C=S, lower=True)
+    ref = S0 - P @ P.t()
+    assert relerr(S.tril(), ref.tril()) < (1e-13 if dtype == torch.float64 else 2e-3)
+    # tiles strictly above the diagonal are untouched
+    assert torch.equal(S[:128, 128:].cpu().double(), S0[:128, 128:].to(dtype).double())
+
+
+# ------------------------------------------------------------------ Cholesky / solves
+def spd(n, dtype=torch.float64, seed=0):
+    torch.manual_seed(seed)
+    x = torch.randn(n, 3, dtype=torch.float64)
+    s = R.KernelSpec([comp("rbf", [0.5, 0.5, 0.5], 0.5)])
+    return R.gram(s, x) + 0.05 * n ** 0.5 * torch.eye(n, dtype=torch.float64)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("n", [1, 7, 128, 129, 300, 1000])
+def test_potrf_vs_lapack(dtype, n):
+    A = spd(n)
+    ref = torch.linalg.cholesky(A)
+    L = dev(A, dtype).clone()
+    info = ops().potrf_(L)
+    assert info.item() == 0
+    L = L.tril()
+    assert relerr(L, ref) < (1e-12 if dtype == torch.float64 else 2e-3)
+    assert relerr(L.double() @ L.double().t(), A) < (1e-13 if dtype == torch.float64 else 2e-3)
+    # logdet
+    ld = ops().logdet_chol(L)
+    assert abs(ld.item() - torch.logdet(A).item()) < (1e-9 if dtype == torch.float64 else 1e-3) * max(1.0, abs(torch.logdet(A).item()))
+
+
+def test_potrf_reports_first_bad_pivot():
+    A = spd(300)
+    A[200, 200] = -1.0
+    L = dev(A, torch.float64).clone()
+    info = ops().potrf_(L)
+    assert info.item() == 201
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("n,m", [(5, 1), (128, 40), (300, 129), (1000, 64)])
+def test_trsm_and_potrs_vs_lapack(dtype, n, m):
+    A = spd(n, seed=n)
+    Lref = torch.linalg.cholesky(A)
+    torch.manual_seed(m)
+    B = torch.randn(n, m, dtype=torch.float64)
+    L = dev(Lref, dtype)
+    tol = 1e-11 if dtype == torch.float64 else 3e-3
+    X0 = ops().trsm_(L, dev(B, dtype).clone(), trans=False)
+    assert relerr(X0, torch.linalg.solve_triangular(Lref, B, upper=False)) < tol
+    X1 = ops().trsm_(L, dev(B, dtype).clone(), trans=True)
+    assert relerr(X1, torch.linalg.solve_triangular(Lref.t(), B, upper=True)) < tol
+    X2 = ops().potrs_(L, dev(B, dtype).clone())
+    assert relerr(X2, torch.cholesky_solve(B, Lref)) < tol
+    # size-independent property: residual of the solve
+    assert relerr(dev(A, torch.float64) @ X2.double(), B) < (1e-11 if dtype == torch.float64 else 3e-3)
+
+
+# ------------------------------------------------------------------ bag kernels
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_bag_kernels_vs_oracle(dtype):
+    torch.manual_seed(9)
+    sizes = [5, 1, 300, 17, 64, 2]
+    N, M, d = sum(sizes), 140, 3
+    offs = torch.tensor([0] + list(torch.tensor(sizes).cumsum(0)), dtype=torch.int64)
+    x, z = torch.randn(N, d, dtype=torch.float64), torch.randn(M, d, dtype=torch.float64)
+    raw = torch.randn(3, dtype=torch.float64)
+    s = R.KernelSpec([comp("rbf", raw, 0.2)])
+    Kzx, Kxx = R.gram(s, z, x), R.gram(s, x)
+    E = torch.zeros(N, len(sizes), dtype=torch.float64)
+    for a in range(len(sizes)):
+        E[offs[a]:offs[a + 1], a] = 1
+    fs = flat(s, dtype)
+    tol = 1e-10 if dtype == torch.float64 else 5e-5
+    out = ops().gram_bagsum(fs, dev(z, dtype), dev(x, dtype), offs.to(DEV))
+    assert relerr(out, (Kzx @ E).t()) < tol
+    bs = ops().gram_bag_blocksum(fs, dev(x, dtype), offs.to(DEV))
+    assert relerr(bs, (E.t() @ Kxx @ E).diagonal()) < tol
+    X = torch.randn(N, 37, dtype=torch.float64)
+    assert relerr(ops().bag_sum(dev(X, dtype), offs.to(DEV)), E.t() @ X) < tol
+    # backward of the bag-summed cross Gram == dense gram_bwd with G expanded over the bag
+    Gup = torch.randn(len(sizes), M, dtype=torch.float64)
+    dls, dos, dz = ops().gram_bagsum_bwd(fs, dev(z, dtype), dev(x, dtype), offs.to(DEV), dev(Gup, dtype))
+    dls2, dos2, dz2 = ops().gram_bwd(fs, dev(z, dtype), dev(x, dtype), dev((E @ Gup).t().contiguous(), dtype), need_dx1=True)
+    t2 = 1e-9 if dtype == torch.float64 else 2e-4
+    assert relerr(dls, dls2) < t2 and relerr(dos, dos2) < t2 and relerr(dz, dz2) < t2
+    g = torch.randn(len(sizes), dtype=torch.float64)
+    dls3, dos3 = ops().gram_bag_blocksum_bwd(fs, dev(x, dtype), offs.to(DEV), dev(g, dtype))
+    Gd = (E * g) @ E.t()
+    dls4, dos4, _ = ops().gram_bwd(fs, dev(x, dtype), None, dev(Gd, dtype))
+    assert relerr(dls3, dls4) < t2 and relerr(dos3, dos4) < t2
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_whitened_kl_vs_oracle(dtype):
+    torch.manual_seed(3)
+    M = 200
+    m = torch.randn(M, dtype=torch.float64, requires_grad=True)
+    raw = (torch.eye(M, dtype=torch.float64) + 0.1 * torch.randn(M, M, dtype=torch.float64)).requires_grad_()
+    kl = R.whitened_kl(m, raw)
+    kl.backward()
+    out, dm, dLs = ops().whitened_kl(dev(m.detach(), dtype), dev(raw.detach(), dtype), need_grad=True)
+    tol = 1e-12 if dtype == torch.float64 else 1e-5
+    assert abs(out.item() - kl.item()) < tol * abs(kl.item())
+    assert relerr(dm, m.grad) < tol and relerr(dLs, raw.grad) < tol
