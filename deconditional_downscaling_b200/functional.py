@@ -1,0 +1,374 @@
+"""Differentiable building blocks of the hot path: torch.autograd.Function
+wrappers whose forward AND backward are libdcgp kernels (ops.py).
+
+Backward passes are written by hand so that no O(N^3) adjoint is ever formed
+for the big bag-covariance solve: `kernel_solve` returns W = (l(y~,y~)+cI)^{-1}B
+and back-propagates the rank-m adjoint -(Lambda^{-1} gW) W^T straight into the
+Gram-shaped hyper-parameter reduction.
+"""
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch.autograd import Function
+
+from . import ops
+from .ops import FlatSpec
+
+
+class NotPSDError(RuntimeError):
+    """Raised when a Cholesky factorisation meets a non-positive pivot (same
+    name and role as gpytorch.utils.errors.NotPSDError, which the reference
+    harness catches at experiments/swiss_roll/core/metrics.py:30)."""
+
+
+@dataclass(frozen=True)
+class KernelMeta:
+    kinds: Tuple[str, ...]
+    dims: Tuple[Tuple[int, ...], ...]
+    diag_const: float = 0.0
+
+
+def _spec(meta: KernelMeta, hyp: Sequence[torch.Tensor]) -> FlatSpec:
+    return FlatSpec(meta.kinds, meta.dims, [h.detach() for h in hyp[0::2]], [h.detach() for h in hyp[1::2]])
+
+
+def _hyper_grads(meta: KernelMeta, hyp, dls, dos, needs):
+    out = []
+    for c in range(len(meta.kinds)):
+        ls, os_ = hyp[2 * c], hyp[2 * c + 1]
+        out.append(dls[c, :ls.numel()].reshape(ls.shape).to(ls.dtype) if needs[2 * c] else None)
+        out.append(dos[c].reshape(os_.shape).to(os_.dtype) if needs[2 * c + 1] else None)
+    return out
+
+
+# ---------------------------------------------------------------------- Gram
+class _GramFn(Function):
+    @staticmethod
+    def forward(ctx, meta, x1, x2, diag_dev, *hyp):
+        spec = _spec(meta, hyp)
+        K = ops.gram(spec, x1, x2, diag_dev=diag_dev, diag_const=meta.diag_const)
+        ctx.meta, ctx.same = meta, x2 is None
+        ctx.save_for_backward(x1, x2 if x2 is not None else x1, *hyp)
+        return K
+
+    @staticmethod
+    def backward(ctx, G):
+        x1, x2, *hyp = ctx.saved_tensors
+        meta, same = ctx.meta, ctx.same
+        spec = _spec(meta, hyp)
+        G = G.contiguous()
+        need = ctx.needs_input_grad
+        dls, dos, dx1 = ops.gram_bwd(spec, x1, None if same else x2, G, need_dx1=need[1])
+        dx2 = None
+        if not same and need[2]:
+            dx2 = ops.gram_bwd(spec, x2, x1, G.t().contiguous(), need_dx1=True)[2]
+        ddiag = G.diagonal().sum().reshape(1) if (need[3] and same) else None
+        return (None, dx1, dx2, ddiag, *_hyper_grads(meta, hyp, dls, dos, need[4:]))
+
+
+def gram(meta: KernelMeta, hyp: Sequence[torch.Tensor], x1, x2=None, diag_dev=None):
+    """Dense k(x1, x2) (+ diag on x2 is None).  hyp = [ls_0, os_0, ls_1, os_1, ...]."""
+    return _GramFn.apply(meta, x1, x2, diag_dev, *hyp)
+
+
+# ---------------------------------------------------------------------- GEMM
+class _MatmulFn(Function):
+    @staticmethod
+    def forward(ctx, A, B, ta, tb):
+        ctx.ta, ctx.tb = ta, tb
+        ctx.save_for_backward(A, B)
+        return ops.gemm(A, B, transa=ta, transb=tb)
+
+    @staticmethod
+    def backward(ctx, gC):
+        A, B = ctx.saved_tensors
+        ta, tb = ctx.ta, ctx.tb
+        gC = gC.contiguous()
+        gA = gB = None
+        if ctx.needs_input_grad[0]:
+            gA = ops.gemm(B, gC, transa=tb, transb=True) if ta else ops.gemm(gC, B, transa=False, transb=not tb)
+        if ctx.needs_input_grad[1]:
+            gB = ops.gemm(gC, A, transa=True, transb=ta) if tb else ops.gemm(A, gC, transa=not ta, transb=False)
+        return gA, gB, None, None
+
+
+def matmul(A, B, transa=False, transb=False):
+    """op(A) @ op(B) on the tensor cores; 1-D B is treated as a column."""
+    vec = B.dim() == 1
+    if vec:
+        B = B.unsqueeze(-1)
+    out = _MatmulFn.apply(A, B, transa, transb)
+    return out.squeeze(-1) if vec else out
+
+
+# ---------------------------------------------------------------------- Cholesky & solves
+def _raise_if_not_pd(info):
+    i = int(info.item())
+    if i != 0:
+        raise NotPSDError(f"Cholesky failed: leading minor {i} is not positive definite")
+
+
+class _CholeskyFn(Function):
+    @staticmethod
+    def forward(ctx, A, check):
+        L = A.detach().clone(memory_format=torch.contiguous_format)
+        info = ops.potrf_(L)
+        if check:
+            _raise_if_not_pd(info)
+        L = L.tril_()
+        ctx.save_for_backward(L)
+        return L
+
+    @staticmethod
+    def backward(ctx, gL):
+        (L,) = ctx.saved_tensors
+        # Phi = tril(L^T gL) with halved diagonal ; gA = sym(L^{-T} Phi L^{-1})
+        P = ops.gemm(L, gL.tril().contiguous(), transa=True)
+        P = P.tril_()
+        P.diagonal().mul_(0.5)
+        X = ops.trsm_(L, P, trans=True)                 # L^{-T} Phi
+        St = ops.trsm_(L, X.t().contiguous(), trans=True)  # (X L^{-1})^T
+        return 0.5 * (St + St.t()), None
+
+
+def cholesky(A, check=True):
+    """Lower Cholesky factor (row-major); raises NotPSDError when `check`."""
+    return _CholeskyFn.apply(A, check)
+
+
+def psd_safe_cholesky(A, max_tries=3):
+    """gpytorch.utils.cholesky.psd_safe_cholesky semantics: retry with
+    jitter 1e-6*10^i (fp32) / 1e-8*10^i (fp64) on failure, then raise NotPSDError."""
+    try:
+        return cholesky(A)
+    except NotPSDError:
+        base = 1e-8 if A.dtype == torch.float64 else 1e-6
+        eye = torch.eye(A.size(0), dtype=A.dtype, device=A.device)
+        for i in range(max_tries):
+            try:
+                return cholesky(A + (base * 10 ** i) * eye)
+            except NotPSDError:
+                continue
+        raise
+
+
+class _TrsmFn(Function):
+    @staticmethod
+    def forward(ctx, L, B, trans):
+        X = ops.trsm_(L, B.detach().clone(memory_format=torch.contiguous_format), trans=trans)
+        ctx.trans = trans
+        ctx.save_for_backward(L, X)
+        return X
+
+    @staticmethod
+    def backward(ctx, gX):
+        L, X = ctx.saved_tensors
+        gB = ops.trsm_(L, gX.detach().clone(memory_format=torch.contiguous_format), trans=not ctx.trans)
+        gL = None
+        if ctx.needs_input_grad[0]:
+            gL = ops.gemm(X, gB, transb=True, alpha=-1.0) if ctx.trans else ops.gemm(gB, X, transb=True, alpha=-1.0)
+            gL = gL.tril_()
+        return gL, gB, None
+
+
+def trsm(L, B, trans=False):
+    """Solve L X = B (trans=False) or L^T X = B (trans=True) for lower-triangular L."""
+    vec = B.dim() == 1
+    if vec:
+        B = B.unsqueeze(-1)
+    X = _TrsmFn.apply(L, B, trans)
+    return X.squeeze(-1) if vec else X
+
+
+def chol_solve(L, B):
+    """(L L^T)^{-1} B."""
+    return trsm(L, trsm(L, B, False), True)
+
+
+class _LogdetFn(Function):
+    @staticmethod
+    def forward(ctx, L):
+        ctx.save_for_backward(L)
+        return ops.logdet_chol(L)
+
+    @staticmethod
+    def backward(ctx, g):
+        (L,) = ctx.saved_tensors
+        return torch.diag_embed(2.0 * g / L.diagonal())
+
+
+def logdet_from_chol(L):
+    """log det(L L^T) = 2 sum log L_ii."""
+    return _LogdetFn.apply(L)
+
+
+# ---------------------------------------------------------------------- fused kernel-matrix ops
+class _KernelSolveFn(Function):
+    """W = (k(x,x) + c I)^{-1} B with a cached Cholesky factor and a low-rank adjoint."""
+
+    @staticmethod
+    def forward(ctx, meta, x, L, B, *hyp):
+        W = ops.potrs_(L, B.detach().clone(memory_format=torch.contiguous_format))
+        ctx.meta = meta
+        ctx.save_for_backward(x, L, W, *hyp)
+        return W
+
+    @staticmethod
+    def backward(ctx, gW):
+        x, L, W, *hyp = ctx.saved_tensors
+        meta = ctx.meta
+        need = ctx.needs_input_grad
+        gB = ops.potrs_(L, gW.detach().clone(memory_format=torch.contiguous_format))
+        hg = [None] * len(hyp)
+        if any(need[4:]):
+            dLam = ops.gemm(gB, W, transb=True, alpha=-1.0)      # -(Lambda^{-1} gW) W^T
+            dls, dos, _ = ops.gram_bwd(_spec(meta, hyp), x, None, dLam)
+            hg = _hyper_grads(meta, hyp, dls, dos, need[4:])
+        return (None, None, None, gB if need[3] else None, *hg)
+
+
+def kernel_solve(meta, hyp, x, L, B):
+    vec = B.dim() == 1
+    if vec:
+        B = B.unsqueeze(-1)
+    W = _KernelSolveFn.apply(meta, x, L, B, *hyp)
+    return W.squeeze(-1) if vec else W
+
+
+def kernel_factor(meta, hyp, x, check=True):
+    """Cholesky factor of k(x,x) + diag_const*I (no autograd: consumed by kernel_solve)."""
+    with torch.no_grad():
+        L = ops.gram(_spec(meta, hyp), x, None, diag_const=meta.diag_const)
+        info = ops.potrf_(L)
+        if check:
+            _raise_if_not_pd(info)
+    return L
+
+
+class _KernelMatmulFn(Function):
+    """(k(x1,x2) [+ diag]) @ W; K is re-assembled in the backward instead of being saved."""
+
+    @staticmethod
+    def forward(ctx, meta, x1, x2, W, diag_dev, *hyp):
+        K = ops.gram(_spec(meta, hyp), x1, x2, diag_dev=diag_dev, diag_const=meta.diag_const)
+        out = ops.gemm(K, W)
+        ctx.meta, ctx.same = meta, x2 is None
+        ctx.save_for_backward(x1, x2 if x2 is not None else x1, W, diag_dev if diag_dev is not None else W.new_zeros(1), *hyp)
+        ctx.has_diag = diag_dev is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gO):
+        x1, x2, W, diag_dev, *hyp = ctx.saved_tensors
+        meta, same = ctx.meta, ctx.same
+        need = ctx.needs_input_grad
+        gO = gO.contiguous()
+        spec = _spec(meta, hyp)
+        gW = None
+        if need[3]:
+            K = ops.gram(spec, x1, None if same else x2, diag_dev=diag_dev if ctx.has_diag else None,
+                         diag_const=meta.diag_const)
+            gW = ops.gemm(K, gO, transa=True)
+            del K
+        dx1 = dx2 = None
+        hg = [None] * len(hyp)
+        if need[1] or need[2] or any(need[5:]):
+            dK = ops.gemm(gO, W, transb=True)
+            dls, dos, dx1 = ops.gram_bwd(spec, x1, None if same else x2, dK, need_dx1=need[1])
+            if not same and need[2]:
+                dx2 = ops.gram_bwd(spec, x2, x1, dK.t().contiguous(), need_dx1=True)[2]
+            hg = _hyper_grads(meta, hyp, dls, dos, need[5:])
+        ddiag = (gO * W).sum().reshape(1) if (ctx.has_diag and need[4]) else None
+        return (None, dx1, dx2, gW, ddiag, *hg)
+
+
+def kernel_matmul(meta, hyp, x1, x2, W, diag_dev=None):
+    vec = W.dim() == 1
+    if vec:
+        W = W.unsqueeze(-1)
+    out = _KernelMatmulFn.apply(meta, x1, x2, W, diag_dev, *hyp)
+    return out.squeeze(-1) if vec else out
+
+
+# ---------------------------------------------------------------------- bag aggregation
+class _GramBagsumFn(Function):
+    @staticmethod
+    def forward(ctx, meta, z, x, offsets, *hyp):
+        out = ops.gram_bagsum(_spec(meta, hyp), z, x, offsets)
+        ctx.meta = meta
+        ctx.save_for_backward(z, x, offsets, *hyp)
+        return out
+
+    @staticmethod
+    def backward(ctx, G):
+        z, x, offsets, *hyp = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        dls, dos, dz = ops.gram_bagsum_bwd(_spec(ctx.meta, hyp), z, x, offsets, G.contiguous(), need_dz=need[1])
+        return (None, dz, None, None, *_hyper_grads(ctx.meta, hyp, dls, dos, need[4:]))
+
+
+def gram_bagsum(meta, hyp, z, x, offsets):
+    """out[a, i] = sum_{j in bag a} k(z_i, x_j)  (n_bags x M)."""
+    return _GramBagsumFn.apply(meta, z, x, offsets, *hyp)
+
+
+class _GramBagBlocksumFn(Function):
+    @staticmethod
+    def forward(ctx, meta, x, offsets, *hyp):
+        out = ops.gram_bag_blocksum(_spec(meta, hyp), x, offsets)
+        ctx.meta = meta
+        ctx.save_for_backward(x, offsets, *hyp)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, offsets, *hyp = ctx.saved_tensors
+        dls, dos = ops.gram_bag_blocksum_bwd(_spec(ctx.meta, hyp), x, offsets, g.contiguous())
+        return (None, None, None, *_hyper_grads(ctx.meta, hyp, dls, dos, ctx.needs_input_grad[3:]))
+
+
+def gram_bag_blocksum(meta, hyp, x, offsets):
+    """out[a] = sum_{i,j in bag a} k(x_i, x_j)."""
+    return _GramBagBlocksumFn.apply(meta, x, offsets, *hyp)
+
+
+class _BagSumFn(Function):
+    @staticmethod
+    def forward(ctx, X, offsets):
+        ctx.save_for_backward(offsets)
+        ctx.n = X.size(0)
+        return ops.bag_sum(X, offsets)
+
+    @staticmethod
+    def backward(ctx, g):
+        (offsets,) = ctx.saved_tensors
+        sizes = offsets[1:] - offsets[:-1]
+        return torch.repeat_interleave(g, sizes, dim=0, output_size=ctx.n), None
+
+
+def bag_sum(X, offsets):
+    vec = X.dim() == 1
+    if vec:
+        X = X.unsqueeze(-1)
+    out = _BagSumFn.apply(X, offsets)
+    return out.squeeze(-1) if vec else out
+
+
+class _WhitenedKLFn(Function):
+    @staticmethod
+    def forward(ctx, m, Ls):
+        val, dm, dLs = ops.whitened_kl(m.detach(), Ls.detach(), need_grad=True)
+        ctx.save_for_backward(dm, dLs)
+        return val
+
+    @staticmethod
+    def backward(ctx, g):
+        dm, dLs = ctx.saved_tensors
+        return g * dm, g * dLs
+
+
+def whitened_kl(variational_mean, chol_variational_covar):
+    """KL(N(m, tril(Ls) tril(Ls)^T) || N(0, I)) in one pass; the lower mask of
+    CholeskyVariationalDistribution is applied inside the kernel."""
+    return _WhitenedKLFn.apply(variational_mean, chol_variational_covar)

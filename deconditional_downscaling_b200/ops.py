@@ -50,6 +50,11 @@ def _rowmajor(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def _inplace_ok(t: torch.Tensor):
+    if t.dim() != 2 or (t.size(1) > 1 and t.stride(1) != 1) or (t.size(0) > 1 and t.stride(0) < t.size(1)):
+        raise ValueError("in-place libdcgp ops need a 2-D row-major tensor")
+
+
 def _ld(t: torch.Tensor) -> int:
     return t.stride(0) if t.size(0) > 1 else max(t.size(1), 1)
 
@@ -150,6 +155,7 @@ def _workspace(nbytes, device):
 
 def potrf_(A, info=None):
     """In-place lower Cholesky of the (row-major) square matrix A.  Returns the device info tensor."""
+    _inplace_ok(A)
     _req(A)
     n = A.size(0)
     if info is None:
@@ -163,6 +169,8 @@ def potrf_(A, info=None):
 
 def trsm_(L, B, trans=False):
     """In-place solve op(L) X = B, B is (n, m) row-major."""
+    L = _rowmajor(L)
+    _inplace_ok(B)
     _req(L, B)
     n, m = B.size(0), B.size(1)
     lib = _lib.load()
@@ -173,6 +181,8 @@ def trsm_(L, B, trans=False):
 
 
 def potrs_(L, B):
+    L = _rowmajor(L)
+    _inplace_ok(B)
     _req(L, B)
     n, m = B.size(0), B.size(1)
     lib = _lib.load()
@@ -183,6 +193,7 @@ def potrs_(L, B):
 
 
 def logdet_chol(L):
+    L = _rowmajor(L)
     _req(L)
     out = torch.empty(1, dtype=L.dtype, device=L.device)
     check(_lib.load().dcgp_logdet_chol(_ptr(L), L.size(0), _ld(L), _ptr(out), _dt(L), _stream()), "dcgp_logdet_chol")
