@@ -57,6 +57,10 @@ _SIGNATURES = {
                                        c_int, c_void_p]),
     "dcgp_gram_bag_blocksum_bwd": (c_int, [POINTER(KernelSpec), c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                            c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "dcgp_rff_features": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
+                                  c_int, c_void_p]),
+    "dcgp_rff_features_bwd": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p, c_void_p,
+                                      c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "dcgp_whitened_kl": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                  c_void_p]),
 }

@@ -272,3 +272,28 @@ def whitened_kl(m, Ls, need_grad=False):
     check(_lib.load().dcgp_whitened_kl(_ptr(m), _ptr(Ls), m.numel(), _ld(Ls), _ptr(out), _ptr(dm), _ptr(dLs),
                                        _ld(dLs) if need_grad else 0, _dt(m), _stream()), "dcgp_whitened_kl")
     return out[0], dm, dLs
+
+
+def rff_features(x, W, lengthscale):
+    """Phi = [cos(x W / l), sin(x W / l)]; x: N x d (active dims only), W: d x D."""
+    x, W = _rowmajor(x), _rowmajor(W)
+    ls = lengthscale.reshape(-1).contiguous()
+    _req(x, W, ls)
+    n, d, D = x.size(0), x.size(1), W.size(1)
+    out = torch.empty(n, 2 * D, dtype=x.dtype, device=x.device)
+    check(_lib.load().dcgp_rff_features(_ptr(x), n, _ld(x), d, _ptr(W), D, _ptr(ls), _ptr(out), _ld(out), _dt(x),
+                                        _stream()), "dcgp_rff_features")
+    return out
+
+
+def rff_features_bwd(x, W, lengthscale, dphi, need_dx=True):
+    x, W, dphi = _rowmajor(x), _rowmajor(W), _rowmajor(dphi)
+    ls = lengthscale.reshape(-1).contiguous()
+    _req(x, W, ls, dphi)
+    n, d, D = x.size(0), x.size(1), W.size(1)
+    dx = torch.zeros_like(x) if need_dx else None
+    dls = torch.zeros(d, dtype=x.dtype, device=x.device)
+    check(_lib.load().dcgp_rff_features_bwd(_ptr(x), n, _ld(x), d, _ptr(W), D, _ptr(ls), _ptr(dphi), _ld(dphi),
+                                            _ptr(dx), _ld(dx) if need_dx else 0, _ptr(dls), _dt(x), _stream()),
+          "dcgp_rff_features_bwd")
+    return dx, dls

@@ -1,0 +1,155 @@
+"""Whitened sparse variational GP machinery with gpytorch's class surface
+(CholeskyVariationalDistribution, VariationalStrategy) and the reference's override
+(src/variational/variational_strategy.py:10-68), evaluated lazily: q(f) is a
+VariationalPosterior that hands the likelihoods exactly the reductions they need
+(A^T Sigma_q A, diag Sigma_q, per-bag sums) instead of a dense N x N covariance.
+
+FP64 island kept as in the reference (variational_strategy.py:35-44): K_ZZ + 1e-3 I is
+factored and K_Zx solved in double even when the model runs in float32.
+"""
+import torch
+from torch import nn
+
+from . import functional as F
+from .distributions import MultivariateNormal
+from .kernels import _as_2d
+from .lazy import LazyCovariance
+from .module import Module
+
+
+class CholeskyVariationalDistribution(Module):
+    def __init__(self, num_inducing_points, batch_shape=None, mean_init_std=1e-3, **kwargs):
+        super().__init__()
+        self.num_inducing_points = num_inducing_points
+        self.mean_init_std = mean_init_std
+        self.register_parameter("variational_mean", nn.Parameter(torch.zeros(num_inducing_points)))
+        self.register_parameter("chol_variational_covar", nn.Parameter(torch.eye(num_inducing_points)))
+
+    def initialize_variational_distribution(self):
+        """First-call init from the whitened prior N(0, I): mean <- 1e-3 * randn, chol <- I
+        (`_VariationalStrategy.__call__`)."""
+        with torch.no_grad():
+            self.variational_mean.zero_()
+            self.variational_mean.add_(torch.randn_like(self.variational_mean), alpha=self.mean_init_std)
+            self.chol_variational_covar.copy_(torch.eye(self.num_inducing_points).to(self.chol_variational_covar))
+
+
+class VariationalPosterior(MultivariateNormal):
+    """q(f) at inputs x:  mu_q = A~^T m + mu(x),  Sigma_q = K_xx + 1e-4 I + A~^T (L_S L_S^T - I) A~,
+    A~ = L_Z^{-1} K_Zx,  L_Z = chol(K_ZZ + 1e-3 I)   (src/variational/variational_strategy.py:14-68).
+    Everything is computed on demand and cached for the lifetime of the object (one step)."""
+
+    def __init__(self, kernel, mean_module, Z, x, variational_mean, chol_variational_covar):
+        self.kernel, self.mean_module = kernel, mean_module
+        self.Z, self.x = Z, _as_2d(x)
+        self.m, self.Ls_raw = variational_mean, chol_variational_covar
+        self.kops = kernel.ops(self.x)
+        self._c = {}
+        n = self.x.size(0)
+        self._covar = LazyCovariance(self._dense_covar, self._variance, n)
+
+    # ---- cached pieces -------------------------------------------------------------------
+    def _get(self, key, fn):
+        if key not in self._c:
+            self._c[key] = fn()
+        return self._c[key]
+
+    @property
+    def dtype(self):
+        return self.x.dtype
+
+    @property
+    def Ls(self):
+        return self._get("Ls", lambda: self.Ls_raw.to(self.dtype).tril())
+
+    @property
+    def Lz(self):
+        """chol(K_ZZ + 1e-3 I) in float64 (psd_safe_cholesky semantics)."""
+        return self._get("Lz", lambda: F.psd_safe_cholesky(self.kops.gram(self.Z, None, diag_const=1e-3).double()))
+
+    @property
+    def At(self):
+        """A~ = L_Z^{-1} K_Zx (solved in float64, stored in the model dtype), M x N."""
+        return self._get("At", lambda: F.trsm(self.Lz, self.kops.gram(self.Z, self.x).double(), trans=False).to(self.dtype))
+
+    @property
+    def loc(self):
+        return self._get("mean", lambda: F.matmul(self.At, self.m.to(self.dtype), transa=True) + self.mean_module(self.x).to(self.dtype))
+
+    @loc.setter
+    def loc(self, v):
+        pass
+
+    def _variance(self):
+        def fn():
+            At = self.At
+            LsA = F.matmul(self.Ls, At, transa=True)
+            return self.kops.diag(self.x) + 1e-4 + (LsA * LsA).sum(0) - (At * At).sum(0)
+        return self._get("var", fn)
+
+    def _dense_covar(self):
+        def fn():
+            At = self.At
+            LsA = F.matmul(self.Ls, At, transa=True)
+            return self.kops.gram(self.x, None, diag_const=1e-4) + F.matmul(LsA, LsA, transa=True) - F.matmul(At, At, transa=True)
+        return self._get("cov", fn)
+
+    # ---- reductions for the likelihoods ---------------------------------------------------------
+    def quad_form(self, A):
+        """A^T Sigma_q A for A (N x n) without forming Sigma_q:
+        A^T (K_xx + 1e-4 I) A + (L_S^T U)^T (L_S^T U) - U^T U,  U = A~ A  (SURVEY.md §8a row 13)."""
+        KA = self.kops.matmul(self.x, None, A, diag_const=1e-4)
+        U = F.matmul(self.At, A)
+        LsU = F.matmul(self.Ls, U, transa=True)
+        return F.matmul(A, KA, transa=True) + F.matmul(LsU, LsU, transa=True) - F.matmul(U, U, transa=True)
+
+    def bag_stats(self, offsets):
+        """S_a = 1_a^T mu_q and T_a = 1_a^T Sigma_q 1_a for contiguous bags, from the bag-summed
+        cross Gram (K_Zx is never formed): u_a = L_Z^{-1} (K_Zx 1_a),
+        T_a = 1_a^T K_xx 1_a + 1e-4 n_a + |L_S^T u_a|^2 - |u_a|^2  (SURVEY.md §8a row 15)."""
+        sizes = (offsets[1:] - offsets[:-1]).to(self.dtype)
+        KbZ = self.kops.bagsum(self.Z, self.x, offsets)                    # n_bags x M
+        Ub = F.trsm(self.Lz, KbZ.t().double(), trans=False).to(self.dtype)   # M x n_bags
+        S = F.matmul(Ub, self.m.to(self.dtype), transa=True) + F.bag_sum(self.mean_module(self.x).to(self.dtype), offsets)
+        LsU = F.matmul(self.Ls, Ub, transa=True)
+        T = self.kops.bag_blocksum(self.x, offsets) + 1e-4 * sizes + (LsU * LsU).sum(0) - (Ub * Ub).sum(0)
+        return S, T
+
+
+class VariationalStrategy(Module):
+    def __init__(self, model, inducing_points, variational_distribution, learn_inducing_locations=True):
+        super().__init__()
+        object.__setattr__(self, "model", model)
+        inducing_points = inducing_points.clone()
+        if inducing_points.dim() == 1:
+            inducing_points = inducing_points.unsqueeze(-1)
+        if learn_inducing_locations:
+            self.register_parameter("inducing_points", nn.Parameter(inducing_points))
+        else:
+            self.register_buffer("inducing_points", inducing_points)
+        self._variational_distribution = variational_distribution
+        self.register_buffer("variational_params_initialized", torch.tensor(0))
+        self.register_buffer("updated_strategy", torch.tensor(True))
+
+    def kl_divergence(self):
+        """KL(N(m, L_S L_S^T) || N(0, I)) in one pass over L_S (bag_variational_elbo.py:49)."""
+        vd = self._variational_distribution
+        return F.whitened_kl(vd.variational_mean, vd.chol_variational_covar)
+
+    def _prior_modules(self):
+        m = self.model
+        if hasattr(m, "individuals_kernel"):       # VariationalCMP (src/models/variational_cmp.py:76-79)
+            return m.individuals_kernel, m.individuals_mean
+        return m.covar_module, m.mean_module        # VariationalGP (src/models/variational_gp.py:54-55)
+
+    def __call__(self, x, prior=False, **kwargs):
+        if prior:
+            return self.model.forward(x, **kwargs)
+        if not bool(self.variational_params_initialized.item()):
+            self._variational_distribution.initialize_variational_distribution()
+            self.variational_params_initialized.fill_(1)
+        kernel, mean = self._prior_modules()
+        vd = self._variational_distribution
+        Z = self.inducing_points
+        x = _as_2d(x)
+        return VariationalPosterior(kernel, mean, Z.to(x.dtype), x, vd.variational_mean, vd.chol_variational_covar)

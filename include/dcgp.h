@@ -158,6 +158,17 @@ DCGP_API int dcgp_gram_bag_blocksum_bwd(const dcgp_kernel_spec* spec, const void
                                int64_t n_bags, const void* g, void* dls, void* dos, int dtype, int flags,
                                void* stream);
 
+/* ---- random Fourier features ------------------------------------------------------
+ * out[i, j] = cos(p_ij), out[i, D + j] = sin(p_ij), p_ij = sum_k x[i,k] W[k,j] / l_k   (N x 2D)
+ * x: N x d (d <= DCGP_MAX_DIMS, already restricted to the active dims), W: d x D row-major.
+ * Replaces RFFKernel._featurize (src/kernels/rff_kernel.py:82-89; gpytorch RFFKernel).
+ * _bwd: dx (N x d, overwritten, optional) and dls[d] (accumulated, optional) for upstream dphi. */
+DCGP_API int dcgp_rff_features(const void* x, int64_t n, int64_t ldx, int d, const void* W, int64_t D,
+                               const void* lengthscale, void* out, int64_t ldo, int dtype, void* stream);
+DCGP_API int dcgp_rff_features_bwd(const void* x, int64_t n, int64_t ldx, int d, const void* W, int64_t D,
+                                   const void* lengthscale, const void* dphi, int64_t ldg, void* dx, int64_t lddx,
+                                   void* dls, int dtype, void* stream);
+
 /* ---- whitened KL ---------------------------------------------------------------
  * out[0] = 0.5 * (||tril(Ls)||_F^2 + ||m||^2 - M - sum_i log Ls_ii^2) in one pass over Ls
  * (src/mlls/bag_variational_elbo.py:49 -> variational_strategy.kl_divergence()).
