@@ -33,6 +33,7 @@ class DcgpError(RuntimeError):
 _SIGNATURES = {
     "dcgp_version": (c_int, []),
     "dcgp_arch": (c_int, []),
+    "dcgp_launch_count": (ctypes.c_ulonglong, []),
     "dcgp_gram": (c_int, [POINTER(KernelSpec), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
                           c_int64, c_void_p, c_double, c_int, c_int, c_void_p]),
     "dcgp_gram_bwd": (c_int, [POINTER(KernelSpec), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,

@@ -10,10 +10,13 @@
 #endif
 
 #define DCGP_CUDA_ERR(e) (-(1000 + (int)(e)))
+// number of kernel launches issued by this library since load (diagnostic only)
+void dcgp_count_launch();
 #define DCGP_CHECK_LAUNCH()                                 \
     do {                                                    \
         cudaError_t _e = cudaGetLastError();                \
         if (_e != cudaSuccess) return DCGP_CUDA_ERR(_e);    \
+        dcgp_count_launch();                                \
     } while (0)
 
 constexpr int kMaxTotalDims = 16;  // sum of active dims over the additive components

@@ -68,9 +68,8 @@ class ExactCMP(ExactGPBase, CMP):
         self.covar_module = None
         self.individuals_prediction_strategy = None
         # The reference factors Lambda here on the CPU and moves R in `.to()`; libdcgp has no CPU
-        # path, so the (gradient-free) initial factorisation happens at first use on the device.
-        if train_individuals.is_cuda:
-            self._init_cmp_mean_covar_modules(self.train_individuals, self.extended_train_bags)
+        # path, so the (gradient-free) initial factorisation happens at first use on the device
+        # (see _ensure_cme_modules), once data and hyper-parameters both live there.
 
     def _ensure_cme_modules(self):
         if self.mean_module is None:

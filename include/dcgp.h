@@ -13,7 +13,8 @@
  *   - plain C: pointers + sizes, no C++/torch types.  All data pointers are
  *     DEVICE pointers unless stated; the caller owns every buffer (inputs,
  *     outputs, workspace); the library never allocates device memory, never
- *     synchronises the stream and keeps no mutable global state.
+ *     synchronises the stream and keeps no mutable global state (except a
+ *     relaxed-atomic diagnostic launch counter).
  *   - matrices are ROW-MAJOR with an explicit leading dimension (elements
  *     between consecutive rows).
  *   - dtype: DCGP_F64 computes and stores in double (FP64 tensor/vector
@@ -77,6 +78,8 @@ typedef struct dcgp_kernel_spec {
 DCGP_API int dcgp_version(void);
 /* compiled SM architecture * 10 (1000 for sm_100a) */
 DCGP_API int dcgp_arch(void);
+/* kernels launched by the library since it was loaded (diagnostic counter, relaxed atomic) */
+DCGP_API unsigned long long dcgp_launch_count(void);
 
 /* ---- Gram assembly ---------------------------------------------------
  * K[i,j] = sum_c os_c * phi_c(|| (x1_i - x2_j)[dims_c] / l_c ||)  (+ diag on i==j if SAME)
