@@ -49,9 +49,9 @@ def make_shard(wl, rank, dtype=torch.float32):
     """Synthetic shard of rank `rank`: individuals x ~ N(0, I_d) grouped in contiguous bags,
     bag covariates y ~ N(0, I_r), per-individual bag covariates y~ = y_bag + 0.3 eps, targets z."""
     g = torch.Generator().manual_seed(1234 + rank)
-    n_ind = wl["n_total"] // wl["shards"]
     n_bags = wl["n_bags_total"] // wl["shards"]
-    per_bag = n_ind // n_bags
+    per_bag = wl["n_total"] // wl["n_bags_total"]          # 102 individuals per bag (1,044,480 used of 1,048,576)
+    n_ind = n_bags * per_bag
     x = torch.randn(n_ind, wl["d"], generator=g, dtype=dtype)
     y = torch.randn(n_bags, wl["r"], generator=g, dtype=dtype)
     ext = y.repeat_interleave(per_bag, dim=0) + 0.3 * torch.randn(n_ind, wl["r"], generator=g, dtype=dtype)

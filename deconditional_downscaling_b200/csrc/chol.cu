@@ -19,7 +19,6 @@ int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, doub
                    const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype, int flags,
                    cudaStream_t st);
 
-#define DCGP_GEMM_NO_SPLITK 2
 
 namespace {
 
@@ -149,24 +148,43 @@ int set_smem_attr(const void* fn) {
 }
 
 template <typename T>
-int potrf_impl(T* A, int64_t n, int64_t lda, int* info, T* ws, int dtype, cudaStream_t st) {
+int potrf_impl(T* A, int64_t n, int64_t lda, int* info, T* ws, int dtype, int xf, cudaStream_t st) {
     const size_t smem = (size_t)NB * SP * sizeof(T);
     int rc = set_smem_attr<T>((const void*)potrf_diag_kernel<T>);
     if (rc) return rc;
-    int64_t blk = 0;
-    for (int64_t j0 = 0; j0 < n; j0 += NB, ++blk) {
-        const int nb = (int)((n - j0 < NB) ? (n - j0) : NB);
-        T* inv = ws + blk * NB * NB;
-        potrf_diag_kernel<T><<<1, NTHREADS, smem, st>>>(A + j0 * lda + j0, lda, nb, inv, info, j0);
-        DCGP_CHECK_LAUNCH();
-        const int64_t rem = n - j0 - nb;
+    // Two-level blocking: an NBO-wide panel is factored with NB-wide steps whose updates stay
+    // inside the panel (K = NB, O(n NBO^2) flops); the rest of the matrix is then updated ONCE per
+    // panel with K = NBO, so ~(1 - NBO/n) of all flops run in deep-K tensor-core GEMMs whose C
+    // tile traffic is amortised over NBO/16 k-steps.
+    const int64_t NBO = (n >= 4096) ? 512 : ((n >= 1024) ? 256 : NB);
+    for (int64_t J0 = 0; J0 < n; J0 += NBO) {
+        const int64_t jb = (n - J0 < NBO) ? (n - J0) : NBO;
+        const int64_t Jend = J0 + jb;
+        for (int64_t j0 = J0; j0 < Jend; j0 += NB) {
+            const int nb = (int)((Jend - j0 < NB) ? (Jend - j0) : NB);
+            T* inv = ws + (j0 / NB) * NB * NB;
+            potrf_diag_kernel<T><<<1, NTHREADS, smem, st>>>(A + j0 * lda + j0, lda, nb, inv, info, j0);
+            DCGP_CHECK_LAUNCH();
+            const int64_t rem = n - j0 - nb;
+            if (rem > 0) {
+                T* A21 = A + (j0 + nb) * lda + j0;
+                rc = dcgp_gemm_impl(0, 1, rem, nb, nb, 1.0, A21, lda, inv, NB, 0.0, A21, lda, dtype,
+                                    DCGP_GEMM_NO_SPLITK | xf, st);
+                if (rc) return rc;
+                const int64_t pc = Jend - (j0 + nb);  // panel columns still to be updated
+                if (pc > 0) {
+                    rc = dcgp_gemm_impl(0, 1, rem, pc, nb, -1.0, A21, lda, A21, lda, 1.0,
+                                        A + (j0 + nb) * lda + (j0 + nb), lda, dtype,
+                                        DCGP_GEMM_LOWER | DCGP_GEMM_NO_SPLITK | xf, st);
+                    if (rc) return rc;
+                }
+            }
+        }
+        const int64_t rem = n - Jend;
         if (rem > 0) {
-            T* A21 = A + (j0 + nb) * lda + j0;
-            T* A22 = A + (j0 + nb) * lda + (j0 + nb);
-            rc = dcgp_gemm_impl(0, 1, rem, nb, nb, 1.0, A21, lda, inv, NB, 0.0, A21, lda, dtype, DCGP_GEMM_NO_SPLITK, st);
-            if (rc) return rc;
-            rc = dcgp_gemm_impl(0, 1, rem, rem, nb, -1.0, A21, lda, A21, lda, 1.0, A22, lda, dtype,
-                                DCGP_GEMM_LOWER | DCGP_GEMM_NO_SPLITK, st);
+            T* P = A + Jend * lda + J0;  // rem x jb panel of L
+            rc = dcgp_gemm_impl(0, 1, rem, rem, jb, -1.0, P, lda, P, lda, 1.0, A + Jend * lda + Jend, lda, dtype,
+                                DCGP_GEMM_LOWER | DCGP_GEMM_NO_SPLITK | xf, st);
             if (rc) return rc;
         }
     }
@@ -174,7 +192,7 @@ int potrf_impl(T* A, int64_t n, int64_t lda, int* info, T* ws, int dtype, cudaSt
 }
 
 template <typename T>
-int trsm_impl(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t m, int64_t ldb, T* ws, int dtype,
+int trsm_impl(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t m, int64_t ldb, T* ws, int dtype, int xf,
               cudaStream_t st) {
     const size_t smem = (size_t)NB * SP * sizeof(T);
     int rc = set_smem_attr<T>((const void*)trtri_blocks_kernel<T>);
@@ -182,32 +200,56 @@ int trsm_impl(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t m, in
     const int64_t nblk = (n + NB - 1) / NB;
     trtri_blocks_kernel<T><<<(unsigned)nblk, NTHREADS, smem, st>>>(L, ldl, n, ws);
     DCGP_CHECK_LAUNCH();
+    // Two-level blocking as in potrf: NB-wide substitution steps update only the rows of their
+    // NBO-wide outer block; all other rows are updated once per outer block with K = NBO.
+    const int64_t NBO = (n >= 4096) ? 512 : ((n >= 1024) ? 256 : NB);
+    const int64_t nouter = (n + NBO - 1) / NBO;
     if (!trans) {
-        for (int64_t b = 0; b < nblk; ++b) {
-            const int64_t i0 = b * NB;
-            const int64_t nb = (n - i0 < NB) ? (n - i0) : NB;
-            T* Bi = B + i0 * ldb;
-            rc = dcgp_gemm_impl(0, 0, nb, m, nb, 1.0, ws + b * NB * NB, NB, Bi, ldb, 0.0, Bi, ldb, dtype,
-                                DCGP_GEMM_NO_SPLITK, st);
-            if (rc) return rc;
-            const int64_t rem = n - i0 - nb;
+        for (int64_t ob = 0; ob < nouter; ++ob) {
+            const int64_t I0 = ob * NBO;
+            const int64_t Iend = (n < I0 + NBO) ? n : I0 + NBO;
+            for (int64_t i0 = I0; i0 < Iend; i0 += NB) {
+                const int64_t nb = (Iend - i0 < NB) ? (Iend - i0) : NB;
+                T* Bi = B + i0 * ldb;
+                rc = dcgp_gemm_impl(0, 0, nb, m, nb, 1.0, ws + (i0 / NB) * NB * NB, NB, Bi, ldb, 0.0, Bi, ldb, dtype,
+                                    DCGP_GEMM_NO_SPLITK | xf, st);
+                if (rc) return rc;
+                const int64_t rin = Iend - i0 - nb;  // rows below, inside the outer block
+                if (rin > 0) {
+                    rc = dcgp_gemm_impl(0, 0, rin, m, nb, -1.0, L + (i0 + nb) * ldl + i0, ldl, Bi, ldb, 1.0,
+                                        B + (i0 + nb) * ldb, ldb, dtype, DCGP_GEMM_NO_SPLITK | xf, st);
+                    if (rc) return rc;
+                }
+            }
+            const int64_t rem = n - Iend;
             if (rem > 0) {
-                rc = dcgp_gemm_impl(0, 0, rem, m, nb, -1.0, L + (i0 + nb) * ldl + i0, ldl, Bi, ldb, 1.0,
-                                    B + (i0 + nb) * ldb, ldb, dtype, DCGP_GEMM_NO_SPLITK, st);
+                rc = dcgp_gemm_impl(0, 0, rem, m, Iend - I0, -1.0, L + Iend * ldl + I0, ldl, B + I0 * ldb, ldb, 1.0,
+                                    B + Iend * ldb, ldb, dtype, DCGP_GEMM_NO_SPLITK | xf, st);
                 if (rc) return rc;
             }
         }
     } else {
-        for (int64_t b = nblk - 1; b >= 0; --b) {
-            const int64_t i0 = b * NB;
-            const int64_t nb = (n - i0 < NB) ? (n - i0) : NB;
-            T* Bi = B + i0 * ldb;
-            rc = dcgp_gemm_impl(1, 0, nb, m, nb, 1.0, ws + b * NB * NB, NB, Bi, ldb, 0.0, Bi, ldb, dtype,
-                                DCGP_GEMM_NO_SPLITK, st);
-            if (rc) return rc;
-            if (i0 > 0) {
-                rc = dcgp_gemm_impl(1, 0, i0, m, nb, -1.0, L + i0 * ldl, ldl, Bi, ldb, 1.0, B, ldb, dtype,
-                                    DCGP_GEMM_NO_SPLITK, st);
+        for (int64_t ob = nouter - 1; ob >= 0; --ob) {
+            const int64_t I0 = ob * NBO;
+            const int64_t Iend = (n < I0 + NBO) ? n : I0 + NBO;
+            const int64_t nin = (Iend - I0 + NB - 1) / NB;
+            for (int64_t ib = nin - 1; ib >= 0; --ib) {
+                const int64_t i0 = I0 + ib * NB;
+                const int64_t nb = (Iend - i0 < NB) ? (Iend - i0) : NB;
+                T* Bi = B + i0 * ldb;
+                rc = dcgp_gemm_impl(1, 0, nb, m, nb, 1.0, ws + (i0 / NB) * NB * NB, NB, Bi, ldb, 0.0, Bi, ldb, dtype,
+                                    DCGP_GEMM_NO_SPLITK | xf, st);
+                if (rc) return rc;
+                const int64_t rin = i0 - I0;  // rows above, inside the outer block
+                if (rin > 0) {
+                    rc = dcgp_gemm_impl(1, 0, rin, m, nb, -1.0, L + i0 * ldl + I0, ldl, Bi, ldb, 1.0, B + I0 * ldb, ldb,
+                                        dtype, DCGP_GEMM_NO_SPLITK | xf, st);
+                    if (rc) return rc;
+                }
+            }
+            if (I0 > 0) {
+                rc = dcgp_gemm_impl(1, 0, I0, m, Iend - I0, -1.0, L + I0 * ldl, ldl, B + I0 * ldb, ldb, 1.0, B, ldb,
+                                    dtype, DCGP_GEMM_NO_SPLITK | xf, st);
                 if (rc) return rc;
             }
         }
@@ -237,8 +279,8 @@ extern "C" int dcgp_potrf(void* A, int64_t n, int64_t lda, int* info, void* work
         cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
         if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
     }
-    if (dtype == DCGP_F64) return potrf_impl<double>((double*)A, n, lda, info, (double*)workspace, dtype, st);
-    return potrf_impl<float>((float*)A, n, lda, info, (float*)workspace, dtype, st);
+    if (dtype == DCGP_F64) return potrf_impl<double>((double*)A, n, lda, info, (double*)workspace, dtype, flags & DCGP_GEMM_TF32X3, st);
+    return potrf_impl<float>((float*)A, n, lda, info, (float*)workspace, dtype, flags & DCGP_GEMM_TF32X3, st);
 }
 
 extern "C" size_t dcgp_trsm_workspace(int64_t n, int64_t m, int dtype) { return n > 0 ? inv_ws_bytes(n, dtype) : 0; }
@@ -254,8 +296,8 @@ extern "C" int dcgp_trsm(int trans, const void* L, int64_t n, int64_t ldl, void*
     if (!workspace || workspace_bytes < inv_ws_bytes(n, dtype)) return -8;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == DCGP_F64)
-        return trsm_impl<double>(trans, (const double*)L, n, ldl, (double*)B, m, ldb, (double*)workspace, dtype, st);
-    return trsm_impl<float>(trans, (const float*)L, n, ldl, (float*)B, m, ldb, (float*)workspace, dtype, st);
+        return trsm_impl<double>(trans, (const double*)L, n, ldl, (double*)B, m, ldb, (double*)workspace, dtype, flags & DCGP_GEMM_TF32X3, st);
+    return trsm_impl<float>(trans, (const float*)L, n, ldl, (float*)B, m, ldb, (float*)workspace, dtype, flags & DCGP_GEMM_TF32X3, st);
 }
 
 extern "C" int dcgp_potrs(const void* L, int64_t n, int64_t ldl, void* B, int64_t m, int64_t ldb, void* workspace,

@@ -2,17 +2,20 @@
 //
 // FP64: tcgen05 has no f64 kind, so double precision runs on the legacy tensor path
 // (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4).  128x128x16 CTA tile, 8 warps (2x4), 64x32 warp
-// tile = 32 DMMA per k-step with 128 accumulator registers per thread; operands are staged
-// global -> registers -> shared (double-buffered, one __syncthreads per k-tile) and always
-// laid out K-contiguous in shared memory with a pitch of 20 doubles, which makes every
-// fragment read bank-conflict free for both half-warps.
+// tile = 32 DMMA per k-step with 128 accumulator registers per thread.  Operands stream
+// global -> shared with cp.async (LDGSTS) through a 3-stage ring, one __syncthreads per k-tile;
+// they are always laid out K-contiguous in shared memory with a pitch of 20 doubles, which makes
+// every fragment read bank-conflict free for both half-warps (transposed operands are scattered
+// into that layout by 8-byte cp.async).
 //
-// FP32 storage contracts on TF32 tensor cores (mma.sync.m16n8k8.tf32, operands rounded to
-// TF32 with cvt.rna when they are staged into shared memory, FP32 accumulation).
+// FP32 storage contracts on TF32 tensor cores (mma.sync.m16n8k8.tf32, FP32 accumulation).
+// Two precisions: single-pass TF32 (cvt.rna at fragment load) and error-compensated "3xTF32"
+// (a = a_hi + a_lo, three MMAs: lo*hi + hi*lo + hi*hi) which recovers ~FP32 accuracy.
 //
 // DCGP_GEMM_LOWER restricts the grid to tiles that intersect the lower triangle (SYRK
 // trailing update of the blocked Cholesky).
 #include "common.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -25,8 +28,9 @@ struct GemmParams {
     void* C;
     int64_t ldc;
     double alpha, beta;
-    int lower;
+    int lower;   // bit0: lower tiles only; bit1: never split K (C aliases an input)
     int ksplit;  // number of K slices (gridDim.z); >1 => atomicAdd epilogue on pre-scaled C
+    int vecA, vecB;  // 16-byte cp.async allowed for the K-contiguous layout of A / B
 };
 
 __device__ __forceinline__ void mma_f64(double (&c)[2], double a, double b) {
@@ -42,68 +46,83 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-__device__ __forceinline__ float to_tf32(float x) {
+__device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return r;
 }
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = to_tf32(x);
+    lo = to_tf32(x - __uint_as_float(hi));
+}
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem, const void* gmem, int src_bytes) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(s), "l"(gmem), "n"(BYTES), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
 template <typename T> struct Tile;
 template <> struct Tile<double> {
-    static constexpr int BM = 128, BN = 128, BK = 16, PK = 20;
+    static constexpr int BM = 128, BN = 128, BK = 16, PK = 20, STAGES = 3;
 };
 template <> struct Tile<float> {
-    static constexpr int BM = 128, BN = 128, BK = 32, PK = 36;
+    static constexpr int BM = 128, BN = 128, BK = 32, PK = 36, STAGES = 3;
 };
 
-// stage one operand tile (ROWS x BK of op(X)[row, k]) global -> registers
-template <typename T, int ROWS, int BK>
-__device__ __forceinline__ void load_tile(const T* __restrict__ X, int64_t srow, int64_t sk, int64_t row0, int64_t nrows,
-                                          int64_t k0, int64_t kend, T (&reg)[ROWS * BK / 256]) {
-    constexpr int PER = ROWS * BK / 256;
-    const bool kcontig = (sk == 1);
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        const int e = threadIdx.x + i * 256;
-        int r, kk;
-        if (kcontig) {
-            r = e / BK;
-            kk = e % BK;
-        } else {
-            kk = e / ROWS;
-            r = e % ROWS;
-        }
-        const int64_t gr = row0 + r, gk = k0 + kk;
-        reg[i] = (gr < nrows && gk < kend) ? X[gr * srow + gk * sk] : T(0);
-    }
-}
-
+// issue the cp.async copies of one operand tile: ROWS x BK of op(X)[row, k] -> S[row][k] (pitch PK)
 template <typename T, int ROWS, int BK, int PK>
-__device__ __forceinline__ void store_tile(T* __restrict__ S, int64_t sk, const T (&reg)[ROWS * BK / 256]) {
-    constexpr int PER = ROWS * BK / 256;
-    const bool kcontig = (sk == 1);
+__device__ __forceinline__ void issue_tile(T* __restrict__ S, const T* __restrict__ X, int64_t srow, int64_t sk,
+                                           int64_t row0, int64_t nrows, int64_t k0, int64_t kend, int vec) {
+    constexpr int VE = 16 / sizeof(T);  // elements per 16-byte chunk
+    if (sk == 1 && vec) {
+        constexpr int CPR = BK / VE;  // chunks per row
+        constexpr int PER = ROWS * CPR / 256;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        const int e = threadIdx.x + i * 256;
-        int r, kk;
-        if (kcontig) {
-            r = e / BK;
-            kk = e % BK;
-        } else {
-            kk = e / ROWS;
-            r = e % ROWS;
+        for (int i = 0; i < PER; ++i) {
+            const int e = threadIdx.x + i * 256;
+            const int r = e / CPR, kk = (e % CPR) * VE;
+            const int64_t gr = row0 + r, gk = k0 + kk;
+            int bytes = 0;
+            if (gr < nrows && gk < kend) bytes = (int)min((int64_t)VE, kend - gk) * (int)sizeof(T);
+            const T* src = bytes ? X + gr * srow + gk : X;
+            cp_async<16>(S + r * PK + kk, src, bytes);
         }
-        if constexpr (sizeof(T) == 4) S[r * PK + kk] = to_tf32(reg[i]);
-        else S[r * PK + kk] = reg[i];
+    } else {
+        constexpr int PER = ROWS * BK / 256;
+        const bool kcontig = (sk == 1);
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int e = threadIdx.x + i * 256;
+            int r, kk;
+            if (kcontig) {
+                r = e / BK;
+                kk = e % BK;
+            } else {
+                kk = e / ROWS;
+                r = e % ROWS;
+            }
+            const int64_t gr = row0 + r, gk = k0 + kk;
+            const bool ok = gr < nrows && gk < kend;
+            const T* src = ok ? X + gr * srow + gk * sk : X;
+            cp_async<(int)sizeof(T)>(S + r * PK + kk, src, ok ? (int)sizeof(T) : 0);
+        }
     }
 }
 
-template <typename T>
+template <typename T, bool X3>
 __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
-    constexpr int BM = Tile<T>::BM, BN = Tile<T>::BN, BK = Tile<T>::BK, PK = Tile<T>::PK;
+    constexpr int BM = Tile<T>::BM, BN = Tile<T>::BN, BK = Tile<T>::BK, PK = Tile<T>::PK, ST = Tile<T>::STAGES;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* As = reinterpret_cast<T*>(smem_raw);  // [2][BM][PK]
-    T* Bs = As + 2 * BM * PK;                // [2][BN][PK]
+    T* As = reinterpret_cast<T*>(smem_raw);  // [ST][BM][PK]
+    T* Bs = As + ST * BM * PK;               // [ST][BN][PK]
 
     const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
     if ((p.lower & 1) && n0 > m0 + BM - 1) return;
@@ -114,6 +133,7 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
     const int64_t kt1 = min(ktiles, kt0 + per);
     if (kt0 >= kt1 && p.ksplit > 1) return;
     const int64_t kend = min(p.k, kt1 * BK);
+    const int nkt = (int)max((int64_t)0, kt1 - kt0);
 
     const T* A = (const T*)p.A;
     const T* B = (const T*)p.B;
@@ -132,21 +152,28 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
 #pragma unroll
             for (int q = 0; q < NACC; ++q) acc[i][j][q] = T(0);
 
-    T ra[BM * BK / 256], rb[BN * BK / 256];
-    if (kt0 < kt1) {
-        load_tile<T, BM, BK>(A, p.sam, p.sak, m0, p.m, kt0 * BK, kend, ra);
-        load_tile<T, BN, BK>(B, p.sbn, p.sbk, n0, p.n, kt0 * BK, kend, rb);
-        store_tile<T, BM, BK, PK>(As, p.sak, ra);
-        store_tile<T, BN, BK, PK>(Bs, p.sbk, rb);
-    }
-    __syncthreads();
-    for (int64_t kt = kt0; kt < kt1; ++kt) {
-        const int buf = (int)((kt - kt0) & 1);
-        const bool more = kt + 1 < kt1;
-        if (more) {
-            load_tile<T, BM, BK>(A, p.sam, p.sak, m0, p.m, (kt + 1) * BK, kend, ra);
-            load_tile<T, BN, BK>(B, p.sbn, p.sbk, n0, p.n, (kt + 1) * BK, kend, rb);
+    // prologue: ST-1 tiles in flight
+#pragma unroll
+    for (int s = 0; s < ST - 1; ++s) {
+        if (s < nkt) {
+            issue_tile<T, BM, BK, PK>(As + s * BM * PK, A, p.sam, p.sak, m0, p.m, (kt0 + s) * BK, kend, p.vecA);
+            issue_tile<T, BN, BK, PK>(Bs + s * BN * PK, B, p.sbn, p.sbk, n0, p.n, (kt0 + s) * BK, kend, p.vecB);
         }
+        cp_async_commit();
+    }
+    for (int it = 0; it < nkt; ++it) {
+        cp_async_wait<ST - 2>();
+        __syncthreads();  // tile `it` has landed for every thread; everyone is done with tile it-1's buffer
+        {
+            const int nx = it + ST - 1;
+            if (nx < nkt) {
+                const int sb = nx % ST;
+                issue_tile<T, BM, BK, PK>(As + sb * BM * PK, A, p.sam, p.sak, m0, p.m, (kt0 + nx) * BK, kend, p.vecA);
+                issue_tile<T, BN, BK, PK>(Bs + sb * BN * PK, B, p.sbn, p.sbk, n0, p.n, (kt0 + nx) * BK, kend, p.vecB);
+            }
+            cp_async_commit();
+        }
+        const int buf = it % ST;
         const T* as = As + buf * BM * PK + (wm * 64) * PK;
         const T* bs = Bs + buf * BN * PK + (wn * 32) * PK;
         if constexpr (sizeof(T) == 8) {
@@ -165,39 +192,50 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
         } else {
 #pragma unroll
             for (int ks = 0; ks < BK / 8; ++ks) {
-                uint32_t af[MT][4], bf[NT][2];
+                uint32_t ah[MT][4], bh[NT][2];
+                uint32_t al[X3 ? MT : 1][4], bl[X3 ? NT : 1][2];
 #pragma unroll
                 for (int i = 0; i < MT; ++i) {
                     const float* base = as + (i * 16 + g) * PK + ks * 8 + t;
-                    af[i][0] = __float_as_uint(base[0]);
-                    af[i][1] = __float_as_uint(base[8 * PK]);
-                    af[i][2] = __float_as_uint(base[4]);
-                    af[i][3] = __float_as_uint(base[8 * PK + 4]);
+                    const float v[4] = {base[0], base[8 * PK], base[4], base[8 * PK + 4]};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if constexpr (X3) split_tf32(v[q], ah[i][q], al[i][q]);
+                        else ah[i][q] = to_tf32(v[q]);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
                     const float* base = bs + (j * 8 + g) * PK + ks * 8 + t;
-                    bf[j][0] = __float_as_uint(base[0]);
-                    bf[j][1] = __float_as_uint(base[4]);
+                    const float v[2] = {base[0], base[4]};
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        if constexpr (X3) split_tf32(v[q], bh[j][q], bl[j][q]);
+                        else bh[j][q] = to_tf32(v[q]);
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < MT; ++i)
 #pragma unroll
-                    for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], af[i], bf[j]);
+                    for (int j = 0; j < NT; ++j) {
+                        if constexpr (X3) {
+                            mma_tf32(acc[i][j], al[i], bh[j]);
+                            mma_tf32(acc[i][j], ah[i], bl[j]);
+                        }
+                        mma_tf32(acc[i][j], ah[i], bh[j]);
+                    }
             }
         }
-        if (more) {
-            store_tile<T, BM, BK, PK>(As + (buf ^ 1) * BM * PK, p.sak, ra);
-            store_tile<T, BN, BK, PK>(Bs + (buf ^ 1) * BN * PK, p.sbk, rb);
-        }
-        __syncthreads();
     }
+    cp_async_wait<0>();
 
-    // epilogue
+    // epilogue: each thread owns column pairs (2t, 2t+1) -> 16-byte (f64) / 8-byte (f32) accesses
     T* C = (T*)p.C;
     const T alpha = (T)p.alpha, beta = (T)p.beta;
     const bool atomic = p.ksplit > 1;
+    const bool pair_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) % (2 * sizeof(T))) == 0);
     constexpr int RT = (sizeof(T) == 8) ? 8 : 16;  // rows per m-tile
+    using T2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
 #pragma unroll
@@ -207,14 +245,25 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
                 const int64_t col = n0 + wn * 32 + j * 8 + 2 * t;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    if (col + q < p.n) {
-                        T* dst = C + row * p.ldc + col + q;
-                        const T v = alpha * acc[i][j][h * 2 + q];
-                        if (atomic) atomicAdd(dst, v);
-                        else *dst = (beta == T(0)) ? v : fma(beta, *dst, v);
+                T* dst = C + row * p.ldc + col;
+                const T v0 = alpha * acc[i][j][h * 2], v1 = alpha * acc[i][j][h * 2 + 1];
+                if (atomic) {
+                    if (col < p.n) atomicAdd(dst, v0);
+                    if (col + 1 < p.n) atomicAdd(dst + 1, v1);
+                } else if (pair_ok && col + 1 < p.n) {
+                    T2 o;
+                    if (beta == T(0)) {
+                        o.x = v0;
+                        o.y = v1;
+                    } else {
+                        const T2 c = *reinterpret_cast<const T2*>(dst);
+                        o.x = fma(beta, c.x, v0);
+                        o.y = fma(beta, c.y, v1);
                     }
+                    *reinterpret_cast<T2*>(dst) = o;
+                } else {
+                    if (col < p.n) dst[0] = (beta == T(0)) ? v0 : fma(beta, dst[0], v0);
+                    if (col + 1 < p.n) dst[1] = (beta == T(0)) ? v1 : fma(beta, dst[1], v1);
                 }
             }
         }
@@ -234,15 +283,16 @@ __global__ void scale_kernel(T* C, int64_t m, int64_t n, int64_t ldc, T beta, in
 }
 
 template <typename T>
+int vec_ok(const void* X, int64_t ld) {
+    return (reinterpret_cast<uintptr_t>(X) % 16 == 0) && ((ld * (int64_t)sizeof(T)) % 16 == 0);
+}
+
+template <typename T, bool X3>
 int launch_gemm(GemmParams p, cudaStream_t st) {
-    constexpr int BM = Tile<T>::BM, BN = Tile<T>::BN, BK = Tile<T>::BK, PK = Tile<T>::PK;
-    const size_t smem = (size_t)2 * (BM + BN) * PK * sizeof(T);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
-        attr_set = true;
-    }
+    constexpr int BM = Tile<T>::BM, BN = Tile<T>::BN, BK = Tile<T>::BK, PK = Tile<T>::PK, ST = Tile<T>::STAGES;
+    const size_t smem = (size_t)ST * (BM + BN) * PK * sizeof(T);
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<T, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
     const int64_t gm = (p.m + BM - 1) / BM, gn = (p.n + BN - 1) / BN;
     // split K when the output grid cannot fill the machine and K is deep
     int64_t tiles = (p.lower & 1) ? gm * (gm + 1) / 2 : gm * gn;
@@ -260,14 +310,14 @@ int launch_gemm(GemmParams p, cudaStream_t st) {
         scale_kernel<T><<<g, 256, 0, st>>>((T*)p.C, p.m, p.n, p.ldc, (T)p.beta, p.lower & 1);
     }
     dim3 grid((unsigned)gn, (unsigned)gm, (unsigned)ksplit);
-    gemm_kernel<T><<<grid, 256, smem, st>>>(p);
+    gemm_kernel<T, X3><<<grid, 256, smem, st>>>(p);
     DCGP_CHECK_LAUNCH();
     return 0;
 }
 
 }  // namespace
 
-// internal entry used by the Cholesky / TRSM drivers (same translation-unit-independent ABI)
+// internal entry used by the Cholesky / TRSM drivers
 int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
                    const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype, int flags,
                    cudaStream_t st) {
@@ -290,8 +340,17 @@ int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, doub
     // bit0: lower-only tiles; bit1: caller aliases C with an input, never split K
     p.lower = ((flags & DCGP_GEMM_LOWER) ? 1 : 0) | ((flags & DCGP_GEMM_NO_SPLITK) ? 2 : 0);
     p.ksplit = 1;
-    if (dtype == DCGP_F64) return launch_gemm<double>(p, st);
-    if (dtype == DCGP_F32) return launch_gemm<float>(p, st);
+    if (dtype == DCGP_F64) {
+        p.vecA = vec_ok<double>(A, lda);
+        p.vecB = vec_ok<double>(B, ldb);
+        return launch_gemm<double, false>(p, st);
+    }
+    if (dtype == DCGP_F32) {
+        p.vecA = vec_ok<float>(A, lda);
+        p.vecB = vec_ok<float>(B, ldb);
+        if (flags & DCGP_GEMM_TF32X3) return launch_gemm<float, true>(p, st);
+        return launch_gemm<float, false>(p, st);
+    }
     return -14;
 }
 

@@ -17,6 +17,20 @@ KINDS = {"rbf": _lib.KIND_RBF, "matern32": _lib.KIND_MATERN32, "matern12": _lib.
          "matern52": _lib.KIND_MATERN52}
 
 
+# FP32 contraction precision: "fast" = single-pass TF32 everywhere, "x3" = error-compensated
+# 3xTF32 (~FP32 accuracy) everywhere, "auto" = 3xTF32 for small (latency-bound) problems and
+# single-pass TF32 for the large contractions that carry the flops.
+TF32_MODE = "auto"
+X3_GEMM_LIMIT = 512 ** 3
+X3_SOLVE_LIMIT = 1024
+
+
+def _x3(t, small):
+    if t.dtype != torch.float32 or TF32_MODE == "fast":
+        return 0
+    return _lib.GEMM_TF32X3 if (TF32_MODE == "x3" or small) else 0
+
+
 def _dt(t: torch.Tensor) -> int:
     if t.dtype == torch.float64:
         return F64
@@ -142,7 +156,7 @@ def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, C=None, lower=Fa
     if C is None:
         C = torch.empty(m, n, dtype=A.dtype, device=A.device)
         beta = 0.0
-    flags = (GEMM_LOWER if lower else 0) | (_lib.GEMM_NO_SPLITK if no_splitk else 0)
+    flags = (GEMM_LOWER if lower else 0) | (_lib.GEMM_NO_SPLITK if no_splitk else 0) | _x3(A, m * n * k <= X3_GEMM_LIMIT)
     rc = _lib.load().dcgp_gemm(int(transa), int(transb), m, n, k, float(alpha), _ptr(A), _ld(A), _ptr(B), _ld(B),
                                float(beta), _ptr(C), _ld(C), _dt(A), flags, _stream())
     check(rc, "dcgp_gemm")
@@ -162,7 +176,7 @@ def potrf_(A, info=None):
         info = torch.zeros(1, dtype=torch.int32, device=A.device)
     lib = _lib.load()
     ws = _workspace(lib.dcgp_potrf_workspace(n, _dt(A)), A.device)
-    rc = lib.dcgp_potrf(_ptr(A), n, _ld(A), _ptr(info), _ptr(ws), ws.numel(), _dt(A), 0, _stream())
+    rc = lib.dcgp_potrf(_ptr(A), n, _ld(A), _ptr(info), _ptr(ws), ws.numel(), _dt(A), _x3(A, n <= X3_SOLVE_LIMIT), _stream())
     check(rc, "dcgp_potrf")
     return info
 
@@ -175,7 +189,7 @@ def trsm_(L, B, trans=False):
     n, m = B.size(0), B.size(1)
     lib = _lib.load()
     ws = _workspace(lib.dcgp_trsm_workspace(n, m, _dt(L)), L.device)
-    rc = lib.dcgp_trsm(int(trans), _ptr(L), n, _ld(L), _ptr(B), m, _ld(B), _ptr(ws), ws.numel(), _dt(L), 0, _stream())
+    rc = lib.dcgp_trsm(int(trans), _ptr(L), n, _ld(L), _ptr(B), m, _ld(B), _ptr(ws), ws.numel(), _dt(L), _x3(L, n <= X3_SOLVE_LIMIT), _stream())
     check(rc, "dcgp_trsm")
     return B
 
@@ -187,7 +201,7 @@ def potrs_(L, B):
     n, m = B.size(0), B.size(1)
     lib = _lib.load()
     ws = _workspace(lib.dcgp_trsm_workspace(n, m, _dt(L)), L.device)
-    rc = lib.dcgp_potrs(_ptr(L), n, _ld(L), _ptr(B), m, _ld(B), _ptr(ws), ws.numel(), _dt(L), 0, _stream())
+    rc = lib.dcgp_potrs(_ptr(L), n, _ld(L), _ptr(B), m, _ld(B), _ptr(ws), ws.numel(), _dt(L), _x3(L, n <= X3_SOLVE_LIMIT), _stream())
     check(rc, "dcgp_potrs")
     return B
 
