@@ -1,15 +1,18 @@
-// Blocked right-looking Cholesky and triangular solves (row-major, lower).
+// Recursive blocked Cholesky and triangular solves (row-major, lower).
 //
-//   for each 128-wide block column j:
-//     1. potrf_diag_kernel  : one CTA factors the 128x128 diagonal block in shared memory and
-//                             inverts the triangular factor (stored in the workspace);
-//     2. panel "TRSM"       : L21 = A21 * inv(L11)^T as a tensor-core GEMM (in place);
-//     3. trailing "SYRK"    : A22 -= L21 L21^T on the lower tiles only (tensor-core GEMM).
+//   chol(A[nb]):  nb <= 128 -> potrf_diag_kernel (one CTA: factor the block in shared memory and
+//                              invert its triangular factor into the workspace)
+//                 else      -> chol(A11); A21 <- A21 L11^{-T} (rtrsm); A22 -= A21 A21^T; chol(A22)
+//   rtrsm(B, L[nt]): nt <= 128 -> B <- B inv(L)^T as one tensor-core GEMM (in place, K = nt)
+//                    else      -> rtrsm(B1, La); B2 -= B1 Lc^T; rtrsm(B2, Lb)
 //
-// Steps 2-3 carry all O(n^3) work and run in dcgp_gemm (DMMA for FP64, TF32 for FP32); step 1
-// is O(n * 128^2) on CUDA cores.  Triangular solves with many right-hand sides use the same
-// inverted diagonal blocks: X_i = inv(L_ii) B_i followed by a rank-128 GEMM update of all
-// remaining block rows (right-looking, so every update fills the machine).
+// The recursion halves the block at every level, so all but ~n^2*128 of the n^3/3 flops run in
+// tensor-core GEMMs whose inner dimension is as deep as the problem allows (n/2 at the top):
+// DMMA (mma.sync m8n8k4.f64) for FP64, TF32 for FP32 - see gemm.cu.  The only CUDA-core work is
+// the 128x128 diagonal block (O(n * 128^2) in total), which is register-blocked in 16-wide
+// sub-panels so that it costs a few tens of microseconds on the critical path.
+//
+// Left-side solves op(L) X = B with many right-hand sides recurse the same way.
 //
 // LAPACK-style failure reporting: *info (device) receives the 1-based index of the first
 // non-positive pivot; nothing here synchronises the stream.
@@ -19,71 +22,221 @@ int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, doub
                    const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype, int flags,
                    cudaStream_t st);
 
-
 namespace {
 
-constexpr int NB = 128;       // block size
-constexpr int SP = NB + 1;    // shared-memory pitch (conflict-free column walks)
-constexpr int NTHREADS = 512;
+constexpr int NB = 128;     // leaf block size
+constexpr int SP = NB + 1;  // shared-memory pitch (conflict-free row AND column walks)
+constexpr int NTHREADS = 256;
+constexpr int SB = 16;      // sub-panel width inside the leaf
 
-// Factor the nb x nb block held in S (lower triangle) in place: right-looking, whole CTA.
+// ---------------------------------------------------------------------------------------------
+// Leaf factorisation in shared memory, right-looking over 16-wide sub-panels:
+//   (1) warp 0 factors the 16x16 diagonal block (lanes 0..15 own a row each, shuffles broadcast);
+//   (2) every thread owning a row below solves its 16 entries against that block (registers);
+//   (3) the trailing lower triangle gets a rank-16 update, 4x4 register tiles per thread.
+// Three barriers per sub-panel (24 per leaf) instead of three per column.
+// ---------------------------------------------------------------------------------------------
 template <typename T>
 __device__ void block_potrf(T* S, int nb, int* info, int64_t j0) {
-    for (int j = 0; j < nb; ++j) {
-        __shared__ T pivot;
-        if (threadIdx.x == 0) {
-            T d = S[j * SP + j];
-            if (!(d > T(0))) {
-                if (info && *info == 0) *info = (int)(j0 + j + 1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int p0 = 0; p0 < nb; p0 += SB) {
+        const int pw = min(SB, nb - p0);
+        // (1) diagonal sub-block
+        if (warp == 0) {
+            const int r = lane;  // row within the sub-block
+            T row[SB];
+#pragma unroll
+            for (int c = 0; c < SB; ++c) row[c] = (r < pw && c <= r && c < pw) ? S[(p0 + r) * SP + p0 + c] : T(0);
+#pragma unroll
+            for (int c = 0; c < SB; ++c) {
+                if (c < pw) {
+                    // pivot row c broadcasts its (already updated) entries
+                    T d = __shfl_sync(0xffffffffu, row[c], c);
+                    if (!(d > T(0)) && lane == 0 && info && *info == 0) *info = (int)(j0 + p0 + c + 1);
+                    const T piv = t_sqrt<T>(d);
+                    const T inv = T(1) / piv;
+                    if (r == c) row[c] = piv;
+                    else if (r > c) row[c] *= inv;
+                    const T lrc = row[c];
+#pragma unroll
+                    for (int k = 0; k < SB; ++k) {
+                        if (k > c) {
+                            const T lkc = __shfl_sync(0xffffffffu, row[c], k);  // L[k][c]
+                            if (r >= k) row[k] = fma(-lrc, lkc, row[k]);
+                        }
+                    }
+                }
             }
-            pivot = t_sqrt<T>(d);
-            S[j * SP + j] = pivot;
+#pragma unroll
+            for (int c = 0; c < SB; ++c)
+                if (r < pw && c <= r && c < pw) S[(p0 + r) * SP + p0 + c] = row[c];
         }
         __syncthreads();
-        const T inv = T(1) / pivot;
-        for (int i = j + 1 + threadIdx.x; i < nb; i += NTHREADS) S[i * SP + j] *= inv;
-        __syncthreads();
-        // trailing update of the lower triangle: (i, k) with j < k <= i < nb
-        {
-            const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-            for (int i = j + 1 + ty; i < nb; i += NTHREADS / 32) {
-                const T lij = S[i * SP + j];
-                for (int k = j + 1 + tx; k <= i; k += 32) S[i * SP + k] = fma(-lij, S[k * SP + j], S[i * SP + k]);
+        // (2) column sub-panel below: row i solves x L_d^T = a  (L_d = the 16x16 block just factored)
+        for (int i = p0 + pw + tid; i < nb; i += NTHREADS) {
+            T x[SB];
+#pragma unroll
+            for (int c = 0; c < SB; ++c) x[c] = (c < pw) ? S[i * SP + p0 + c] : T(0);
+#pragma unroll
+            for (int c = 0; c < SB; ++c) {
+                if (c < pw) {
+                    T s = x[c];
+#pragma unroll
+                    for (int k = 0; k < SB; ++k)
+                        if (k < c) s = fma(-x[k], S[(p0 + c) * SP + p0 + k], s);
+                    x[c] = s / S[(p0 + c) * SP + p0 + c];
+                }
             }
+#pragma unroll
+            for (int c = 0; c < SB; ++c)
+                if (c < pw) S[i * SP + p0 + c] = x[c];
+        }
+        __syncthreads();
+        // (3) rank-pw update of the trailing lower triangle in 4x4 register tiles
+        const int t0 = p0 + pw;
+        const int nt = (nb - t0 + 3) / 4;  // tiles per side
+        for (int e = tid; e < nt * (nt + 1) / 2; e += NTHREADS) {
+            // unrank e -> (ti >= tj) in the lower triangle of the nt x nt tile grid
+            int ti = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+            while ((ti + 1) * (ti + 2) / 2 <= e) ++ti;
+            while (ti * (ti + 1) / 2 > e) --ti;
+            const int tj = e - ti * (ti + 1) / 2;
+            const int i0 = t0 + 4 * ti, k0 = t0 + 4 * tj;
+            T acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = T(0);
+#pragma unroll
+            for (int c = 0; c < SB; ++c) {
+                if (c < pw) {
+                    T li[4], lk[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        li[a] = (i0 + a < nb) ? S[(i0 + a) * SP + p0 + c] : T(0);
+                        lk[a] = (k0 + a < nb) ? S[(k0 + a) * SP + p0 + c] : T(0);
+                    }
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[a][b] = fma(li[a], lk[b], acc[a][b]);
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (i0 + a < nb && k0 + b <= i0 + a) S[(i0 + a) * SP + k0 + b] -= acc[a][b];
         }
         __syncthreads();
     }
 }
 
-// Invert the lower-triangular factor held in S.  X = L^{-1} is lower triangular; its strict
-// lower part is written into the (free) strict upper triangle of S transposed
-// (X[i][c] -> S[c][i], i > c); the diagonal is 1 / L_ii.  Four lanes cooperate on a column.
+// Invert the lower-triangular factor held in S.  X = L^{-1} (lower triangular) is written into the
+// unused upper part of the same tile, transposed and shifted by one column:
+//   X(i, c), i >= c   <->   S[c][i + 1]        (pitch 129, so column 128 exists)
+// Column-block forward substitution in 16-wide sub-panels:
+//   X_dd = inv(L_dd) (one column per thread);  for block rows i > d:
+//   X_id = -X_ii * sum_{d <= k < i} L_ik X_kd, 4x4 register tiles, O(nb/16) barriers.
+#define XX(i, c) S[(c) * SP + (i) + 1]
 template <typename T>
 __device__ void block_trtri(T* S, int nb) {
-    const int c = threadIdx.x >> 2, q = threadIdx.x & 3;
-    const unsigned gmask = 0xFu << ((threadIdx.x & 31) & ~3);  // the 4 lanes sharing column c
-    if (c < nb) {
-        for (int i = c + 1; i < nb; ++i) {
-            // X_ic = -( L_ic * X_cc + sum_{k=c+1}^{i-1} L_ik X_kc ) / L_ii
-            T s = T(0);
-            for (int k = c + 1 + q; k < i; k += 4) s = fma(S[i * SP + k], S[c * SP + k], s);
-            s += __shfl_xor_sync(gmask, s, 1);
-            s += __shfl_xor_sync(gmask, s, 2);
-            if (q == 0) S[c * SP + i] = -(S[i * SP + c] / S[c * SP + c] + s) / S[i * SP + i];
-            __syncwarp(gmask);
+    const int tid = threadIdx.x;
+    // thread-per-column substitution on the 16x16 diagonal sub-blocks (all sub-blocks in parallel)
+    for (int e = tid; e < nb; e += NTHREADS) {
+        const int d0 = (e / SB) * SB, c = e;  // column c of the sub-block starting at d0
+        const int dw = min(SB, nb - d0);
+        T x[SB];
+#pragma unroll
+        for (int r = 0; r < SB; ++r) {
+            const int i = d0 + r;
+            T s = (i == c) ? T(1) : T(0);
+            if (r < dw && i >= c) {
+#pragma unroll
+                for (int k = 0; k < SB; ++k)
+                    if (k < r && d0 + k >= c) s = fma(-S[i * SP + d0 + k], x[k], s);
+                x[r] = s / S[i * SP + i];
+            } else {
+                x[r] = T(0);
+            }
         }
+#pragma unroll
+        for (int r = 0; r < SB; ++r)
+            if (r < dw && d0 + r >= c) XX(d0 + r, c) = x[r];
     }
     __syncthreads();
+    // off-diagonal sub-blocks, one block "distance" at a time (pairs at equal distance are independent)
+    const int nsb = (nb + SB - 1) / SB;
+    for (int dist = 1; dist < nsb; ++dist) {
+        const int npairs = nsb - dist;
+        // phase A: T = L[i-block, d..i) X[d..i, d-block]  -> parked in X[i-block, d-block]
+        for (int e = tid; e < npairs * 16; e += NTHREADS) {
+            const int pr = e / 16, tt = e % 16;
+            const int ib = pr + dist, db = pr;
+            const int i0 = ib * SB + 4 * (tt / 4), c0 = db * SB + 4 * (tt % 4);
+            T acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = T(0);
+            for (int k = db * SB; k < ib * SB; ++k) {
+                T l[4], x[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    l[a] = (i0 + a < nb) ? S[(i0 + a) * SP + k] : T(0);
+                    x[a] = (k >= c0 + a) ? XX(k, c0 + a) : T(0);
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = fma(l[a], x[b], acc[a][b]);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (i0 + a < nb) XX(i0 + a, c0 + b) = acc[a][b];
+        }
+        __syncthreads();
+        // phase B: X[i-block, d-block] = -X_ii * T   (X_ii lower triangular 16x16)
+        for (int e = tid; e < npairs * SB; e += NTHREADS) {
+            const int pr = e / SB, cc = e % SB;
+            const int ib = pr + dist, db = pr;
+            const int c = db * SB + cc;
+            const int iw = min(SB, nb - ib * SB);
+            T tcol[SB], out[SB];
+#pragma unroll
+            for (int r = 0; r < SB; ++r) tcol[r] = (r < iw) ? XX(ib * SB + r, c) : T(0);
+#pragma unroll
+            for (int r = 0; r < SB; ++r) {
+                T s = T(0);
+#pragma unroll
+                for (int k = 0; k < SB; ++k)
+                    if (k <= r && r < iw) s = fma(XX(ib * SB + r, ib * SB + k), tcol[k], s);
+                out[r] = -s;
+            }
+#pragma unroll
+            for (int r = 0; r < SB; ++r)
+                if (r < iw) XX(ib * SB + r, c) = out[r];
+        }
+        __syncthreads();
+    }
 }
 
 template <typename T>
 __device__ void store_inverse(const T* S, int nb, T* inv) {  // inv: NB x NB row-major (lower, zero above)
-    for (int e = threadIdx.x; e < nb * nb; e += NTHREADS) {
-        const int i = e / nb, c = e % nb;
-        T v = T(0);
-        if (i == c) v = T(1) / S[i * SP + i];
-        else if (i > c) v = S[c * SP + i];
-        inv[i * NB + c] = v;
+    for (int e = threadIdx.x; e < nb * NB; e += NTHREADS) {
+        const int i = e / NB, c = e % NB;
+        inv[i * NB + c] = (c <= i && c < nb) ? XX(i, c) : T(0);
+    }
+}
+#undef XX
+
+template <typename T>
+__device__ void load_lower(T* S, const T* A, int64_t lda, int nb) {
+    for (int e = threadIdx.x; e < nb * NB; e += NTHREADS) {
+        const int i = e / NB, k = e % NB;
+        if (k <= i) S[i * SP + k] = A[(int64_t)i * lda + k];
     }
 }
 
@@ -92,14 +245,11 @@ __global__ void __launch_bounds__(NTHREADS) potrf_diag_kernel(T* __restrict__ A,
                                                               T* __restrict__ inv, int* info, int64_t j0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* S = reinterpret_cast<T*>(smem_raw);
-    for (int e = threadIdx.x; e < nb * nb; e += NTHREADS) {
-        const int i = e / nb, k = e % nb;
-        if (k <= i) S[i * SP + k] = A[(int64_t)i * lda + k];
-    }
+    load_lower<T>(S, A, lda, nb);
     __syncthreads();
     block_potrf<T>(S, nb, info, j0);
-    for (int e = threadIdx.x; e < nb * nb; e += NTHREADS) {
-        const int i = e / nb, k = e % nb;
+    for (int e = threadIdx.x; e < nb * NB; e += NTHREADS) {
+        const int i = e / NB, k = e % NB;
         if (k <= i) A[(int64_t)i * lda + k] = S[i * SP + k];
     }
     __syncthreads();
@@ -115,11 +265,7 @@ __global__ void __launch_bounds__(NTHREADS) trtri_blocks_kernel(const T* __restr
     T* S = reinterpret_cast<T*>(smem_raw);
     const int64_t i0 = (int64_t)blockIdx.x * NB;
     const int nb = (int)min((int64_t)NB, n - i0);
-    const T* Lb = L + i0 * ldl + i0;
-    for (int e = threadIdx.x; e < nb * nb; e += NTHREADS) {
-        const int i = e / nb, k = e % nb;
-        if (k <= i) S[i * SP + k] = Lb[(int64_t)i * ldl + k];
-    }
+    load_lower<T>(S, L + i0 * ldl + i0, ldl, nb);
     __syncthreads();
     block_trtri<T>(S, nb);
     store_inverse<T>(S, nb, inv + (int64_t)blockIdx.x * NB * NB);
@@ -142,119 +288,123 @@ __global__ void __launch_bounds__(256) logdet_kernel(const T* __restrict__ L, in
 }
 
 template <typename T>
+constexpr size_t leaf_smem() { return (size_t)NB * SP * sizeof(T); }
+
+template <typename T>
 int set_smem_attr(const void* fn) {
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NB * SP * sizeof(T)));
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem<T>());
     return e == cudaSuccess ? 0 : DCGP_CUDA_ERR(e);
+}
+
+inline int64_t split_point(int64_t nb) {  // first half, a multiple of the leaf size
+    int64_t h = ((nb / 2 + NB - 1) / NB) * NB;
+    return h >= nb ? nb - NB : h;
+}
+
+template <typename T>
+struct Ctx {
+    T* A;
+    int64_t lda;
+    T* ws;
+    int* info;
+    int dtype, xf;
+    cudaStream_t st;
+};
+
+// B = A[r0 : r0+nr, t0 : t0+nt]  <-  B * L[t0 : t0+nt, t0 : t0+nt]^{-T}
+template <typename T>
+int rtrsm_rec(const Ctx<T>& c, int64_t r0, int64_t nr, int64_t t0, int64_t nt) {
+    if (nt <= NB) {
+        T* Bp = c.A + r0 * c.lda + t0;
+        return dcgp_gemm_impl(0, 1, nr, nt, nt, 1.0, Bp, c.lda, c.ws + (t0 / NB) * NB * NB, NB, 0.0, Bp, c.lda, c.dtype,
+                              DCGP_GEMM_NO_SPLITK | c.xf, c.st);
+    }
+    const int64_t t1 = split_point(nt), t2 = nt - t1;
+    int rc = rtrsm_rec(c, r0, nr, t0, t1);
+    if (rc) return rc;
+    // B2 -= B1 * Lc^T,  Lc = L[t0+t1 : t0+nt, t0 : t0+t1]
+    rc = dcgp_gemm_impl(0, 1, nr, t2, t1, -1.0, c.A + r0 * c.lda + t0, c.lda, c.A + (t0 + t1) * c.lda + t0, c.lda, 1.0,
+                        c.A + r0 * c.lda + t0 + t1, c.lda, c.dtype, DCGP_GEMM_NO_SPLITK | c.xf, c.st);
+    if (rc) return rc;
+    return rtrsm_rec(c, r0, nr, t0 + t1, t2);
+}
+
+template <typename T>
+int chol_rec(const Ctx<T>& c, int64_t j0, int64_t nb) {
+    if (nb <= NB) {
+        potrf_diag_kernel<T><<<1, NTHREADS, leaf_smem<T>(), c.st>>>(c.A + j0 * c.lda + j0, c.lda, (int)nb,
+                                                                    c.ws + (j0 / NB) * NB * NB, c.info, j0);
+        DCGP_CHECK_LAUNCH();
+        return 0;
+    }
+    const int64_t n1 = split_point(nb), n2 = nb - n1;
+    int rc = chol_rec(c, j0, n1);
+    if (rc) return rc;
+    rc = rtrsm_rec(c, j0 + n1, n2, j0, n1);  // A21 <- A21 L11^{-T}
+    if (rc) return rc;
+    T* A21 = c.A + (j0 + n1) * c.lda + j0;
+    rc = dcgp_gemm_impl(0, 1, n2, n2, n1, -1.0, A21, c.lda, A21, c.lda, 1.0, c.A + (j0 + n1) * c.lda + j0 + n1, c.lda,
+                        c.dtype, DCGP_GEMM_LOWER | DCGP_GEMM_NO_SPLITK | c.xf, c.st);
+    if (rc) return rc;
+    return chol_rec(c, j0 + n1, n2);
 }
 
 template <typename T>
 int potrf_impl(T* A, int64_t n, int64_t lda, int* info, T* ws, int dtype, int xf, cudaStream_t st) {
-    const size_t smem = (size_t)NB * SP * sizeof(T);
     int rc = set_smem_attr<T>((const void*)potrf_diag_kernel<T>);
     if (rc) return rc;
-    // Two-level blocking: an NBO-wide panel is factored with NB-wide steps whose updates stay
-    // inside the panel (K = NB, O(n NBO^2) flops); the rest of the matrix is then updated ONCE per
-    // panel with K = NBO, so ~(1 - NBO/n) of all flops run in deep-K tensor-core GEMMs whose C
-    // tile traffic is amortised over NBO/16 k-steps.
-    const int64_t NBO = (n >= 4096) ? 512 : ((n >= 1024) ? 256 : NB);
-    for (int64_t J0 = 0; J0 < n; J0 += NBO) {
-        const int64_t jb = (n - J0 < NBO) ? (n - J0) : NBO;
-        const int64_t Jend = J0 + jb;
-        for (int64_t j0 = J0; j0 < Jend; j0 += NB) {
-            const int nb = (int)((Jend - j0 < NB) ? (Jend - j0) : NB);
-            T* inv = ws + (j0 / NB) * NB * NB;
-            potrf_diag_kernel<T><<<1, NTHREADS, smem, st>>>(A + j0 * lda + j0, lda, nb, inv, info, j0);
-            DCGP_CHECK_LAUNCH();
-            const int64_t rem = n - j0 - nb;
-            if (rem > 0) {
-                T* A21 = A + (j0 + nb) * lda + j0;
-                rc = dcgp_gemm_impl(0, 1, rem, nb, nb, 1.0, A21, lda, inv, NB, 0.0, A21, lda, dtype,
-                                    DCGP_GEMM_NO_SPLITK | xf, st);
-                if (rc) return rc;
-                const int64_t pc = Jend - (j0 + nb);  // panel columns still to be updated
-                if (pc > 0) {
-                    rc = dcgp_gemm_impl(0, 1, rem, pc, nb, -1.0, A21, lda, A21, lda, 1.0,
-                                        A + (j0 + nb) * lda + (j0 + nb), lda, dtype,
-                                        DCGP_GEMM_LOWER | DCGP_GEMM_NO_SPLITK | xf, st);
-                    if (rc) return rc;
-                }
-            }
-        }
-        const int64_t rem = n - Jend;
-        if (rem > 0) {
-            T* P = A + Jend * lda + J0;  // rem x jb panel of L
-            rc = dcgp_gemm_impl(0, 1, rem, rem, jb, -1.0, P, lda, P, lda, 1.0, A + Jend * lda + Jend, lda, dtype,
-                                DCGP_GEMM_LOWER | DCGP_GEMM_NO_SPLITK | xf, st);
-            if (rc) return rc;
-        }
+    Ctx<T> c{A, lda, ws, info, dtype, xf, st};
+    return chol_rec(c, 0, n);
+}
+
+// left-side solve with L[i0 : i0+nn, i0 : i0+nn] on the rows i0 .. i0+nn of B (n x m)
+template <typename T>
+struct LCtx {
+    const T* L;
+    int64_t ldl;
+    T* B;
+    int64_t m, ldb;
+    T* ws;
+    int dtype, xf;
+    cudaStream_t st;
+};
+
+template <typename T>
+int ltrsm_rec(const LCtx<T>& c, int trans, int64_t i0, int64_t nn) {
+    if (nn <= NB) {
+        T* Bi = c.B + i0 * c.ldb;
+        return dcgp_gemm_impl(trans, 0, nn, c.m, nn, 1.0, c.ws + (i0 / NB) * NB * NB, NB, Bi, c.ldb, 0.0, Bi, c.ldb,
+                              c.dtype, DCGP_GEMM_NO_SPLITK | c.xf, c.st);
     }
-    return 0;
+    const int64_t n1 = split_point(nn), n2 = nn - n1;
+    const T* Lc = c.L + (i0 + n1) * c.ldl + i0;  // n2 x n1
+    int rc;
+    if (!trans) {
+        rc = ltrsm_rec(c, trans, i0, n1);
+        if (rc) return rc;
+        rc = dcgp_gemm_impl(0, 0, n2, c.m, n1, -1.0, Lc, c.ldl, c.B + i0 * c.ldb, c.ldb, 1.0, c.B + (i0 + n1) * c.ldb,
+                            c.ldb, c.dtype, DCGP_GEMM_NO_SPLITK | c.xf, c.st);
+        if (rc) return rc;
+        return ltrsm_rec(c, trans, i0 + n1, n2);
+    }
+    rc = ltrsm_rec(c, trans, i0 + n1, n2);
+    if (rc) return rc;
+    rc = dcgp_gemm_impl(1, 0, n1, c.m, n2, -1.0, Lc, c.ldl, c.B + (i0 + n1) * c.ldb, c.ldb, 1.0, c.B + i0 * c.ldb, c.ldb,
+                        c.dtype, DCGP_GEMM_NO_SPLITK | c.xf, c.st);
+    if (rc) return rc;
+    return ltrsm_rec(c, trans, i0, n1);
 }
 
 template <typename T>
 int trsm_impl(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t m, int64_t ldb, T* ws, int dtype, int xf,
               cudaStream_t st) {
-    const size_t smem = (size_t)NB * SP * sizeof(T);
     int rc = set_smem_attr<T>((const void*)trtri_blocks_kernel<T>);
     if (rc) return rc;
     const int64_t nblk = (n + NB - 1) / NB;
-    trtri_blocks_kernel<T><<<(unsigned)nblk, NTHREADS, smem, st>>>(L, ldl, n, ws);
+    trtri_blocks_kernel<T><<<(unsigned)nblk, NTHREADS, leaf_smem<T>(), st>>>(L, ldl, n, ws);
     DCGP_CHECK_LAUNCH();
-    // Two-level blocking as in potrf: NB-wide substitution steps update only the rows of their
-    // NBO-wide outer block; all other rows are updated once per outer block with K = NBO.
-    const int64_t NBO = (n >= 4096) ? 512 : ((n >= 1024) ? 256 : NB);
-    const int64_t nouter = (n + NBO - 1) / NBO;
-    if (!trans) {
-        for (int64_t ob = 0; ob < nouter; ++ob) {
-            const int64_t I0 = ob * NBO;
-            const int64_t Iend = (n < I0 + NBO) ? n : I0 + NBO;
-            for (int64_t i0 = I0; i0 < Iend; i0 += NB) {
-                const int64_t nb = (Iend - i0 < NB) ? (Iend - i0) : NB;
-                T* Bi = B + i0 * ldb;
-                rc = dcgp_gemm_impl(0, 0, nb, m, nb, 1.0, ws + (i0 / NB) * NB * NB, NB, Bi, ldb, 0.0, Bi, ldb, dtype,
-                                    DCGP_GEMM_NO_SPLITK | xf, st);
-                if (rc) return rc;
-                const int64_t rin = Iend - i0 - nb;  // rows below, inside the outer block
-                if (rin > 0) {
-                    rc = dcgp_gemm_impl(0, 0, rin, m, nb, -1.0, L + (i0 + nb) * ldl + i0, ldl, Bi, ldb, 1.0,
-                                        B + (i0 + nb) * ldb, ldb, dtype, DCGP_GEMM_NO_SPLITK | xf, st);
-                    if (rc) return rc;
-                }
-            }
-            const int64_t rem = n - Iend;
-            if (rem > 0) {
-                rc = dcgp_gemm_impl(0, 0, rem, m, Iend - I0, -1.0, L + Iend * ldl + I0, ldl, B + I0 * ldb, ldb, 1.0,
-                                    B + Iend * ldb, ldb, dtype, DCGP_GEMM_NO_SPLITK | xf, st);
-                if (rc) return rc;
-            }
-        }
-    } else {
-        for (int64_t ob = nouter - 1; ob >= 0; --ob) {
-            const int64_t I0 = ob * NBO;
-            const int64_t Iend = (n < I0 + NBO) ? n : I0 + NBO;
-            const int64_t nin = (Iend - I0 + NB - 1) / NB;
-            for (int64_t ib = nin - 1; ib >= 0; --ib) {
-                const int64_t i0 = I0 + ib * NB;
-                const int64_t nb = (Iend - i0 < NB) ? (Iend - i0) : NB;
-                T* Bi = B + i0 * ldb;
-                rc = dcgp_gemm_impl(1, 0, nb, m, nb, 1.0, ws + (i0 / NB) * NB * NB, NB, Bi, ldb, 0.0, Bi, ldb, dtype,
-                                    DCGP_GEMM_NO_SPLITK | xf, st);
-                if (rc) return rc;
-                const int64_t rin = i0 - I0;  // rows above, inside the outer block
-                if (rin > 0) {
-                    rc = dcgp_gemm_impl(1, 0, rin, m, nb, -1.0, L + i0 * ldl + I0, ldl, Bi, ldb, 1.0, B + I0 * ldb, ldb,
-                                        dtype, DCGP_GEMM_NO_SPLITK | xf, st);
-                    if (rc) return rc;
-                }
-            }
-            if (I0 > 0) {
-                rc = dcgp_gemm_impl(1, 0, I0, m, Iend - I0, -1.0, L + I0 * ldl, ldl, B + I0 * ldb, ldb, 1.0, B, ldb,
-                                    dtype, DCGP_GEMM_NO_SPLITK | xf, st);
-                if (rc) return rc;
-            }
-        }
-    }
-    return 0;
+    LCtx<T> c{L, ldl, B, m, ldb, ws, dtype, xf, st};
+    return ltrsm_rec(c, trans, 0, n);
 }
 
 size_t inv_ws_bytes(int64_t n, int dtype) {
@@ -279,7 +429,8 @@ extern "C" int dcgp_potrf(void* A, int64_t n, int64_t lda, int* info, void* work
         cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
         if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
     }
-    if (dtype == DCGP_F64) return potrf_impl<double>((double*)A, n, lda, info, (double*)workspace, dtype, flags & DCGP_GEMM_TF32X3, st);
+    if (dtype == DCGP_F64)
+        return potrf_impl<double>((double*)A, n, lda, info, (double*)workspace, dtype, flags & DCGP_GEMM_TF32X3, st);
     return potrf_impl<float>((float*)A, n, lda, info, (float*)workspace, dtype, flags & DCGP_GEMM_TF32X3, st);
 }
 
@@ -296,8 +447,10 @@ extern "C" int dcgp_trsm(int trans, const void* L, int64_t n, int64_t ldl, void*
     if (!workspace || workspace_bytes < inv_ws_bytes(n, dtype)) return -8;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == DCGP_F64)
-        return trsm_impl<double>(trans, (const double*)L, n, ldl, (double*)B, m, ldb, (double*)workspace, dtype, flags & DCGP_GEMM_TF32X3, st);
-    return trsm_impl<float>(trans, (const float*)L, n, ldl, (float*)B, m, ldb, (float*)workspace, dtype, flags & DCGP_GEMM_TF32X3, st);
+        return trsm_impl<double>(trans, (const double*)L, n, ldl, (double*)B, m, ldb, (double*)workspace, dtype,
+                                 flags & DCGP_GEMM_TF32X3, st);
+    return trsm_impl<float>(trans, (const float*)L, n, ldl, (float*)B, m, ldb, (float*)workspace, dtype,
+                            flags & DCGP_GEMM_TF32X3, st);
 }
 
 extern "C" int dcgp_potrs(const void* L, int64_t n, int64_t ldl, void* B, int64_t m, int64_t ldb, void* workspace,
