@@ -317,6 +317,9 @@ int launch_gemm(GemmParams p, cudaStream_t st) {
 
 }  // namespace
 
+int dcgp_gemm_tc_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
+                      const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int flags, cudaStream_t st);
+
 // internal entry used by the Cholesky / TRSM drivers
 int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
                    const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype, int flags,
@@ -349,6 +352,13 @@ int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, doub
         p.vecA = vec_ok<float>(A, lda);
         p.vecB = vec_ok<float>(B, ldb);
         if (flags & DCGP_GEMM_TF32X3) return launch_gemm<float, true>(p, st);
+        // large single-pass TF32 contractions go to the tcgen05 / TMA / TMEM kernel (gemm_tc.cu);
+        // small or split-K-shaped problems stay on the mma.sync kernel below
+        if (!(flags & DCGP_GEMM_NO_TCGEN05) && m >= 128 && n >= 160 && k >= 64 &&
+            ((m + 127) / 128) * ((n + 255) / 256) >= 24) {
+            const int rc = dcgp_gemm_tc_impl(transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, st);
+            if (rc <= 0) return rc;
+        }
         return launch_gemm<float, false>(p, st);
     }
     return -14;

@@ -1,0 +1,314 @@
+// Blackwell-native TF32 contraction: C = alpha * op(A) op(B) + beta * C with FP32 storage.
+//
+//   * operands move global -> shared with TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) through a
+//     4-stage mbarrier ring; one elected lane of warp 0 is the producer;
+//   * one elected lane of warp 1 issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = 256,
+//     K = 8 per instruction, 4 per 128-byte k-tile) and releases stages with tcgen05.commit;
+//   * the 128 x 256 FP32 accumulator lives in TMEM (256 columns); warps 2..5 drain it with
+//     tcgen05.ld (32 lanes x 32 columns per instruction), apply alpha/beta and store rows of C.
+//
+// Both operand majors are supported through the instruction descriptor (a_major / b_major) and
+// the matching canonical shared-memory layouts:
+//   K-major  (row-major R x K in global): one TMA box {32 k, R rows}; rows are 128-byte lines,
+//            8-row swizzle atoms every 1024 B (SBO); a k-step advances the start address by 32 B.
+//   MN-major (row-major K x R in global): R/32 TMA boxes {32 r, 32 k}; each box is a 4 KB chunk of
+//            32 k-rows x 128 B; LBO = 4096 B between chunks, SBO = 1024 B between 8-k groups; a
+//            k-step advances the start address by 1024 B.
+// TMA zero-fills out-of-bounds elements, so ragged M / N / K need no special casing in the main
+// loop; the epilogue guards its stores.
+//
+// Shapes this kernel does not take (tiny problems, split-K candidates, unaligned leading
+// dimensions, 3xTF32) stay on the mma.sync kernel in gemm.cu.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int TM = 128, TN = 256, TK = 32;  // CTA tile; TK floats = one 128-byte swizzle line
+constexpr int STAGES = 4;
+constexpr int A_BYTES = TM * TK * 4;  // 16 KB
+constexpr int B_BYTES = TN * TK * 4;  // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int NTHREADS_TC = 192;  // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-5 epilogue
+constexpr int TMEM_COLS = 256;
+constexpr size_t SMEM_TC = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TcParams {
+    int64_t m, n, k;
+    float* C;
+    int64_t ldc;
+    float alpha, beta;
+    int lower;
+    int a_mn, b_mn;  // operand is MN-major (stored K x R)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_c),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// shared-memory matrix descriptor, 128-byte swizzle, sm_100 version bit set
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
+
+__global__ void __launch_bounds__(NTHREADS_TC, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ TcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m0 = (int64_t)blockIdx.y * TM, n0 = (int64_t)blockIdx.x * TN;
+    if (p.lower && n0 > m0 + TM - 1) return;
+    const int nkt = (int)((p.k + TK - 1) / TK);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            for (int kt = 0; kt < nkt; ++kt) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (uint32_t)(kt / STAGES) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                unsigned char* sa = tiles + (size_t)s * STAGE_BYTES;
+                unsigned char* sb = sa + A_BYTES;
+                mbar_expect_tx(&full[s], STAGE_BYTES);
+                const int k0 = kt * TK;
+                if (!p.a_mn) {
+                    tma_load_2d(sa, &mapA, &full[s], k0, (int)m0);
+                } else {
+                    for (int c = 0; c < TM / 32; ++c) tma_load_2d(sa + c * 4096, &mapA, &full[s], (int)m0 + 32 * c, k0);
+                }
+                if (!p.b_mn) {
+                    tma_load_2d(sb, &mapB, &full[s], k0, (int)n0);
+                } else {
+                    for (int c = 0; c < TN / 32; ++c) tma_load_2d(sb + c * 4096, &mapB, &full[s], (int)n0 + 32 * c, k0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            // instruction descriptor: D = F32, A = B = TF32, majors, N >> 3, M >> 4
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                                   ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            for (int kt = 0; kt < nkt; ++kt) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (uint32_t)(kt / STAGES) & 1u;
+                mbar_wait(&full[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+                const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < TK / 8; ++kk) {
+                    const uint64_t ad = p.a_mn ? make_desc(sa + kk * 1024, 4096, 1024) : make_desc(sa + kk * 32, 16, 1024);
+                    const uint64_t bd = p.b_mn ? make_desc(sb + kk * 1024, 4096, 1024) : make_desc(sb + kk * 32, 16, 1024);
+                    umma_tf32(tmem_base, ad, bd, idesc, (kt > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);  // frees the stage once the MMAs above have read it
+            }
+            umma_commit(tmem_full);  // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
+        const int q = warp & 3;
+        const int64_t row = m0 + q * 32 + lane;
+        if (nkt > 0) {
+            mbar_wait(tmem_full, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+            uint32_t r[32];
+            if (nkt > 0) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+                      "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+                      "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0u;
+            }
+            if (row < p.m) {
+                const int64_t col = n0 + c0;
+                float* dst = p.C + row * p.ldc + col;
+                if (vec && col + 32 <= p.n) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o;
+                        o.x = p.alpha * __uint_as_float(r[j]);
+                        o.y = p.alpha * __uint_as_float(r[j + 1]);
+                        o.z = p.alpha * __uint_as_float(r[j + 2]);
+                        o.w = p.alpha * __uint_as_float(r[j + 3]);
+                        if (p.beta != 0.f) {
+                            const float4 c = *reinterpret_cast<const float4*>(dst + j);
+                            o.x = fmaf(p.beta, c.x, o.x);
+                            o.y = fmaf(p.beta, c.y, o.y);
+                            o.z = fmaf(p.beta, c.z, o.z);
+                            o.w = fmaf(p.beta, c.w, o.w);
+                        }
+                        *reinterpret_cast<float4*>(dst + j) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (col + j < p.n) {
+                            const float v = p.alpha * __uint_as_float(r[j]);
+                            dst[j] = (p.beta != 0.f) ? fmaf(p.beta, dst[j], v) : v;
+                        }
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+// 2-D FP32 tensor map over a row-major matrix with `rows` rows of `cols` contiguous elements
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return 1;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 1;
+}
+
+}  // namespace
+
+// Returns 0 on success, 1 if the shape/alignment is not taken by this kernel (caller falls through
+// to the mma.sync kernel), < 0 on CUDA errors.
+int dcgp_gemm_tc_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
+                      const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int flags, cudaStream_t st) {
+    if (k < 1) return 1;
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (lda & 3) || (ldb & 3)) return 1;
+    if (m > 0x7fffffff || n > 0x7fffffff || k > 0x7fffffff) return 1;
+    CUtensorMap mapA, mapB;
+    // op(A)[m, k]: notrans -> A is m x k (K-major); trans -> A is k x m (MN-major)
+    if (!transa) {
+        if (make_map(&mapA, A, m, k, lda, TK, TM)) return 1;
+    } else {
+        if (make_map(&mapA, A, k, m, lda, 32, TK)) return 1;
+    }
+    // op(B)[k, n]: trans -> B is n x k (K-major); notrans -> B is k x n (MN-major)
+    if (transb) {
+        if (make_map(&mapB, B, n, k, ldb, TK, TN)) return 1;
+    } else {
+        if (make_map(&mapB, B, k, n, ldb, 32, TK)) return 1;
+    }
+    TcParams p;
+    p.m = m; p.n = n; p.k = k;
+    p.C = (float*)C; p.ldc = ldc;
+    p.alpha = (float)alpha; p.beta = (float)beta;
+    p.lower = (flags & DCGP_GEMM_LOWER) ? 1 : 0;
+    p.a_mn = transa ? 1 : 0;
+    p.b_mn = transb ? 0 : 1;
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC);
+    if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
+    dim3 grid((unsigned)((n + TN - 1) / TN), (unsigned)((m + TM - 1) / TM));
+    gemm_tc_kernel<<<grid, NTHREADS_TC, SMEM_TC, st>>>(mapA, mapB, p);
+    DCGP_CHECK_LAUNCH();
+    return 0;
+}

@@ -145,6 +145,9 @@ def gram_bwd(spec: FlatSpec, x1, x2, G, need_dx1=False):
     return dls, dos, dx1
 
 
+USE_TCGEN05 = True   # False keeps FP32 contractions on the mma.sync kernel (A/B comparisons)
+
+
 def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, C=None, lower=False, no_splitk=False):
     """C = alpha * op(A) @ op(B) + beta * C."""
     A, B = _rowmajor(A), _rowmajor(B)
@@ -156,7 +159,8 @@ def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, C=None, lower=Fa
     if C is None:
         C = torch.empty(m, n, dtype=A.dtype, device=A.device)
         beta = 0.0
-    flags = (GEMM_LOWER if lower else 0) | (_lib.GEMM_NO_SPLITK if no_splitk else 0) | _x3(A, m * n * k <= X3_GEMM_LIMIT)
+    flags = (GEMM_LOWER if lower else 0) | (_lib.GEMM_NO_SPLITK if no_splitk else 0) | _x3(A, m * n * k <= X3_GEMM_LIMIT) \
+        | (0 if USE_TCGEN05 else _lib.GEMM_NO_TCGEN05)
     rc = _lib.load().dcgp_gemm(int(transa), int(transb), m, n, k, float(alpha), _ptr(A), _ld(A), _ptr(B), _ld(B),
                                float(beta), _ptr(C), _ld(C), _dt(A), flags, _stream())
     check(rc, "dcgp_gemm")

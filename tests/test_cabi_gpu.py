@@ -265,3 +265,47 @@ def test_whitened_kl_vs_oracle(dtype):
     tol = 1e-12 if dtype == torch.float64 else 1e-5
     assert abs(out.item() - kl.item()) < tol * abs(kl.item())
     assert relerr(dm, m.grad) < tol and relerr(dLs, raw.grad) < tol
+
+
+# ------------------------------------------------------------------ tcgen05 / TMA / TMEM TF32 GEMM
+@pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("m,n,k", [(1024, 2048, 512), (1000, 1500, 328), (2052, 1028, 96)])
+def test_tcgen05_gemm_all_layouts(ta, tb, m, n, k):
+    """Shapes large enough to be routed to the tcgen05 kernel (gemm_tc.cu): every operand major,
+    ragged M/N/K (TMA zero fill + guarded epilogue), alpha/beta epilogue."""
+    o = ops()
+    torch.manual_seed(m + n + k)
+    A = torch.randn((k, m) if ta else (m, k), dtype=torch.float64)
+    B = torch.randn((n, k) if tb else (k, n), dtype=torch.float64)
+    C0 = torch.randn(m, n, dtype=torch.float64)
+    ref = 0.7 * (A.t() if ta else A) @ (B.t() if tb else B) - 0.3 * C0
+    Ad, Bd = dev(A, torch.float32), dev(B, torch.float32)
+    o.TF32_MODE = "fast"
+    try:
+        C = dev(C0, torch.float32).clone()
+        o.gemm(Ad, Bd, transa=ta, transb=tb, alpha=0.7, beta=-0.3, C=C)
+        o.USE_TCGEN05 = False
+        C2 = dev(C0, torch.float32).clone()
+        o.gemm(Ad, Bd, transa=ta, transb=tb, alpha=0.7, beta=-0.3, C=C2)
+    finally:
+        o.USE_TCGEN05 = True
+        o.TF32_MODE = "auto"
+    assert relerr(C, ref) < 2e-3          # TF32 operands, FP32 accumulation
+    assert relerr(C, C2) < 1e-3           # tcgen05 kernel agrees with the mma.sync kernel
+
+
+def test_tcgen05_syrk_lower_tiles():
+    o = ops()
+    torch.manual_seed(2)
+    P = torch.randn(3000, 512, dtype=torch.float64)
+    S0 = torch.randn(3000, 3000, dtype=torch.float64)
+    o.TF32_MODE = "fast"
+    try:
+        S = dev(S0, torch.float32).clone()
+        o.gemm(dev(P, torch.float32), dev(P, torch.float32), transb=True, alpha=-1.0, beta=1.0, C=S, lower=True)
+    finally:
+        o.TF32_MODE = "auto"
+    ref = S0 - P @ P.t()
+    assert relerr(S.tril(), ref.tril()) < 2e-3
+    # tiles strictly above the diagonal (128-row x 256-col tiles) are untouched
+    assert torch.equal(S[:128, 256:].cpu().double(), S0[:128, 256:].float().double())
