@@ -21,6 +21,7 @@
 // dimensions, 3xTF32) stay on the mma.sync kernel in gemm.cu.
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace {
 
@@ -40,6 +41,7 @@ struct TcParams {
     float alpha, beta;
     int lower;
     int a_mn, b_mn;  // operand is MN-major (stored K x R)
+    int variant;     // debug: descriptor variant for MN-major operands
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -86,13 +88,15 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // shared-memory matrix descriptor, 128-byte swizzle, sm_100 version bit set
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout: 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms, MN-major 32-bit data)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    d |= (uint64_t)layout << 61;
     return d;
 }
 
@@ -167,8 +171,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const uint32_t sb = sa + A_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < TK / 8; ++kk) {
-                    const uint64_t ad = p.a_mn ? make_desc(sa + kk * 1024, 4096, 1024) : make_desc(sa + kk * 32, 16, 1024);
-                    const uint64_t bd = p.b_mn ? make_desc(sb + kk * 1024, 4096, 1024) : make_desc(sb + kk * 32, 16, 1024);
+                    // MN-major 32-bit operands use the 32-byte-atom flavour of the 128-byte swizzle:
+                    // atoms of 4 k-rows x 128 B (SBO = 512 B), 32-float chunks 4096 B apart (LBO)
+                    uint32_t lbo = 4096, sbo = 512, kadv = 1024;
+                    if (p.variant == 1) { lbo = 512; sbo = 4096; }
+                    if (p.variant == 2) { sbo = 1024; }
+                    const uint64_t ad = p.a_mn ? make_desc(sa + kk * kadv, lbo, sbo, 1) : make_desc(sa + kk * 32, 16, 1024, 2);
+                    const uint64_t bd = p.b_mn ? make_desc(sb + kk * kadv, lbo, sbo, 1) : make_desc(sb + kk * 32, 16, 1024, 2);
                     umma_tf32(tmem_base, ad, bd, idesc, (kt > 0 || kk > 0) ? 1u : 0u);
                 }
                 umma_commit(&empty[s]);  // frees the stage once the MMAs above have read it
@@ -263,7 +272,8 @@ EncodeTiledFn get_encode() {
 }
 
 // 2-D FP32 tensor map over a row-major matrix with `rows` rows of `cols` contiguous elements
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+             CUtensorMapSwizzle swz) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return 1;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -271,7 +281,7 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : 1;
 }
@@ -288,15 +298,15 @@ int dcgp_gemm_tc_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, d
     CUtensorMap mapA, mapB;
     // op(A)[m, k]: notrans -> A is m x k (K-major); trans -> A is k x m (MN-major)
     if (!transa) {
-        if (make_map(&mapA, A, m, k, lda, TK, TM)) return 1;
+        if (make_map(&mapA, A, m, k, lda, TK, TM, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     } else {
-        if (make_map(&mapA, A, k, m, lda, 32, TK)) return 1;
+        if (make_map(&mapA, A, k, m, lda, 32, TK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
     }
     // op(B)[k, n]: trans -> B is n x k (K-major); notrans -> B is k x n (MN-major)
     if (transb) {
-        if (make_map(&mapB, B, n, k, ldb, TK, TN)) return 1;
+        if (make_map(&mapB, B, n, k, ldb, TK, TN, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     } else {
-        if (make_map(&mapB, B, k, n, ldb, 32, TK)) return 1;
+        if (make_map(&mapB, B, k, n, ldb, 32, TK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
     }
     TcParams p;
     p.m = m; p.n = n; p.k = k;
@@ -305,6 +315,7 @@ int dcgp_gemm_tc_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, d
     p.lower = (flags & DCGP_GEMM_LOWER) ? 1 : 0;
     p.a_mn = transa ? 1 : 0;
     p.b_mn = transb ? 0 : 1;
+    { const char* v = getenv("DCGP_TC_VARIANT"); p.variant = v ? atoi(v) : 0; }
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC);
     if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
     dim3 grid((unsigned)((n + TN - 1) / TN), (unsigned)((m + TM - 1) / TM));

@@ -17,12 +17,18 @@ KINDS = {"rbf": _lib.KIND_RBF, "matern32": _lib.KIND_MATERN32, "matern12": _lib.
          "matern52": _lib.KIND_MATERN52}
 
 
-# FP32 contraction precision: "fast" = single-pass TF32 everywhere, "x3" = error-compensated
-# 3xTF32 (~FP32 accuracy) everywhere, "auto" = 3xTF32 for small (latency-bound) problems and
-# single-pass TF32 for the large contractions that carry the flops.
+# FP32 contraction precision.  Measured on the bench workload (tools/acc_probe.py, profiles/):
+# single-pass TF32 inside the Cholesky factorisation and the triangular solves of the bag
+# covariance (cond ~ 1e4) puts the ELBO 5e-3 off the FP64 value, outside the 1e-3 tolerance;
+# with those on error-compensated 3xTF32 and plain products on single-pass TF32 the ELBO is
+# 5e-5 off.  Hence the default "auto":
+#   "fast" = single-pass TF32 everywhere, "x3" = 3xTF32 (~FP32 accuracy) everywhere,
+#   "auto" = 3xTF32 for dcgp_potrf / dcgp_trsm / dcgp_potrs and for small GEMMs,
+#            single-pass TF32 (tcgen05 kernel) for the large products.
 TF32_MODE = "auto"
 X3_GEMM_LIMIT = 512 ** 3
-X3_SOLVE_LIMIT = 1024
+X3_SOLVE_LIMIT = 1 << 62  # dcgp_trsm / dcgp_potrs: always compensated in "auto"
+X3_POTRF_LIMIT = 1 << 62  # dcgp_potrf
 
 
 def _x3(t, small):
@@ -180,7 +186,7 @@ def potrf_(A, info=None):
         info = torch.zeros(1, dtype=torch.int32, device=A.device)
     lib = _lib.load()
     ws = _workspace(lib.dcgp_potrf_workspace(n, _dt(A)), A.device)
-    rc = lib.dcgp_potrf(_ptr(A), n, _ld(A), _ptr(info), _ptr(ws), ws.numel(), _dt(A), _x3(A, n <= X3_SOLVE_LIMIT), _stream())
+    rc = lib.dcgp_potrf(_ptr(A), n, _ld(A), _ptr(info), _ptr(ws), ws.numel(), _dt(A), _x3(A, n <= X3_POTRF_LIMIT), _stream())
     check(rc, "dcgp_potrf")
     return info
 
