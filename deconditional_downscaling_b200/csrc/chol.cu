@@ -20,7 +20,8 @@
 
 int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
                    const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype, int flags,
-                   cudaStream_t st);
+                   cudaStream_t st, const void* Alo, const void* Blo);
+int dcgp_split_lo_impl(const void* src, void* dst, int64_t rows, int64_t cols, int64_t lds, int64_t ldd, cudaStream_t st);
 
 namespace {
 
@@ -309,6 +310,7 @@ struct Ctx {
     int* info;
     int dtype, xf;
     cudaStream_t st;
+    T* Alo;  // FP32 3xTF32 only: x - trunc_tf32(x) of the finished off-diagonal blocks of L (layout of A), or null
 };
 
 // B = A[r0 : r0+nr, t0 : t0+nt]  <-  B * L[t0 : t0+nt, t0 : t0+nt]^{-T}
@@ -316,15 +318,21 @@ template <typename T>
 int rtrsm_rec(const Ctx<T>& c, int64_t r0, int64_t nr, int64_t t0, int64_t nt) {
     if (nt <= NB) {
         T* Bp = c.A + r0 * c.lda + t0;
-        return dcgp_gemm_impl(0, 1, nr, nt, nt, 1.0, Bp, c.lda, c.ws + (t0 / NB) * NB * NB, NB, 0.0, Bp, c.lda, c.dtype,
-                              DCGP_GEMM_NO_SPLITK | c.xf, c.st);
+        int rc = dcgp_gemm_impl(0, 1, nr, nt, nt, 1.0, Bp, c.lda, c.ws + (t0 / NB) * NB * NB, NB, 0.0, Bp, c.lda,
+                                c.dtype, DCGP_GEMM_NO_SPLITK | c.xf, c.st, nullptr, nullptr);
+        if (rc) return rc;
+        // these entries of L are final: publish their TF32 remainders for the tcgen05 3xTF32 products
+        if (c.Alo) rc = dcgp_split_lo_impl(Bp, c.Alo + r0 * c.lda + t0, nr, nt, c.lda, c.lda, c.st);
+        return rc;
     }
     const int64_t t1 = split_point(nt), t2 = nt - t1;
     int rc = rtrsm_rec(c, r0, nr, t0, t1);
     if (rc) return rc;
     // B2 -= B1 * Lc^T,  Lc = L[t0+t1 : t0+nt, t0 : t0+t1]
-    rc = dcgp_gemm_impl(0, 1, nr, t2, t1, -1.0, c.A + r0 * c.lda + t0, c.lda, c.A + (t0 + t1) * c.lda + t0, c.lda, 1.0,
-                        c.A + r0 * c.lda + t0 + t1, c.lda, c.dtype, DCGP_GEMM_NO_SPLITK | c.xf, c.st);
+    const int64_t oa = r0 * c.lda + t0, ob = (t0 + t1) * c.lda + t0;
+    rc = dcgp_gemm_impl(0, 1, nr, t2, t1, -1.0, c.A + oa, c.lda, c.A + ob, c.lda, 1.0, c.A + r0 * c.lda + t0 + t1, c.lda,
+                        c.dtype, DCGP_GEMM_NO_SPLITK | c.xf, c.st, c.Alo ? c.Alo + oa : nullptr,
+                        c.Alo ? c.Alo + ob : nullptr);
     if (rc) return rc;
     return rtrsm_rec(c, r0, nr, t0 + t1, t2);
 }
@@ -342,18 +350,28 @@ int chol_rec(const Ctx<T>& c, int64_t j0, int64_t nb) {
     if (rc) return rc;
     rc = rtrsm_rec(c, j0 + n1, n2, j0, n1);  // A21 <- A21 L11^{-T}
     if (rc) return rc;
-    T* A21 = c.A + (j0 + n1) * c.lda + j0;
+    const int64_t o21 = (j0 + n1) * c.lda + j0;
+    T* A21 = c.A + o21;
+    const T* A21lo = c.Alo ? c.Alo + o21 : nullptr;
     rc = dcgp_gemm_impl(0, 1, n2, n2, n1, -1.0, A21, c.lda, A21, c.lda, 1.0, c.A + (j0 + n1) * c.lda + j0 + n1, c.lda,
-                        c.dtype, DCGP_GEMM_LOWER | DCGP_GEMM_NO_SPLITK | c.xf, c.st);
+                        c.dtype, DCGP_GEMM_LOWER | DCGP_GEMM_NO_SPLITK | c.xf, c.st, A21lo, A21lo);
     if (rc) return rc;
     return chol_rec(c, j0 + n1, n2);
 }
 
+size_t inv_ws_bytes(int64_t n, int dtype) {
+    const int64_t nblk = (n + NB - 1) / NB;
+    return (size_t)nblk * NB * NB * (dtype == DCGP_F64 ? 8 : 4);
+}
+
 template <typename T>
-int potrf_impl(T* A, int64_t n, int64_t lda, int* info, T* ws, int dtype, int xf, cudaStream_t st) {
+int potrf_impl(T* A, int64_t n, int64_t lda, int* info, T* ws, size_t ws_bytes, int dtype, int xf, cudaStream_t st) {
     int rc = set_smem_attr<T>((const void*)potrf_diag_kernel<T>);
     if (rc) return rc;
-    Ctx<T> c{A, lda, ws, info, dtype, xf, st};
+    T* lo = nullptr;
+    if (sizeof(T) == 4 && xf && n > 2 * NB && ws_bytes >= inv_ws_bytes(n, dtype) + (size_t)n * lda * 4)
+        lo = ws + inv_ws_bytes(n, dtype) / sizeof(T);
+    Ctx<T> c{A, lda, ws, info, dtype, xf, st, lo};
     return chol_rec(c, 0, n);
 }
 
@@ -367,54 +385,70 @@ struct LCtx {
     T* ws;
     int dtype, xf;
     cudaStream_t st;
+    const T* Llo;  // remainders of L (layout of L) and of the solved rows of B (layout of B), or null
+    T* Blo;
 };
 
 template <typename T>
 int ltrsm_rec(const LCtx<T>& c, int trans, int64_t i0, int64_t nn) {
     if (nn <= NB) {
         T* Bi = c.B + i0 * c.ldb;
-        return dcgp_gemm_impl(trans, 0, nn, c.m, nn, 1.0, c.ws + (i0 / NB) * NB * NB, NB, Bi, c.ldb, 0.0, Bi, c.ldb,
-                              c.dtype, DCGP_GEMM_NO_SPLITK | c.xf, c.st);
+        int rc = dcgp_gemm_impl(trans, 0, nn, c.m, nn, 1.0, c.ws + (i0 / NB) * NB * NB, NB, Bi, c.ldb, 0.0, Bi, c.ldb,
+                                c.dtype, DCGP_GEMM_NO_SPLITK | c.xf, c.st, nullptr, nullptr);
+        if (rc) return rc;
+        if (c.Blo) rc = dcgp_split_lo_impl(Bi, c.Blo + i0 * c.ldb, nn, c.m, c.ldb, c.ldb, c.st);
+        return rc;
     }
     const int64_t n1 = split_point(nn), n2 = nn - n1;
-    const T* Lc = c.L + (i0 + n1) * c.ldl + i0;  // n2 x n1
+    const int64_t oc = (i0 + n1) * c.ldl + i0;
+    const T* Lc = c.L + oc;  // n2 x n1
+    const T* Lclo = c.Llo ? c.Llo + oc : nullptr;
     int rc;
     if (!trans) {
         rc = ltrsm_rec(c, trans, i0, n1);
         if (rc) return rc;
         rc = dcgp_gemm_impl(0, 0, n2, c.m, n1, -1.0, Lc, c.ldl, c.B + i0 * c.ldb, c.ldb, 1.0, c.B + (i0 + n1) * c.ldb,
-                            c.ldb, c.dtype, DCGP_GEMM_NO_SPLITK | c.xf, c.st);
+                            c.ldb, c.dtype, DCGP_GEMM_NO_SPLITK | c.xf, c.st, Lclo,
+                            c.Blo ? c.Blo + i0 * c.ldb : nullptr);
         if (rc) return rc;
         return ltrsm_rec(c, trans, i0 + n1, n2);
     }
     rc = ltrsm_rec(c, trans, i0 + n1, n2);
     if (rc) return rc;
     rc = dcgp_gemm_impl(1, 0, n1, c.m, n2, -1.0, Lc, c.ldl, c.B + (i0 + n1) * c.ldb, c.ldb, 1.0, c.B + i0 * c.ldb, c.ldb,
-                        c.dtype, DCGP_GEMM_NO_SPLITK | c.xf, c.st);
+                        c.dtype, DCGP_GEMM_NO_SPLITK | c.xf, c.st, Lclo, c.Blo ? c.Blo + (i0 + n1) * c.ldb : nullptr);
     if (rc) return rc;
     return ltrsm_rec(c, trans, i0, n1);
 }
 
 template <typename T>
-int trsm_impl(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t m, int64_t ldb, T* ws, int dtype, int xf,
-              cudaStream_t st) {
+int trsm_impl(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t m, int64_t ldb, T* ws, size_t ws_bytes,
+              int dtype, int xf, cudaStream_t st) {
     int rc = set_smem_attr<T>((const void*)trtri_blocks_kernel<T>);
     if (rc) return rc;
     const int64_t nblk = (n + NB - 1) / NB;
     trtri_blocks_kernel<T><<<(unsigned)nblk, NTHREADS, leaf_smem<T>(), st>>>(L, ldl, n, ws);
     DCGP_CHECK_LAUNCH();
-    LCtx<T> c{L, ldl, B, m, ldb, ws, dtype, xf, st};
+    T *llo = nullptr, *blo = nullptr;
+    const size_t inv = inv_ws_bytes(n, dtype);
+    if (sizeof(T) == 4 && xf && n > 2 * NB && m >= 160 && ws_bytes >= inv + ((size_t)n * ldl + (size_t)n * ldb) * 4) {
+        llo = ws + inv / sizeof(T);
+        blo = llo + (size_t)n * ldl;
+        rc = dcgp_split_lo_impl(L, llo, n, n, ldl, ldl, st);
+        if (rc) return rc;
+    }
+    LCtx<T> c{L, ldl, B, m, ldb, ws, dtype, xf, st, llo, blo};
     return ltrsm_rec(c, trans, 0, n);
-}
-
-size_t inv_ws_bytes(int64_t n, int dtype) {
-    const int64_t nblk = (n + NB - 1) / NB;
-    return (size_t)nblk * NB * NB * (dtype == DCGP_F64 ? 8 : 4);
 }
 
 }  // namespace
 
-extern "C" size_t dcgp_potrf_workspace(int64_t n, int dtype) { return n > 0 ? inv_ws_bytes(n, dtype) : 0; }
+// FP32 workspaces also hold the TF32-remainder matrices of the 3xTF32 tcgen05 path (assuming packed
+// leading dimensions; with padded ones the drivers fall back to the mma.sync 3xTF32 kernel).
+extern "C" size_t dcgp_potrf_workspace(int64_t n, int dtype) {
+    if (n <= 0) return 0;
+    return inv_ws_bytes(n, dtype) + (dtype == DCGP_F32 ? (size_t)n * n * 4 : 0);
+}
 
 extern "C" int dcgp_potrf(void* A, int64_t n, int64_t lda, int* info, void* workspace, size_t workspace_bytes,
                           int dtype, int flags, void* stream) {
@@ -430,11 +464,16 @@ extern "C" int dcgp_potrf(void* A, int64_t n, int64_t lda, int* info, void* work
         if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
     }
     if (dtype == DCGP_F64)
-        return potrf_impl<double>((double*)A, n, lda, info, (double*)workspace, dtype, flags & DCGP_GEMM_TF32X3, st);
-    return potrf_impl<float>((float*)A, n, lda, info, (float*)workspace, dtype, flags & DCGP_GEMM_TF32X3, st);
+        return potrf_impl<double>((double*)A, n, lda, info, (double*)workspace, workspace_bytes, dtype,
+                                  flags & DCGP_GEMM_TF32X3, st);
+    return potrf_impl<float>((float*)A, n, lda, info, (float*)workspace, workspace_bytes, dtype,
+                             flags & DCGP_GEMM_TF32X3, st);
 }
 
-extern "C" size_t dcgp_trsm_workspace(int64_t n, int64_t m, int dtype) { return n > 0 ? inv_ws_bytes(n, dtype) : 0; }
+extern "C" size_t dcgp_trsm_workspace(int64_t n, int64_t m, int dtype) {
+    if (n <= 0) return 0;
+    return inv_ws_bytes(n, dtype) + (dtype == DCGP_F32 ? ((size_t)n * n + (size_t)n * m) * 4 : 0);
+}
 
 extern "C" int dcgp_trsm(int trans, const void* L, int64_t n, int64_t ldl, void* B, int64_t m, int64_t ldb,
                          void* workspace, size_t workspace_bytes, int dtype, int flags, void* stream) {
@@ -447,10 +486,10 @@ extern "C" int dcgp_trsm(int trans, const void* L, int64_t n, int64_t ldl, void*
     if (!workspace || workspace_bytes < inv_ws_bytes(n, dtype)) return -8;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == DCGP_F64)
-        return trsm_impl<double>(trans, (const double*)L, n, ldl, (double*)B, m, ldb, (double*)workspace, dtype,
-                                 flags & DCGP_GEMM_TF32X3, st);
-    return trsm_impl<float>(trans, (const float*)L, n, ldl, (float*)B, m, ldb, (float*)workspace, dtype,
-                            flags & DCGP_GEMM_TF32X3, st);
+        return trsm_impl<double>(trans, (const double*)L, n, ldl, (double*)B, m, ldb, (double*)workspace,
+                                 workspace_bytes, dtype, flags & DCGP_GEMM_TF32X3, st);
+    return trsm_impl<float>(trans, (const float*)L, n, ldl, (float*)B, m, ldb, (float*)workspace, workspace_bytes,
+                            dtype, flags & DCGP_GEMM_TF32X3, st);
 }
 
 extern "C" int dcgp_potrs(const void* L, int64_t n, int64_t ldl, void* B, int64_t m, int64_t ldb, void* workspace,

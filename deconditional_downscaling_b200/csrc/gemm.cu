@@ -318,12 +318,15 @@ int launch_gemm(GemmParams p, cudaStream_t st) {
 }  // namespace
 
 int dcgp_gemm_tc_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
-                      const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int flags, cudaStream_t st);
+                      const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int flags, const void* Alo,
+                      const void* Blo, cudaStream_t st);
 
 // internal entry used by the Cholesky / TRSM drivers
+// Alo / Blo: optional x - trunc_tf32(x) companions of A / B (same layout) that let a 3xTF32 request run on
+// the tcgen05 kernel; without them compensated contractions use the mma.sync kernel.
 int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
                    const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype, int flags,
-                   cudaStream_t st) {
+                   cudaStream_t st, const void* Alo, const void* Blo) {
     if (m < 0) return -3;
     if (n < 0) return -4;
     if (k < 0) return -5;
@@ -351,14 +354,18 @@ int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, doub
     if (dtype == DCGP_F32) {
         p.vecA = vec_ok<float>(A, lda);
         p.vecB = vec_ok<float>(B, ldb);
-        if (flags & DCGP_GEMM_TF32X3) return launch_gemm<float, true>(p, st);
-        // large single-pass TF32 contractions go to the tcgen05 / TMA / TMEM kernel (gemm_tc.cu);
-        // small or split-K-shaped problems stay on the mma.sync kernel below
-        if (!(flags & DCGP_GEMM_NO_TCGEN05) && m >= 128 && n >= 160 && k >= 64 &&
-            ((m + 127) / 128) * ((n + 255) / 256) >= 24) {
-            const int rc = dcgp_gemm_tc_impl(transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, st);
+        // large TF32 contractions go to the tcgen05 / TMA / TMEM kernel (gemm_tc.cu): single-pass, or
+        // 3xTF32 when the caller supplies the lo companions; small or split-K-shaped problems stay on
+        // the mma.sync kernel below
+        const bool x3 = (flags & DCGP_GEMM_TF32X3) != 0;
+        const int64_t tc_tiles = ((m + 127) / 128) * ((n + 255) / 256);
+        if (!(flags & DCGP_GEMM_NO_TCGEN05) && m >= 128 && n >= 160 && k >= 64 && (!x3 || (Alo && Blo)) &&
+            tc_tiles >= (x3 ? 4 : 24)) {
+            const int rc = dcgp_gemm_tc_impl(transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags,
+                                             x3 ? Alo : nullptr, x3 ? Blo : nullptr, st);
             if (rc <= 0) return rc;
         }
+        if (x3) return launch_gemm<float, true>(p, st);
         return launch_gemm<float, false>(p, st);
     }
     return -14;
@@ -368,5 +375,5 @@ extern "C" int dcgp_gemm(int transa, int transb, int64_t m, int64_t n, int64_t k
                          int64_t lda, const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype,
                          int flags, void* stream) {
     return dcgp_gemm_impl(transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, dtype, flags,
-                          (cudaStream_t)stream);
+                          (cudaStream_t)stream, nullptr, nullptr);
 }

@@ -41,7 +41,7 @@ struct TcParams {
     float alpha, beta;
     int lower;
     int a_mn, b_mn;  // operand is MN-major (stored K x R)
-    int variant;     // debug: descriptor variant for MN-major operands
+    int x3;          // error-compensated: 3 virtual k-tiles (A_lo B, A B_lo, A B) per real k-tile
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -102,6 +102,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 
 __global__ void __launch_bounds__(NTHREADS_TC, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapBlo,
                const __grid_constant__ TcParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -114,6 +115,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int64_t m0 = (int64_t)blockIdx.y * TM, n0 = (int64_t)blockIdx.x * TN;
     if (p.lower && n0 > m0 + TM - 1) return;
     const int nkt = (int)((p.k + TK - 1) / TK);
+    // 3xTF32: the tensor core reads FP32 operands truncated to TF32 (x_hi); with x_lo = x - x_hi given as
+    // separate matrices, A B ~= A_lo B_hi + A_hi B_lo + A_hi B_hi, accumulated in the same TMEM tile.
+    const int nv = p.x3 ? 3 * nkt : nkt;  // virtual k-tiles
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -136,23 +140,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
-            for (int kt = 0; kt < nkt; ++kt) {
-                const int s = kt % STAGES;
-                const uint32_t ph = (uint32_t)(kt / STAGES) & 1u;
+            for (int v = 0; v < nv; ++v) {
+                const int s = v % STAGES;
+                const uint32_t ph = (uint32_t)(v / STAGES) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
                 unsigned char* sa = tiles + (size_t)s * STAGE_BYTES;
                 unsigned char* sb = sa + A_BYTES;
                 mbar_expect_tx(&full[s], STAGE_BYTES);
+                const int kt = p.x3 ? v / 3 : v;
+                const int sel = p.x3 ? v % 3 : 2;  // 0: A_lo B, 1: A B_lo, 2: A B
+                const CUtensorMap* ma = (sel == 0) ? &mapAlo : &mapA;
+                const CUtensorMap* mb = (sel == 1) ? &mapBlo : &mapB;
                 const int k0 = kt * TK;
                 if (!p.a_mn) {
-                    tma_load_2d(sa, &mapA, &full[s], k0, (int)m0);
+                    tma_load_2d(sa, ma, &full[s], k0, (int)m0);
                 } else {
-                    for (int c = 0; c < TM / 32; ++c) tma_load_2d(sa + c * 4096, &mapA, &full[s], (int)m0 + 32 * c, k0);
+                    for (int c = 0; c < TM / 32; ++c) tma_load_2d(sa + c * 4096, ma, &full[s], (int)m0 + 32 * c, k0);
                 }
                 if (!p.b_mn) {
-                    tma_load_2d(sb, &mapB, &full[s], k0, (int)n0);
+                    tma_load_2d(sb, mb, &full[s], k0, (int)n0);
                 } else {
-                    for (int c = 0; c < TN / 32; ++c) tma_load_2d(sb + c * 4096, &mapB, &full[s], (int)n0 + 32 * c, k0);
+                    for (int c = 0; c < TN / 32; ++c) tma_load_2d(sb + c * 4096, mb, &full[s], (int)n0 + 32 * c, k0);
                 }
             }
         }
@@ -162,7 +170,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // instruction descriptor: D = F32, A = B = TF32, majors, N >> 3, M >> 4
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                                    ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-            for (int kt = 0; kt < nkt; ++kt) {
+            for (int kt = 0; kt < nv; ++kt) {
                 const int s = kt % STAGES;
                 const uint32_t ph = (uint32_t)(kt / STAGES) & 1u;
                 mbar_wait(&full[s], ph);
@@ -173,9 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (int kk = 0; kk < TK / 8; ++kk) {
                     // MN-major 32-bit operands use the 32-byte-atom flavour of the 128-byte swizzle:
                     // atoms of 4 k-rows x 128 B (SBO = 512 B), 32-float chunks 4096 B apart (LBO)
-                    uint32_t lbo = 4096, sbo = 512, kadv = 1024;
-                    if (p.variant == 1) { lbo = 512; sbo = 4096; }
-                    if (p.variant == 2) { sbo = 1024; }
+                    const uint32_t lbo = 4096, sbo = 512, kadv = 1024;
                     const uint64_t ad = p.a_mn ? make_desc(sa + kk * kadv, lbo, sbo, 1) : make_desc(sa + kk * 32, 16, 1024, 2);
                     const uint64_t bd = p.b_mn ? make_desc(sb + kk * kadv, lbo, sbo, 1) : make_desc(sb + kk * 32, 16, 1024, 2);
                     umma_tf32(tmem_base, ad, bd, idesc, (kt > 0 || kk > 0) ? 1u : 0u);
@@ -253,6 +259,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
 }
 
+// lo = x - trunc_tf32(x): what the tensor core drops when it reads an FP32 operand as TF32
+__global__ void split_lo_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int64_t cols,
+                                int64_t lds, int64_t ldd) {
+    const int64_t total = rows * cols;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / cols, c = e % cols;
+        const float x = src[r * lds + c];
+        dst[r * ldd + c] = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -288,26 +305,39 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int
 
 }  // namespace
 
+int dcgp_split_lo_impl(const void* src, void* dst, int64_t rows, int64_t cols, int64_t lds, int64_t ldd, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return 0;
+    const int64_t total = rows * cols;
+    unsigned grid = (unsigned)min((int64_t)(num_sms() * 16), (total + 255) / 256);
+    split_lo_kernel<<<grid, 256, 0, st>>>((const float*)src, (float*)dst, rows, cols, lds, ldd);
+    DCGP_CHECK_LAUNCH();
+    return 0;
+}
+
 // Returns 0 on success, 1 if the shape/alignment is not taken by this kernel (caller falls through
 // to the mma.sync kernel), < 0 on CUDA errors.
+// Alo / Blo (optional, same shape and leading dimension as A / B): x - trunc_tf32(x), enables 3xTF32.
 int dcgp_gemm_tc_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
-                      const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int flags, cudaStream_t st) {
+                      const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int flags, const void* Alo,
+                      const void* Blo, cudaStream_t st) {
     if (k < 1) return 1;
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (lda & 3) || (ldb & 3)) return 1;
     if (m > 0x7fffffff || n > 0x7fffffff || k > 0x7fffffff) return 1;
-    CUtensorMap mapA, mapB;
+    const int x3 = (Alo && Blo) ? 1 : 0;
+    if (x3 && ((reinterpret_cast<uintptr_t>(Alo) & 15) || (reinterpret_cast<uintptr_t>(Blo) & 15))) return 1;
+    CUtensorMap mapA, mapB, mapAlo, mapBlo;
     // op(A)[m, k]: notrans -> A is m x k (K-major); trans -> A is k x m (MN-major)
-    if (!transa) {
-        if (make_map(&mapA, A, m, k, lda, TK, TM, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
-    } else {
-        if (make_map(&mapA, A, k, m, lda, 32, TK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
-    }
     // op(B)[k, n]: trans -> B is n x k (K-major); notrans -> B is k x n (MN-major)
-    if (transb) {
-        if (make_map(&mapB, B, n, k, ldb, TK, TN, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
-    } else {
-        if (make_map(&mapB, B, k, n, ldb, 32, TK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
-    }
+    auto mk_a = [&](CUtensorMap* mp, const void* X) {
+        return transa ? make_map(mp, X, k, m, lda, 32, TK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+                      : make_map(mp, X, m, k, lda, TK, TM, CU_TENSOR_MAP_SWIZZLE_128B);
+    };
+    auto mk_b = [&](CUtensorMap* mp, const void* X) {
+        return transb ? make_map(mp, X, n, k, ldb, TK, TN, CU_TENSOR_MAP_SWIZZLE_128B)
+                      : make_map(mp, X, k, n, ldb, 32, TK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    };
+    if (mk_a(&mapA, A) || mk_b(&mapB, B)) return 1;
+    if (mk_a(&mapAlo, x3 ? Alo : A) || mk_b(&mapBlo, x3 ? Blo : B)) return 1;
     TcParams p;
     p.m = m; p.n = n; p.k = k;
     p.C = (float*)C; p.ldc = ldc;
@@ -315,11 +345,11 @@ int dcgp_gemm_tc_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, d
     p.lower = (flags & DCGP_GEMM_LOWER) ? 1 : 0;
     p.a_mn = transa ? 1 : 0;
     p.b_mn = transb ? 0 : 1;
-    { const char* v = getenv("DCGP_TC_VARIANT"); p.variant = v ? atoi(v) : 0; }
+    p.x3 = x3;
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC);
     if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
     dim3 grid((unsigned)((n + TN - 1) / TN), (unsigned)((m + TM - 1) / TM));
-    gemm_tc_kernel<<<grid, NTHREADS_TC, SMEM_TC, st>>>(mapA, mapB, p);
+    gemm_tc_kernel<<<grid, NTHREADS_TC, SMEM_TC, st>>>(mapA, mapB, mapAlo, mapBlo, p);
     DCGP_CHECK_LAUNCH();
     return 0;
 }
