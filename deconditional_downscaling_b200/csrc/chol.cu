@@ -17,6 +17,7 @@
 // LAPACK-style failure reporting: *info (device) receives the 1-based index of the first
 // non-positive pivot; nothing here synchronises the stream.
 #include "common.cuh"
+#include <cstdio>
 
 int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
                    const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype, int flags,
@@ -31,14 +32,29 @@ constexpr int NTHREADS = 256;
 constexpr int SB = 16;      // sub-panel width inside the leaf
 
 // ---------------------------------------------------------------------------------------------
+// 1/sqrt(d) without the IEEE sqrt / div subroutines (they dominate the serial pivot chain):
+// hardware rsqrt seed + Newton steps y <- y (1.5 - 0.5 d y^2).  d <= 0 or NaN yields NaN.
+template <typename T> __device__ __forceinline__ T fast_rsqrt(T d);
+template <> __device__ __forceinline__ float fast_rsqrt<float>(float d) {
+    float y = rsqrtf(d);
+    return y * fmaf(-0.5f * d, y * y, 1.5f);
+}
+template <> __device__ __forceinline__ double fast_rsqrt<double>(double d) {
+    double y = (double)rsqrtf((float)d);
+    y = y * fma(-0.5 * d, y * y, 1.5);
+    y = y * fma(-0.5 * d, y * y, 1.5);
+    return y * fma(-0.5 * d, y * y, 1.5);
+}
+
 // Leaf factorisation in shared memory, right-looking over 16-wide sub-panels:
-//   (1) warp 0 factors the 16x16 diagonal block (lanes 0..15 own a row each, shuffles broadcast);
-//   (2) every thread owning a row below solves its 16 entries against that block (registers);
-//   (3) the trailing lower triangle gets a rank-16 update, 4x4 register tiles per thread.
+//   (1) warp 0 factors the 16x16 diagonal block in registers (one row per lane, shuffles broadcast
+//       the pivot row); pivots use fast_rsqrt, reciprocal diagonals go to rinv[];
+//   (2) every thread owning a row below solves its 16 entries against that block (division-free);
+//   (3) the trailing lower triangle gets a rank-16 update in 4x4 register tiles.
 // Three barriers per sub-panel (24 per leaf) instead of three per column.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__device__ void block_potrf(T* S, int nb, int* info, int64_t j0) {
+__device__ void block_potrf(T* S, T* rinv, int nb, int* info, int64_t j0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int p0 = 0; p0 < nb; p0 += SB) {
         const int pw = min(SB, nb - p0);
@@ -46,18 +62,21 @@ __device__ void block_potrf(T* S, int nb, int* info, int64_t j0) {
         if (warp == 0) {
             const int r = lane;  // row within the sub-block
             T row[SB];
+            T myinv = T(0);
 #pragma unroll
             for (int c = 0; c < SB; ++c) row[c] = (r < pw && c <= r && c < pw) ? S[(p0 + r) * SP + p0 + c] : T(0);
 #pragma unroll
             for (int c = 0; c < SB; ++c) {
                 if (c < pw) {
-                    // pivot row c broadcasts its (already updated) entries
-                    T d = __shfl_sync(0xffffffffu, row[c], c);
+                    const T d = __shfl_sync(0xffffffffu, row[c], c);  // pivot (already updated)
                     if (!(d > T(0)) && lane == 0 && info && *info == 0) *info = (int)(j0 + p0 + c + 1);
-                    const T piv = t_sqrt<T>(d);
-                    const T inv = T(1) / piv;
-                    if (r == c) row[c] = piv;
-                    else if (r > c) row[c] *= inv;
+                    const T y = fast_rsqrt<T>(d);
+                    if (r == c) {
+                        row[c] = d * y;
+                        myinv = y;
+                    } else if (r > c) {
+                        row[c] *= y;
+                    }
                     const T lrc = row[c];
 #pragma unroll
                     for (int k = 0; k < SB; ++k) {
@@ -71,6 +90,7 @@ __device__ void block_potrf(T* S, int nb, int* info, int64_t j0) {
 #pragma unroll
             for (int c = 0; c < SB; ++c)
                 if (r < pw && c <= r && c < pw) S[(p0 + r) * SP + p0 + c] = row[c];
+            if (r < pw) rinv[p0 + r] = myinv;
         }
         __syncthreads();
         // (2) column sub-panel below: row i solves x L_d^T = a  (L_d = the 16x16 block just factored)
@@ -85,7 +105,7 @@ __device__ void block_potrf(T* S, int nb, int* info, int64_t j0) {
 #pragma unroll
                     for (int k = 0; k < SB; ++k)
                         if (k < c) s = fma(-x[k], S[(p0 + c) * SP + p0 + k], s);
-                    x[c] = s / S[(p0 + c) * SP + p0 + c];
+                    x[c] = s * rinv[p0 + c];
                 }
             }
 #pragma unroll
@@ -96,12 +116,9 @@ __device__ void block_potrf(T* S, int nb, int* info, int64_t j0) {
         // (3) rank-pw update of the trailing lower triangle in 4x4 register tiles
         const int t0 = p0 + pw;
         const int nt = (nb - t0 + 3) / 4;  // tiles per side
-        for (int e = tid; e < nt * (nt + 1) / 2; e += NTHREADS) {
-            // unrank e -> (ti >= tj) in the lower triangle of the nt x nt tile grid
-            int ti = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-            while ((ti + 1) * (ti + 2) / 2 <= e) ++ti;
-            while (ti * (ti + 1) / 2 > e) --ti;
-            const int tj = e - ti * (ti + 1) / 2;
+        for (int e = tid; e < nt * nt; e += NTHREADS) {
+            const int ti = e / nt, tj = e - ti * nt;
+            if (tj > ti) continue;
             const int i0 = t0 + 4 * ti, k0 = t0 + 4 * tj;
             T acc[4][4];
 #pragma unroll
@@ -114,8 +131,8 @@ __device__ void block_potrf(T* S, int nb, int* info, int64_t j0) {
                     T li[4], lk[4];
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
-                        li[a] = (i0 + a < nb) ? S[(i0 + a) * SP + p0 + c] : T(0);
-                        lk[a] = (k0 + a < nb) ? S[(k0 + a) * SP + p0 + c] : T(0);
+                        li[a] = S[min(i0 + a, nb - 1) * SP + p0 + c];
+                        lk[a] = S[min(k0 + a, nb - 1) * SP + p0 + c];
                     }
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
@@ -133,17 +150,18 @@ __device__ void block_potrf(T* S, int nb, int* info, int64_t j0) {
     }
 }
 
-// Invert the lower-triangular factor held in S.  X = L^{-1} (lower triangular) is written into the
-// unused upper part of the same tile, transposed and shifted by one column:
+// Invert the lower-triangular factor held in S by recursive doubling.  X = L^{-1} is kept in the
+// unused upper part of the tile, transposed and shifted by one column:
 //   X(i, c), i >= c   <->   S[c][i + 1]        (pitch 129, so column 128 exists)
-// Column-block forward substitution in 16-wide sub-panels:
-//   X_dd = inv(L_dd) (one column per thread);  for block rows i > d:
-//   X_id = -X_ii * sum_{d <= k < i} L_ik X_kd, 4x4 register tiles, O(nb/16) barriers.
+// Level 0 inverts the 16x16 diagonal blocks (one column per thread, division-free with rinv[]);
+// level b in {16, 32, 64} completes every 2b x 2b diagonal block from its two b x b halves:
+//   X21 = -X22 (L21 X11)      as two tiled products (4x4 register tiles, all 256 threads).
+// L21 is dead once T = L21 X11 is formed, so its storage receives X21 before it moves to XX.
+// Requires the factor to have been saved elsewhere: the lower triangle of S is destroyed.
 #define XX(i, c) S[(c) * SP + (i) + 1]
 template <typename T>
-__device__ void block_trtri(T* S, int nb) {
+__device__ void block_trtri(T* S, const T* rinv, int nb) {
     const int tid = threadIdx.x;
-    // thread-per-column substitution on the 16x16 diagonal sub-blocks (all sub-blocks in parallel)
     for (int e = tid; e < nb; e += NTHREADS) {
         const int d0 = (e / SB) * SB, c = e;  // column c of the sub-block starting at d0
         const int dw = min(SB, nb - d0);
@@ -156,7 +174,7 @@ __device__ void block_trtri(T* S, int nb) {
 #pragma unroll
                 for (int k = 0; k < SB; ++k)
                     if (k < r && d0 + k >= c) s = fma(-S[i * SP + d0 + k], x[k], s);
-                x[r] = s / S[i * SP + i];
+                x[r] = s * rinv[i];
             } else {
                 x[r] = T(0);
             }
@@ -166,59 +184,75 @@ __device__ void block_trtri(T* S, int nb) {
             if (r < dw && d0 + r >= c) XX(d0 + r, c) = x[r];
     }
     __syncthreads();
-    // off-diagonal sub-blocks, one block "distance" at a time (pairs at equal distance are independent)
-    const int nsb = (nb + SB - 1) / SB;
-    for (int dist = 1; dist < nsb; ++dist) {
-        const int npairs = nsb - dist;
-        // phase A: T = L[i-block, d..i) X[d..i, d-block]  -> parked in X[i-block, d-block]
-        for (int e = tid; e < npairs * 16; e += NTHREADS) {
-            const int pr = e / 16, tt = e % 16;
-            const int ib = pr + dist, db = pr;
-            const int i0 = ib * SB + 4 * (tt / 4), c0 = db * SB + 4 * (tt % 4);
+    for (int b = SB; b < nb; b *= 2) {
+        const int npairs = (nb + 2 * b - 1) / (2 * b);
+        const int tb = b / 4;  // 4x4 tiles per block side
+        // step A: T = L21 X11 -> parked at XX(i, c), i in half 2, c in half 1
+        for (int e = tid; e < npairs * tb * tb; e += NTHREADS) {
+            const int pr = e / (tb * tb), tt = e - pr * tb * tb;
+            const int base = pr * 2 * b;
+            const int i0 = base + b + 4 * (tt / tb), c0 = base + 4 * (tt % tb);
+            if (i0 >= nb) continue;
             T acc[4][4];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = T(0);
-            for (int k = db * SB; k < ib * SB; ++k) {
+                for (int q = 0; q < 4; ++q) acc[a][q] = T(0);
+            for (int k = c0; k < base + b; ++k) {  // X11 is lower triangular: rows k >= c only
                 T l[4], x[4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
-                    l[a] = (i0 + a < nb) ? S[(i0 + a) * SP + k] : T(0);
+                    l[a] = S[min(i0 + a, nb - 1) * SP + k];
                     x[a] = (k >= c0 + a) ? XX(k, c0 + a) : T(0);
                 }
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[a][b] = fma(l[a], x[b], acc[a][b]);
+                    for (int q = 0; q < 4; ++q) acc[a][q] = fma(l[a], x[q], acc[a][q]);
             }
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (i0 + a < nb) XX(i0 + a, c0 + b) = acc[a][b];
+                for (int q = 0; q < 4; ++q)
+                    if (i0 + a < nb) XX(i0 + a, c0 + q) = acc[a][q];
         }
         __syncthreads();
-        // phase B: X[i-block, d-block] = -X_ii * T   (X_ii lower triangular 16x16)
-        for (int e = tid; e < npairs * SB; e += NTHREADS) {
-            const int pr = e / SB, cc = e % SB;
-            const int ib = pr + dist, db = pr;
-            const int c = db * SB + cc;
-            const int iw = min(SB, nb - ib * SB);
-            T tcol[SB], out[SB];
+        // step B: X21 = -X22 T  -> written over the (dead) L21 block in the lower triangle
+        for (int e = tid; e < npairs * tb * tb; e += NTHREADS) {
+            const int pr = e / (tb * tb), tt = e - pr * tb * tb;
+            const int base = pr * 2 * b;
+            const int i0 = base + b + 4 * (tt / tb), c0 = base + 4 * (tt % tb);
+            if (i0 >= nb) continue;
+            T acc[4][4];
 #pragma unroll
-            for (int r = 0; r < SB; ++r) tcol[r] = (r < iw) ? XX(ib * SB + r, c) : T(0);
+            for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int r = 0; r < SB; ++r) {
-                T s = T(0);
+                for (int q = 0; q < 4; ++q) acc[a][q] = T(0);
+            const int kend = min(i0 + 4, nb);
+            for (int k = base + b; k < kend; ++k) {  // X22 lower triangular: k <= i
+                T x22[4], t[4];
 #pragma unroll
-                for (int k = 0; k < SB; ++k)
-                    if (k <= r && r < iw) s = fma(XX(ib * SB + r, ib * SB + k), tcol[k], s);
-                out[r] = -s;
+                for (int a = 0; a < 4; ++a) {
+                    x22[a] = (k <= i0 + a && i0 + a < nb) ? XX(i0 + a, k) : T(0);
+                    t[a] = XX(k, c0 + a);
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[a][q] = fma(x22[a], t[q], acc[a][q]);
             }
 #pragma unroll
-            for (int r = 0; r < SB; ++r)
-                if (r < iw) XX(ib * SB + r, c) = out[r];
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (i0 + a < nb) S[(i0 + a) * SP + c0 + q] = -acc[a][q];
+        }
+        __syncthreads();
+        // step C: move X21 into the overlay
+        for (int e = tid; e < npairs * b * b; e += NTHREADS) {
+            const int pr = e / (b * b), tt = e - pr * b * b;
+            const int i = pr * 2 * b + b + tt / b, c = pr * 2 * b + tt % b;
+            if (i < nb) XX(i, c) = S[i * SP + c];
         }
         __syncthreads();
     }
@@ -226,19 +260,21 @@ __device__ void block_trtri(T* S, int nb) {
 
 template <typename T>
 __device__ void store_inverse(const T* S, int nb, T* inv) {  // inv: NB x NB row-major (lower, zero above)
-    for (int e = threadIdx.x; e < nb * NB; e += NTHREADS) {
-        const int i = e / NB, c = e % NB;
-        inv[i * NB + c] = (c <= i && c < nb) ? XX(i, c) : T(0);
-    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = warp; i < nb; i += NTHREADS / 32)
+        for (int c = lane; c < NB; c += 32) inv[i * NB + c] = (c <= i) ? XX(i, c) : T(0);
 }
 #undef XX
 
 template <typename T>
-__device__ void load_lower(T* S, const T* A, int64_t lda, int nb) {
-    for (int e = threadIdx.x; e < nb * NB; e += NTHREADS) {
-        const int i = e / NB, k = e % NB;
-        if (k <= i) S[i * SP + k] = A[(int64_t)i * lda + k];
-    }
+__device__ void load_lower(T* S, T* rinv, const T* A, int64_t lda, int nb, bool want_rinv) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = warp; i < nb; i += NTHREADS / 32)
+        for (int k = lane; k <= i; k += 32) {
+            const T v = A[(int64_t)i * lda + k];
+            S[i * SP + k] = v;
+            if (want_rinv && k == i) rinv[i] = T(1) / v;
+        }
 }
 
 template <typename T>
@@ -246,16 +282,39 @@ __global__ void __launch_bounds__(NTHREADS) potrf_diag_kernel(T* __restrict__ A,
                                                               T* __restrict__ inv, int* info, int64_t j0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* S = reinterpret_cast<T*>(smem_raw);
-    load_lower<T>(S, A, lda, nb);
+#ifdef DCGP_LEAF_TIMING
+    long long t0 = clock64();
+#endif
+    __shared__ T rinv[NB];
+    load_lower<T>(S, rinv, A, lda, nb, false);
     __syncthreads();
-    block_potrf<T>(S, nb, info, j0);
-    for (int e = threadIdx.x; e < nb * NB; e += NTHREADS) {
-        const int i = e / NB, k = e % NB;
-        if (k <= i) A[(int64_t)i * lda + k] = S[i * SP + k];
+#ifdef DCGP_LEAF_TIMING
+    long long t1 = clock64();
+#endif
+    block_potrf<T>(S, rinv, nb, info, j0);
+#ifdef DCGP_LEAF_TIMING
+    long long t2 = clock64();
+#endif
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int i = warp; i < nb; i += NTHREADS / 32)
+            for (int k = lane; k <= i; k += 32) A[(int64_t)i * lda + k] = S[i * SP + k];
     }
     __syncthreads();
-    block_trtri<T>(S, nb);
+#ifdef DCGP_LEAF_TIMING
+    long long t3 = clock64();
+#endif
+    block_trtri<T>(S, rinv, nb);
+#ifdef DCGP_LEAF_TIMING
+    long long t4 = clock64();
+#endif
     store_inverse<T>(S, nb, inv);
+#ifdef DCGP_LEAF_TIMING
+    __syncthreads();
+    if (threadIdx.x == 0)
+        printf("leaf nb=%d load %lld potrf %lld store %lld trtri %lld storeinv %lld\n", nb, t1 - t0, t2 - t1, t3 - t2,
+               t4 - t3, clock64() - t4);
+#endif
 }
 
 // batched inversion of the diagonal blocks of an existing factor
@@ -266,9 +325,10 @@ __global__ void __launch_bounds__(NTHREADS) trtri_blocks_kernel(const T* __restr
     T* S = reinterpret_cast<T*>(smem_raw);
     const int64_t i0 = (int64_t)blockIdx.x * NB;
     const int nb = (int)min((int64_t)NB, n - i0);
-    load_lower<T>(S, L + i0 * ldl + i0, ldl, nb);
+    __shared__ T rinv[NB];
+    load_lower<T>(S, rinv, L + i0 * ldl + i0, ldl, nb, true);
     __syncthreads();
-    block_trtri<T>(S, nb);
+    block_trtri<T>(S, rinv, nb);
     store_inverse<T>(S, nb, inv + (int64_t)blockIdx.x * NB * NB);
 }
 
