@@ -28,7 +28,7 @@ namespace {
 
 constexpr int NB = 128;     // leaf block size
 constexpr int SP = NB + 1;  // shared-memory pitch (conflict-free row AND column walks)
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 512;
 constexpr int SB = 16;      // sub-panel width inside the leaf
 
 // ---------------------------------------------------------------------------------------------
@@ -56,43 +56,48 @@ template <> __device__ __forceinline__ double fast_rsqrt<double>(double d) {
 template <typename T>
 __device__ void block_potrf(T* S, T* rinv, int nb, int* info, int64_t j0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef DCGP_LEAF_TIMING
+    long long acc1 = 0, acc2 = 0, acc3 = 0, tq = clock64();
+#endif
     for (int p0 = 0; p0 < nb; p0 += SB) {
         const int pw = min(SB, nb - p0);
-        // (1) diagonal sub-block
+        // (1) diagonal sub-block.  A single warp is latency-bound on instruction count, so the loop is
+        // predicate-free: lanes / columns outside the valid block behave as an identity padding and
+        // every lane updates all of its registers (entries above the diagonal are junk that is never
+        // stored).
         if (warp == 0) {
             const int r = lane;  // row within the sub-block
             T row[SB];
             T myinv = T(0);
+            int bad = 0;
 #pragma unroll
-            for (int c = 0; c < SB; ++c) row[c] = (r < pw && c <= r && c < pw) ? S[(p0 + r) * SP + p0 + c] : T(0);
+            for (int c = 0; c < SB; ++c)
+                row[c] = (r < pw && c <= r) ? S[(p0 + r) * SP + p0 + c] : ((r == c) ? T(1) : T(0));
 #pragma unroll
             for (int c = 0; c < SB; ++c) {
-                if (c < pw) {
-                    const T d = __shfl_sync(0xffffffffu, row[c], c);  // pivot (already updated)
-                    if (!(d > T(0)) && lane == 0 && info && *info == 0) *info = (int)(j0 + p0 + c + 1);
-                    const T y = fast_rsqrt<T>(d);
-                    if (r == c) {
-                        row[c] = d * y;
-                        myinv = y;
-                    } else if (r > c) {
-                        row[c] *= y;
-                    }
-                    const T lrc = row[c];
+                const T d = __shfl_sync(0xffffffffu, row[c], c);  // pivot (already updated)
+                if (!(d > T(0)) && bad == 0) bad = c + 1;
+                const T y = fast_rsqrt<T>(d);
+                const T scaled = row[c] * y;
+                row[c] = (r == c) ? d * y : scaled;
+                if (r == c) myinv = y;
+                const T lrc = row[c];
 #pragma unroll
-                    for (int k = 0; k < SB; ++k) {
-                        if (k > c) {
-                            const T lkc = __shfl_sync(0xffffffffu, row[c], k);  // L[k][c]
-                            if (r >= k) row[k] = fma(-lrc, lkc, row[k]);
-                        }
-                    }
+                for (int k = c + 1; k < SB; ++k) {
+                    const T lkc = __shfl_sync(0xffffffffu, row[c], k);  // L[k][c]
+                    row[k] = fma(-lrc, lkc, row[k]);
                 }
             }
 #pragma unroll
             for (int c = 0; c < SB; ++c)
-                if (r < pw && c <= r && c < pw) S[(p0 + r) * SP + p0 + c] = row[c];
+                if (r < pw && c <= r) S[(p0 + r) * SP + p0 + c] = row[c];
             if (r < pw) rinv[p0 + r] = myinv;
+            if (lane == 0 && bad != 0 && bad <= pw && info && *info == 0) *info = (int)(j0 + p0 + bad);
         }
         __syncthreads();
+#ifdef DCGP_LEAF_TIMING
+        { long long t = clock64(); acc1 += t - tq; tq = t; }
+#endif
         // (2) column sub-panel below: row i solves x L_d^T = a  (L_d = the 16x16 block just factored)
         for (int i = p0 + pw + tid; i < nb; i += NTHREADS) {
             T x[SB];
@@ -113,13 +118,18 @@ __device__ void block_potrf(T* S, T* rinv, int nb, int* info, int64_t j0) {
                 if (c < pw) S[i * SP + p0 + c] = x[c];
         }
         __syncthreads();
-        // (3) rank-pw update of the trailing lower triangle in 4x4 register tiles
+#ifdef DCGP_LEAF_TIMING
+        { long long t = clock64(); acc2 += t - tq; tq = t; }
+#endif
+        // (3) rank-pw update of the trailing block in 4x4 register tiles.  A thread's 4 rows / 4 columns
+        // are strided by G (not adjacent) so that the lanes of a warp walk CONSECUTIVE rows of S:
+        // with the odd pitch that is bank-conflict free, where adjacent 4x4 tiles were 4-way conflicted.
+        // The full square is computed (2x the triangle's FMAs, still ~5k cycles) and only col <= row stored.
         const int t0 = p0 + pw;
-        const int nt = (nb - t0 + 3) / 4;  // tiles per side
-        for (int e = tid; e < nt * nt; e += NTHREADS) {
-            const int ti = e / nt, tj = e - ti * nt;
-            if (tj > ti) continue;
-            const int i0 = t0 + 4 * ti, k0 = t0 + 4 * tj;
+        const int rr = nb - t0;
+        const int G = (rr + 3) / 4;
+        for (int e = tid; e < G * G; e += NTHREADS) {
+            const int ti = e / G, tj = e - ti * G;
             T acc[4][4];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
@@ -131,8 +141,8 @@ __device__ void block_potrf(T* S, T* rinv, int nb, int* info, int64_t j0) {
                     T li[4], lk[4];
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
-                        li[a] = S[min(i0 + a, nb - 1) * SP + p0 + c];
-                        lk[a] = S[min(k0 + a, nb - 1) * SP + p0 + c];
+                        li[a] = S[min(t0 + ti + G * a, nb - 1) * SP + p0 + c];
+                        lk[a] = S[min(t0 + tj + G * a, nb - 1) * SP + p0 + c];
                     }
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
@@ -143,11 +153,19 @@ __device__ void block_potrf(T* S, T* rinv, int nb, int* info, int64_t j0) {
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (i0 + a < nb && k0 + b <= i0 + a) S[(i0 + a) * SP + k0 + b] -= acc[a][b];
+                for (int b = 0; b < 4; ++b) {
+                    const int row = t0 + ti + G * a, col = t0 + tj + G * b;
+                    if (row < nb && col <= row) S[row * SP + col] -= acc[a][b];
+                }
         }
         __syncthreads();
+#ifdef DCGP_LEAF_TIMING
+        { long long t = clock64(); acc3 += t - tq; tq = t; }
+#endif
     }
+#ifdef DCGP_LEAF_TIMING
+    if (tid == 0) printf("  potrf steps: diag %lld  panel %lld  trailing %lld\n", acc1, acc2, acc3);
+#endif
 }
 
 // Invert the lower-triangular factor held in S by recursive doubling.  X = L^{-1} is kept in the
@@ -187,12 +205,13 @@ __device__ void block_trtri(T* S, const T* rinv, int nb) {
     for (int b = SB; b < nb; b *= 2) {
         const int npairs = (nb + 2 * b - 1) / (2 * b);
         const int tb = b / 4;  // 4x4 tiles per block side
-        // step A: T = L21 X11 -> parked at XX(i, c), i in half 2, c in half 1
+        // step A: T = L21 X11 -> parked at XX(i, c), i in half 2, c in half 1 (strided 4x4 tiles, see above)
         for (int e = tid; e < npairs * tb * tb; e += NTHREADS) {
             const int pr = e / (tb * tb), tt = e - pr * tb * tb;
             const int base = pr * 2 * b;
-            const int i0 = base + b + 4 * (tt / tb), c0 = base + 4 * (tt % tb);
-            if (i0 >= nb) continue;
+            const int ti = tt / tb, tj = tt - ti * tb;
+            const int r0 = base + b + ti, c0 = base + tj;  // rows r0 + tb*a, cols c0 + tb*q
+            if (r0 >= nb) continue;
             T acc[4][4];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
@@ -202,8 +221,8 @@ __device__ void block_trtri(T* S, const T* rinv, int nb) {
                 T l[4], x[4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
-                    l[a] = S[min(i0 + a, nb - 1) * SP + k];
-                    x[a] = (k >= c0 + a) ? XX(k, c0 + a) : T(0);
+                    l[a] = S[min(r0 + tb * a, nb - 1) * SP + k];
+                    x[a] = (k >= c0 + tb * a) ? XX(k, c0 + tb * a) : T(0);
                 }
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
@@ -214,27 +233,29 @@ __device__ void block_trtri(T* S, const T* rinv, int nb) {
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                    if (i0 + a < nb) XX(i0 + a, c0 + q) = acc[a][q];
+                    if (r0 + tb * a < nb) XX(r0 + tb * a, c0 + tb * q) = acc[a][q];
         }
         __syncthreads();
         // step B: X21 = -X22 T  -> written over the (dead) L21 block in the lower triangle
         for (int e = tid; e < npairs * tb * tb; e += NTHREADS) {
             const int pr = e / (tb * tb), tt = e - pr * tb * tb;
             const int base = pr * 2 * b;
-            const int i0 = base + b + 4 * (tt / tb), c0 = base + 4 * (tt % tb);
-            if (i0 >= nb) continue;
+            const int ti = tt / tb, tj = tt - ti * tb;
+            const int r0 = base + b + ti, c0 = base + tj;
+            if (r0 >= nb) continue;
             T acc[4][4];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) acc[a][q] = T(0);
-            const int kend = min(i0 + 4, nb);
+            const int kend = min(base + 2 * b, nb);
             for (int k = base + b; k < kend; ++k) {  // X22 lower triangular: k <= i
                 T x22[4], t[4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
-                    x22[a] = (k <= i0 + a && i0 + a < nb) ? XX(i0 + a, k) : T(0);
-                    t[a] = XX(k, c0 + a);
+                    const int row = r0 + tb * a;
+                    x22[a] = (k <= row && row < nb) ? XX(row, k) : T(0);
+                    t[a] = XX(k, c0 + tb * a);
                 }
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
@@ -245,7 +266,7 @@ __device__ void block_trtri(T* S, const T* rinv, int nb) {
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                    if (i0 + a < nb) S[(i0 + a) * SP + c0 + q] = -acc[a][q];
+                    if (r0 + tb * a < nb) S[(r0 + tb * a) * SP + c0 + tb * q] = -acc[a][q];
         }
         __syncthreads();
         // step C: move X21 into the overlay
@@ -268,13 +289,26 @@ __device__ void store_inverse(const T* S, int nb, T* inv) {  // inv: NB x NB row
 
 template <typename T>
 __device__ void load_lower(T* S, T* rinv, const T* A, int64_t lda, int nb, bool want_rinv) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = warp; i < nb; i += NTHREADS / 32)
-        for (int k = lane; k <= i; k += 32) {
-            const T v = A[(int64_t)i * lda + k];
-            S[i * SP + k] = v;
-            if (want_rinv && k == i) rinv[i] = T(1) / v;
+    // flat mapping, 16 independent loads in flight per thread
+    constexpr int UN = 16;
+    for (int e0 = 0; e0 < NB * NB; e0 += NTHREADS * UN) {
+        T v[UN];
+#pragma unroll
+        for (int j = 0; j < UN; ++j) {
+            const int e = e0 + j * NTHREADS + threadIdx.x;
+            const int i = e >> 7, k = e & (NB - 1);
+            v[j] = (i < nb && k <= i) ? A[(int64_t)i * lda + k] : T(0);
         }
+#pragma unroll
+        for (int j = 0; j < UN; ++j) {
+            const int e = e0 + j * NTHREADS + threadIdx.x;
+            const int i = e >> 7, k = e & (NB - 1);
+            if (i < nb && k <= i) {
+                S[i * SP + k] = v[j];
+                if (want_rinv && k == i) rinv[i] = T(1) / v[j];
+            }
+        }
+    }
 }
 
 template <typename T>
@@ -379,7 +413,7 @@ int rtrsm_rec(const Ctx<T>& c, int64_t r0, int64_t nr, int64_t t0, int64_t nt) {
     if (nt <= NB) {
         T* Bp = c.A + r0 * c.lda + t0;
         int rc = dcgp_gemm_impl(0, 1, nr, nt, nt, 1.0, Bp, c.lda, c.ws + (t0 / NB) * NB * NB, NB, 0.0, Bp, c.lda,
-                                c.dtype, DCGP_GEMM_NO_SPLITK | c.xf, c.st, nullptr, nullptr);
+                                c.dtype, DCGP_GEMM_INPLACE | c.xf, c.st, nullptr, nullptr);
         if (rc) return rc;
         // these entries of L are final: publish their TF32 remainders for the tcgen05 3xTF32 products
         if (c.Alo) rc = dcgp_split_lo_impl(Bp, c.Alo + r0 * c.lda + t0, nr, nt, c.lda, c.lda, c.st);
@@ -391,7 +425,7 @@ int rtrsm_rec(const Ctx<T>& c, int64_t r0, int64_t nr, int64_t t0, int64_t nt) {
     // B2 -= B1 * Lc^T,  Lc = L[t0+t1 : t0+nt, t0 : t0+t1]
     const int64_t oa = r0 * c.lda + t0, ob = (t0 + t1) * c.lda + t0;
     rc = dcgp_gemm_impl(0, 1, nr, t2, t1, -1.0, c.A + oa, c.lda, c.A + ob, c.lda, 1.0, c.A + r0 * c.lda + t0 + t1, c.lda,
-                        c.dtype, DCGP_GEMM_NO_SPLITK | c.xf, c.st, c.Alo ? c.Alo + oa : nullptr,
+                        c.dtype, c.xf, c.st, c.Alo ? c.Alo + oa : nullptr,
                         c.Alo ? c.Alo + ob : nullptr);
     if (rc) return rc;
     return rtrsm_rec(c, r0, nr, t0 + t1, t2);
@@ -414,7 +448,7 @@ int chol_rec(const Ctx<T>& c, int64_t j0, int64_t nb) {
     T* A21 = c.A + o21;
     const T* A21lo = c.Alo ? c.Alo + o21 : nullptr;
     rc = dcgp_gemm_impl(0, 1, n2, n2, n1, -1.0, A21, c.lda, A21, c.lda, 1.0, c.A + (j0 + n1) * c.lda + j0 + n1, c.lda,
-                        c.dtype, DCGP_GEMM_LOWER | DCGP_GEMM_NO_SPLITK | c.xf, c.st, A21lo, A21lo);
+                        c.dtype, DCGP_GEMM_LOWER | c.xf, c.st, A21lo, A21lo);
     if (rc) return rc;
     return chol_rec(c, j0 + n1, n2);
 }
@@ -454,7 +488,7 @@ int ltrsm_rec(const LCtx<T>& c, int trans, int64_t i0, int64_t nn) {
     if (nn <= NB) {
         T* Bi = c.B + i0 * c.ldb;
         int rc = dcgp_gemm_impl(trans, 0, nn, c.m, nn, 1.0, c.ws + (i0 / NB) * NB * NB, NB, Bi, c.ldb, 0.0, Bi, c.ldb,
-                                c.dtype, DCGP_GEMM_NO_SPLITK | c.xf, c.st, nullptr, nullptr);
+                                c.dtype, DCGP_GEMM_INPLACE | c.xf, c.st, nullptr, nullptr);
         if (rc) return rc;
         if (c.Blo) rc = dcgp_split_lo_impl(Bi, c.Blo + i0 * c.ldb, nn, c.m, c.ldb, c.ldb, c.st);
         return rc;
@@ -468,7 +502,7 @@ int ltrsm_rec(const LCtx<T>& c, int trans, int64_t i0, int64_t nn) {
         rc = ltrsm_rec(c, trans, i0, n1);
         if (rc) return rc;
         rc = dcgp_gemm_impl(0, 0, n2, c.m, n1, -1.0, Lc, c.ldl, c.B + i0 * c.ldb, c.ldb, 1.0, c.B + (i0 + n1) * c.ldb,
-                            c.ldb, c.dtype, DCGP_GEMM_NO_SPLITK | c.xf, c.st, Lclo,
+                            c.ldb, c.dtype, c.xf, c.st, Lclo,
                             c.Blo ? c.Blo + i0 * c.ldb : nullptr);
         if (rc) return rc;
         return ltrsm_rec(c, trans, i0 + n1, n2);
@@ -476,7 +510,7 @@ int ltrsm_rec(const LCtx<T>& c, int trans, int64_t i0, int64_t nn) {
     rc = ltrsm_rec(c, trans, i0 + n1, n2);
     if (rc) return rc;
     rc = dcgp_gemm_impl(1, 0, n1, c.m, n2, -1.0, Lc, c.ldl, c.B + (i0 + n1) * c.ldb, c.ldb, 1.0, c.B + i0 * c.ldb, c.ldb,
-                        c.dtype, DCGP_GEMM_NO_SPLITK | c.xf, c.st, Lclo, c.Blo ? c.Blo + (i0 + n1) * c.ldb : nullptr);
+                        c.dtype, c.xf, c.st, Lclo, c.Blo ? c.Blo + (i0 + n1) * c.ldb : nullptr);
     if (rc) return rc;
     return ltrsm_rec(c, trans, i0, n1);
 }

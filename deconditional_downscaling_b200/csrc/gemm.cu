@@ -69,12 +69,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
+// k-tile depth / shared pitch / pipeline depth per type; the CTA tile (BM x BN) is a kernel template
+// parameter: 128 x 128 for problems that fill the machine, 64 x 64 for the many small, latency-bound
+// contractions inside the blocked factorisations (4x more CTAs, 1/4 of the per-CTA critical path).
 template <typename T> struct Tile;
 template <> struct Tile<double> {
-    static constexpr int BM = 128, BN = 128, BK = 16, PK = 20, STAGES = 3;
+    static constexpr int BK = 16, PK = 20, STAGES = 3;
 };
 template <> struct Tile<float> {
-    static constexpr int BM = 128, BN = 128, BK = 32, PK = 36, STAGES = 3;
+    static constexpr int BK = 32, PK = 36, STAGES = 3;
 };
 
 // issue the cp.async copies of one operand tile: ROWS x BK of op(X)[row, k] -> S[row][k] (pitch PK)
@@ -117,9 +120,10 @@ __device__ __forceinline__ void issue_tile(T* __restrict__ S, const T* __restric
     }
 }
 
-template <typename T, bool X3>
-__global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
-    constexpr int BM = Tile<T>::BM, BN = Tile<T>::BN, BK = Tile<T>::BK, PK = Tile<T>::PK, ST = Tile<T>::STAGES;
+template <typename T, bool X3, int BM, int BN>
+__global__ void __launch_bounds__(256, (BM == 128 ? 1 : 2)) gemm_kernel(const __grid_constant__ GemmParams p) {
+    constexpr int BK = Tile<T>::BK, PK = Tile<T>::PK, ST = Tile<T>::STAGES;
+    constexpr int WM = BM / 2, WN = BN / 4;  // 2 x 4 warps
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* As = reinterpret_cast<T*>(smem_raw);  // [ST][BM][PK]
     T* Bs = As + ST * BM * PK;               // [ST][BN][PK]
@@ -138,12 +142,13 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
     const T* A = (const T*)p.A;
     const T* B = (const T*)p.B;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps, warp tile 64 x 32
+    const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps, warp tile WM x WN
     const int g = lane >> 2, t = lane & 3;
 
     constexpr int NACC = (sizeof(T) == 8) ? 2 : 4;
-    constexpr int MT = (sizeof(T) == 8) ? 8 : 4;  // m-tiles per warp (8 or 16 rows each)
-    constexpr int NT = 4;                         // n-tiles per warp (8 cols each)
+    constexpr int RT = (sizeof(T) == 8) ? 8 : 16;  // rows per m-tile
+    constexpr int MT = WM / RT;                    // m-tiles per warp
+    constexpr int NT = WN / 8;                     // n-tiles per warp (8 cols each)
     T acc[MT][NT][NACC];
 #pragma unroll
     for (int i = 0; i < MT; ++i)
@@ -174,8 +179,8 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
             cp_async_commit();
         }
         const int buf = it % ST;
-        const T* as = As + buf * BM * PK + (wm * 64) * PK;
-        const T* bs = Bs + buf * BN * PK + (wn * 32) * PK;
+        const T* as = As + buf * BM * PK + (wm * WM) * PK;
+        const T* bs = Bs + buf * BN * PK + (wn * WN) * PK;
         if constexpr (sizeof(T) == 8) {
 #pragma unroll
             for (int ks = 0; ks < BK / 4; ++ks) {
@@ -234,17 +239,16 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
     const T alpha = (T)p.alpha, beta = (T)p.beta;
     const bool atomic = p.ksplit > 1;
     const bool pair_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) % (2 * sizeof(T))) == 0);
-    constexpr int RT = (sizeof(T) == 8) ? 8 : 16;  // rows per m-tile
     using T2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
 #pragma unroll
         for (int h = 0; h < NACC / 2; ++h) {
-            const int64_t row = m0 + wm * 64 + i * RT + g + h * 8;
+            const int64_t row = m0 + wm * WM + i * RT + g + h * 8;
             if (row >= p.m) continue;
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
-                const int64_t col = n0 + wn * 32 + j * 8 + 2 * t;
+                const int64_t col = n0 + wn * WN + j * 8 + 2 * t;
                 T* dst = C + row * p.ldc + col;
                 const T v0 = alpha * acc[i][j][h * 2], v1 = alpha * acc[i][j][h * 2 + 1];
                 if (atomic) {
@@ -272,11 +276,11 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
 
 // C *= beta (or zero) ahead of a split-K accumulation
 template <typename T>
-__global__ void scale_kernel(T* C, int64_t m, int64_t n, int64_t ldc, T beta, int lower) {
+__global__ void scale_kernel(T* C, int64_t m, int64_t n, int64_t ldc, T beta, int lower, int bm, int bn) {
     const int64_t total = m * n;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = e / n, c = e % n;
-        if (lower && (c / 128) * 128 > (r / 128) * 128 + 127) continue;
+        if (lower && (c / bn) * bn > (r / bm) * bm + bm - 1) continue;
         T* d = C + r * ldc + c;
         *d = (beta == T(0)) ? T(0) : beta * *d;
     }
@@ -287,11 +291,12 @@ int vec_ok(const void* X, int64_t ld) {
     return (reinterpret_cast<uintptr_t>(X) % 16 == 0) && ((ld * (int64_t)sizeof(T)) % 16 == 0);
 }
 
-template <typename T, bool X3>
-int launch_gemm(GemmParams p, cudaStream_t st) {
-    constexpr int BM = Tile<T>::BM, BN = Tile<T>::BN, BK = Tile<T>::BK, PK = Tile<T>::PK, ST = Tile<T>::STAGES;
+template <typename T, bool X3, int BM, int BN>
+int launch_gemm_tile(GemmParams p, cudaStream_t st) {
+    constexpr int BK = Tile<T>::BK, PK = Tile<T>::PK, ST = Tile<T>::STAGES;
     const size_t smem = (size_t)ST * (BM + BN) * PK * sizeof(T);
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<T, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<T, X3, BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
     if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
     const int64_t gm = (p.m + BM - 1) / BM, gn = (p.n + BN - 1) / BN;
     // split K when the output grid cannot fill the machine and K is deep
@@ -307,12 +312,26 @@ int launch_gemm(GemmParams p, cudaStream_t st) {
     if (ksplit > 1) {
         int64_t total = p.m * p.n;
         unsigned g = (unsigned)min((int64_t)(num_sms() * 8), (total + 255) / 256);
-        scale_kernel<T><<<g, 256, 0, st>>>((T*)p.C, p.m, p.n, p.ldc, (T)p.beta, p.lower & 1);
+        scale_kernel<T><<<g, 256, 0, st>>>((T*)p.C, p.m, p.n, p.ldc, (T)p.beta, p.lower & 1, BM, BN);
     }
     dim3 grid((unsigned)gn, (unsigned)gm, (unsigned)ksplit);
-    gemm_kernel<T, X3><<<grid, 256, smem, st>>>(p);
+    gemm_kernel<T, X3, BM, BN><<<grid, 256, smem, st>>>(p);
     DCGP_CHECK_LAUNCH();
     return 0;
+}
+
+template <typename T, bool X3>
+int launch_gemm(GemmParams p, cudaStream_t st) {
+    if (p.lower & 4) {
+        // C aliases an operand (triangular-solve leaves): one CTA must own every column (row) of the
+        // aliased operand it reads, i.e. a single tile along the short dimension
+        if (p.n <= 128) return launch_gemm_tile<T, X3, 64, 128>(p, st);
+        if (p.m <= 128) return launch_gemm_tile<T, X3, 128, 64>(p, st);
+        return -16;
+    }
+    const int64_t t128 = ((p.m + 127) / 128) * ((p.n + 127) / 128);
+    if (t128 < num_sms() / 2) return launch_gemm_tile<T, X3, 64, 64>(p, st);
+    return launch_gemm_tile<T, X3, 128, 128>(p, st);
 }
 
 }  // namespace
@@ -343,8 +362,9 @@ int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, doub
     p.sbn = transb ? ldb : 1;
     p.sbk = transb ? 1 : ldb;
     p.alpha = alpha; p.beta = beta;
-    // bit0: lower-only tiles; bit1: caller aliases C with an input, never split K
-    p.lower = ((flags & DCGP_GEMM_LOWER) ? 1 : 0) | ((flags & DCGP_GEMM_NO_SPLITK) ? 2 : 0);
+    // bit0: lower-only tiles; bit1: never split K; bit2: C aliases an operand (in-place leaf)
+    p.lower = ((flags & DCGP_GEMM_LOWER) ? 1 : 0) | ((flags & (DCGP_GEMM_NO_SPLITK | DCGP_GEMM_INPLACE)) ? 2 : 0) |
+              ((flags & DCGP_GEMM_INPLACE) ? 4 : 0);
     p.ksplit = 1;
     if (dtype == DCGP_F64) {
         p.vecA = vec_ok<double>(A, lda);
@@ -359,7 +379,7 @@ int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, doub
         // the mma.sync kernel below
         const bool x3 = (flags & DCGP_GEMM_TF32X3) != 0;
         const int64_t tc_tiles = ((m + 127) / 128) * ((n + 255) / 256);
-        if (!(flags & DCGP_GEMM_NO_TCGEN05) && m >= 128 && n >= 160 && k >= 64 && (!x3 || (Alo && Blo)) &&
+        if (!(flags & (DCGP_GEMM_NO_TCGEN05 | DCGP_GEMM_INPLACE)) && m >= 128 && n >= 160 && k >= 64 && (!x3 || (Alo && Blo)) &&
             tc_tiles >= (x3 ? 4 : 24)) {
             const int rc = dcgp_gemm_tc_impl(transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags,
                                              x3 ? Alo : nullptr, x3 ? Blo : nullptr, st);
