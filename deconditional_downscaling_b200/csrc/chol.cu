@@ -17,11 +17,12 @@
 // LAPACK-style failure reporting: *info (device) receives the 1-based index of the first
 // non-positive pivot; nothing here synchronises the stream.
 #include "common.cuh"
+#include "mma.cuh"
 #include <cstdio>
 
 int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
                    const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype, int flags,
-                   cudaStream_t st, const void* Alo, const void* Blo);
+                   cudaStream_t st, const void* Alo, const void* Blo, void* Clo);
 int dcgp_split_lo_impl(const void* src, void* dst, int64_t rows, int64_t cols, int64_t lds, int64_t ldd, cudaStream_t st);
 
 namespace {
@@ -121,42 +122,30 @@ __device__ void block_potrf(T* S, T* rinv, int nb, int* info, int64_t j0) {
 #ifdef DCGP_LEAF_TIMING
         { long long t = clock64(); acc2 += t - tq; tq = t; }
 #endif
-        // (3) rank-pw update of the trailing block in 4x4 register tiles.  A thread's 4 rows / 4 columns
-        // are strided by G (not adjacent) so that the lanes of a warp walk CONSECUTIVE rows of S:
-        // with the odd pitch that is bank-conflict free, where adjacent 4x4 tiles were 4-way conflicted.
-        // The full square is computed (2x the triangle's FMAs, still ~5k cycles) and only col <= row stored.
+        // (3) rank-pw update of the trailing lower triangle on the tensor cores: each warp takes
+        // 8x8 (DMMA) / 16x8 (3xTF32) output tiles, K = 16, operands read straight from the tile.
         const int t0 = p0 + pw;
         const int rr = nb - t0;
-        const int G = (rr + 3) / 4;
-        for (int e = tid; e < G * G; e += NTHREADS) {
-            const int ti = e / G, tj = e - ti * G;
-            T acc[4][4];
+        {
+            constexpr int TR = WarpTile<T>::ROWS, TC = WarpTile<T>::COLS, NA = WarpTile<T>::NACC;
+            const int ntr = (rr + TR - 1) / TR, ntc = (rr + TC - 1) / TC;
+            for (int e = warp; e < ntr * ntc; e += NTHREADS / 32) {
+                const int mi = e / ntc, nj = e - mi * ntc;
+                const int row0 = t0 + mi * TR, col0 = t0 + nj * TC;
+                if (col0 > row0 + TR - 1) continue;  // tile entirely above the diagonal
+                T acc[4] = {T(0), T(0), T(0), T(0)};
+                warp_tile_mma(
+                    acc, SB,
+                    [&](int rl, int k) { return (row0 + rl < nb && k < pw) ? S[(row0 + rl) * SP + p0 + k] : T(0); },
+                    [&](int k, int cl) { return (col0 + cl < nb && k < pw) ? S[(col0 + cl) * SP + p0 + k] : T(0); });
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = T(0);
-#pragma unroll
-            for (int c = 0; c < SB; ++c) {
-                if (c < pw) {
-                    T li[4], lk[4];
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        li[a] = S[min(t0 + ti + G * a, nb - 1) * SP + p0 + c];
-                        lk[a] = S[min(t0 + tj + G * a, nb - 1) * SP + p0 + c];
-                    }
-#pragma unroll
-                    for (int a = 0; a < 4; ++a)
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) acc[a][b] = fma(li[a], lk[b], acc[a][b]);
+                for (int q = 0; q < NA; ++q) {
+                    int rl, cl;
+                    warp_tile_coord<T>(q, rl, cl);
+                    const int row = row0 + rl, col = col0 + cl;
+                    if (row < nb && col <= row) S[row * SP + col] -= acc[q];
                 }
             }
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int row = t0 + ti + G * a, col = t0 + tj + G * b;
-                    if (row < nb && col <= row) S[row * SP + col] -= acc[a][b];
-                }
         }
         __syncthreads();
 #ifdef DCGP_LEAF_TIMING
@@ -204,69 +193,48 @@ __device__ void block_trtri(T* S, const T* rinv, int nb) {
     __syncthreads();
     for (int b = SB; b < nb; b *= 2) {
         const int npairs = (nb + 2 * b - 1) / (2 * b);
-        const int tb = b / 4;  // 4x4 tiles per block side
-        // step A: T = L21 X11 -> parked at XX(i, c), i in half 2, c in half 1 (strided 4x4 tiles, see above)
-        for (int e = tid; e < npairs * tb * tb; e += NTHREADS) {
-            const int pr = e / (tb * tb), tt = e - pr * tb * tb;
+        // step A: T = L21 X11 -> parked at XX(i, c), i in half 2, c in half 1 (tensor-core tiles)
+        constexpr int TR = WarpTile<T>::ROWS, TC = WarpTile<T>::COLS, NA = WarpTile<T>::NACC;
+        const int warp = tid >> 5;
+        const int tpr = b / TR, tpc = b / TC;  // tiles per pair: rows x cols (b is a multiple of 16)
+        for (int e = warp; e < npairs * tpr * tpc; e += NTHREADS / 32) {
+            const int pr = e / (tpr * tpc), tt = e - pr * tpr * tpc;
             const int base = pr * 2 * b;
-            const int ti = tt / tb, tj = tt - ti * tb;
-            const int r0 = base + b + ti, c0 = base + tj;  // rows r0 + tb*a, cols c0 + tb*q
-            if (r0 >= nb) continue;
-            T acc[4][4];
+            const int row0 = base + b + (tt / tpc) * TR, col0 = base + (tt % tpc) * TC;
+            if (row0 >= nb) continue;
+            T acc[4] = {T(0), T(0), T(0), T(0)};
+            warp_tile_mma(
+                acc, b, [&](int rl, int k) { return (row0 + rl < nb) ? S[(row0 + rl) * SP + base + k] : T(0); },
+                [&](int k, int cl) { return (base + k >= col0 + cl) ? XX(base + k, col0 + cl) : T(0); });
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) acc[a][q] = T(0);
-            for (int k = c0; k < base + b; ++k) {  // X11 is lower triangular: rows k >= c only
-                T l[4], x[4];
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    l[a] = S[min(r0 + tb * a, nb - 1) * SP + k];
-                    x[a] = (k >= c0 + tb * a) ? XX(k, c0 + tb * a) : T(0);
-                }
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[a][q] = fma(l[a], x[q], acc[a][q]);
+            for (int q = 0; q < NA; ++q) {
+                int rl, cl;
+                warp_tile_coord<T>(q, rl, cl);
+                if (row0 + rl < nb) XX(row0 + rl, col0 + cl) = acc[q];
             }
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (r0 + tb * a < nb) XX(r0 + tb * a, c0 + tb * q) = acc[a][q];
         }
         __syncthreads();
         // step B: X21 = -X22 T  -> written over the (dead) L21 block in the lower triangle
-        for (int e = tid; e < npairs * tb * tb; e += NTHREADS) {
-            const int pr = e / (tb * tb), tt = e - pr * tb * tb;
+        for (int e = warp; e < npairs * tpr * tpc; e += NTHREADS / 32) {
+            const int pr = e / (tpr * tpc), tt = e - pr * tpr * tpc;
             const int base = pr * 2 * b;
-            const int ti = tt / tb, tj = tt - ti * tb;
-            const int r0 = base + b + ti, c0 = base + tj;
-            if (r0 >= nb) continue;
-            T acc[4][4];
+            const int row0 = base + b + (tt / tpc) * TR, col0 = base + (tt % tpc) * TC;
+            if (row0 >= nb) continue;
+            const int h2 = base + b;  // first row / column of the second half
+            T acc[4] = {T(0), T(0), T(0), T(0)};
+            warp_tile_mma(
+                acc, b,
+                [&](int rl, int k) {
+                    const int row = row0 + rl, kk = h2 + k;
+                    return (row < nb && kk <= row) ? XX(row, kk) : T(0);
+                },
+                [&](int k, int cl) { return (h2 + k < nb) ? XX(h2 + k, col0 + cl) : T(0); });
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) acc[a][q] = T(0);
-            const int kend = min(base + 2 * b, nb);
-            for (int k = base + b; k < kend; ++k) {  // X22 lower triangular: k <= i
-                T x22[4], t[4];
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const int row = r0 + tb * a;
-                    x22[a] = (k <= row && row < nb) ? XX(row, k) : T(0);
-                    t[a] = XX(k, c0 + tb * a);
-                }
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[a][q] = fma(x22[a], t[q], acc[a][q]);
+            for (int q = 0; q < NA; ++q) {
+                int rl, cl;
+                warp_tile_coord<T>(q, rl, cl);
+                if (row0 + rl < nb) S[(row0 + rl) * SP + col0 + cl] = -acc[q];
             }
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (r0 + tb * a < nb) S[(r0 + tb * a) * SP + c0 + tb * q] = -acc[a][q];
         }
         __syncthreads();
         // step C: move X21 into the overlay
@@ -413,10 +381,10 @@ int rtrsm_rec(const Ctx<T>& c, int64_t r0, int64_t nr, int64_t t0, int64_t nt) {
     if (nt <= NB) {
         T* Bp = c.A + r0 * c.lda + t0;
         int rc = dcgp_gemm_impl(0, 1, nr, nt, nt, 1.0, Bp, c.lda, c.ws + (t0 / NB) * NB * NB, NB, 0.0, Bp, c.lda,
-                                c.dtype, DCGP_GEMM_INPLACE | c.xf, c.st, nullptr, nullptr);
-        if (rc) return rc;
-        // these entries of L are final: publish their TF32 remainders for the tcgen05 3xTF32 products
-        if (c.Alo) rc = dcgp_split_lo_impl(Bp, c.Alo + r0 * c.lda + t0, nr, nt, c.lda, c.lda, c.st);
+                                c.dtype, DCGP_GEMM_INPLACE | c.xf, c.st, nullptr, nullptr,
+                                // these entries of L are final: the epilogue also publishes their TF32
+                                // remainders for the tcgen05 3xTF32 products
+                                c.Alo ? c.Alo + r0 * c.lda + t0 : nullptr);
         return rc;
     }
     const int64_t t1 = split_point(nt), t2 = nt - t1;
@@ -426,7 +394,7 @@ int rtrsm_rec(const Ctx<T>& c, int64_t r0, int64_t nr, int64_t t0, int64_t nt) {
     const int64_t oa = r0 * c.lda + t0, ob = (t0 + t1) * c.lda + t0;
     rc = dcgp_gemm_impl(0, 1, nr, t2, t1, -1.0, c.A + oa, c.lda, c.A + ob, c.lda, 1.0, c.A + r0 * c.lda + t0 + t1, c.lda,
                         c.dtype, c.xf, c.st, c.Alo ? c.Alo + oa : nullptr,
-                        c.Alo ? c.Alo + ob : nullptr);
+                        c.Alo ? c.Alo + ob : nullptr, nullptr);
     if (rc) return rc;
     return rtrsm_rec(c, r0, nr, t0 + t1, t2);
 }
@@ -448,7 +416,7 @@ int chol_rec(const Ctx<T>& c, int64_t j0, int64_t nb) {
     T* A21 = c.A + o21;
     const T* A21lo = c.Alo ? c.Alo + o21 : nullptr;
     rc = dcgp_gemm_impl(0, 1, n2, n2, n1, -1.0, A21, c.lda, A21, c.lda, 1.0, c.A + (j0 + n1) * c.lda + j0 + n1, c.lda,
-                        c.dtype, DCGP_GEMM_LOWER | c.xf, c.st, A21lo, A21lo);
+                        c.dtype, DCGP_GEMM_LOWER | c.xf, c.st, A21lo, A21lo, nullptr);
     if (rc) return rc;
     return chol_rec(c, j0 + n1, n2);
 }
@@ -488,9 +456,8 @@ int ltrsm_rec(const LCtx<T>& c, int trans, int64_t i0, int64_t nn) {
     if (nn <= NB) {
         T* Bi = c.B + i0 * c.ldb;
         int rc = dcgp_gemm_impl(trans, 0, nn, c.m, nn, 1.0, c.ws + (i0 / NB) * NB * NB, NB, Bi, c.ldb, 0.0, Bi, c.ldb,
-                                c.dtype, DCGP_GEMM_INPLACE | c.xf, c.st, nullptr, nullptr);
-        if (rc) return rc;
-        if (c.Blo) rc = dcgp_split_lo_impl(Bi, c.Blo + i0 * c.ldb, nn, c.m, c.ldb, c.ldb, c.st);
+                                c.dtype, DCGP_GEMM_INPLACE | c.xf, c.st, nullptr, nullptr,
+                                c.Blo ? c.Blo + i0 * c.ldb : nullptr);
         return rc;
     }
     const int64_t n1 = split_point(nn), n2 = nn - n1;
@@ -503,14 +470,14 @@ int ltrsm_rec(const LCtx<T>& c, int trans, int64_t i0, int64_t nn) {
         if (rc) return rc;
         rc = dcgp_gemm_impl(0, 0, n2, c.m, n1, -1.0, Lc, c.ldl, c.B + i0 * c.ldb, c.ldb, 1.0, c.B + (i0 + n1) * c.ldb,
                             c.ldb, c.dtype, c.xf, c.st, Lclo,
-                            c.Blo ? c.Blo + i0 * c.ldb : nullptr);
+                            c.Blo ? c.Blo + i0 * c.ldb : nullptr, nullptr);
         if (rc) return rc;
         return ltrsm_rec(c, trans, i0 + n1, n2);
     }
     rc = ltrsm_rec(c, trans, i0 + n1, n2);
     if (rc) return rc;
     rc = dcgp_gemm_impl(1, 0, n1, c.m, n2, -1.0, Lc, c.ldl, c.B + (i0 + n1) * c.ldb, c.ldb, 1.0, c.B + i0 * c.ldb, c.ldb,
-                        c.dtype, c.xf, c.st, Lclo, c.Blo ? c.Blo + (i0 + n1) * c.ldb : nullptr);
+                        c.dtype, c.xf, c.st, Lclo, c.Blo ? c.Blo + (i0 + n1) * c.ldb : nullptr, nullptr);
     if (rc) return rc;
     return ltrsm_rec(c, trans, i0, n1);
 }

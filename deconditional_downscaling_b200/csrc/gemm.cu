@@ -15,6 +15,7 @@
 // DCGP_GEMM_LOWER restricts the grid to tiles that intersect the lower triangle (SYRK
 // trailing update of the blocked Cholesky).
 #include "common.cuh"
+#include "mma.cuh"
 #include <type_traits>
 
 namespace {
@@ -31,31 +32,8 @@ struct GemmParams {
     int lower;   // bit0: lower tiles only; bit1: never split K (C aliases an input)
     int ksplit;  // number of K slices (gridDim.z); >1 => atomicAdd epilogue on pre-scaled C
     int vecA, vecB;  // 16-byte cp.async allowed for the K-contiguous layout of A / B
+    void* Clo;       // optional (FP32): receives c - trunc_tf32(c) for every stored element of C (same ld)
 };
-
-__device__ __forceinline__ void mma_f64(double (&c)[2], double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c[0]), "+d"(c[1])
-                 : "d"(a), "d"(b));
-}
-
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    hi = to_tf32(x);
-    lo = to_tf32(x - __uint_as_float(hi));
-}
 
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void* smem, const void* gmem, int src_bytes) {
@@ -265,9 +243,27 @@ __global__ void __launch_bounds__(256, (BM == 128 ? 1 : 2)) gemm_kernel(const __
                         o.y = fma(beta, c.y, v1);
                     }
                     *reinterpret_cast<T2*>(dst) = o;
+                    if constexpr (sizeof(T) == 4) {
+                        if (p.Clo) {  // TF32 remainders of the finished values (3xTF32 operands of later products)
+                            float* lo = (float*)p.Clo + row * p.ldc + col;
+                            lo[0] = o.x - __uint_as_float(__float_as_uint(o.x) & 0xFFFFE000u);
+                            lo[1] = o.y - __uint_as_float(__float_as_uint(o.y) & 0xFFFFE000u);
+                        }
+                    }
                 } else {
-                    if (col < p.n) dst[0] = (beta == T(0)) ? v0 : fma(beta, dst[0], v0);
-                    if (col + 1 < p.n) dst[1] = (beta == T(0)) ? v1 : fma(beta, dst[1], v1);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        if (col + q < p.n) {
+                            const T vq = q ? v1 : v0;
+                            const T o = (beta == T(0)) ? vq : fma(beta, dst[q], vq);
+                            dst[q] = o;
+                            if constexpr (sizeof(T) == 4) {
+                                if (p.Clo)
+                                    ((float*)p.Clo)[row * p.ldc + col + q] =
+                                        o - __uint_as_float(__float_as_uint(o) & 0xFFFFE000u);
+                            }
+                        }
+                    }
                 }
             }
         }
@@ -345,7 +341,7 @@ int dcgp_gemm_tc_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, d
 // the tcgen05 kernel; without them compensated contractions use the mma.sync kernel.
 int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
                    const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype, int flags,
-                   cudaStream_t st, const void* Alo, const void* Blo) {
+                   cudaStream_t st, const void* Alo, const void* Blo, void* Clo) {
     if (m < 0) return -3;
     if (n < 0) return -4;
     if (k < 0) return -5;
@@ -366,6 +362,7 @@ int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, doub
     p.lower = ((flags & DCGP_GEMM_LOWER) ? 1 : 0) | ((flags & (DCGP_GEMM_NO_SPLITK | DCGP_GEMM_INPLACE)) ? 2 : 0) |
               ((flags & DCGP_GEMM_INPLACE) ? 4 : 0);
     p.ksplit = 1;
+    p.Clo = (flags & DCGP_GEMM_INPLACE) ? Clo : nullptr;  // only the in-place leaves publish remainders
     if (dtype == DCGP_F64) {
         p.vecA = vec_ok<double>(A, lda);
         p.vecB = vec_ok<double>(B, ldb);
@@ -395,5 +392,5 @@ extern "C" int dcgp_gemm(int transa, int transb, int64_t m, int64_t n, int64_t k
                          int64_t lda, const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype,
                          int flags, void* stream) {
     return dcgp_gemm_impl(transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, dtype, flags,
-                          (cudaStream_t)stream, nullptr, nullptr);
+                          (cudaStream_t)stream, nullptr, nullptr, nullptr);
 }
