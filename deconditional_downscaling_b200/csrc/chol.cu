@@ -24,6 +24,9 @@ int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, doub
                    const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype, int flags,
                    cudaStream_t st, const void* Alo, const void* Blo, void* Clo);
 int dcgp_split_lo_impl(const void* src, void* dst, int64_t rows, int64_t cols, int64_t lds, int64_t ldd, cudaStream_t st);
+int dcgp_gemm_batched_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A,
+                           int64_t lda, int64_t strideA, const void* B, int64_t ldb, int64_t strideB, double beta,
+                           void* C, int64_t ldc, int64_t strideC, int batch, int dtype, int flags, cudaStream_t st);
 
 namespace {
 
@@ -248,10 +251,10 @@ __device__ void block_trtri(T* S, const T* rinv, int nb) {
 }
 
 template <typename T>
-__device__ void store_inverse(const T* S, int nb, T* inv) {  // inv: NB x NB row-major (lower, zero above)
+__device__ void store_inverse(const T* S, int nb, T* inv, int ld) {  // nb x NB block (lower, zero above), pitch ld
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = warp; i < nb; i += NTHREADS / 32)
-        for (int c = lane; c < NB; c += 32) inv[i * NB + c] = (c <= i) ? XX(i, c) : T(0);
+        for (int c = lane; c < NB; c += 32) inv[(int64_t)i * ld + c] = (c <= i) ? XX(i, c) : T(0);
 }
 #undef XX
 
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(NTHREADS) potrf_diag_kernel(T* __restrict__ A,
 #ifdef DCGP_LEAF_TIMING
     long long t4 = clock64();
 #endif
-    store_inverse<T>(S, nb, inv);
+    store_inverse<T>(S, nb, inv, NB);
 #ifdef DCGP_LEAF_TIMING
     __syncthreads();
     if (threadIdx.x == 0)
@@ -321,8 +324,10 @@ __global__ void __launch_bounds__(NTHREADS) potrf_diag_kernel(T* __restrict__ A,
 
 // batched inversion of the diagonal blocks of an existing factor
 template <typename T>
+// `group` 128-blocks form one (group*128)-wide output block with pitch group*128 (group = 1: the packed
+// NB x NB workspace blocks of the factorisation; group = 4: the diagonal of the 512-wide inverse blocks)
 __global__ void __launch_bounds__(NTHREADS) trtri_blocks_kernel(const T* __restrict__ L, int64_t ldl, int64_t n,
-                                                                T* __restrict__ inv) {
+                                                                T* __restrict__ inv, int group) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* S = reinterpret_cast<T*>(smem_raw);
     const int64_t i0 = (int64_t)blockIdx.x * NB;
@@ -331,7 +336,8 @@ __global__ void __launch_bounds__(NTHREADS) trtri_blocks_kernel(const T* __restr
     load_lower<T>(S, rinv, L + i0 * ldl + i0, ldl, nb, true);
     __syncthreads();
     block_trtri<T>(S, rinv, nb);
-    store_inverse<T>(S, nb, inv + (int64_t)blockIdx.x * NB * NB);
+    const int64_t big = blockIdx.x / group, q = blockIdx.x % group, ld = (int64_t)group * NB;
+    store_inverse<T>(S, nb, inv + big * ld * ld + q * NB * ld + q * NB, (int)ld);
 }
 
 template <typename T>
@@ -483,12 +489,12 @@ int ltrsm_rec(const LCtx<T>& c, int trans, int64_t i0, int64_t nn) {
 }
 
 template <typename T>
-int trsm_impl(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t m, int64_t ldb, T* ws, size_t ws_bytes,
-              int dtype, int xf, cudaStream_t st) {
+int trsm128_impl(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t m, int64_t ldb, T* ws, size_t ws_bytes,
+                 int dtype, int xf, cudaStream_t st) {
     int rc = set_smem_attr<T>((const void*)trtri_blocks_kernel<T>);
     if (rc) return rc;
     const int64_t nblk = (n + NB - 1) / NB;
-    trtri_blocks_kernel<T><<<(unsigned)nblk, NTHREADS, leaf_smem<T>(), st>>>(L, ldl, n, ws);
+    trtri_blocks_kernel<T><<<(unsigned)nblk, NTHREADS, leaf_smem<T>(), st>>>(L, ldl, n, ws, 1);
     DCGP_CHECK_LAUNCH();
     T *llo = nullptr, *blo = nullptr;
     const size_t inv = inv_ws_bytes(n, dtype);
@@ -500,6 +506,147 @@ int trsm_impl(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t m, in
     }
     LCtx<T> c{L, ldl, B, m, ldb, ws, dtype, xf, st, llo, blo};
     return ltrsm_rec(c, trans, 0, n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Solves with many right-hand sides on 512-wide inverted diagonal blocks.  The dependent chain of a
+// substitution sweep shrinks from n/128 to n/512 steps, every step being a tensor-core GEMM:
+//   (a) 128-wide diagonal inverses (trtri_blocks_kernel) written on the diagonal of 512-wide blocks;
+//   (b) two doubling levels (128 -> 256 -> 512), X21 = -X22 (L21 X11), batched over all blocks;
+//   (c) recursion on 512-row leaves: X_i = op(inv512_i) B_i (out of place) + deep-K updates.
+// ---------------------------------------------------------------------------------------------
+constexpr int NBI = 512;
+
+template <typename T>
+struct L5Ctx {
+    const T* L;
+    int64_t ldl;
+    T* B;
+    int64_t m, ldb;
+    T* inv;   // [nbig][NBI][NBI]
+    T* X;     // solved rows (layout of B)
+    int dtype, xf;
+    cudaStream_t st;
+    const T* Llo;
+    T* Xlo;
+};
+
+template <typename T>
+int build_inv512(const T* L, int64_t n, int64_t ldl, T* inv, T* tmp, int dtype, int xf, cudaStream_t st) {
+    const int64_t nbig = (n + NBI - 1) / NBI, nfull = n / NBI;
+    cudaError_t e = cudaMemsetAsync(inv, 0, (size_t)nbig * NBI * NBI * sizeof(T), st);
+    if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
+    int rc = set_smem_attr<T>((const void*)trtri_blocks_kernel<T>);
+    if (rc) return rc;
+    const int64_t nblk = (n + NB - 1) / NB;
+    trtri_blocks_kernel<T><<<(unsigned)nblk, NTHREADS, leaf_smem<T>(), st>>>(L, ldl, n, inv, NBI / NB);
+    DCGP_CHECK_LAUNCH();
+    const int64_t sL = (int64_t)NBI * (ldl + 1), sX = (int64_t)NBI * NBI;
+    for (int b = NB; b < NBI; b *= 2) {
+        for (int j = 0; j < NBI / (2 * b); ++j) {
+            const int64_t o1 = (int64_t)j * 2 * b, o2 = o1 + b;  // first / second half inside the 512 block
+            // full blocks, batched:  T = L21 X11 ;  X21 = -X22 T
+            if (nfull > 0) {
+                rc = dcgp_gemm_batched_impl(0, 0, b, b, b, 1.0, L + o2 * ldl + o1, ldl, sL, inv + o1 * NBI + o1, NBI, sX, 0.0,
+                                            tmp + o2 * NBI + o1, NBI, sX, (int)nfull, dtype, xf, st);
+                if (rc) return rc;
+                rc = dcgp_gemm_batched_impl(0, 0, b, b, b, -1.0, inv + o2 * NBI + o2, NBI, sX, tmp + o2 * NBI + o1, NBI, sX,
+                                            0.0, inv + o2 * NBI + o1, NBI, sX, (int)nfull, dtype, xf, st);
+                if (rc) return rc;
+            }
+            // ragged last block
+            const int64_t rem = n - nfull * NBI;
+            if (rem > o2) {
+                const int64_t r2 = (rem - o2 < b) ? (rem - o2) : b;  // valid rows of the second half
+                const T* Lp = L + nfull * sL;
+                T* ip = inv + nfull * sX;
+                T* tp = tmp + nfull * sX;
+                rc = dcgp_gemm_batched_impl(0, 0, r2, b, b, 1.0, Lp + o2 * ldl + o1, ldl, 0, ip + o1 * NBI + o1, NBI, 0, 0.0,
+                                            tp + o2 * NBI + o1, NBI, 0, 1, dtype, xf, st);
+                if (rc) return rc;
+                rc = dcgp_gemm_batched_impl(0, 0, r2, b, r2, -1.0, ip + o2 * NBI + o2, NBI, 0, tp + o2 * NBI + o1, NBI, 0, 0.0,
+                                            ip + o2 * NBI + o1, NBI, 0, 1, dtype, xf, st);
+                if (rc) return rc;
+            }
+        }
+    }
+    return 0;
+}
+
+inline int64_t split_point512(int64_t nn) {
+    int64_t h = ((nn / 2 + NBI - 1) / NBI) * NBI;
+    return h >= nn ? nn - NBI : h;
+}
+
+template <typename T>
+int ltrsm512_rec(const L5Ctx<T>& c, int trans, int64_t i0, int64_t nn) {
+    if (nn <= NBI) {
+        // X_i = op(inv512_i) B_i, out of place; the epilogue publishes the TF32 remainders of X_i
+        return dcgp_gemm_impl(trans, 0, nn, c.m, nn, 1.0, c.inv + (i0 / NBI) * NBI * NBI, NBI, c.B + i0 * c.ldb, c.ldb, 0.0,
+                              c.X + i0 * c.ldb, c.ldb, c.dtype, c.xf | DCGP_GEMM_NO_TCGEN05, c.st, nullptr, nullptr,
+                              c.Xlo ? c.Xlo + i0 * c.ldb : nullptr);
+    }
+    const int64_t n1 = split_point512(nn), n2 = nn - n1;
+    const int64_t oc = (i0 + n1) * c.ldl + i0;
+    const T* Lc = c.L + oc;  // n2 x n1
+    const T* Lclo = c.Llo ? c.Llo + oc : nullptr;
+    int rc;
+    if (!trans) {
+        rc = ltrsm512_rec(c, trans, i0, n1);
+        if (rc) return rc;
+        rc = dcgp_gemm_impl(0, 0, n2, c.m, n1, -1.0, Lc, c.ldl, c.X + i0 * c.ldb, c.ldb, 1.0, c.B + (i0 + n1) * c.ldb, c.ldb,
+                            c.dtype, c.xf, c.st, Lclo, c.Xlo ? c.Xlo + i0 * c.ldb : nullptr, nullptr);
+        if (rc) return rc;
+        return ltrsm512_rec(c, trans, i0 + n1, n2);
+    }
+    rc = ltrsm512_rec(c, trans, i0 + n1, n2);
+    if (rc) return rc;
+    rc = dcgp_gemm_impl(1, 0, n1, c.m, n2, -1.0, Lc, c.ldl, c.X + (i0 + n1) * c.ldb, c.ldb, 1.0, c.B + i0 * c.ldb, c.ldb,
+                        c.dtype, c.xf, c.st, Lclo, c.Xlo ? c.Xlo + (i0 + n1) * c.ldb : nullptr, nullptr);
+    if (rc) return rc;
+    return ltrsm512_rec(c, trans, i0, n1);
+}
+
+size_t trsm512_ws_bytes(int64_t n, int64_t ldl, int64_t m_ld, int dtype) {
+    const size_t es = dtype == DCGP_F64 ? 8 : 4;
+    const size_t nbig = (size_t)(n + NBI - 1) / NBI;
+    size_t b = 2 * nbig * NBI * NBI * es + (size_t)n * m_ld * es;
+    if (dtype == DCGP_F32) b += ((size_t)n * ldl + (size_t)n * m_ld) * 4;
+    return b;
+}
+
+// trans: 0 = L X = B, 1 = L^T X = B, 2 = both in sequence ((L L^T) X = B, shares the inverted blocks)
+template <typename T>
+int trsm_impl(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t m, int64_t ldb, T* ws, size_t ws_bytes,
+              int dtype, int xf, cudaStream_t st) {
+    if (n < 2 * NBI || m < 64 || ws_bytes < trsm512_ws_bytes(n, ldl, ldb, dtype)) {
+        if (trans != 2) return trsm128_impl<T>(trans, L, n, ldl, B, m, ldb, ws, ws_bytes, dtype, xf, st);
+        int rc = trsm128_impl<T>(0, L, n, ldl, B, m, ldb, ws, ws_bytes, dtype, xf, st);
+        if (rc) return rc;
+        return trsm128_impl<T>(1, L, n, ldl, B, m, ldb, ws, ws_bytes, dtype, xf, st);
+    }
+    const int64_t nbig = (n + NBI - 1) / NBI;
+    T* inv = ws;
+    T* tmp = inv + nbig * NBI * NBI;
+    T* X = tmp + nbig * NBI * NBI;
+    T *llo = nullptr, *xlo = nullptr;
+    if (sizeof(T) == 4 && xf) {
+        llo = X + (size_t)n * ldb;
+        xlo = llo + (size_t)n * ldl;
+        int rc = dcgp_split_lo_impl(L, llo, n, n, ldl, ldl, st);
+        if (rc) return rc;
+    }
+    int rc = build_inv512<T>(L, n, ldl, inv, tmp, dtype, xf, st);
+    if (rc) return rc;
+    L5Ctx<T> c{L, ldl, B, m, ldb, inv, X, dtype, xf, st, llo, xlo};
+    for (int sweep = (trans == 1 ? 1 : 0); sweep <= (trans == 0 ? 0 : 1); ++sweep) {
+        rc = ltrsm512_rec(c, sweep, 0, n);
+        if (rc) return rc;
+        cudaError_t e = cudaMemcpy2DAsync(B, (size_t)ldb * sizeof(T), X, (size_t)ldb * sizeof(T), (size_t)m * sizeof(T),
+                                          (size_t)n, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
+    }
+    return 0;
 }
 
 }  // namespace
@@ -533,7 +680,9 @@ extern "C" int dcgp_potrf(void* A, int64_t n, int64_t lda, int* info, void* work
 
 extern "C" size_t dcgp_trsm_workspace(int64_t n, int64_t m, int dtype) {
     if (n <= 0) return 0;
-    return inv_ws_bytes(n, dtype) + (dtype == DCGP_F32 ? ((size_t)n * n + (size_t)n * m) * 4 : 0);
+    const size_t small = inv_ws_bytes(n, dtype) + (dtype == DCGP_F32 ? ((size_t)n * n + (size_t)n * m) * 4 : 0);
+    const size_t big = trsm512_ws_bytes(n, n, m, dtype);
+    return small > big ? small : big;
 }
 
 extern "C" int dcgp_trsm(int trans, const void* L, int64_t n, int64_t ldl, void* B, int64_t m, int64_t ldb,
@@ -555,9 +704,7 @@ extern "C" int dcgp_trsm(int trans, const void* L, int64_t n, int64_t ldl, void*
 
 extern "C" int dcgp_potrs(const void* L, int64_t n, int64_t ldl, void* B, int64_t m, int64_t ldb, void* workspace,
                           size_t workspace_bytes, int dtype, int flags, void* stream) {
-    int rc = dcgp_trsm(0, L, n, ldl, B, m, ldb, workspace, workspace_bytes, dtype, flags, stream);
-    if (rc) return rc;
-    return dcgp_trsm(1, L, n, ldl, B, m, ldb, workspace, workspace_bytes, dtype, flags, stream);
+    return dcgp_trsm(2, L, n, ldl, B, m, ldb, workspace, workspace_bytes, dtype, flags, stream);
 }
 
 extern "C" int dcgp_logdet_chol(const void* L, int64_t n, int64_t ldl, void* out, int dtype, void* stream) {

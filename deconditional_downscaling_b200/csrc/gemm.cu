@@ -32,6 +32,8 @@ struct GemmParams {
     int lower;   // bit0: lower tiles only; bit1: never split K (C aliases an input)
     int ksplit;  // number of K slices (gridDim.z); >1 => atomicAdd epilogue on pre-scaled C
     int vecA, vecB;  // 16-byte cp.async allowed for the K-contiguous layout of A / B
+    int batch;       // > 1: blockIdx.z enumerates independent problems (no split-K)
+    int64_t strideA, strideB, strideC;  // element strides between batch members
     void* Clo;       // optional (FP32): receives c - trunc_tf32(c) for every stored element of C (same ld)
 };
 
@@ -111,14 +113,15 @@ __global__ void __launch_bounds__(256, (BM == 128 ? 1 : 2)) gemm_kernel(const __
     // K slice of this CTA
     const int64_t ktiles = (p.k + BK - 1) / BK;
     const int64_t per = (ktiles + p.ksplit - 1) / p.ksplit;
-    const int64_t kt0 = (int64_t)blockIdx.z * per;
+    const int64_t kt0 = (p.batch > 1) ? 0 : (int64_t)blockIdx.z * per;
     const int64_t kt1 = min(ktiles, kt0 + per);
     if (kt0 >= kt1 && p.ksplit > 1) return;
     const int64_t kend = min(p.k, kt1 * BK);
     const int nkt = (int)max((int64_t)0, kt1 - kt0);
 
-    const T* A = (const T*)p.A;
-    const T* B = (const T*)p.B;
+    const int64_t bz = (p.batch > 1) ? (int64_t)blockIdx.z : 0;
+    const T* A = (const T*)p.A + bz * p.strideA;
+    const T* B = (const T*)p.B + bz * p.strideB;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps, warp tile WM x WN
     const int g = lane >> 2, t = lane & 3;
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(256, (BM == 128 ? 1 : 2)) gemm_kernel(const __
     cp_async_wait<0>();
 
     // epilogue: each thread owns column pairs (2t, 2t+1) -> 16-byte (f64) / 8-byte (f32) accesses
-    T* C = (T*)p.C;
+    T* C = (T*)p.C + bz * p.strideC;
     const T alpha = (T)p.alpha, beta = (T)p.beta;
     const bool atomic = p.ksplit > 1;
     const bool pair_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) % (2 * sizeof(T))) == 0);
@@ -304,13 +307,14 @@ int launch_gemm_tile(GemmParams p, cudaStream_t st) {
         if (ksplit < 1) ksplit = 1;
         if (ksplit > 64) ksplit = 64;
     }
+    if (p.batch > 1) ksplit = 1;
     p.ksplit = ksplit;
     if (ksplit > 1) {
         int64_t total = p.m * p.n;
         unsigned g = (unsigned)min((int64_t)(num_sms() * 8), (total + 255) / 256);
         scale_kernel<T><<<g, 256, 0, st>>>((T*)p.C, p.m, p.n, p.ldc, (T)p.beta, p.lower & 1, BM, BN);
     }
-    dim3 grid((unsigned)gn, (unsigned)gm, (unsigned)ksplit);
+    dim3 grid((unsigned)gn, (unsigned)gm, (unsigned)(p.batch > 1 ? p.batch : ksplit));
     gemm_kernel<T, X3, BM, BN><<<grid, 256, smem, st>>>(p);
     DCGP_CHECK_LAUNCH();
     return 0;
@@ -325,7 +329,7 @@ int launch_gemm(GemmParams p, cudaStream_t st) {
         if (p.m <= 128) return launch_gemm_tile<T, X3, 128, 64>(p, st);
         return -16;
     }
-    const int64_t t128 = ((p.m + 127) / 128) * ((p.n + 127) / 128);
+    const int64_t t128 = ((p.m + 127) / 128) * ((p.n + 127) / 128) * (p.batch > 1 ? p.batch : 1);
     if (t128 < num_sms() / 2) return launch_gemm_tile<T, X3, 64, 64>(p, st);
     return launch_gemm_tile<T, X3, 128, 128>(p, st);
 }
@@ -362,7 +366,9 @@ int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, doub
     p.lower = ((flags & DCGP_GEMM_LOWER) ? 1 : 0) | ((flags & (DCGP_GEMM_NO_SPLITK | DCGP_GEMM_INPLACE)) ? 2 : 0) |
               ((flags & DCGP_GEMM_INPLACE) ? 4 : 0);
     p.ksplit = 1;
-    p.Clo = (flags & DCGP_GEMM_INPLACE) ? Clo : nullptr;  // only the in-place leaves publish remainders
+    p.batch = 1;
+    p.strideA = p.strideB = p.strideC = 0;
+    p.Clo = Clo;  // FP32: the epilogue also publishes the TF32 remainders of C (operands of later 3xTF32 products)
     if (dtype == DCGP_F64) {
         p.vecA = vec_ok<double>(A, lda);
         p.vecB = vec_ok<double>(B, ldb);
@@ -386,6 +392,35 @@ int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, doub
         return launch_gemm<float, false>(p, st);
     }
     return -14;
+}
+
+// Batched variant for the small independent products of the blocked triangular inversion (mma.sync kernel).
+int dcgp_gemm_batched_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A,
+                           int64_t lda, int64_t strideA, const void* B, int64_t ldb, int64_t strideB, double beta,
+                           void* C, int64_t ldc, int64_t strideC, int batch, int dtype, int flags, cudaStream_t st) {
+    if (m <= 0 || n <= 0 || batch <= 0) return 0;
+    GemmParams p;
+    p.m = m; p.n = n; p.k = k;
+    p.A = A; p.B = B; p.C = C; p.ldc = ldc;
+    p.sam = transa ? 1 : lda;
+    p.sak = transa ? lda : 1;
+    p.sbn = transb ? ldb : 1;
+    p.sbk = transb ? 1 : ldb;
+    p.alpha = alpha; p.beta = beta;
+    p.lower = 2;
+    p.ksplit = 1;
+    p.batch = batch;
+    p.strideA = strideA; p.strideB = strideB; p.strideC = strideC;
+    p.Clo = nullptr;
+    if (dtype == DCGP_F64) {
+        p.vecA = vec_ok<double>(A, lda) && (strideA % 2 == 0);
+        p.vecB = vec_ok<double>(B, ldb) && (strideB % 2 == 0);
+        return launch_gemm<double, false>(p, st);
+    }
+    p.vecA = vec_ok<float>(A, lda) && (strideA % 4 == 0);
+    p.vecB = vec_ok<float>(B, ldb) && (strideB % 4 == 0);
+    if (flags & DCGP_GEMM_TF32X3) return launch_gemm<float, true>(p, st);
+    return launch_gemm<float, false>(p, st);
 }
 
 extern "C" int dcgp_gemm(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A,
