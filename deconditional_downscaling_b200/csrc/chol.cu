@@ -673,9 +673,9 @@ extern "C" int dcgp_potrf(void* A, int64_t n, int64_t lda, int* info, void* work
     }
     if (dtype == DCGP_F64)
         return potrf_impl<double>((double*)A, n, lda, info, (double*)workspace, workspace_bytes, dtype,
-                                  flags & DCGP_GEMM_TF32X3, st);
+                                  flags & (DCGP_GEMM_TF32X3 | DCGP_GEMM_NO_TCGEN05), st);
     return potrf_impl<float>((float*)A, n, lda, info, (float*)workspace, workspace_bytes, dtype,
-                             flags & DCGP_GEMM_TF32X3, st);
+                             flags & (DCGP_GEMM_TF32X3 | DCGP_GEMM_NO_TCGEN05), st);
 }
 
 extern "C" size_t dcgp_trsm_workspace(int64_t n, int64_t m, int dtype) {
@@ -697,9 +697,9 @@ extern "C" int dcgp_trsm(int trans, const void* L, int64_t n, int64_t ldl, void*
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == DCGP_F64)
         return trsm_impl<double>(trans, (const double*)L, n, ldl, (double*)B, m, ldb, (double*)workspace,
-                                 workspace_bytes, dtype, flags & DCGP_GEMM_TF32X3, st);
+                                 workspace_bytes, dtype, flags & (DCGP_GEMM_TF32X3 | DCGP_GEMM_NO_TCGEN05), st);
     return trsm_impl<float>(trans, (const float*)L, n, ldl, (float*)B, m, ldb, (float*)workspace, workspace_bytes,
-                            dtype, flags & DCGP_GEMM_TF32X3, st);
+                            dtype, flags & (DCGP_GEMM_TF32X3 | DCGP_GEMM_NO_TCGEN05), st);
 }
 
 extern "C" int dcgp_potrs(const void* L, int64_t n, int64_t ldl, void* B, int64_t m, int64_t ldb, void* workspace,

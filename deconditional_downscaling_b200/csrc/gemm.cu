@@ -369,6 +369,7 @@ int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, doub
     p.batch = 1;
     p.strideA = p.strideB = p.strideC = 0;
     p.Clo = Clo;  // FP32: the epilogue also publishes the TF32 remainders of C (operands of later 3xTF32 products)
+    if (Clo) p.lower |= 2;  // ... which the split-K (atomic) epilogue cannot do
     if (dtype == DCGP_F64) {
         p.vecA = vec_ok<double>(A, lda);
         p.vecB = vec_ok<double>(B, ldb);

@@ -26,15 +26,17 @@ KINDS = {"rbf": _lib.KIND_RBF, "matern32": _lib.KIND_MATERN32, "matern12": _lib.
 #   "auto" = 3xTF32 for dcgp_potrf / dcgp_trsm / dcgp_potrs and for small GEMMs,
 #            single-pass TF32 (tcgen05 kernel) for the large products.
 TF32_MODE = "auto"
+USE_TCGEN05 = True   # False keeps FP32 contractions on the mma.sync kernel (A/B comparisons)
 X3_GEMM_LIMIT = 512 ** 3
 X3_SOLVE_LIMIT = 1 << 62  # dcgp_trsm / dcgp_potrs: always compensated in "auto"
 X3_POTRF_LIMIT = 1 << 62  # dcgp_potrf
 
 
 def _x3(t, small):
+    notc = 0 if USE_TCGEN05 else _lib.GEMM_NO_TCGEN05
     if t.dtype != torch.float32 or TF32_MODE == "fast":
-        return 0
-    return _lib.GEMM_TF32X3 if (TF32_MODE == "x3" or small) else 0
+        return notc
+    return (_lib.GEMM_TF32X3 if (TF32_MODE == "x3" or small) else 0) | notc
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -151,9 +153,6 @@ def gram_bwd(spec: FlatSpec, x1, x2, G, need_dx1=False):
     return dls, dos, dx1
 
 
-USE_TCGEN05 = True   # False keeps FP32 contractions on the mma.sync kernel (A/B comparisons)
-
-
 def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, C=None, lower=False, no_splitk=False):
     """C = alpha * op(A) @ op(B) + beta * C."""
     A, B = _rowmajor(A), _rowmajor(B)
@@ -165,8 +164,7 @@ def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, C=None, lower=Fa
     if C is None:
         C = torch.empty(m, n, dtype=A.dtype, device=A.device)
         beta = 0.0
-    flags = (GEMM_LOWER if lower else 0) | (_lib.GEMM_NO_SPLITK if no_splitk else 0) | _x3(A, m * n * k <= X3_GEMM_LIMIT) \
-        | (0 if USE_TCGEN05 else _lib.GEMM_NO_TCGEN05)
+    flags = (GEMM_LOWER if lower else 0) | (_lib.GEMM_NO_SPLITK if no_splitk else 0) | _x3(A, m * n * k <= X3_GEMM_LIMIT)
     rc = _lib.load().dcgp_gemm(int(transa), int(transb), m, n, k, float(alpha), _ptr(A), _ld(A), _ptr(B), _ld(B),
                                float(beta), _ptr(C), _ld(C), _dt(A), flags, _stream())
     check(rc, "dcgp_gemm")
