@@ -62,3 +62,28 @@ def test_flat_grads_views_alias_parameter_grads():
     f.zero()
     assert a.grad.abs().sum() == 0 and b.grad.abs().sum() == 0
     assert f.nbytes == 40
+
+
+def _gather_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from deconditional_downscaling_b200.parallel import sharded_rows_matmul
+    torch.manual_seed(0)
+    K = torch.randn(11, 7, dtype=torch.float64)      # 11 rows over 2 ranks: ragged blocks (6, 5)
+    W = torch.randn(7, 3, dtype=torch.float64)
+    res = sharded_rows_matmul(lambda lo, hi: K[lo:hi] @ W, 11, 3, torch.float64, "cpu")
+    out[rank] = (res, K @ W)
+    dist.destroy_process_group()
+
+
+def test_row_block_sharded_product_two_ranks():
+    """Row-block sharding + one all-gather reproduces the unsharded product on every rank."""
+    from deconditional_downscaling_b200.parallel import row_block
+    assert [row_block(11, r, 2) for r in range(2)] == [(0, 6), (6, 11)]
+    assert [row_block(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gather_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for r in range(2):
+        res, ref = out[r]
+        torch.testing.assert_close(res, ref, rtol=1e-13, atol=1e-13)
