@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "mma.cuh"
 #include <cstdio>
+#include <cstdlib>
 
 int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
                    const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype, int flags,
@@ -379,6 +380,7 @@ struct Ctx {
     int dtype, xf;
     cudaStream_t st;
     T* Alo;  // FP32 3xTF32 only: x - trunc_tf32(x) of the finished off-diagonal blocks of L (layout of A), or null
+    int64_t la_pw = 0;  // look-ahead panel width: 0 = choose by policy, -1 = plain recursion
 };
 
 // B = A[r0 : r0+nr, t0 : t0+nt]  <-  B * L[t0 : t0+nt, t0 : t0+nt]^{-T}
@@ -406,12 +408,24 @@ int rtrsm_rec(const Ctx<T>& c, int64_t r0, int64_t nr, int64_t t0, int64_t nt) {
 }
 
 template <typename T>
+int chol_la(const Ctx<T>& c, int64_t j0, int64_t nb);
+inline int64_t la_panel(int dtype, int64_t nb);
+
+template <typename T>
 int chol_rec(const Ctx<T>& c, int64_t j0, int64_t nb) {
     if (nb <= NB) {
         potrf_diag_kernel<T><<<1, NTHREADS, leaf_smem<T>(), c.st>>>(c.A + j0 * c.lda + j0, c.lda, (int)nb,
                                                                     c.ws + (j0 / NB) * NB * NB, c.info, j0);
         DCGP_CHECK_LAUNCH();
         return 0;
+    }
+    if (c.la_pw >= 0) {
+        const int64_t pw = c.la_pw ? c.la_pw : la_panel(c.dtype, nb);
+        if (pw && nb > 2 * pw) {
+            Ctx<T> cl = c;
+            cl.la_pw = pw;
+            return chol_la(cl, j0, nb);
+        }
     }
     const int64_t n1 = split_point(nb), n2 = nb - n1;
     int rc = chol_rec(c, j0, n1);
@@ -425,6 +439,120 @@ int chol_rec(const Ctx<T>& c, int64_t j0, int64_t nb) {
                         c.dtype, DCGP_GEMM_LOWER | c.xf, c.st, A21lo, A21lo, nullptr);
     if (rc) return rc;
     return chol_rec(c, j0 + n1, n2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Look-ahead right-looking factorisation of one diagonal block (the base case of chol_rec).
+//
+// The recursion above runs every kernel on one stream, so the 128-wide leaves (one CTA each) sit
+// in series with all the GEMMs between them.  Here the leaf chain gets its own lane:
+//   stream A (high priority): leaf(j) -> row block j+1 <- row * inv_j^T -> tile(j+1,j+1) -= P P^T -> leaf(j+1)
+//   stream B (low priority) : rows below j+1 <- rows * inv_j^T; column j+1 and the trailing square -= P P^T
+// so the rank-128 trailing update of panel j overlaps leaf j+1.  Both lanes are forked from and joined back
+// into the caller's stream with events only, which keeps the call capturable in a CUDA graph.
+struct LookAhead {
+    cudaStream_t sh = nullptr, sb = nullptr;  // chain (highest priority) and bulk (lowest) lanes
+    cudaEvent_t leaf[4] = {}, row[4] = {}, upd[4] = {}, fork = nullptr, join = nullptr;
+    int dev = -1;
+    int init() {
+        int d = 0;
+        cudaGetDevice(&d);
+        if (d == dev && sb) return 0;
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaError_t e = cudaStreamCreateWithPriority(&sh, cudaStreamNonBlocking, hi);
+        if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
+        e = cudaStreamCreateWithPriority(&sb, cudaStreamNonBlocking, lo);
+        if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
+        for (int i = 0; i < 4; ++i) {
+            cudaEventCreateWithFlags(&leaf[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&row[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&upd[i], cudaEventDisableTiming);
+        }
+        cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
+        e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+        if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
+        dev = d;
+        return 0;
+    }
+};
+thread_local LookAhead g_la;
+
+// Panel width of the look-ahead factorisation of an nb-wide diagonal block (0 = plain recursion).
+// Narrow panels shorten the serial chain but make the trailing updates shallow (K = panel width).
+inline int64_t la_panel(int dtype, int64_t nb) {
+    static int64_t force[2] = {-2, -2};  // DCGP_LA_PW_F64 / DCGP_LA_PW_F32: tuning override (0 disables)
+    if (force[0] == -2) {
+        const char* e;
+        force[1] = (e = getenv("DCGP_LA_PW_F32")) ? atoll(e) : -1;
+        force[0] = (e = getenv("DCGP_LA_PW_F64")) ? atoll(e) : -1;
+    }
+    const int i = dtype == DCGP_F64 ? 0 : 1;
+    int64_t pw;
+    if (force[i] >= 0) pw = force[i];
+    else if (i == 1) pw = nb <= 8192 ? 128 : (nb <= 16384 ? 256 : 512);      // measured on B200 (tools/potrf_sweep.py)
+    else pw = nb <= 4096 ? 128 : (nb <= 8192 ? 512 : 1024);
+    return (pw > 0 && nb > 2 * pw) ? pw : 0;
+}
+
+#define DCGP_CU(x)                                           \
+    do {                                                     \
+        cudaError_t e_ = (x);                                \
+        if (e_ != cudaSuccess) return DCGP_CUDA_ERR(e_);     \
+    } while (0)
+
+template <typename T>
+int chol_la(const Ctx<T>& c, int64_t j0, int64_t nb) {
+    LookAhead& x = g_la;
+    int rc = x.init();
+    if (rc) return rc;
+    const int64_t pw = c.la_pw, q = (nb + pw - 1) / pw, end = j0 + nb;
+    const cudaStream_t sa = x.sh, sb = x.sb;
+    Ctx<T> ca = c, cb = c;
+    ca.la_pw = cb.la_pw = -1;  // panels themselves: plain recursion on their own stream
+    ca.st = sa;
+    cb.st = sb;
+    DCGP_CU(cudaEventRecord(x.fork, c.st));
+    DCGP_CU(cudaStreamWaitEvent(sa, x.fork, 0));
+    DCGP_CU(cudaStreamWaitEvent(sb, x.fork, 0));
+    for (int64_t j = 0; j < q; ++j) {
+        const int64_t bj = j0 + j * pw, wj = (end - bj < pw) ? end - bj : pw;
+        rc = chol_rec(ca, bj, wj);
+        if (rc) return rc;
+        if (j == q - 1) break;
+        const int e = (int)(j & 3), ep = (int)((j + 3) & 3);
+        DCGP_CU(cudaEventRecord(x.leaf[e], sa));
+        const int64_t b1 = bj + pw, w1 = (end - b1 < pw) ? end - b1 : pw, r0 = b1 + w1, nr = end - r0;
+        // stream A: the next block row and its diagonal block (needs the trailing update of panel j-1)
+        if (j > 0) DCGP_CU(cudaStreamWaitEvent(sa, x.upd[ep], 0));
+        rc = rtrsm_rec(ca, b1, w1, bj, pw);
+        if (rc) return rc;
+        DCGP_CU(cudaEventRecord(x.row[e], sa));
+        T* P1 = c.A + b1 * c.lda + bj;
+        const T* P1lo = c.Alo ? c.Alo + b1 * c.lda + bj : nullptr;
+        rc = dcgp_gemm_impl(0, 1, w1, w1, pw, -1.0, P1, c.lda, P1, c.lda, 1.0, c.A + b1 * c.lda + b1, c.lda, c.dtype,
+                            DCGP_GEMM_LOWER | c.xf, sa, P1lo, P1lo, nullptr);
+        if (rc) return rc;
+        if (nr <= 0) continue;
+        // stream B: everything below
+        DCGP_CU(cudaStreamWaitEvent(sb, x.leaf[e], 0));
+        rc = rtrsm_rec(cb, r0, nr, bj, pw);
+        if (rc) return rc;
+        T* P2 = c.A + r0 * c.lda + bj;
+        const T* P2lo = c.Alo ? c.Alo + r0 * c.lda + bj : nullptr;
+        DCGP_CU(cudaStreamWaitEvent(sb, x.row[e], 0));
+        rc = dcgp_gemm_impl(0, 1, nr, w1, pw, -1.0, P2, c.lda, P1, c.lda, 1.0, c.A + r0 * c.lda + b1, c.lda, c.dtype, c.xf,
+                            sb, P2lo, P1lo, nullptr);
+        if (rc) return rc;
+        rc = dcgp_gemm_impl(0, 1, nr, nr, pw, -1.0, P2, c.lda, P2, c.lda, 1.0, c.A + r0 * c.lda + r0, c.lda, c.dtype,
+                            DCGP_GEMM_LOWER | c.xf, sb, P2lo, P2lo, nullptr);
+        if (rc) return rc;
+        DCGP_CU(cudaEventRecord(x.upd[e], sb));
+    }
+    // the chain lane has waited for every bulk update it needs, which is all of them (q >= 3)
+    DCGP_CU(cudaEventRecord(x.join, sa));
+    DCGP_CU(cudaStreamWaitEvent(c.st, x.join, 0));
+    return 0;
 }
 
 size_t inv_ws_bytes(int64_t n, int dtype) {
