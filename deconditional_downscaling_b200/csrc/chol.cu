@@ -20,6 +20,7 @@
 #include "mma.cuh"
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
                    const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype, int flags,
@@ -28,6 +29,10 @@ int dcgp_split_lo_impl(const void* src, void* dst, int64_t rows, int64_t cols, i
 int dcgp_gemm_batched_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A,
                            int64_t lda, int64_t strideA, const void* B, int64_t ldb, int64_t strideB, double beta,
                            void* C, int64_t ldc, int64_t strideC, int batch, int dtype, int flags, cudaStream_t st);
+
+int dcgp_gemm_tc_ex(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
+                    const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int flags, const void* Alo, const void* Blo,
+                    void* Clo, int64_t lower_off, int64_t clo_cols, cudaStream_t st);
 
 namespace {
 
@@ -252,10 +257,10 @@ __device__ void block_trtri(T* S, const T* rinv, int nb) {
 }
 
 template <typename T>
-__device__ void store_inverse(const T* S, int nb, T* inv, int ld) {  // nb x NB block (lower, zero above), pitch ld
+__device__ void store_inverse(const T* S, int nb, T* inv, int64_t ld, int ncols = NB) {  // nb x ncols block (lower, zero above)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = warp; i < nb; i += NTHREADS / 32)
-        for (int c = lane; c < NB; c += 32) inv[(int64_t)i * ld + c] = (c <= i) ? XX(i, c) : T(0);
+        for (int c = lane; c < ncols; c += 32) inv[(int64_t)i * ld + c] = (c <= i) ? XX(i, c) : T(0);
 }
 #undef XX
 
@@ -323,12 +328,107 @@ __global__ void __launch_bounds__(NTHREADS) potrf_diag_kernel(T* __restrict__ A,
 #endif
 }
 
+// Look-ahead step kernel (FP32): the whole serial link between two diagonal blocks in one launch.
+//   R  = A[j+1, j] (a private copy made before the bulk lane solves that panel in place), X = inv(L_jj):
+//   P  = R X^T                                  (block row j+1 of L, kept in shared memory only)
+//   S  = A[j+1, j+1] - P P^T                    (all earlier panels were applied by the bulk lane)
+//   then as potrf_diag_kernel: S = L L^T, L -> A, inv(L) -> workspace.
+// Both products run as register-blocked 3xTF32 tiles (32 x 32 per warp) straight from shared memory.
+__global__ void __launch_bounds__(NTHREADS) potrf_step_kernel(float* __restrict__ A, int64_t lda, int nb,
+                                                              float* __restrict__ inv, int* info, int64_t j0,
+                                                              const float* __restrict__ R, const float* __restrict__ invp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* S = reinterpret_cast<float*>(smem_raw);
+    float* Rb = S + NB * SP;
+    float* Ib = Rb + NB * SP;
+    __shared__ float rinv[NB];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef DCGP_LEAF_TIMING
+    long long tq0 = clock64();
+#endif
+    // R (nb x NB, pitch NB) and X (NB x NB lower, pitch NB): contiguous, 16-byte vectors
+    for (int e = tid; e < NB * NB / 4; e += NTHREADS) {
+        const int i = e >> 5, k = (e & 31) * 4;
+        const float4 r = (i < nb) ? *reinterpret_cast<const float4*>(R + i * NB + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 x = *reinterpret_cast<const float4*>(invp + i * NB + k);
+        Rb[i * SP + k] = r.x; Rb[i * SP + k + 1] = r.y; Rb[i * SP + k + 2] = r.z; Rb[i * SP + k + 3] = r.w;
+        Ib[i * SP + k] = x.x; Ib[i * SP + k + 1] = x.y; Ib[i * SP + k + 2] = x.z; Ib[i * SP + k + 3] = x.w;
+    }
+    load_lower<float>(S, rinv, A, lda, nb, false);
+    __syncthreads();
+#ifdef DCGP_LEAF_TIMING
+    long long tq1 = clock64();
+#endif
+    {
+        // P = R X^T: warp (bm, bn) owns rows 32 bm.., columns 32 bn..; X is lower triangular, so k < 32 bn + 32
+        const int bm = warp >> 2, bn = warp & 3;
+        float acc[2][4][4] = {};
+        warp_block_mma<2, 4>(
+            acc, 32 * bn + 32, [&](int r, int k) { return Rb[(32 * bm + r) * SP + k]; },
+            [&](int k, int c) { return Ib[(32 * bn + c) * SP + k]; });
+        __syncthreads();  // every warp is done reading R
+        const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int row = 32 * bm + 16 * mi + g + ((q >> 1) << 3), col = 32 * bn + 8 * ni + 2 * t + (q & 1);
+                    Rb[row * SP + col] = acc[mi][ni][q];
+                }
+    }
+    __syncthreads();
+#ifdef DCGP_LEAF_TIMING
+    long long tq2 = clock64();
+#endif
+    if (warp < 10) {
+        // S -= P P^T on the 10 lower 32 x 32 blocks
+        int bm = 0, e = warp;
+        while (e > bm) { e -= bm + 1; ++bm; }
+        const int bn = e;
+        float acc[2][4][4] = {};
+        warp_block_mma<2, 4>(
+            acc, NB, [&](int r, int k) { return Rb[(32 * bm + r) * SP + k]; },
+            [&](int k, int c) { return Rb[(32 * bn + c) * SP + k]; });
+        const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int row = 32 * bm + 16 * mi + g + ((q >> 1) << 3), col = 32 * bn + 8 * ni + 2 * t + (q & 1);
+                    if (col <= row && row < nb) S[row * SP + col] -= acc[mi][ni][q];
+                }
+    }
+    __syncthreads();
+#ifdef DCGP_LEAF_TIMING
+    long long tq3 = clock64();
+#endif
+    block_potrf<float>(S, rinv, nb, info, j0);
+#ifdef DCGP_LEAF_TIMING
+    long long tq4 = clock64();
+#endif
+    for (int i = warp; i < nb; i += NTHREADS / 32)
+        for (int k = lane; k <= i; k += 32) A[(int64_t)i * lda + k] = S[i * SP + k];
+    __syncthreads();
+    block_trtri<float>(S, rinv, nb);
+    store_inverse<float>(S, nb, inv, NB);
+#ifdef DCGP_LEAF_TIMING
+    __syncthreads();
+    if (tid == 0 && j0 == 256)
+        printf("step kernel: load %lld  P %lld  syrk %lld  potrf %lld  rest %lld\n", tq1 - tq0, tq2 - tq1, tq3 - tq2, tq4 - tq3,
+               clock64() - tq4);
+#endif
+}
+
 // batched inversion of the diagonal blocks of an existing factor
 template <typename T>
 // `group` 128-blocks form one (group*128)-wide output block with pitch group*128 (group = 1: the packed
 // NB x NB workspace blocks of the factorisation; group = 4: the diagonal of the 512-wide inverse blocks)
 __global__ void __launch_bounds__(NTHREADS) trtri_blocks_kernel(const T* __restrict__ L, int64_t ldl, int64_t n,
-                                                                T* __restrict__ inv, int group) {
+                                                                T* __restrict__ inv, int group, int64_t ldo = 0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* S = reinterpret_cast<T*>(smem_raw);
     const int64_t i0 = (int64_t)blockIdx.x * NB;
@@ -337,8 +437,12 @@ __global__ void __launch_bounds__(NTHREADS) trtri_blocks_kernel(const T* __restr
     load_lower<T>(S, rinv, L + i0 * ldl + i0, ldl, nb, true);
     __syncthreads();
     block_trtri<T>(S, rinv, nb);
+    if (ldo > 0) {  // straight onto the diagonal of an n x n matrix with pitch ldo
+        store_inverse<T>(S, nb, inv + i0 * ldo + i0, ldo, nb);
+        return;
+    }
     const int64_t big = blockIdx.x / group, q = blockIdx.x % group, ld = (int64_t)group * NB;
-    store_inverse<T>(S, nb, inv + big * ld * ld + q * NB * ld + q * NB, (int)ld);
+    store_inverse<T>(S, nb, inv + big * ld * ld + q * NB * ld + q * NB, ld);
 }
 
 template <typename T>
@@ -381,6 +485,7 @@ struct Ctx {
     cudaStream_t st;
     T* Alo;  // FP32 3xTF32 only: x - trunc_tf32(x) of the finished off-diagonal blocks of L (layout of A), or null
     int64_t la_pw = 0;  // look-ahead panel width: 0 = choose by policy, -1 = plain recursion
+    float* rcopy = nullptr;  // FP32: 2 x 128 x 128 scratch of the fused look-ahead path
 };
 
 // B = A[r0 : r0+nr, t0 : t0+nt]  <-  B * L[t0 : t0+nt, t0 : t0+nt]^{-T}
@@ -408,6 +513,9 @@ int rtrsm_rec(const Ctx<T>& c, int64_t r0, int64_t nr, int64_t t0, int64_t nt) {
 }
 
 template <typename T>
+struct Ctx;
+int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy);
+template <typename T>
 int chol_la(const Ctx<T>& c, int64_t j0, int64_t nb);
 inline int64_t la_panel(int dtype, int64_t nb);
 
@@ -424,6 +532,10 @@ int chol_rec(const Ctx<T>& c, int64_t j0, int64_t nb) {
         if (pw && nb > 2 * pw) {
             Ctx<T> cl = c;
             cl.la_pw = pw;
+            if constexpr (sizeof(T) == 4) {
+                if (pw == NB && c.Alo && c.rcopy && (c.lda & 3) == 0 && (reinterpret_cast<uintptr_t>(c.A) & 15) == 0)
+                    return chol_la_fused(cl, j0, nb, c.rcopy);
+            }
             return chol_la(cl, j0, nb);
         }
     }
@@ -478,6 +590,31 @@ struct LookAhead {
 };
 thread_local LookAhead g_la;
 
+#ifdef DCGP_TRACE
+struct Trace {  // debug builds only: device timeline of the two lanes
+    struct Rec { const char* what; int64_t step; cudaEvent_t ev; };
+    std::vector<Rec> recs;
+    cudaEvent_t base;
+    void begin(cudaStream_t st) { recs.clear(); cudaEventCreate(&base); cudaEventRecord(base, st); }
+    void mark(const char* what, int64_t step, cudaStream_t st) {
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); recs.push_back({what, step, e});
+    }
+    void dump() {
+        cudaDeviceSynchronize();
+        for (auto& r : recs) { float ms = 0; cudaEventElapsedTime(&ms, base, r.ev); printf("TRACE %s %lld %.1f\n", r.what, (long long)r.step, ms * 1e3f); cudaEventDestroy(r.ev); }
+        cudaEventDestroy(base);
+    }
+};
+thread_local Trace g_trace;
+#define TRACE_BEGIN(st) g_trace.begin(st)
+#define TRACE_MARK(w, s, st) g_trace.mark(w, s, st)
+#define TRACE_DUMP() g_trace.dump()
+#else
+#define TRACE_BEGIN(st)
+#define TRACE_MARK(w, s, st)
+#define TRACE_DUMP()
+#endif
+
 // Panel width of the look-ahead factorisation of an nb-wide diagonal block (0 = plain recursion).
 // Narrow panels shorten the serial chain but make the trailing updates shallow (K = panel width).
 inline int64_t la_panel(int dtype, int64_t nb) {
@@ -501,6 +638,92 @@ inline int64_t la_panel(int dtype, int64_t nb) {
         if (e_ != cudaSuccess) return DCGP_CUDA_ERR(e_);     \
     } while (0)
 
+// FP32 / 3xTF32 flavour with 128-wide panels: the chain lane is ONE kernel per block (potrf_step_kernel);
+// the bulk lane solves the whole panel in place (block row j+1 included) and applies it to everything
+// right of it in a single tcgen05 launch (lower tiles only, offset diagonal), then hands the chain lane a
+// private copy of the next block row so that the two lanes never touch the same memory.
+int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
+    LookAhead& x = g_la;
+    int rc = x.init();
+    if (rc) return rc;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(potrf_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(3 * NB * SP * sizeof(float)));
+        if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
+        attr = true;
+    }
+    const int64_t q = (nb + NB - 1) / NB, end = j0 + nb;
+    const cudaStream_t sa = x.sh, sb = x.sb;
+    auto copy_row = [&](int64_t brow, int64_t bcol, int64_t rows, int slot, cudaStream_t st) {
+        return cudaMemcpy2DAsync(rcopy + (size_t)slot * NB * NB, NB * sizeof(float), c.A + brow * c.lda + bcol,
+                                 (size_t)c.lda * sizeof(float), NB * sizeof(float), (size_t)rows, cudaMemcpyDeviceToDevice, st);
+    };
+    {
+        const int64_t b1 = j0 + NB, w1 = (end - b1 < NB) ? end - b1 : NB;
+        DCGP_CU(copy_row(b1, j0, w1, 0, c.st));
+    }
+    DCGP_CU(cudaEventRecord(x.fork, c.st));
+    DCGP_CU(cudaStreamWaitEvent(sa, x.fork, 0));
+    DCGP_CU(cudaStreamWaitEvent(sb, x.fork, 0));
+    TRACE_BEGIN(c.st);
+    potrf_diag_kernel<float><<<1, NTHREADS, leaf_smem<float>(), sa>>>(c.A + j0 * c.lda + j0, c.lda, NB, c.ws + (j0 / NB) * NB * NB,
+                                                                       c.info, j0);
+    DCGP_CHECK_LAUNCH();
+    for (int64_t j = 0; j + 1 < q; ++j) {
+        const int64_t bj = j0 + j * NB;
+        const int64_t b1 = bj + NB, w1 = (end - b1 < NB) ? end - b1 : NB, r0 = b1 + w1, nr = end - r0;
+        const int e = (int)(j & 3), ep = (int)((j + 3) & 3);
+        float* invj = c.ws + (bj / NB) * NB * NB;
+        TRACE_MARK("A.leaf", j, sa);
+        DCGP_CU(cudaEventRecord(x.leaf[e], sa));
+        // ---- bulk lane: panel j
+        DCGP_CU(cudaStreamWaitEvent(sb, x.leaf[e], 0));
+        TRACE_MARK("B.start", j, sb);
+        float* P = c.A + b1 * c.lda + bj;          // rows b1 .. end of panel j
+        float* Plo = c.Alo + b1 * c.lda + bj;
+        rc = dcgp_gemm_impl(0, 1, end - b1, NB, NB, 1.0, P, c.lda, invj, NB, 0.0, P, c.lda, c.dtype, DCGP_GEMM_INPLACE | c.xf, sb,
+                            nullptr, nullptr, Plo);
+        if (rc) return rc;
+        TRACE_MARK("B.trsm", j, sb);
+        if (nr > 0) {
+            float* P2 = c.A + r0 * c.lda + bj;
+            const float* P2lo = c.Alo + r0 * c.lda + bj;
+            rc = 1;
+            if (nr >= NB)
+                rc = dcgp_gemm_tc_ex(0, 1, nr, w1 + nr, NB, -1.0, P2, c.lda, P, c.lda, 1.0, c.A + r0 * c.lda + b1, c.lda,
+                                     DCGP_GEMM_LOWER, P2lo, Plo, nullptr, w1, 0, sb);
+            if (rc < 0) return rc;
+            if (rc == 1) {  // shape / alignment not taken by the tcgen05 kernel
+                rc = dcgp_gemm_impl(0, 1, nr, w1, NB, -1.0, P2, c.lda, P, c.lda, 1.0, c.A + r0 * c.lda + b1, c.lda, c.dtype, c.xf,
+                                    sb, P2lo, Plo, nullptr);
+                if (rc) return rc;
+                rc = dcgp_gemm_impl(0, 1, nr, nr, NB, -1.0, P2, c.lda, P2, c.lda, 1.0, c.A + r0 * c.lda + r0, c.lda, c.dtype,
+                                    DCGP_GEMM_LOWER | c.xf, sb, P2lo, P2lo, nullptr);
+                if (rc) return rc;
+            }
+            TRACE_MARK("B.trail", j, sb);
+            const int64_t w2 = (end - r0 < NB) ? end - r0 : NB;
+            DCGP_CU(copy_row(r0, b1, w2, (int)((j + 1) & 1), sb));
+            DCGP_CU(cudaEventRecord(x.upd[e], sb));
+        }
+        // ---- chain lane: block j+1 (its inputs were completed by the bulk update of panel j-1)
+        if (j > 0) DCGP_CU(cudaStreamWaitEvent(sa, x.upd[ep], 0));
+        TRACE_MARK("A.waited", j, sa);
+        potrf_step_kernel<<<1, NTHREADS, 3 * NB * SP * sizeof(float), sa>>>(c.A + b1 * c.lda + b1, c.lda, (int)w1,
+                                                                           c.ws + (b1 / NB) * NB * NB, c.info, b1,
+                                                                           rcopy + (size_t)(j & 1) * NB * NB, invj);
+        DCGP_CHECK_LAUNCH();
+    }
+    // join both lanes: the last panel solve on the bulk lane has no later consumer on the chain lane
+    DCGP_CU(cudaEventRecord(x.join, sa));
+    DCGP_CU(cudaStreamWaitEvent(c.st, x.join, 0));
+    DCGP_CU(cudaEventRecord(x.fork, sb));
+    DCGP_CU(cudaStreamWaitEvent(c.st, x.fork, 0));
+    TRACE_DUMP();
+    return 0;
+}
+
 template <typename T>
 int chol_la(const Ctx<T>& c, int64_t j0, int64_t nb) {
     LookAhead& x = g_la;
@@ -515,43 +738,53 @@ int chol_la(const Ctx<T>& c, int64_t j0, int64_t nb) {
     DCGP_CU(cudaEventRecord(x.fork, c.st));
     DCGP_CU(cudaStreamWaitEvent(sa, x.fork, 0));
     DCGP_CU(cudaStreamWaitEvent(sb, x.fork, 0));
+    TRACE_BEGIN(c.st);
     for (int64_t j = 0; j < q; ++j) {
         const int64_t bj = j0 + j * pw, wj = (end - bj < pw) ? end - bj : pw;
         rc = chol_rec(ca, bj, wj);
         if (rc) return rc;
+        TRACE_MARK("A.leaf", j, sa);
         if (j == q - 1) break;
         const int e = (int)(j & 3), ep = (int)((j + 3) & 3);
         DCGP_CU(cudaEventRecord(x.leaf[e], sa));
         const int64_t b1 = bj + pw, w1 = (end - b1 < pw) ? end - b1 : pw, r0 = b1 + w1, nr = end - r0;
         // stream A: the next block row and its diagonal block (needs the trailing update of panel j-1)
         if (j > 0) DCGP_CU(cudaStreamWaitEvent(sa, x.upd[ep], 0));
+        TRACE_MARK("A.waited", j, sa);
         rc = rtrsm_rec(ca, b1, w1, bj, pw);
         if (rc) return rc;
+        TRACE_MARK("A.row", j, sa);
         DCGP_CU(cudaEventRecord(x.row[e], sa));
         T* P1 = c.A + b1 * c.lda + bj;
         const T* P1lo = c.Alo ? c.Alo + b1 * c.lda + bj : nullptr;
         rc = dcgp_gemm_impl(0, 1, w1, w1, pw, -1.0, P1, c.lda, P1, c.lda, 1.0, c.A + b1 * c.lda + b1, c.lda, c.dtype,
                             DCGP_GEMM_LOWER | c.xf, sa, P1lo, P1lo, nullptr);
         if (rc) return rc;
+        TRACE_MARK("A.syrk", j, sa);
         if (nr <= 0) continue;
         // stream B: everything below
         DCGP_CU(cudaStreamWaitEvent(sb, x.leaf[e], 0));
+        TRACE_MARK("B.start", j, sb);
         rc = rtrsm_rec(cb, r0, nr, bj, pw);
         if (rc) return rc;
+        TRACE_MARK("B.trsm", j, sb);
         T* P2 = c.A + r0 * c.lda + bj;
         const T* P2lo = c.Alo ? c.Alo + r0 * c.lda + bj : nullptr;
         DCGP_CU(cudaStreamWaitEvent(sb, x.row[e], 0));
         rc = dcgp_gemm_impl(0, 1, nr, w1, pw, -1.0, P2, c.lda, P1, c.lda, 1.0, c.A + r0 * c.lda + b1, c.lda, c.dtype, c.xf,
                             sb, P2lo, P1lo, nullptr);
         if (rc) return rc;
+        TRACE_MARK("B.col", j, sb);
         rc = dcgp_gemm_impl(0, 1, nr, nr, pw, -1.0, P2, c.lda, P2, c.lda, 1.0, c.A + r0 * c.lda + r0, c.lda, c.dtype,
                             DCGP_GEMM_LOWER | c.xf, sb, P2lo, P2lo, nullptr);
         if (rc) return rc;
+        TRACE_MARK("B.trail", j, sb);
         DCGP_CU(cudaEventRecord(x.upd[e], sb));
     }
     // the chain lane has waited for every bulk update it needs, which is all of them (q >= 3)
     DCGP_CU(cudaEventRecord(x.join, sa));
     DCGP_CU(cudaStreamWaitEvent(c.st, x.join, 0));
+    TRACE_DUMP();
     return 0;
 }
 
@@ -565,9 +798,11 @@ int potrf_impl(T* A, int64_t n, int64_t lda, int* info, T* ws, size_t ws_bytes, 
     int rc = set_smem_attr<T>((const void*)potrf_diag_kernel<T>);
     if (rc) return rc;
     T* lo = nullptr;
-    if (sizeof(T) == 4 && xf && n > 2 * NB && ws_bytes >= inv_ws_bytes(n, dtype) + (size_t)n * lda * 4)
-        lo = ws + inv_ws_bytes(n, dtype) / sizeof(T);
+    const size_t rcopy_bytes = 2 * NB * NB * 4;
+    if (sizeof(T) == 4 && xf && n > 2 * NB && ws_bytes >= inv_ws_bytes(n, dtype) + rcopy_bytes + (size_t)n * lda * 4)
+        lo = ws + (inv_ws_bytes(n, dtype) + rcopy_bytes) / sizeof(T);
     Ctx<T> c{A, lda, ws, info, dtype, xf, st, lo};
+    if (lo) c.rcopy = reinterpret_cast<float*>(ws) + inv_ws_bytes(n, dtype) / 4;
     return chol_rec(c, 0, n);
 }
 
@@ -657,6 +892,7 @@ struct L5Ctx {
     cudaStream_t st;
     const T* Llo;
     T* Xlo;
+    int64_t n;
 };
 
 template <typename T>
@@ -735,6 +971,60 @@ int ltrsm512_rec(const L5Ctx<T>& c, int trans, int64_t i0, int64_t nn) {
     return ltrsm512_rec(c, trans, i0, n1);
 }
 
+// Right-looking sweep over the 512-row blocks on the two look-ahead lanes (see chol_la):
+//   chain: X_i = op(inv_i) B_i ; the neighbouring block B_{i+-1} -= op(L_{.,.}) X_i
+//   bulk : all remaining blocks -= op(L) X_i        (wide, fills the machine, overlaps the chain)
+// The recursion above serialises GEMMs whose 512..4096-row outputs cover a fraction of the SMs.
+template <typename T>
+int ltrsm512_la(const L5Ctx<T>& c, int trans) {
+    LookAhead& x = g_la;
+    int rc = x.init();
+    if (rc) return rc;
+    const int64_t n = c.n, q = (n + NBI - 1) / NBI;
+    const cudaStream_t sa = x.sh, sb = x.sb;
+    DCGP_CU(cudaEventRecord(x.fork, c.st));
+    DCGP_CU(cudaStreamWaitEvent(sa, x.fork, 0));
+    DCGP_CU(cudaStreamWaitEvent(sb, x.fork, 0));
+    const int near_flags = c.xf | DCGP_GEMM_NO_TCGEN05;
+    for (int64_t s = 0; s < q; ++s) {
+        const int64_t i = trans ? q - 1 - s : s;                    // block solved at this step
+        const int64_t r = i * NBI, w = (n - r < NBI) ? n - r : NBI;
+        const int e = (int)(s & 3), ep = (int)((s + 3) & 3);
+        T* Xi = c.X + r * c.ldb;
+        T* Xilo = c.Xlo ? c.Xlo + r * c.ldb : nullptr;
+        rc = dcgp_gemm_impl(trans, 0, w, c.m, w, 1.0, c.inv + i * NBI * NBI, NBI, c.B + r * c.ldb, c.ldb, 0.0, Xi, c.ldb,
+                            c.dtype, near_flags, sa, nullptr, nullptr, Xilo);
+        if (rc) return rc;
+        if (s == q - 1) break;
+        DCGP_CU(cudaEventRecord(x.leaf[e], sa));
+        if (s > 0) DCGP_CU(cudaStreamWaitEvent(sa, x.upd[ep], 0));
+        if (!trans) {
+            const int64_t r1 = r + NBI, w1 = (n - r1 < NBI) ? n - r1 : NBI, r2 = r1 + w1, nr = n - r2;
+            rc = dcgp_gemm_impl(0, 0, w1, c.m, w, -1.0, c.L + r1 * c.ldl + r, c.ldl, Xi, c.ldb, 1.0, c.B + r1 * c.ldb, c.ldb,
+                                c.dtype, near_flags, sa, nullptr, nullptr, nullptr);
+            if (rc) return rc;
+            if (nr <= 0) continue;
+            DCGP_CU(cudaStreamWaitEvent(sb, x.leaf[e], 0));
+            rc = dcgp_gemm_impl(0, 0, nr, c.m, w, -1.0, c.L + r2 * c.ldl + r, c.ldl, Xi, c.ldb, 1.0, c.B + r2 * c.ldb, c.ldb,
+                                c.dtype, c.xf, sb, c.Llo ? c.Llo + r2 * c.ldl + r : nullptr, Xilo, nullptr);
+        } else {
+            const int64_t r1 = r - NBI, nr = r1;  // neighbour block i-1 (always full), rows [0, r1) remain
+            rc = dcgp_gemm_impl(1, 0, NBI, c.m, w, -1.0, c.L + r * c.ldl + r1, c.ldl, Xi, c.ldb, 1.0, c.B + r1 * c.ldb, c.ldb,
+                                c.dtype, near_flags, sa, nullptr, nullptr, nullptr);
+            if (rc) return rc;
+            if (nr <= 0) continue;
+            DCGP_CU(cudaStreamWaitEvent(sb, x.leaf[e], 0));
+            rc = dcgp_gemm_impl(1, 0, nr, c.m, w, -1.0, c.L + r * c.ldl, c.ldl, Xi, c.ldb, 1.0, c.B, c.ldb, c.dtype, c.xf, sb,
+                                c.Llo ? c.Llo + r * c.ldl : nullptr, Xilo, nullptr);
+        }
+        if (rc) return rc;
+        DCGP_CU(cudaEventRecord(x.upd[e], sb));
+    }
+    DCGP_CU(cudaEventRecord(x.join, sa));
+    DCGP_CU(cudaStreamWaitEvent(c.st, x.join, 0));
+    return 0;
+}
+
 size_t trsm512_ws_bytes(int64_t n, int64_t ldl, int64_t m_ld, int dtype) {
     const size_t es = dtype == DCGP_F64 ? 8 : 4;
     const size_t nbig = (size_t)(n + NBI - 1) / NBI;
@@ -766,13 +1056,50 @@ int trsm_impl(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t m, in
     }
     int rc = build_inv512<T>(L, n, ldl, inv, tmp, dtype, xf, st);
     if (rc) return rc;
-    L5Ctx<T> c{L, ldl, B, m, ldb, inv, X, dtype, xf, st, llo, xlo};
+    L5Ctx<T> c{L, ldl, B, m, ldb, inv, X, dtype, xf, st, llo, xlo, n};
+    static const int use_la = getenv("DCGP_TRSM_LA") ? atoi(getenv("DCGP_TRSM_LA")) : 1;
     for (int sweep = (trans == 1 ? 1 : 0); sweep <= (trans == 0 ? 0 : 1); ++sweep) {
-        rc = ltrsm512_rec(c, sweep, 0, n);
+        rc = (use_la && nbig >= 4) ? ltrsm512_la(c, sweep) : ltrsm512_rec(c, sweep, 0, n);
         if (rc) return rc;
         cudaError_t e = cudaMemcpy2DAsync(B, (size_t)ldb * sizeof(T), X, (size_t)ldb * sizeof(T), (size_t)m * sizeof(T),
                                           (size_t)n, cudaMemcpyDeviceToDevice, st);
         if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
+    }
+    return 0;
+}
+
+// W = L^{-1} (lower, zero above) by blocked recursive doubling: 128-wide diagonal inverses, then for
+// b = 128, 256, ... every 2b-wide diagonal block is completed from its halves, X21 = -X22 (L21 X11),
+// batched over the blocks of a level.  2 log2(n / 128) GEMM launches in total.
+template <typename T>
+int trtri_impl(const T* L, int64_t n, int64_t ldl, T* W, int64_t ldw, T* tmp, int dtype, int xf, cudaStream_t st) {
+    cudaError_t e = cudaMemset2DAsync(W, (size_t)ldw * sizeof(T), 0, (size_t)n * sizeof(T), (size_t)n, st);
+    if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
+    int rc = set_smem_attr<T>((const void*)trtri_blocks_kernel<T>);
+    if (rc) return rc;
+    trtri_blocks_kernel<T><<<(unsigned)((n + NB - 1) / NB), NTHREADS, leaf_smem<T>(), st>>>(L, ldl, n, W, 1, ldw);
+    DCGP_CHECK_LAUNCH();
+    for (int64_t b = NB; b < n; b *= 2) {
+        const int64_t nfull = n / (2 * b);                 // pairs with both halves complete
+        const int64_t sL = 2 * b * (ldl + 1), sW = 2 * b * (ldw + 1);
+        if (nfull > 0) {
+            rc = dcgp_gemm_batched_impl(0, 0, b, b, b, 1.0, L + b * ldl, ldl, sL, W, ldw, sW, 0.0, tmp + b * ldw, ldw, sW,
+                                        (int)nfull, dtype, xf, st);
+            if (rc) return rc;
+            rc = dcgp_gemm_batched_impl(0, 0, b, b, b, -1.0, W + b * (ldw + 1), ldw, sW, tmp + b * ldw, ldw, sW, 0.0,
+                                        W + b * ldw, ldw, sW, (int)nfull, dtype, xf, st);
+            if (rc) return rc;
+        }
+        const int64_t o1 = nfull * 2 * b, o2 = o1 + b;     // ragged last pair
+        if (o2 < n) {
+            const int64_t r2 = n - o2;
+            rc = dcgp_gemm_batched_impl(0, 0, r2, b, b, 1.0, L + o2 * ldl + o1, ldl, 0, W + o1 * (ldw + 1), ldw, 0, 0.0,
+                                        tmp + o2 * ldw + o1, ldw, 0, 1, dtype, xf, st);
+            if (rc) return rc;
+            rc = dcgp_gemm_batched_impl(0, 0, r2, b, r2, -1.0, W + o2 * (ldw + 1), ldw, 0, tmp + o2 * ldw + o1, ldw, 0, 0.0,
+                                        W + o2 * ldw + o1, ldw, 0, 1, dtype, xf, st);
+            if (rc) return rc;
+        }
     }
     return 0;
 }
@@ -783,7 +1110,7 @@ int trsm_impl(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t m, in
 // leading dimensions; with padded ones the drivers fall back to the mma.sync 3xTF32 kernel).
 extern "C" size_t dcgp_potrf_workspace(int64_t n, int dtype) {
     if (n <= 0) return 0;
-    return inv_ws_bytes(n, dtype) + (dtype == DCGP_F32 ? (size_t)n * n * 4 : 0);
+    return inv_ws_bytes(n, dtype) + (dtype == DCGP_F32 ? (size_t)n * n * 4 + 2 * NB * NB * 4 : 0);
 }
 
 extern "C" int dcgp_potrf(void* A, int64_t n, int64_t lda, int* info, void* workspace, size_t workspace_bytes,
@@ -843,4 +1170,25 @@ extern "C" int dcgp_logdet_chol(const void* L, int64_t n, int64_t ldl, void* out
     else return -5;
     DCGP_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" size_t dcgp_trtri_workspace(int64_t n, int dtype) {
+    if (n <= 0) return 0;
+    return (size_t)n * n * (dtype == DCGP_F64 ? 8 : 4);
+}
+
+extern "C" int dcgp_trtri(const void* L, int64_t n, int64_t ldl, void* W, int64_t ldw, void* workspace,
+                          size_t workspace_bytes, int dtype, int flags, void* stream) {
+    if (n < 0) return -2;
+    if (n == 0) return 0;
+    if (!L || !W) return -1;
+    if (ldl < n || ldw < n) return -3;
+    if (dtype != DCGP_F64 && dtype != DCGP_F32) return -8;
+    if (ldw != n) return -5;  // the scratch matrix shares W's packed layout
+    if (!workspace || workspace_bytes < dcgp_trtri_workspace(n, dtype)) return -6;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int xf = flags & DCGP_GEMM_TF32X3;
+    if (dtype == DCGP_F64)
+        return trtri_impl<double>((const double*)L, n, ldl, (double*)W, ldw, (double*)workspace, dtype, xf, st);
+    return trtri_impl<float>((const float*)L, n, ldl, (float*)W, ldw, (float*)workspace, dtype, xf, st);
 }

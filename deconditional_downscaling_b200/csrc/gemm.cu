@@ -338,7 +338,7 @@ int launch_gemm(GemmParams p, cudaStream_t st) {
 
 int dcgp_gemm_tc_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
                       const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int flags, const void* Alo,
-                      const void* Blo, cudaStream_t st);
+                      const void* Blo, void* Clo, cudaStream_t st);
 
 // internal entry used by the Cholesky / TRSM drivers
 // Alo / Blo: optional x - trunc_tf32(x) companions of A / B (same layout) that let a 3xTF32 request run on
@@ -382,11 +382,11 @@ int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, doub
         // 3xTF32 when the caller supplies the lo companions; small or split-K-shaped problems stay on
         // the mma.sync kernel below
         const bool x3 = (flags & DCGP_GEMM_TF32X3) != 0;
-        const int64_t tc_tiles = ((m + 127) / 128) * ((n + 255) / 256);
-        if (!(flags & (DCGP_GEMM_NO_TCGEN05 | DCGP_GEMM_INPLACE)) && m >= 128 && n >= 160 && k >= 64 && (!x3 || (Alo && Blo)) &&
-            tc_tiles >= (x3 ? 4 : 24)) {
+        const int64_t tc_tiles = ((m + 127) / 128) * ((n + 127) / 128);  // narrow (128 x 128) tiles
+        if (!(flags & (DCGP_GEMM_NO_TCGEN05 | DCGP_GEMM_INPLACE)) && m >= 128 && n >= 128 && k >= 64 && (!x3 || (Alo && Blo)) &&
+            tc_tiles >= (x3 ? 4 : 32)) {
             const int rc = dcgp_gemm_tc_impl(transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags,
-                                             x3 ? Alo : nullptr, x3 ? Blo : nullptr, st);
+                                             x3 ? Alo : nullptr, x3 ? Blo : nullptr, Clo, st);
             if (rc <= 0) return rc;
         }
         if (x3) return launch_gemm<float, true>(p, st);

@@ -1,47 +1,60 @@
 // Blackwell-native TF32 contraction: C = alpha * op(A) op(B) + beta * C with FP32 storage.
 //
-//   * operands move global -> shared with TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) through a
-//     4-stage mbarrier ring; one elected lane of warp 0 is the producer;
-//   * one elected lane of warp 1 issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = 256,
-//     K = 8 per instruction, 4 per 128-byte k-tile) and releases stages with tcgen05.commit;
-//   * the 128 x 256 FP32 accumulator lives in TMEM (256 columns); warps 2..5 drain it with
-//     tcgen05.ld (32 lanes x 32 columns per instruction), apply alpha/beta and store rows of C.
+// Persistent, warp-specialised CTAs (one per SM), each walking a strided list of 128 x TN output tiles:
+//   * warp 0 (one elected lane): TMA producer - operands move global -> shared with
+//     cp.async.bulk.tensor.2d (128-byte swizzle) through a 4-stage mbarrier ring that runs on across tiles;
+//   * warp 1 (one elected lane): issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = TN, K = 8 per
+//     instruction, 4 per 128-byte k-tile), releases stages with tcgen05.commit;
+//   * the FP32 accumulators live in TMEM, double-buffered (2 x TN columns), so the MMAs of tile i+1 run
+//     while warps 2..9 drain tile i: tcgen05.ld (32 lanes x 32 columns), a per-warp shared-memory
+//     transpose so that global traffic is 128-byte-line coalesced, alpha/beta, optional TF32 remainder
+//     output for the 3xTF32 consumers of C.
+// Tiles are ordered in groups of 16 tile-rows (column-major inside a group) so that the ~148 tiles in
+// flight share operand panels in L2.
 //
 // Both operand majors are supported through the instruction descriptor (a_major / b_major) and
 // the matching canonical shared-memory layouts:
 //   K-major  (row-major R x K in global): one TMA box {32 k, R rows}; rows are 128-byte lines,
 //            8-row swizzle atoms every 1024 B (SBO); a k-step advances the start address by 32 B.
 //   MN-major (row-major K x R in global): R/32 TMA boxes {32 r, 32 k}; each box is a 4 KB chunk of
-//            32 k-rows x 128 B; LBO = 4096 B between chunks, SBO = 1024 B between 8-k groups; a
+//            32 k-rows x 128 B; LBO = 4096 B between chunks, SBO = 512 B between 4-k groups; a
 //            k-step advances the start address by 1024 B.
 // TMA zero-fills out-of-bounds elements, so ragged M / N / K need no special casing in the main
 // loop; the epilogue guards its stores.
 //
 // Shapes this kernel does not take (tiny problems, split-K candidates, unaligned leading
-// dimensions, 3xTF32) stay on the mma.sync kernel in gemm.cu.
+// dimensions, 3xTF32 without remainder matrices) stay on the mma.sync kernel in gemm.cu.
 #include "common.cuh"
 #include <cuda.h>
 #include <cstdlib>
 
 namespace {
 
-constexpr int TM = 128, TN = 256, TK = 32;  // CTA tile; TK floats = one 128-byte swizzle line
+constexpr int TM = 128, TK = 32;  // CTA tile rows; TK floats = one 128-byte swizzle line
 constexpr int STAGES = 4;
 constexpr int A_BYTES = TM * TK * 4;  // 16 KB
-constexpr int B_BYTES = TN * TK * 4;  // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int NTHREADS_TC = 192;  // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-5 epilogue
-constexpr int TMEM_COLS = 256;
-constexpr size_t SMEM_TC = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_WARPS = 8;
+constexpr int NTHREADS_TC = 64 + 32 * EPI_WARPS;  // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-9 epilogue
+constexpr int STG_PITCH = 33;                     // epilogue transpose buffers: 32 x 33 floats per warp
+constexpr int STG_BYTES = 32 * STG_PITCH * 4;
+constexpr int GROUP_M = 16;
+template <int TN> constexpr int stage_bytes() { return A_BYTES + TN * TK * 4; }
+template <int TN> constexpr size_t smem_tc() {
+    return (size_t)STAGES * stage_bytes<TN>() + (size_t)EPI_WARPS * STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+}
 
 struct TcParams {
     int64_t m, n, k;
     float* C;
+    float* Clo;  // optional: C - trunc_tf32(C)
     int64_t ldc;
     float alpha, beta;
     int lower;
     int a_mn, b_mn;  // operand is MN-major (stored K x R)
     int x3;          // error-compensated: 3 virtual k-tiles (A_lo B, A B_lo, A B) per real k-tile
+    int tiles_m, tiles_n;
+    int64_t lower_off;  // lower: keep tiles with col0 <= row0 + TM - 1 + lower_off
+    int64_t clo_cols;   // Clo is written for columns < clo_cols only (0 = all)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -100,31 +113,48 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
     return d;
 }
 
+// tile index -> (tile row, tile column), grouped for L2 reuse
+__device__ __forceinline__ void tile_coord(const TcParams& p, int t, int& tm, int& tn) {
+    const int per_group = GROUP_M * p.tiles_n;
+    const int g = t / per_group, first = g * GROUP_M;
+    const int gsz = min(GROUP_M, p.tiles_m - first);
+    const int r = t - g * per_group;
+    tm = first + r % gsz;
+    tn = r / gsz;
+}
+
+template <int TN>
 __global__ void __launch_bounds__(NTHREADS_TC, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapBlo,
                const __grid_constant__ TcParams p) {
+    constexpr int STAGE_BYTES = stage_bytes<TN>();
+    constexpr int TMEM_COLS = 2 * TN;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)STAGES * STAGE_BYTES);
+    float* stg_all = reinterpret_cast<float*>(tiles + (size_t)STAGES * STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)STAGES * STAGE_BYTES + (size_t)EPI_WARPS * STG_BYTES);
     uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_full = empty + STAGES;   // [2]
+    uint64_t* tmem_empty = tmem_full + 2;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t m0 = (int64_t)blockIdx.y * TM, n0 = (int64_t)blockIdx.x * TN;
-    if (p.lower && n0 > m0 + TM - 1) return;
     const int nkt = (int)((p.k + TK - 1) / TK);
     // 3xTF32: the tensor core reads FP32 operands truncated to TF32 (x_hi); with x_lo = x - x_hi given as
     // separate matrices, A B ~= A_lo B_hi + A_hi B_lo + A_hi B_hi, accumulated in the same TMEM tile.
-    const int nv = p.x3 ? 3 * nkt : nkt;  // virtual k-tiles
+    const int nv = p.x3 ? 3 * nkt : nkt;  // virtual k-tiles per output tile
+    const int ntiles = p.tiles_m * p.tiles_n;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(tmem_full, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], EPI_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -140,27 +170,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
-            for (int v = 0; v < nv; ++v) {
-                const int s = v % STAGES;
-                const uint32_t ph = (uint32_t)(v / STAGES) & 1u;
-                mbar_wait(&empty[s], ph ^ 1u);
-                unsigned char* sa = tiles + (size_t)s * STAGE_BYTES;
-                unsigned char* sb = sa + A_BYTES;
-                mbar_expect_tx(&full[s], STAGE_BYTES);
-                const int kt = p.x3 ? v / 3 : v;
-                const int sel = p.x3 ? v % 3 : 2;  // 0: A_lo B, 1: A B_lo, 2: A B
-                const CUtensorMap* ma = (sel == 0) ? &mapAlo : &mapA;
-                const CUtensorMap* mb = (sel == 1) ? &mapBlo : &mapB;
-                const int k0 = kt * TK;
-                if (!p.a_mn) {
-                    tma_load_2d(sa, ma, &full[s], k0, (int)m0);
-                } else {
-                    for (int c = 0; c < TM / 32; ++c) tma_load_2d(sa + c * 4096, ma, &full[s], (int)m0 + 32 * c, k0);
-                }
-                if (!p.b_mn) {
-                    tma_load_2d(sb, mb, &full[s], k0, (int)n0);
-                } else {
-                    for (int c = 0; c < TN / 32; ++c) tma_load_2d(sb + c * 4096, mb, &full[s], (int)n0 + 32 * c, k0);
+            uint32_t it = 0;  // virtual k-tiles issued so far (ring position carries across tiles)
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                int tm, tn;
+                tile_coord(p, t, tm, tn);
+                const int m0 = tm * TM, n0 = tn * TN;
+                if (p.lower && n0 > m0 + TM - 1 + p.lower_off) continue;
+                for (int v = 0; v < nv; ++v, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    unsigned char* sa = tiles + (size_t)s * STAGE_BYTES;
+                    unsigned char* sb = sa + A_BYTES;
+                    mbar_expect_tx(&full[s], STAGE_BYTES);
+                    const int kt = p.x3 ? v / 3 : v;
+                    const int sel = p.x3 ? v % 3 : 2;  // 0: A_lo B, 1: A B_lo, 2: A B
+                    const CUtensorMap* ma = (sel == 0) ? &mapAlo : &mapA;
+                    const CUtensorMap* mb = (sel == 1) ? &mapBlo : &mapB;
+                    const int k0 = kt * TK;
+                    if (!p.a_mn) {
+                        tma_load_2d(sa, ma, &full[s], k0, m0);
+                    } else {
+                        for (int c = 0; c < TM / 32; ++c) tma_load_2d(sa + c * 4096, ma, &full[s], m0 + 32 * c, k0);
+                    }
+                    if (!p.b_mn) {
+                        tma_load_2d(sb, mb, &full[s], k0, n0);
+                    } else {
+                        for (int c = 0; c < TN / 32; ++c) tma_load_2d(sb + c * 4096, mb, &full[s], n0 + 32 * c, k0);
+                    }
                 }
             }
         }
@@ -170,40 +207,72 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // instruction descriptor: D = F32, A = B = TF32, majors, N >> 3, M >> 4
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                                    ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-            for (int kt = 0; kt < nv; ++kt) {
-                const int s = kt % STAGES;
-                const uint32_t ph = (uint32_t)(kt / STAGES) & 1u;
-                mbar_wait(&full[s], ph);
+            uint32_t it = 0, lt = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                int tm, tn;
+                tile_coord(p, t, tm, tn);
+                if (p.lower && tn * TN > tm * TM + TM - 1 + p.lower_off) continue;
+                const uint32_t buf = lt & 1u;
+                mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem_u32(tiles + (size_t)s * STAGE_BYTES);
-                const uint32_t sb = sa + A_BYTES;
+                const uint32_t tacc = tmem_base + buf * TN;
+                for (int v = 0; v < nv; ++v, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(&full[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+                    const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-                for (int kk = 0; kk < TK / 8; ++kk) {
-                    // MN-major 32-bit operands use the 32-byte-atom flavour of the 128-byte swizzle:
-                    // atoms of 4 k-rows x 128 B (SBO = 512 B), 32-float chunks 4096 B apart (LBO)
-                    const uint32_t lbo = 4096, sbo = 512, kadv = 1024;
-                    const uint64_t ad = p.a_mn ? make_desc(sa + kk * kadv, lbo, sbo, 1) : make_desc(sa + kk * 32, 16, 1024, 2);
-                    const uint64_t bd = p.b_mn ? make_desc(sb + kk * kadv, lbo, sbo, 1) : make_desc(sb + kk * 32, 16, 1024, 2);
-                    umma_tf32(tmem_base, ad, bd, idesc, (kt > 0 || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < TK / 8; ++kk) {
+                        // MN-major 32-bit operands use the 32-byte-atom flavour of the 128-byte swizzle:
+                        // atoms of 4 k-rows x 128 B (SBO = 512 B), 32-float chunks 4096 B apart (LBO)
+                        const uint32_t lbo = 4096, sbo = 512, kadv = 1024;
+                        const uint64_t ad = p.a_mn ? make_desc(sa + kk * kadv, lbo, sbo, 1) : make_desc(sa + kk * 32, 16, 1024, 2);
+                        const uint64_t bd = p.b_mn ? make_desc(sb + kk * kadv, lbo, sbo, 1) : make_desc(sb + kk * 32, 16, 1024, 2);
+                        umma_tf32(tacc, ad, bd, idesc, (v > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);  // frees the stage once the MMAs above have read it
                 }
-                umma_commit(&empty[s]);  // frees the stage once the MMAs above have read it
+                umma_commit(&tmem_full[buf]);  // accumulator complete
+                ++lt;
             }
-            umma_commit(tmem_full);  // accumulator complete
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
-        const int q = warp & 3;
-        const int64_t row = m0 + q * 32 + lane;
-        if (nkt > 0) {
-            mbar_wait(tmem_full, 0);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+        // ===== epilogue: warps 2..9; TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 =====
+        const int q = warp & 3, h = (warp - 2) >> 2;
+        float* stg = stg_all + (size_t)(warp - 2) * 32 * STG_PITCH;
+        const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                         (!p.Clo || (reinterpret_cast<uintptr_t>(p.Clo) & 15) == 0);
+        const int rsub = lane >> 3, c4 = (lane & 7) * 4;  // coalesced phase: 4 rows x 128 B per instruction
+        uint32_t lt = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            int tm, tn;
+            tile_coord(p, t, tm, tn);
+            const int64_t m0 = (int64_t)tm * TM, n0 = (int64_t)tn * TN;
+            if (p.lower && n0 > m0 + TM - 1 + p.lower_off) continue;
+            const uint32_t buf = lt & 1u;
+            const int64_t rbase = m0 + q * 32;
 #pragma unroll 1
-        for (int c0 = 0; c0 < TN; c0 += 32) {
-            uint32_t r[32];
-            if (nkt > 0) {
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            for (int ch = 0; ch < TN / 64; ++ch) {
+                const int c0 = h * (TN / 2) + ch * 32;
+                const int64_t col = n0 + c0 + c4;
+                const bool fast = vec && (n0 + c0 + 32 <= p.n);
+                // old C first: these loads do not depend on the accumulator
+                float4 old[8];
+                if (p.beta != 0.f && fast) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int64_t row = rbase + i * 4 + rsub;
+                        old[i] = (row < p.m) ? *reinterpret_cast<const float4*>(p.C + row * p.ldc + col) : make_float4(0, 0, 0, 0);
+                    }
+                }
+                if (ch == 0) {
+                    mbar_wait(&tmem_full[buf], (lt >> 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * TN + (uint32_t)c0;
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -215,43 +284,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                       "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            } else {
+                if (ch == TN / 64 - 1) {
+                    // this warp's last read of the accumulator: hand the buffer back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+                }
+                // transpose through shared memory: thread = row -> 8 lanes = one 128-byte row segment
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0u;
-            }
-            if (row < p.m) {
-                const int64_t col = n0 + c0;
-                float* dst = p.C + row * p.ldc + col;
-                if (vec && col + 32 <= p.n) {
+                for (int j = 0; j < 32; ++j) stg[lane * STG_PITCH + j] = p.alpha * __uint_as_float(r[j]);
+                __syncwarp();
+                if (fast) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = i * 4 + rsub;
+                        const int64_t row = rbase + rr;
                         float4 o;
-                        o.x = p.alpha * __uint_as_float(r[j]);
-                        o.y = p.alpha * __uint_as_float(r[j + 1]);
-                        o.z = p.alpha * __uint_as_float(r[j + 2]);
-                        o.w = p.alpha * __uint_as_float(r[j + 3]);
+                        o.x = stg[rr * STG_PITCH + c4];
+                        o.y = stg[rr * STG_PITCH + c4 + 1];
+                        o.z = stg[rr * STG_PITCH + c4 + 2];
+                        o.w = stg[rr * STG_PITCH + c4 + 3];
                         if (p.beta != 0.f) {
-                            const float4 c = *reinterpret_cast<const float4*>(dst + j);
-                            o.x = fmaf(p.beta, c.x, o.x);
-                            o.y = fmaf(p.beta, c.y, o.y);
-                            o.z = fmaf(p.beta, c.z, o.z);
-                            o.w = fmaf(p.beta, c.w, o.w);
+                            o.x = fmaf(p.beta, old[i].x, o.x);
+                            o.y = fmaf(p.beta, old[i].y, o.y);
+                            o.z = fmaf(p.beta, old[i].z, o.z);
+                            o.w = fmaf(p.beta, old[i].w, o.w);
                         }
-                        *reinterpret_cast<float4*>(dst + j) = o;
+                        if (row < p.m) {
+                            *reinterpret_cast<float4*>(p.C + row * p.ldc + col) = o;
+                            if (p.Clo && (p.clo_cols == 0 || col < p.clo_cols)) {
+                                float4 l;
+                                l.x = o.x - __uint_as_float(__float_as_uint(o.x) & 0xFFFFE000u);
+                                l.y = o.y - __uint_as_float(__float_as_uint(o.y) & 0xFFFFE000u);
+                                l.z = o.z - __uint_as_float(__float_as_uint(o.z) & 0xFFFFE000u);
+                                l.w = o.w - __uint_as_float(__float_as_uint(o.w) & 0xFFFFE000u);
+                                *reinterpret_cast<float4*>(p.Clo + row * p.ldc + col) = l;
+                            }
+                        }
                     }
                 } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (col + j < p.n) {
-                            const float v = p.alpha * __uint_as_float(r[j]);
-                            dst[j] = (p.beta != 0.f) ? fmaf(p.beta, dst[j], v) : v;
+                    // ragged / unaligned edge: one row per iteration, one column per lane
+                    const int64_t cc = n0 + c0 + lane;
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int64_t row = rbase + rr;
+                        if (row < p.m && cc < p.n) {
+                            float v = stg[rr * STG_PITCH + lane];
+                            float* dst = p.C + row * p.ldc + cc;
+                            if (p.beta != 0.f) v = fmaf(p.beta, *dst, v);
+                            *dst = v;
+                            if (p.Clo && (p.clo_cols == 0 || cc < p.clo_cols)) p.Clo[row * p.ldc + cc] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
                         }
                     }
                 }
+                __syncwarp();
             }
+            ++lt;
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -314,17 +404,39 @@ int dcgp_split_lo_impl(const void* src, void* dst, int64_t rows, int64_t cols, i
     return 0;
 }
 
+template <int TN>
+int launch_tc(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapAlo, const CUtensorMap& mapBlo,
+              TcParams& p, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc<TN>());
+        if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
+        attr = true;
+    }
+    p.tiles_m = (int)((p.m + TM - 1) / TM);
+    p.tiles_n = (int)((p.n + TN - 1) / TN);
+    const int64_t nt = (int64_t)p.tiles_m * p.tiles_n;
+    const unsigned grid = (unsigned)(nt < num_sms() ? nt : num_sms());
+    gemm_tc_kernel<TN><<<grid, NTHREADS_TC, smem_tc<TN>(), st>>>(mapA, mapB, mapAlo, mapBlo, p);
+    DCGP_CHECK_LAUNCH();
+    return 0;
+}
+
 // Returns 0 on success, 1 if the shape/alignment is not taken by this kernel (caller falls through
 // to the mma.sync kernel), < 0 on CUDA errors.
 // Alo / Blo (optional, same shape and leading dimension as A / B): x - trunc_tf32(x), enables 3xTF32.
-int dcgp_gemm_tc_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
-                      const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int flags, const void* Alo,
-                      const void* Blo, cudaStream_t st) {
+// Clo (optional, layout of C): receives C - trunc_tf32(C).
+int dcgp_gemm_tc_ex(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
+                    const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int flags, const void* Alo, const void* Blo,
+                    void* Clo, int64_t lower_off, int64_t clo_cols, cudaStream_t st) {
     if (k < 1) return 1;
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (lda & 3) || (ldb & 3)) return 1;
     if (m > 0x7fffffff || n > 0x7fffffff || k > 0x7fffffff) return 1;
     const int x3 = (Alo && Blo) ? 1 : 0;
     if (x3 && ((reinterpret_cast<uintptr_t>(Alo) & 15) || (reinterpret_cast<uintptr_t>(Blo) & 15))) return 1;
+    // narrow tiles when the wide ones would not fill one wave of SMs
+    const int64_t wide = ((m + TM - 1) / TM) * ((n + 255) / 256);
+    const int tn = (2 * wide <= num_sms()) ? 128 : 256;
     CUtensorMap mapA, mapB, mapAlo, mapBlo;
     // op(A)[m, k]: notrans -> A is m x k (K-major); trans -> A is k x m (MN-major)
     // op(B)[k, n]: trans -> B is n x k (K-major); notrans -> B is k x n (MN-major)
@@ -333,23 +445,31 @@ int dcgp_gemm_tc_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, d
                       : make_map(mp, X, m, k, lda, TK, TM, CU_TENSOR_MAP_SWIZZLE_128B);
     };
     auto mk_b = [&](CUtensorMap* mp, const void* X) {
-        return transb ? make_map(mp, X, n, k, ldb, TK, TN, CU_TENSOR_MAP_SWIZZLE_128B)
+        return transb ? make_map(mp, X, n, k, ldb, TK, tn, CU_TENSOR_MAP_SWIZZLE_128B)
                       : make_map(mp, X, k, n, ldb, 32, TK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     };
     if (mk_a(&mapA, A) || mk_b(&mapB, B)) return 1;
-    if (mk_a(&mapAlo, x3 ? Alo : A) || mk_b(&mapBlo, x3 ? Blo : B)) return 1;
+    if (x3) {
+        if (mk_a(&mapAlo, Alo) || mk_b(&mapBlo, Blo)) return 1;
+    } else {
+        mapAlo = mapA;
+        mapBlo = mapB;
+    }
     TcParams p;
     p.m = m; p.n = n; p.k = k;
-    p.C = (float*)C; p.ldc = ldc;
+    p.C = (float*)C; p.Clo = (float*)Clo; p.ldc = ldc;
     p.alpha = (float)alpha; p.beta = (float)beta;
     p.lower = (flags & DCGP_GEMM_LOWER) ? 1 : 0;
     p.a_mn = transa ? 1 : 0;
     p.b_mn = transb ? 0 : 1;
     p.x3 = x3;
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC);
-    if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
-    dim3 grid((unsigned)((n + TN - 1) / TN), (unsigned)((m + TM - 1) / TM));
-    gemm_tc_kernel<<<grid, NTHREADS_TC, SMEM_TC, st>>>(mapA, mapB, mapAlo, mapBlo, p);
-    DCGP_CHECK_LAUNCH();
-    return 0;
+    p.lower_off = lower_off;
+    p.clo_cols = clo_cols;
+    return tn == 128 ? launch_tc<128>(mapA, mapB, mapAlo, mapBlo, p, st) : launch_tc<256>(mapA, mapB, mapAlo, mapBlo, p, st);
+}
+
+int dcgp_gemm_tc_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
+                      const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int flags, const void* Alo,
+                      const void* Blo, void* Clo, cudaStream_t st) {
+    return dcgp_gemm_tc_ex(transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags, Alo, Blo, Clo, 0, 0, st);
 }

@@ -110,11 +110,7 @@ class CMPLikelihood(GaussianLikelihood):
         noise = self.noise.to(z.dtype)
         eye = torch.eye(n, dtype=z.dtype, device=z.device)
         C = individuals_noise.to(z.dtype) * H + noise * eye
-        Lc = F.psd_safe_cholesky(C)
-        half = F.trsm(Lc, z - a, trans=False)
-        mean_term = (half * half).sum()
-        covar_term = F.chol_solve(Lc, G).diagonal().sum()
-        logdet = F.logdet_from_chol(Lc)
+        logdet, mean_term, covar_term = F.gaussian_terms(C, z - a, G)
         return -0.5 * (n * math.log(2 * math.pi) + logdet + mean_term + covar_term)
 
     def _compute_expected_log_prob_without_individuals_noise(self, observations, variational_dist,

@@ -214,6 +214,19 @@ def potrs_(L, B):
     return B
 
 
+def trtri(L):
+    """W = L^{-1} of a lower-triangular factor (dense, zero above the diagonal)."""
+    L = _rowmajor(L)
+    _req(L)
+    n = L.size(0)
+    W = torch.empty(n, n, dtype=L.dtype, device=L.device)
+    lib = _lib.load()
+    ws = _workspace(lib.dcgp_trtri_workspace(n, _dt(L)), L.device)
+    rc = lib.dcgp_trtri(_ptr(L), n, _ld(L), _ptr(W), n, _ptr(ws), ws.numel(), _dt(L), _x3(L, n <= X3_SOLVE_LIMIT), _stream())
+    check(rc, "dcgp_trtri")
+    return W
+
+
 def logdet_chol(L):
     L = _rowmajor(L)
     _req(L)

@@ -142,6 +142,14 @@ DCGP_API int dcgp_potrs(const void* L, int64_t n, int64_t ldl, void* B, int64_t 
 /* out[0] = 2 * sum_i log L_ii   (log det of L L^T) */
 DCGP_API int dcgp_logdet_chol(const void* L, int64_t n, int64_t ldl, void* out, int dtype, void* stream);
 
+/* W = L^{-1} for lower-triangular L (n x n, row-major); W is packed (ldw == n), lower, zero above the
+ * diagonal.  Blocked recursive doubling on the tensor cores.  The bag-level Gaussian terms of
+ * src/likelihoods/cmp_likelihood.py:60-78 (log|C|, e^T C^{-1} e, tr(C^{-1} G) and their adjoints) are all
+ * products with C^{-1} = W^T W, so one inversion replaces eight triangular solves per ELBO step. */
+DCGP_API size_t dcgp_trtri_workspace(int64_t n, int dtype);
+DCGP_API int dcgp_trtri(const void* L, int64_t n, int64_t ldl, void* W, int64_t ldw, void* workspace,
+               size_t workspace_bytes, int dtype, int flags, void* stream);
+
 /* ---- bag aggregation ------------------------------------------------------------
  * Bags are contiguous row ranges: bag a = rows [offsets[a], offsets[a+1]) (int64 device array
  * of n_bags+1 entries).  Replaces the python loops over bags of

@@ -311,3 +311,44 @@ def test_tcgen05_syrk_lower_tiles():
     assert relerr(S.tril(), ref.tril()) < 2e-3
     # tiles strictly above the diagonal (128-row x 256-col tiles) are untouched
     assert torch.equal(S[:128, 256:].cpu().double(), S0[:128, 256:].float().double())
+
+
+@pytest.mark.parametrize("dtype,n,tol", [(torch.float64, 128, 1e-12), (torch.float64, 700, 1e-11), (torch.float64, 1024, 1e-11),
+                                         (torch.float32, 96, 1e-5), (torch.float32, 1024, 1e-4), (torch.float32, 1500, 1e-4)])
+def test_trtri_matches_triangular_solve(dtype, n, tol):
+    """dcgp_trtri: W = L^{-1}, lower, zeros above; ragged sizes go through the partial last pair."""
+    from deconditional_downscaling_b200 import ops
+    torch.manual_seed(n)
+    A = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    A = A @ A.t() / n + torch.eye(n, dtype=torch.float64, device="cuda")
+    L = torch.linalg.cholesky(A).to(dtype).contiguous()
+    W = ops.trtri(L)
+    ref = torch.linalg.solve_triangular(L.double(), torch.eye(n, dtype=torch.float64, device="cuda"), upper=False)
+    assert torch.equal(W.triu(1), torch.zeros_like(W))
+    assert ((W.double() - ref).norm() / ref.norm()).item() < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 2e-4)])
+def test_gaussian_terms_values_and_gradients(dtype, tol):
+    """Fused (log|C|, e^T C^-1 e, tr(C^-1 G)) against torch's Cholesky + solves in float64."""
+    from deconditional_downscaling_b200 import functional as F
+    torch.manual_seed(3)
+    n = 300
+    M = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    C64 = (M @ M.t() / n + 0.5 * torch.eye(n, dtype=torch.float64, device="cuda")).requires_grad_(True)
+    e64 = torch.randn(n, dtype=torch.float64, device="cuda", requires_grad=True)
+    Gm = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    G64 = (Gm @ Gm.t() / n).requires_grad_(True)
+    Lr = torch.linalg.cholesky(C64)
+    ref = torch.stack([2 * Lr.diagonal().log().sum(), (e64 * torch.cholesky_solve(e64[:, None], Lr)[:, 0]).sum(),
+                       torch.cholesky_solve(G64, Lr).diagonal().sum()])
+    wts = torch.tensor([0.7, -1.3, 0.4], dtype=torch.float64, device="cuda")
+    (ref * wts).sum().backward()
+    C, e, G = (t.detach().to(dtype).requires_grad_(True) for t in (C64, e64, G64))
+    got = torch.stack(F.gaussian_terms(C, e, G))
+    (got * wts.to(dtype)).sum().backward()
+    rel = lambda a, b: ((a.double() - b).norm() / b.norm()).item()
+    assert rel(got, ref.detach()) < tol
+    assert rel(e.grad, e64.grad) < tol and rel(G.grad, G64.grad) < tol
+    sym = lambda g: 0.5 * (g + g.t())
+    assert rel(sym(C.grad), sym(C64.grad)) < tol
