@@ -158,8 +158,8 @@ class GemmProbe:
             return (1.0 if lower else 2.0) * m * n * k
         self._wrap("gemm", gemm_flops)
         self._wrap("potrf_", lambda A, info=None: A.size(0) ** 3 / 3.0)
-        self._wrap("trsm_", lambda L, B, trans=False: float(B.size(0)) ** 2 * B.size(1))
-        self._wrap("potrs_", lambda L, B: 2.0 * float(B.size(0)) ** 2 * B.size(1))
+        self._wrap("trsm_", lambda L, B, trans=False, plan=None: float(B.size(0)) ** 2 * B.size(1))
+        self._wrap("potrs_", lambda L, B, plan=None: 2.0 * float(B.size(0)) ** 2 * B.size(1))
 
     def summary(self):
         torch.cuda.synchronize()

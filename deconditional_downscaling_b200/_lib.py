@@ -48,6 +48,10 @@ _SIGNATURES = {
     "dcgp_potrs": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_int, c_int,
                            c_void_p]),
     "dcgp_logdet_chol": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
+    "dcgp_solve_plan_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "dcgp_solve_plan": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "dcgp_trsm_planned": (c_int, [c_int, c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p, c_int64, c_int64,
+                                  c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "dcgp_trtri_workspace": (c_size_t, [c_int64, c_int]),
     "dcgp_trtri": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "dcgp_bag_sum": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]),

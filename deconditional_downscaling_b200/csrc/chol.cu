@@ -893,6 +893,8 @@ struct L5Ctx {
     const T* Llo;
     T* Xlo;
     int64_t n;
+    T* Blo = nullptr;          // look-ahead sweep: remainders of the not yet solved rows of B
+    const T* invlo = nullptr;  // ... and of the inverted diagonal blocks
 };
 
 template <typename T>
@@ -982,18 +984,26 @@ int ltrsm512_la(const L5Ctx<T>& c, int trans) {
     if (rc) return rc;
     const int64_t n = c.n, q = (n + NBI - 1) / NBI;
     const cudaStream_t sa = x.sh, sb = x.sb;
+    // 3xTF32 on the tcgen05 kernel needs the TF32 remainders of every operand: L and the inverted blocks
+    // are split once by the caller; X_i and the block the chain touches next get theirs from the
+    // epilogues (Clo); only the first block of the sweep has to be split here.
+    const bool lo = c.Llo && c.Xlo && c.Blo && c.invlo;
+    if (lo) {
+        const int64_t r = trans ? (q - 1) * NBI : 0, w = (n - r < NBI) ? n - r : NBI;
+        rc = dcgp_split_lo_impl(c.B + r * c.ldb, c.Blo + r * c.ldb, w, c.m, c.ldb, c.ldb, c.st);
+        if (rc) return rc;
+    }
     DCGP_CU(cudaEventRecord(x.fork, c.st));
     DCGP_CU(cudaStreamWaitEvent(sa, x.fork, 0));
     DCGP_CU(cudaStreamWaitEvent(sb, x.fork, 0));
-    const int near_flags = c.xf | DCGP_GEMM_NO_TCGEN05;
     for (int64_t s = 0; s < q; ++s) {
         const int64_t i = trans ? q - 1 - s : s;                    // block solved at this step
         const int64_t r = i * NBI, w = (n - r < NBI) ? n - r : NBI;
         const int e = (int)(s & 3), ep = (int)((s + 3) & 3);
         T* Xi = c.X + r * c.ldb;
-        T* Xilo = c.Xlo ? c.Xlo + r * c.ldb : nullptr;
+        T* Xilo = lo ? c.Xlo + r * c.ldb : nullptr;
         rc = dcgp_gemm_impl(trans, 0, w, c.m, w, 1.0, c.inv + i * NBI * NBI, NBI, c.B + r * c.ldb, c.ldb, 0.0, Xi, c.ldb,
-                            c.dtype, near_flags, sa, nullptr, nullptr, Xilo);
+                            c.dtype, c.xf, sa, lo ? c.invlo + i * NBI * NBI : nullptr, lo ? c.Blo + r * c.ldb : nullptr, Xilo);
         if (rc) return rc;
         if (s == q - 1) break;
         DCGP_CU(cudaEventRecord(x.leaf[e], sa));
@@ -1001,21 +1011,21 @@ int ltrsm512_la(const L5Ctx<T>& c, int trans) {
         if (!trans) {
             const int64_t r1 = r + NBI, w1 = (n - r1 < NBI) ? n - r1 : NBI, r2 = r1 + w1, nr = n - r2;
             rc = dcgp_gemm_impl(0, 0, w1, c.m, w, -1.0, c.L + r1 * c.ldl + r, c.ldl, Xi, c.ldb, 1.0, c.B + r1 * c.ldb, c.ldb,
-                                c.dtype, near_flags, sa, nullptr, nullptr, nullptr);
+                                c.dtype, c.xf, sa, lo ? c.Llo + r1 * c.ldl + r : nullptr, Xilo, lo ? c.Blo + r1 * c.ldb : nullptr);
             if (rc) return rc;
             if (nr <= 0) continue;
             DCGP_CU(cudaStreamWaitEvent(sb, x.leaf[e], 0));
             rc = dcgp_gemm_impl(0, 0, nr, c.m, w, -1.0, c.L + r2 * c.ldl + r, c.ldl, Xi, c.ldb, 1.0, c.B + r2 * c.ldb, c.ldb,
-                                c.dtype, c.xf, sb, c.Llo ? c.Llo + r2 * c.ldl + r : nullptr, Xilo, nullptr);
+                                c.dtype, c.xf, sb, lo ? c.Llo + r2 * c.ldl + r : nullptr, Xilo, nullptr);
         } else {
             const int64_t r1 = r - NBI, nr = r1;  // neighbour block i-1 (always full), rows [0, r1) remain
             rc = dcgp_gemm_impl(1, 0, NBI, c.m, w, -1.0, c.L + r * c.ldl + r1, c.ldl, Xi, c.ldb, 1.0, c.B + r1 * c.ldb, c.ldb,
-                                c.dtype, near_flags, sa, nullptr, nullptr, nullptr);
+                                c.dtype, c.xf, sa, lo ? c.Llo + r * c.ldl + r1 : nullptr, Xilo, lo ? c.Blo + r1 * c.ldb : nullptr);
             if (rc) return rc;
             if (nr <= 0) continue;
             DCGP_CU(cudaStreamWaitEvent(sb, x.leaf[e], 0));
             rc = dcgp_gemm_impl(1, 0, nr, c.m, w, -1.0, c.L + r * c.ldl, c.ldl, Xi, c.ldb, 1.0, c.B, c.ldb, c.dtype, c.xf, sb,
-                                c.Llo ? c.Llo + r * c.ldl : nullptr, Xilo, nullptr);
+                                lo ? c.Llo + r * c.ldl : nullptr, Xilo, nullptr);
         }
         if (rc) return rc;
         DCGP_CU(cudaEventRecord(x.upd[e], sb));
@@ -1025,38 +1035,71 @@ int ltrsm512_la(const L5Ctx<T>& c, int trans) {
     return 0;
 }
 
-size_t trsm512_ws_bytes(int64_t n, int64_t ldl, int64_t m_ld, int dtype) {
+// A solve plan holds everything about L that a sweep needs beyond L itself, so that several solves with
+// one factor (forward and adjoint of the same Lambda^{-1}) prepare it once:
+//   [inv512 blocks][their TF32 remainders (scratch of the inversion)][TF32 remainders of L]
+size_t plan_bytes_impl(int64_t n, int64_t ldl, int dtype) {
     const size_t es = dtype == DCGP_F64 ? 8 : 4;
     const size_t nbig = (size_t)(n + NBI - 1) / NBI;
-    size_t b = 2 * nbig * NBI * NBI * es + (size_t)n * m_ld * es;
-    if (dtype == DCGP_F32) b += ((size_t)n * ldl + (size_t)n * m_ld) * 4;
-    return b;
+    return 2 * nbig * NBI * NBI * es + (dtype == DCGP_F32 ? (size_t)n * ldl * 4 : 0);
+}
+
+size_t trsm512_work_bytes(int64_t n, int64_t m_ld, int dtype) {  // X (+ remainders of X and of B)
+    const size_t es = dtype == DCGP_F64 ? 8 : 4;
+    return (size_t)n * m_ld * es * (dtype == DCGP_F32 ? 3 : 1);
+}
+
+size_t trsm512_ws_bytes(int64_t n, int64_t ldl, int64_t m_ld, int dtype) {
+    return plan_bytes_impl(n, ldl, dtype) + trsm512_work_bytes(n, m_ld, dtype);
+}
+
+template <typename T>
+int plan_build(const T* L, int64_t n, int64_t ldl, T* plan, int dtype, int xf, cudaStream_t st) {
+    const int64_t nbig = (n + NBI - 1) / NBI;
+    T* inv = plan;
+    T* tmp = inv + nbig * NBI * NBI;
+    int rc = build_inv512<T>(L, n, ldl, inv, tmp, dtype, xf, st);
+    if (rc) return rc;
+    if (sizeof(T) == 4 && xf) {
+        // the doubling scratch is dead once the inverted blocks exist: it receives their remainders
+        rc = dcgp_split_lo_impl(inv, tmp, nbig * NBI, NBI, NBI, NBI, st);
+        if (rc) return rc;
+        rc = dcgp_split_lo_impl(L, tmp + nbig * NBI * NBI, n, n, ldl, ldl, st);
+    }
+    return rc;
 }
 
 // trans: 0 = L X = B, 1 = L^T X = B, 2 = both in sequence ((L L^T) X = B, shares the inverted blocks)
+// plan: prepared by plan_build, or null (then it is built at the head of the workspace)
 template <typename T>
 int trsm_impl(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t m, int64_t ldb, T* ws, size_t ws_bytes,
-              int dtype, int xf, cudaStream_t st) {
-    if (n < 2 * NBI || m < 64 || ws_bytes < trsm512_ws_bytes(n, ldl, ldb, dtype)) {
+              int dtype, int xf, cudaStream_t st, const T* plan = nullptr) {
+    const bool big = n >= 2 * NBI && m >= 64 &&
+                     ws_bytes >= (plan ? trsm512_work_bytes(n, ldb, dtype) : trsm512_ws_bytes(n, ldl, ldb, dtype));
+    if (!big) {
+        if (ws_bytes < inv_ws_bytes(n, dtype)) return -8;
         if (trans != 2) return trsm128_impl<T>(trans, L, n, ldl, B, m, ldb, ws, ws_bytes, dtype, xf, st);
         int rc = trsm128_impl<T>(0, L, n, ldl, B, m, ldb, ws, ws_bytes, dtype, xf, st);
         if (rc) return rc;
         return trsm128_impl<T>(1, L, n, ldl, B, m, ldb, ws, ws_bytes, dtype, xf, st);
     }
     const int64_t nbig = (n + NBI - 1) / NBI;
-    T* inv = ws;
-    T* tmp = inv + nbig * NBI * NBI;
-    T* X = tmp + nbig * NBI * NBI;
-    T *llo = nullptr, *xlo = nullptr;
-    if (sizeof(T) == 4 && xf) {
-        llo = X + (size_t)n * ldb;
-        xlo = llo + (size_t)n * ldl;
-        int rc = dcgp_split_lo_impl(L, llo, n, n, ldl, ldl, st);
+    int rc;
+    if (!plan) {
+        rc = plan_build<T>(L, n, ldl, ws, dtype, xf, st);
         if (rc) return rc;
+        plan = ws;
+        ws += plan_bytes_impl(n, ldl, dtype) / sizeof(T);
     }
-    int rc = build_inv512<T>(L, n, ldl, inv, tmp, dtype, xf, st);
-    if (rc) return rc;
-    L5Ctx<T> c{L, ldl, B, m, ldb, inv, X, dtype, xf, st, llo, xlo, n};
+    const T* inv = plan;
+    T* X = ws;
+    L5Ctx<T> c{L, ldl, B, m, ldb, const_cast<T*>(inv), X, dtype, xf, st, nullptr, nullptr, n};
+    if (sizeof(T) == 4 && xf) {
+        c.invlo = inv + nbig * NBI * NBI;
+        c.Llo = c.invlo + nbig * NBI * NBI;
+        c.Xlo = X + (size_t)n * ldb;
+        c.Blo = c.Xlo + (size_t)n * ldb;
+    }
     static const int use_la = getenv("DCGP_TRSM_LA") ? atoi(getenv("DCGP_TRSM_LA")) : 1;
     for (int sweep = (trans == 1 ? 1 : 0); sweep <= (trans == 0 ? 0 : 1); ++sweep) {
         rc = (use_la && nbig >= 4) ? ltrsm512_la(c, sweep) : ltrsm512_rec(c, sweep, 0, n);
@@ -1160,6 +1203,41 @@ extern "C" int dcgp_trsm(int trans, const void* L, int64_t n, int64_t ldl, void*
 extern "C" int dcgp_potrs(const void* L, int64_t n, int64_t ldl, void* B, int64_t m, int64_t ldb, void* workspace,
                           size_t workspace_bytes, int dtype, int flags, void* stream) {
     return dcgp_trsm(2, L, n, ldl, B, m, ldb, workspace, workspace_bytes, dtype, flags, stream);
+}
+
+extern "C" size_t dcgp_solve_plan_bytes(int64_t n, int64_t ldl, int dtype) {
+    if (n < 2 * NBI) return 0;  // small factors are solved on 128-wide blocks, nothing to prepare
+    return plan_bytes_impl(n, ldl, dtype);
+}
+
+extern "C" int dcgp_solve_plan(const void* L, int64_t n, int64_t ldl, void* plan, size_t plan_bytes, int dtype, int flags,
+                               void* stream) {
+    if (n < 2 * NBI) return 0;
+    if (!L || ldl < n) return -2;
+    if (dtype != DCGP_F64 && dtype != DCGP_F32) return -6;
+    if (!plan || plan_bytes < plan_bytes_impl(n, ldl, dtype)) return -5;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int xf = flags & (DCGP_GEMM_TF32X3 | DCGP_GEMM_NO_TCGEN05);
+    if (dtype == DCGP_F64) return plan_build<double>((const double*)L, n, ldl, (double*)plan, dtype, xf, st);
+    return plan_build<float>((const float*)L, n, ldl, (float*)plan, dtype, xf, st);
+}
+
+extern "C" int dcgp_trsm_planned(int trans, const void* L, int64_t n, int64_t ldl, const void* plan, size_t plan_bytes,
+                                 void* B, int64_t m, int64_t ldb, void* workspace, size_t workspace_bytes, int dtype,
+                                 int flags, void* stream) {
+    if (!plan || n < 2 * NBI || m < 64 || plan_bytes < plan_bytes_impl(n, ldl, dtype))
+        return dcgp_trsm(trans, L, n, ldl, B, m, ldb, workspace, workspace_bytes, dtype, flags, stream);
+    if (!L || ldl < n) return -2;
+    if (!B || ldb < m) return -7;
+    if (dtype != DCGP_F64 && dtype != DCGP_F32) return -12;
+    if (!workspace || workspace_bytes < trsm512_work_bytes(n, ldb, dtype)) return -10;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int xf = flags & (DCGP_GEMM_TF32X3 | DCGP_GEMM_NO_TCGEN05);
+    if (dtype == DCGP_F64)
+        return trsm_impl<double>(trans, (const double*)L, n, ldl, (double*)B, m, ldb, (double*)workspace, workspace_bytes,
+                                 dtype, xf, st, (const double*)plan);
+    return trsm_impl<float>(trans, (const float*)L, n, ldl, (float*)B, m, ldb, (float*)workspace, workspace_bytes, dtype, xf,
+                            st, (const float*)plan);
 }
 
 extern "C" int dcgp_logdet_chol(const void* L, int64_t n, int64_t ldl, void* out, int dtype, void* stream) {

@@ -261,7 +261,9 @@ class _KernelSolveFn(Function):
 
     @staticmethod
     def forward(ctx, meta, x, L, B, *hyp):
-        W = ops.potrs_(L, B.detach().clone(memory_format=torch.contiguous_format))
+        # the factor's solve plan (built once by kernel_factor) serves this solve and its adjoint
+        ctx.plan = getattr(L, "_dcgp_plan", None)
+        W = ops.potrs_(L, B.detach().clone(memory_format=torch.contiguous_format), plan=ctx.plan)
         ctx.meta = meta
         ctx.save_for_backward(x, L, W, *hyp)
         return W
@@ -271,7 +273,7 @@ class _KernelSolveFn(Function):
         x, L, W, *hyp = ctx.saved_tensors
         meta = ctx.meta
         need = ctx.needs_input_grad
-        gB = ops.potrs_(L, gW.detach().clone(memory_format=torch.contiguous_format))
+        gB = ops.potrs_(L, gW.detach().clone(memory_format=torch.contiguous_format), plan=ctx.plan)
         hg = [None] * len(hyp)
         if any(need[4:]):
             dLam = ops.gemm(gB, W, transb=True, alpha=-1.0)      # -(Lambda^{-1} gW) W^T
@@ -295,6 +297,7 @@ def kernel_factor(meta, hyp, x, check=True):
         info = ops.potrf_(L)
         if check:
             _raise_if_not_pd(info)
+        L._dcgp_plan = ops.solve_plan(L)
     return L
 
 

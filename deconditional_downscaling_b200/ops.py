@@ -189,29 +189,46 @@ def potrf_(A, info=None):
     return info
 
 
-def trsm_(L, B, trans=False):
+def solve_plan(L):
+    """Prepared form of a Cholesky factor for repeated solves (dcgp_solve_plan); None for small factors."""
+    L = _rowmajor(L)
+    _req(L)
+    lib = _lib.load()
+    nbytes = lib.dcgp_solve_plan_bytes(L.size(0), _ld(L), _dt(L))
+    if nbytes == 0:
+        return None
+    plan = _workspace(nbytes, L.device)
+    rc = lib.dcgp_solve_plan(_ptr(L), L.size(0), _ld(L), _ptr(plan), plan.numel(), _dt(L), _x3(L, L.size(0) <= X3_SOLVE_LIMIT), _stream())
+    check(rc, "dcgp_solve_plan")
+    return plan
+
+
+def _solve(trans, L, B, plan):
+    L = _rowmajor(L)
+    _inplace_ok(B)
+    _req(L, B)
+    n, m = B.size(0), B.size(1)
+    lib = _lib.load()
+    ws = _workspace(lib.dcgp_trsm_workspace(n, m, _dt(L)), L.device)
+    flags = _x3(L, n <= X3_SOLVE_LIMIT)
+    if plan is not None:
+        rc = lib.dcgp_trsm_planned(trans, _ptr(L), n, _ld(L), _ptr(plan), plan.numel(), _ptr(B), m, _ld(B), _ptr(ws), ws.numel(),
+                                   _dt(L), flags, _stream())
+        check(rc, "dcgp_trsm_planned")
+    else:
+        rc = lib.dcgp_trsm(trans, _ptr(L), n, _ld(L), _ptr(B), m, _ld(B), _ptr(ws), ws.numel(), _dt(L), flags, _stream())
+        check(rc, "dcgp_trsm")
+    return B
+
+
+def trsm_(L, B, trans=False, plan=None):
     """In-place solve op(L) X = B, B is (n, m) row-major."""
-    L = _rowmajor(L)
-    _inplace_ok(B)
-    _req(L, B)
-    n, m = B.size(0), B.size(1)
-    lib = _lib.load()
-    ws = _workspace(lib.dcgp_trsm_workspace(n, m, _dt(L)), L.device)
-    rc = lib.dcgp_trsm(int(trans), _ptr(L), n, _ld(L), _ptr(B), m, _ld(B), _ptr(ws), ws.numel(), _dt(L), _x3(L, n <= X3_SOLVE_LIMIT), _stream())
-    check(rc, "dcgp_trsm")
-    return B
+    return _solve(int(trans), L, B, plan)
 
 
-def potrs_(L, B):
-    L = _rowmajor(L)
-    _inplace_ok(B)
-    _req(L, B)
-    n, m = B.size(0), B.size(1)
-    lib = _lib.load()
-    ws = _workspace(lib.dcgp_trsm_workspace(n, m, _dt(L)), L.device)
-    rc = lib.dcgp_potrs(_ptr(L), n, _ld(L), _ptr(B), m, _ld(B), _ptr(ws), ws.numel(), _dt(L), _x3(L, n <= X3_SOLVE_LIMIT), _stream())
-    check(rc, "dcgp_potrs")
-    return B
+def potrs_(L, B, plan=None):
+    """In-place (L L^T) X = B."""
+    return _solve(2, L, B, plan)
 
 
 def trtri(L):

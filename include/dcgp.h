@@ -140,6 +140,19 @@ DCGP_API int dcgp_trsm(int trans, const void* L, int64_t n, int64_t ldl, void* B
 DCGP_API int dcgp_potrs(const void* L, int64_t n, int64_t ldl, void* B, int64_t m, int64_t ldb, void* workspace,
                size_t workspace_bytes, int dtype, int flags, void* stream);
 /* out[0] = 2 * sum_i log L_ii   (log det of L L^T) */
+/* Solve plans: everything about a factor L that a blocked substitution sweep needs beyond L itself (the
+ * inverted 512-wide diagonal blocks and, for 3xTF32, the TF32 remainders of L and of those blocks).  The
+ * forward solve and its adjoint in one ELBO step use the same Lambda^{-1}
+ * (src/models/variational_cmp.py:69-83 and its autograd backward): build the plan once, then
+ * dcgp_trsm_planned(trans = 0 | 1 | 2 (both sweeps, = potrs)).  plan_bytes == 0 (small n) or plan == NULL
+ * falls back to dcgp_trsm with the same workspace contract. */
+DCGP_API size_t dcgp_solve_plan_bytes(int64_t n, int64_t ldl, int dtype);
+DCGP_API int dcgp_solve_plan(const void* L, int64_t n, int64_t ldl, void* plan, size_t plan_bytes, int dtype, int flags,
+                    void* stream);
+DCGP_API int dcgp_trsm_planned(int trans, const void* L, int64_t n, int64_t ldl, const void* plan, size_t plan_bytes,
+                      void* B, int64_t m, int64_t ldb, void* workspace, size_t workspace_bytes, int dtype, int flags,
+                      void* stream);
+
 DCGP_API int dcgp_logdet_chol(const void* L, int64_t n, int64_t ldl, void* out, int dtype, void* stream);
 
 /* W = L^{-1} for lower-triangular L (n x n, row-major); W is packed (ldw == n), lower, zero above the

@@ -352,3 +352,24 @@ def test_gaussian_terms_values_and_gradients(dtype, tol):
     assert rel(e.grad, e64.grad) < tol and rel(G.grad, G64.grad) < tol
     sym = lambda g: 0.5 * (g + g.t())
     assert rel(sym(C.grad), sym(C64.grad)) < tol
+
+
+@pytest.mark.parametrize("dtype,n,m,tol", [(torch.float32, 2300, 700, 1e-4), (torch.float32, 4096, 256, 1e-4),
+                                           (torch.float64, 2048, 128, 1e-11), (torch.float32, 600, 64, 1e-4)])
+def test_planned_solves_match_reference(dtype, n, m, tol):
+    """dcgp_solve_plan + dcgp_trsm_planned (trans 0 / 1 / 2) against float64 triangular solves; a plan
+    is reusable across calls and small factors (no plan) fall back to dcgp_trsm."""
+    from deconditional_downscaling_b200 import ops
+    torch.manual_seed(n + m)
+    A = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    A = A @ A.t() / n + torch.eye(n, dtype=torch.float64, device="cuda")
+    L = torch.linalg.cholesky(A).to(dtype).contiguous()
+    plan = ops.solve_plan(L)
+    assert (plan is None) == (n < 1024)
+    B = torch.randn(n, m, dtype=dtype, device="cuda")
+    Ld, Bd = L.double(), B.double()
+    rel = lambda a, b: ((a.double() - b).norm() / b.norm()).item()
+    for _ in range(2):
+        assert rel(ops.trsm_(L, B.clone(), plan=plan), torch.linalg.solve_triangular(Ld, Bd, upper=False)) < tol
+        assert rel(ops.trsm_(L, B.clone(), trans=True, plan=plan), torch.linalg.solve_triangular(Ld.t(), Bd, upper=True)) < tol
+        assert rel(ops.potrs_(L, B.clone(), plan=plan), torch.cholesky_solve(Bd, Ld)) < 10 * tol
