@@ -146,7 +146,7 @@ class GemmProbe:
             s.record()
             out = orig(*a, **k)
             e.record()
-            probe.rec.append((s, e, flops_fn(*a, **k), name))
+            probe.rec.append((s, e, flops_fn(*a, **k), name, a[0].dtype))
             return out
         setattr(self.ops, name, wrapped)
 
@@ -163,15 +163,21 @@ class GemmProbe:
 
     def summary(self):
         torch.cuda.synchronize()
-        t = sum(s.elapsed_time(e) for s, e, _, _ in self.rec) * 1e-3
-        fl = sum(f for _, _, f, _ in self.rec)
+        t = sum(r[0].elapsed_time(r[1]) for r in self.rec) * 1e-3
+        fl = sum(r[2] for r in self.rec)
         by = {}
-        for s, e, f, name in self.rec:
+        for s, e, f, name, _ in self.rec:
             d = by.setdefault(name, [0, 0.0, 0.0])
             d[0] += 1
             d[1] += s.elapsed_time(e) * 1e-3
             d[2] += f
         return len(self.rec), t, fl, {k: {"calls": v[0], "ms": 1e3 * v[1], "tflops": v[2] / v[1] / 1e12 if v[1] > 0 else None} for k, v in by.items()}
+
+    def tcgen05_products(self, min_flops=2e9):
+        """Direct FP32 dcgp_gemm calls large enough to be one gemm_tc_kernel launch each (gemm.cu dispatch:
+        m, n >= 128, k >= 64, >= 32 tiles): launches, seconds, algorithmic flops."""
+        sel = [r for r in self.rec if r[3] == "gemm" and r[4] == torch.float32 and r[2] >= min_flops]
+        return len(sel), sum(r[0].elapsed_time(r[1]) for r in sel) * 1e-3, sum(r[2] for r in sel)
 
 
 # ------------------------------------------------------------------ our arm
@@ -259,6 +265,7 @@ def run_ours(args):
     clk = clocks.stop() if rank == 0 else None
     final_loss = float(loss.item())
     n_gemm, t_gemm, fl_gemm, gemm_by = probe.summary()
+    n_tc, t_tc, fl_tc = probe.tcgen05_products()
     # ---- end-to-end arm: pinned host -> device copies and loss read-back inside the timed region
     for i in range(min(W_, 2)):
         trainer.step_from_host(host[i], device)
@@ -290,12 +297,20 @@ def run_ours(args):
         "e2e": {"value": world * K_ / t_e2e, "unit": "minibatch ELBO steps/s (whole job)",
                 "h2d_bytes_per_step": batch_bytes(host[0]), "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "final_loss": final_loss,
-        "roofline": {"bound": "tensor", "kernel": "gemm_kernel<float> (TF32 tensor cores): dcgp_gemm launches of the timed steps, "
-                     "direct and inside dcgp_potrf / dcgp_trsm / dcgp_potrs",
-                     "achieved": fl_gemm / t_gemm / 1e12 if t_gemm > 0 else None, "peak": tf32_peak, "unit": "TFLOP/s",
-                     "frac": (fl_gemm / t_gemm / 1e12) / tf32_peak if t_gemm > 0 else None, "traffic": None,
+        # dominant throughput kernel (profiles/r01_launches_bench_step_v9_summary.csv: gemm_tc_kernel 39% of the
+        # kernel time of a step; the single-CTA potrf_step_kernel chain, 24%, is latency- not roofline-bound)
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma kind::tf32, TMA, TMEM): the direct dcgp_gemm "
+                     "products of the timed steps that run as one launch of it each, CUDA events around every launch",
+                     "achieved": fl_tc / t_tc / 1e12 if t_tc > 0 else None, "peak": tf32_peak, "unit": "TFLOP/s",
+                     "frac": (fl_tc / t_tc / 1e12) / tf32_peak if t_tc > 0 else None, "traffic": None,
                      "peak_source": f"{pk['source']}: sustained bf16 cuBLAS rate / 2 (TF32 issues at half the bf16 MMA rate)",
-                     "calls": n_gemm, "share_of_step": t_gemm / t_dev if t_dev > 0 else None, "by_call": gemm_by},
+                     "launches": n_tc, "avg_launch_ms": 1e3 * t_tc / n_tc if n_tc else None,
+                     "share_of_step": t_tc / t_dev if t_dev > 0 else None,
+                     "path": {"what": "all tensor-core contractions of the step (dcgp_gemm, and the GEMMs inside dcgp_potrf / "
+                              "dcgp_trsm_planned incl. their serial leaf chains): algorithmic flops / event time",
+                              "achieved": fl_gemm / t_gemm / 1e12 if t_gemm > 0 else None,
+                              "frac": (fl_gemm / t_gemm / 1e12) / tf32_peak if t_gemm > 0 else None,
+                              "calls": n_gemm, "share_of_step": t_gemm / t_dev if t_dev > 0 else None, "by_call": gemm_by}},
         "allreduce_bytes_per_step": trainer.grads.nbytes,
     }
     if rank == 0:

@@ -424,6 +424,24 @@ int dcgp_gemm_batched_impl(int transa, int transb, int64_t m, int64_t n, int64_t
     return launch_gemm<float, false>(p, st);
 }
 
+int dcgp_split_lo_impl(const void* src, void* dst, int64_t rows, int64_t cols, int64_t lds, int64_t ldd, cudaStream_t st);
+
+extern "C" int dcgp_split_lo(const void* src, void* dst, int64_t rows, int64_t cols, int64_t lds, int64_t ldd,
+                             void* stream) {
+    if (rows < 0 || cols < 0) return -3;
+    if (rows == 0 || cols == 0) return 0;
+    if (!src || !dst || lds < cols || ldd < cols) return -1;
+    return dcgp_split_lo_impl(src, dst, rows, cols, lds, ldd, (cudaStream_t)stream);
+}
+
+extern "C" int dcgp_gemm_ex(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A,
+                            int64_t lda, const void* Alo, const void* B, int64_t ldb, const void* Blo, double beta,
+                            void* C, int64_t ldc, void* Clo, int dtype, int flags, void* stream) {
+    if (dtype != DCGP_F32 && (Alo || Blo || Clo)) return -17;
+    return dcgp_gemm_impl(transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, dtype, flags,
+                          (cudaStream_t)stream, Alo, Blo, Clo);
+}
+
 extern "C" int dcgp_gemm(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A,
                          int64_t lda, const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype,
                          int flags, void* stream) {

@@ -250,6 +250,80 @@ def gaussian_terms(C, e, G, max_tries=3):
         raise
 
 
+class _CholInverseFn(Function):
+    """W = chol(A)^{-1} (lower).  Backward entirely as products with W:
+    dL = -tril(W^T gW W^T);  Phi = tril(L^T dL) with halved diagonal;  dA = sym(W^T Phi W)."""
+
+    @staticmethod
+    def forward(ctx, A):
+        L = A.detach().clone(memory_format=torch.contiguous_format)
+        info = ops.potrf_(L)
+        _raise_if_not_pd(info)
+        L = L.tril_()
+        W = ops.trtri(L)
+        ctx.save_for_backward(L, W)
+        return W
+
+    @staticmethod
+    def backward(ctx, gW):
+        L, W = ctx.saved_tensors
+        T = ops.gemm(W, gW.tril().contiguous(), transa=True)          # W^T gW
+        dL = ops.gemm(T, W, transb=True, alpha=-1.0).tril_()           # -(W^T gW) W^T
+        P = ops.gemm(L, dL, transa=True).tril_()
+        P.diagonal().mul_(0.5)
+        S = ops.gemm(ops.gemm(W, P, transa=True), W)                   # W^T Phi W
+        return 0.5 * (S + S.t())
+
+
+def chol_inverse(A, max_tries=3):
+    """Inverse Cholesky factor with psd_safe_cholesky's jitter retries."""
+    try:
+        return _CholInverseFn.apply(A)
+    except NotPSDError:
+        base = 1e-8 if A.dtype == torch.float64 else 1e-6
+        eye = torch.eye(A.size(0), dtype=A.dtype, device=A.device)
+        for i in range(max_tries):
+            try:
+                return _CholInverseFn.apply(A + (base * 10 ** i) * eye)
+            except NotPSDError:
+                continue
+        raise
+
+
+class _SplitMatmulFn(Function):
+    """W @ K for a float64 W applied to float32 K at ~float32 accuracy on the TF32 tensor cores:
+    W is carried as an FP32 pair (hi + lo, 48 significant bits), each half multiplied with 3xTF32.
+    Backward: gK = W^T g (same pair), gW = tril(g K^T) (W is lower triangular) in float64."""
+
+    @staticmethod
+    def forward(ctx, W, K):
+        Whi = W.detach().float()
+        Wlo = (W.detach() - Whi.double()).float()
+        K = K.detach().contiguous()
+        Klo = ops.split_lo(K)
+        out = ops.gemm_x3(Whi, K, Blo=Klo)
+        ops.gemm_x3(Wlo, K, Blo=Klo, beta=1.0, C=out)
+        ctx.save_for_backward(Whi, Wlo, K)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        Whi, Wlo, K = ctx.saved_tensors
+        g = g.contiguous()
+        gW = gK = None
+        glo = ops.split_lo(g)
+        if ctx.needs_input_grad[1]:
+            gK = ops.gemm_x3(Whi, g, transa=True, Blo=glo)
+            ops.gemm_x3(Wlo, g, transa=True, Blo=glo, beta=1.0, C=gK)
+        if ctx.needs_input_grad[0]:
+            gW = ops.gemm_x3(g, K, transb=True, Alo=glo).tril_().double()
+        return gW, gK
+
+
+def split_matmul(W, K):
+    return _SplitMatmulFn.apply(W, K)
+
+
 def logdet_from_chol(L):
     """log det(L L^T) = 2 sum log L_ii."""
     return _LogdetFn.apply(L)

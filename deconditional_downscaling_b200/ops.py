@@ -171,6 +171,40 @@ def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, C=None, lower=Fa
     return C
 
 
+def split_lo(X):
+    """x - trunc_tf32(x): the part of an FP32 matrix that the tcgen05 TF32 operand read drops."""
+    X = _rowmajor(X)
+    _req(X)
+    if X.dtype != torch.float32:
+        raise TypeError("split_lo is an FP32 operation")
+    out = torch.empty(X.size(0), X.size(1), dtype=X.dtype, device=X.device)
+    check(_lib.load().dcgp_split_lo(_ptr(X), _ptr(out), X.size(0), X.size(1), _ld(X), _ld(out), _stream()), "dcgp_split_lo")
+    return out
+
+
+def gemm_x3(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, C=None, Alo=None, Blo=None):
+    """FP32 product at ~FP32 accuracy: 3xTF32 on the tcgen05 kernel from hi/lo operand pairs (the remainders
+    are computed here unless the caller already holds them)."""
+    A, B = _rowmajor(A), _rowmajor(B)
+    _req(A, B, C)
+    if A.dtype != torch.float32:
+        return gemm(A, B, transa=transa, transb=transb, alpha=alpha, beta=beta, C=C)
+    m, k = (A.size(1), A.size(0)) if transa else (A.size(0), A.size(1))
+    k2, n = (B.size(1), B.size(0)) if transb else (B.size(0), B.size(1))
+    if k != k2:
+        raise ValueError(f"gemm inner dims differ: {k} vs {k2}")
+    if C is None:
+        C = torch.empty(m, n, dtype=A.dtype, device=A.device)
+        beta = 0.0
+    Alo = split_lo(A) if Alo is None else _rowmajor(Alo)
+    Blo = split_lo(B) if Blo is None else _rowmajor(Blo)
+    flags = _lib.GEMM_TF32X3 | (0 if USE_TCGEN05 else _lib.GEMM_NO_TCGEN05)
+    rc = _lib.load().dcgp_gemm_ex(int(transa), int(transb), m, n, k, float(alpha), _ptr(A), _ld(A), _ptr(Alo), _ptr(B), _ld(B),
+                                  _ptr(Blo), float(beta), _ptr(C), _ld(C), None, _dt(A), flags, _stream())
+    check(rc, "dcgp_gemm_ex")
+    return C
+
+
 def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 

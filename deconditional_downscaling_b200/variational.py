@@ -68,9 +68,21 @@ class VariationalPosterior(MultivariateNormal):
         return self._get("Lz", lambda: F.psd_safe_cholesky(self.kops.gram(self.Z, None, diag_const=1e-3).double()))
 
     @property
+    def Wz(self):
+        """L_Z^{-1} in float64 (FP32 models): the whitening products then run as 3xTF32 tensor-core GEMMs on
+        an FP32 hi/lo pair of it instead of float64 triangular solves against 10^3 .. 10^4 columns."""
+        return self._get("Wz", lambda: F.chol_inverse(self.kops.gram(self.Z, None, diag_const=1e-3).double()))
+
+    def _whiten(self, K):
+        """L_Z^{-1} K for K (M x cols) in the model dtype."""
+        if self.dtype == torch.float64:
+            return F.trsm(self.Lz, K, trans=False)
+        return F.split_matmul(self.Wz, K)
+
+    @property
     def At(self):
-        """A~ = L_Z^{-1} K_Zx (solved in float64, stored in the model dtype), M x N."""
-        return self._get("At", lambda: F.trsm(self.Lz, self.kops.gram(self.Z, self.x).double(), trans=False).to(self.dtype))
+        """A~ = L_Z^{-1} K_Zx (float64 factor, result in the model dtype), M x N."""
+        return self._get("At", lambda: self._whiten(self.kops.gram(self.Z, self.x)))
 
     @property
     def loc(self):
@@ -109,7 +121,7 @@ class VariationalPosterior(MultivariateNormal):
         T_a = 1_a^T K_xx 1_a + 1e-4 n_a + |L_S^T u_a|^2 - |u_a|^2  (SURVEY.md §8a row 15)."""
         sizes = (offsets[1:] - offsets[:-1]).to(self.dtype)
         KbZ = self.kops.bagsum(self.Z, self.x, offsets)                    # n_bags x M
-        Ub = F.trsm(self.Lz, KbZ.t().double(), trans=False).to(self.dtype)   # M x n_bags
+        Ub = self._whiten(KbZ.t().contiguous())                               # M x n_bags
         S = F.matmul(Ub, self.m.to(self.dtype), transa=True) + F.bag_sum(self.mean_module(self.x).to(self.dtype), offsets)
         LsU = F.matmul(self.Ls, Ub, transa=True)
         T = self.kops.bag_blocksum(self.x, offsets) + 1e-4 * sizes + (LsU * LsU).sum(0) - (Ub * Ub).sum(0)

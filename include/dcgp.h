@@ -118,6 +118,19 @@ DCGP_API int dcgp_gram_bwd(const dcgp_kernel_spec* spec, const void* x1, int64_t
 DCGP_API int dcgp_gemm(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
               const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype, int flags, void* stream);
 
+/* 3xTF32 with the tensor core's own operand rounding: tcgen05.mma kind::tf32 reads an FP32 operand
+ * truncated to TF32 (x_hi); dcgp_split_lo writes what it drops, x_lo = x - x_hi.  dcgp_gemm_ex takes
+ * the remainder matrices of A and B (same shapes and leading dimensions, FP32 only, may be NULL) and
+ * then evaluates A_lo B_hi + A_hi B_lo + A_hi B_hi in one tcgen05 launch (~FP32 accuracy at a third
+ * of the TF32 rate); Clo (may be NULL) receives the remainders of the result for a later product.
+ * Used for the whitening products L_Z^{-1} K_Zx of the SVGP (gpytorch variational_strategy.py:147-163
+ * keeps that solve in double precision; here the factor and its inverse are FP64 and the product runs
+ * on an FP32 hi/lo pair of the inverse). */
+DCGP_API int dcgp_split_lo(const void* src, void* dst, int64_t rows, int64_t cols, int64_t lds, int64_t ldd, void* stream);
+DCGP_API int dcgp_gemm_ex(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
+                 const void* Alo, const void* B, int64_t ldb, const void* Blo, double beta, void* C, int64_t ldc,
+                 void* Clo, int dtype, int flags, void* stream);
+
 /* ---- Cholesky and triangular solves -----------------------------------------
  * dcgp_potrf: A (n x n, lower triangle read) is overwritten by L (A = L L^T) in its lower
  * triangle; blocked right-looking, panel on CUDA cores, TRSM + SYRK trailing update on

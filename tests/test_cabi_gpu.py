@@ -373,3 +373,27 @@ def test_planned_solves_match_reference(dtype, n, m, tol):
         assert rel(ops.trsm_(L, B.clone(), plan=plan), torch.linalg.solve_triangular(Ld, Bd, upper=False)) < tol
         assert rel(ops.trsm_(L, B.clone(), trans=True, plan=plan), torch.linalg.solve_triangular(Ld.t(), Bd, upper=True)) < tol
         assert rel(ops.potrs_(L, B.clone(), plan=plan), torch.cholesky_solve(Bd, Ld)) < 10 * tol
+
+
+def test_split_matmul_whitening_matches_float64_solve():
+    """FP32 whitening L_Z^{-1} K through the FP64 inverse factor carried as an FP32 hi/lo pair (3xTF32
+    tensor-core products) against the float64 triangular solve, values and both gradients."""
+    from deconditional_downscaling_b200 import functional as F
+    torch.manual_seed(11)
+    M, N = 512, 2048
+    Z = torch.randn(M, 3, dtype=torch.float64, device="cuda")
+    Kzz = (torch.exp(-0.5 * torch.cdist(Z, Z) ** 2) + 1e-3 * torch.eye(M, dtype=torch.float64, device="cuda")).requires_grad_(True)
+    K64 = torch.randn(M, N, dtype=torch.float64, device="cuda").requires_grad_(True)
+    G = torch.randn(M, N, dtype=torch.float64, device="cuda")
+    ref = torch.linalg.solve_triangular(torch.linalg.cholesky(Kzz), K64, upper=False)
+    (ref * G).sum().backward()
+    A2 = Kzz.detach().clone().requires_grad_(True)
+    K32 = K64.detach().float().requires_grad_(True)
+    got = F.split_matmul(F.chol_inverse(A2), K32)
+    (got * G.float()).sum().backward()
+    rel = lambda a, b: ((a.double() - b).norm() / b.norm()).item()
+    assert got.dtype == torch.float32
+    assert rel(got, ref.detach()) < 5e-6
+    assert rel(K32.grad, K64.grad) < 5e-6
+    sym = lambda g: 0.5 * (g + g.t())
+    assert rel(sym(A2.grad), sym(Kzz.grad)) < 1e-4
