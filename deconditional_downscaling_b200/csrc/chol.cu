@@ -18,6 +18,7 @@
 // non-positive pivot; nothing here synchronises the stream.
 #include "common.cuh"
 #include "mma.cuh"
+#include "tc.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -330,79 +331,160 @@ __global__ void __launch_bounds__(NTHREADS) potrf_diag_kernel(T* __restrict__ A,
 
 // Look-ahead step kernel (FP32): the whole serial link between two diagonal blocks in one launch.
 //   R  = A[j+1, j] (a private copy made before the bulk lane solves that panel in place), X = inv(L_jj):
-//   P  = R X^T                                  (block row j+1 of L, kept in shared memory only)
+//   P  = R X^T                                  (block row j+1 of L, kept on chip only)
 //   S  = A[j+1, j+1] - P P^T                    (all earlier panels were applied by the bulk lane)
 //   then as potrf_diag_kernel: S = L L^T, L -> A, inv(L) -> workspace.
-// Both products run as register-blocked 3xTF32 tiles (32 x 32 per warp) straight from shared memory.
+// Both 128^3 products run on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in
+// TMEM) as 3xTF32: the operands are written to shared memory in the canonical K-major 128-byte-swizzle
+// layout by the loading threads themselves (no TMA: the data needs the hi/lo split anyway), three
+// 64 KB operand buffers rotate through {R, X, R_lo}, {R, X, X_lo}, {P, P_lo, S}.
+constexpr int STEP_BUF = 66 * 1024;  // >= 128 x 129 floats (the pitch-129 tile of the factorisation) and 1024-aligned
+constexpr size_t STEP_SMEM = 3 * STEP_BUF + 1024;
+
+// byte offset of element (row r, k) of a 128 x 128 FP32 K-major operand: four 16 KB k-blocks of 128-byte
+// rows whose 16-byte chunks are XOR-swizzled with the row index (what TMA SWIZZLE_128B would produce)
+__device__ __forceinline__ uint32_t canon_off(int r, int k) {
+    return (uint32_t)((k >> 5) * 16384 + r * 128 + ((((k & 31) >> 2) ^ (r & 7)) << 4) + ((k & 3) << 2));
+}
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// 16 MMAs: D[128 x 128] (+)= A[128 x 128] B[128 x 128]^T over K = 128 (both K-major canonical tiles)
+__device__ __forceinline__ void issue_128(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, bool fresh) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+            umma_tf32(tmem_d, make_desc(a_addr + kb * 16384 + kk * 32, 16, 1024, 2),
+                      make_desc(b_addr + kb * 16384 + kk * 32, 16, 1024, 2), idesc, (fresh && kb == 0 && kk == 0) ? 0u : 1u);
+}
+
+#define TMEM_LD32(r, taddr)                                                                                          \
+    asm volatile(                                                                                                    \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                    \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                    \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                    \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), \
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),     \
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),    \
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                  \
+        : "r"(taddr));                                                                                               \
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
+
 __global__ void __launch_bounds__(NTHREADS) potrf_step_kernel(float* __restrict__ A, int64_t lda, int nb,
                                                               float* __restrict__ inv, int* info, int64_t j0,
                                                               const float* __restrict__ R, const float* __restrict__ invp) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* S = reinterpret_cast<float*>(smem_raw);
-    float* Rb = S + NB * SP;
-    float* Ib = Rb + NB * SP;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* B0 = base;
+    unsigned char* B1 = base + STEP_BUF;
+    unsigned char* B2 = base + 2 * STEP_BUF;
     __shared__ float rinv[NB];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef DCGP_LEAF_TIMING
     long long tq0 = clock64();
 #endif
-    // R (nb x NB, pitch NB) and X (NB x NB lower, pitch NB): contiguous, 16-byte vectors
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // R -> B0, R_lo -> B2, X -> B1 (canonical operand layout); 16-byte vectors, 8 lanes per 128-byte row segment
     for (int e = tid; e < NB * NB / 4; e += NTHREADS) {
         const int i = e >> 5, k = (e & 31) * 4;
         const float4 r = (i < nb) ? *reinterpret_cast<const float4*>(R + i * NB + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 x = *reinterpret_cast<const float4*>(invp + i * NB + k);
-        Rb[i * SP + k] = r.x; Rb[i * SP + k + 1] = r.y; Rb[i * SP + k + 2] = r.z; Rb[i * SP + k + 3] = r.w;
-        Ib[i * SP + k] = x.x; Ib[i * SP + k + 1] = x.y; Ib[i * SP + k + 2] = x.z; Ib[i * SP + k + 3] = x.w;
+        const uint32_t off = canon_off(i, k);
+        *reinterpret_cast<float4*>(B0 + off) = r;
+        *reinterpret_cast<float4*>(B2 + off) = make_float4(tf32_lo(r.x), tf32_lo(r.y), tf32_lo(r.z), tf32_lo(r.w));
+        *reinterpret_cast<float4*>(B1 + off) = x;
     }
-    load_lower<float>(S, rinv, A, lda, nb, false);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    const uint32_t a0 = smem_u32(B0), a1 = smem_u32(B1), a2 = smem_u32(B2);
 #ifdef DCGP_LEAF_TIMING
     long long tq1 = clock64();
 #endif
-    {
-        // P = R X^T: warp (bm, bn) owns rows 32 bm.., columns 32 bn..; X is lower triangular, so k < 32 bn + 32
-        const int bm = warp >> 2, bn = warp & 3;
-        float acc[2][4][4] = {};
-        warp_block_mma<2, 4>(
-            acc, 32 * bn + 32, [&](int r, int k) { return Rb[(32 * bm + r) * SP + k]; },
-            [&](int k, int c) { return Ib[(32 * bn + c) * SP + k]; });
-        __syncthreads();  // every warp is done reading R
-        const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int row = 32 * bm + 16 * mi + g + ((q >> 1) << 3), col = 32 * bn + 8 * ni + 2 * t + (q & 1);
-                    Rb[row * SP + col] = acc[mi][ni][q];
-                }
+    // ---- P = R X^T: R_hi X_hi + R_lo X_hi, then (after X_lo replaces R_lo) R_hi X_lo
+    if (tid == 0) {
+        issue_128(tmem, a0, a1, true);
+        issue_128(tmem, a2, a1, false);
+        umma_commit(&bar);
     }
+    mbar_wait(&bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int e = tid; e < NB * NB / 4; e += NTHREADS) {
+        const float4 x = *reinterpret_cast<const float4*>(B1 + e * 16);  // elementwise: same offsets in both buffers
+        *reinterpret_cast<float4*>(B2 + e * 16) = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {
+        issue_128(tmem, a0, a2, false);
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- P (TMEM columns 0..127) -> operand tiles: P in B0, P_lo in B2.  Warp w reads lane quadrant w % 4,
+    // columns 32 (w / 4) ..; a thread holds one row, 32 consecutive k = one k-block of that row.
+    {
+        const int row = (warp & 3) * 32 + lane, kb = warp >> 2;
+        uint32_t r[32];
+        TMEM_LD32(r, tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kb * 32));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float4 v = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]), __uint_as_float(r[4 * c + 2]),
+                                         __uint_as_float(r[4 * c + 3]));
+            const uint32_t off = (uint32_t)(kb * 16384 + row * 128 + ((c ^ (row & 7)) << 4));
+            *reinterpret_cast<float4*>(B0 + off) = v;
+            *reinterpret_cast<float4*>(B2 + off) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #ifdef DCGP_LEAF_TIMING
     long long tq2 = clock64();
 #endif
-    if (warp < 10) {
-        // S -= P P^T on the 10 lower 32 x 32 blocks
-        int bm = 0, e = warp;
-        while (e > bm) { e -= bm + 1; ++bm; }
-        const int bn = e;
-        float acc[2][4][4] = {};
-        warp_block_mma<2, 4>(
-            acc, NB, [&](int r, int k) { return Rb[(32 * bm + r) * SP + k]; },
-            [&](int k, int c) { return Rb[(32 * bn + c) * SP + k]; });
-        const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int row = 32 * bm + 16 * mi + g + ((q >> 1) << 3), col = 32 * bn + 8 * ni + 2 * t + (q & 1);
-                    if (col <= row && row < nb) S[row * SP + col] -= acc[mi][ni][q];
-                }
+    // ---- P P^T into TMEM columns 128..255 while every thread fetches the diagonal tile into B1 (X is dead)
+    if (tid == 0) {
+        issue_128(tmem + 128, a0, a0, true);
+        issue_128(tmem + 128, a2, a0, false);
+        issue_128(tmem + 128, a0, a2, false);
+        umma_commit(&bar);
     }
+    float* S = reinterpret_cast<float*>(B1);
+    load_lower<float>(S, rinv, A, lda, nb, false);
     __syncthreads();
+    mbar_wait(&bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+        const int row = (warp & 3) * 32 + lane, c0 = (warp >> 2) * 32;
+        uint32_t r[32];
+        TMEM_LD32(r, tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(128 + c0));
+        if (row < nb) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (c0 + j <= row) S[row * SP + c0 + j] -= __uint_as_float(r[j]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+    }
 #ifdef DCGP_LEAF_TIMING
     long long tq3 = clock64();
 #endif
@@ -649,7 +731,7 @@ int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(potrf_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(3 * NB * SP * sizeof(float)));
+                                             (int)STEP_SMEM);
         if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
         attr = true;
     }
@@ -662,6 +744,8 @@ int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
     {
         const int64_t b1 = j0 + NB, w1 = (end - b1 < NB) ? end - b1 : NB;
         DCGP_CU(copy_row(b1, j0, w1, 0, c.st));
+        rc = dcgp_split_lo_impl(c.A + b1 * c.lda + j0, c.Alo + b1 * c.lda + j0, end - b1, NB, c.lda, c.lda, c.st);
+        if (rc) return rc;
     }
     DCGP_CU(cudaEventRecord(x.fork, c.st));
     DCGP_CU(cudaStreamWaitEvent(sa, x.fork, 0));
@@ -682,9 +766,21 @@ int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
         TRACE_MARK("B.start", j, sb);
         float* P = c.A + b1 * c.lda + bj;          // rows b1 .. end of panel j
         float* Plo = c.Alo + b1 * c.lda + bj;
-        rc = dcgp_gemm_impl(0, 1, end - b1, NB, NB, 1.0, P, c.lda, invj, NB, 0.0, P, c.lda, c.dtype, DCGP_GEMM_INPLACE | c.xf, sb,
-                            nullptr, nullptr, Plo);
-        if (rc) return rc;
+        // in place on the tcgen05 kernel: a tile owns all 128 columns of its rows, which it has read in full
+        // before its epilogue overwrites them (the remainders of the panel came from the previous update)
+        rc = 1;
+        if (end - b1 >= NB) {
+            float* invlo = rcopy + 2 * NB * NB;
+            rc = dcgp_split_lo_impl(invj, invlo, NB, NB, NB, NB, sb);
+            if (rc) return rc;
+            rc = dcgp_gemm_tc_ex(0, 1, end - b1, NB, NB, 1.0, P, c.lda, invj, NB, 0.0, P, c.lda, 0, Plo, invlo, Plo, 0, 0, sb);
+            if (rc < 0) return rc;
+        }
+        if (rc == 1) {
+            rc = dcgp_gemm_impl(0, 1, end - b1, NB, NB, 1.0, P, c.lda, invj, NB, 0.0, P, c.lda, c.dtype, DCGP_GEMM_INPLACE | c.xf,
+                                sb, nullptr, nullptr, Plo);
+            if (rc) return rc;
+        }
         TRACE_MARK("B.trsm", j, sb);
         if (nr > 0) {
             float* P2 = c.A + r0 * c.lda + bj;
@@ -692,11 +788,11 @@ int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
             rc = 1;
             if (nr >= NB)
                 rc = dcgp_gemm_tc_ex(0, 1, nr, w1 + nr, NB, -1.0, P2, c.lda, P, c.lda, 1.0, c.A + r0 * c.lda + b1, c.lda,
-                                     DCGP_GEMM_LOWER, P2lo, Plo, nullptr, w1, 0, sb);
+                                     DCGP_GEMM_LOWER, P2lo, Plo, c.Alo + r0 * c.lda + b1, w1, w1, sb);  // Clo: next panel only
             if (rc < 0) return rc;
             if (rc == 1) {  // shape / alignment not taken by the tcgen05 kernel
                 rc = dcgp_gemm_impl(0, 1, nr, w1, NB, -1.0, P2, c.lda, P, c.lda, 1.0, c.A + r0 * c.lda + b1, c.lda, c.dtype, c.xf,
-                                    sb, P2lo, Plo, nullptr);
+                                    sb, P2lo, Plo, c.Alo + r0 * c.lda + b1);
                 if (rc) return rc;
                 rc = dcgp_gemm_impl(0, 1, nr, nr, NB, -1.0, P2, c.lda, P2, c.lda, 1.0, c.A + r0 * c.lda + r0, c.lda, c.dtype,
                                     DCGP_GEMM_LOWER | c.xf, sb, P2lo, P2lo, nullptr);
@@ -710,7 +806,7 @@ int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
         // ---- chain lane: block j+1 (its inputs were completed by the bulk update of panel j-1)
         if (j > 0) DCGP_CU(cudaStreamWaitEvent(sa, x.upd[ep], 0));
         TRACE_MARK("A.waited", j, sa);
-        potrf_step_kernel<<<1, NTHREADS, 3 * NB * SP * sizeof(float), sa>>>(c.A + b1 * c.lda + b1, c.lda, (int)w1,
+        potrf_step_kernel<<<1, NTHREADS, STEP_SMEM, sa>>>(c.A + b1 * c.lda + b1, c.lda, (int)w1,
                                                                            c.ws + (b1 / NB) * NB * NB, c.info, b1,
                                                                            rcopy + (size_t)(j & 1) * NB * NB, invj);
         DCGP_CHECK_LAUNCH();
@@ -798,7 +894,7 @@ int potrf_impl(T* A, int64_t n, int64_t lda, int* info, T* ws, size_t ws_bytes, 
     int rc = set_smem_attr<T>((const void*)potrf_diag_kernel<T>);
     if (rc) return rc;
     T* lo = nullptr;
-    const size_t rcopy_bytes = 2 * NB * NB * 4;
+    const size_t rcopy_bytes = 3 * NB * NB * 4;  // two block-row copies + remainders of one inverted block
     if (sizeof(T) == 4 && xf && n > 2 * NB && ws_bytes >= inv_ws_bytes(n, dtype) + rcopy_bytes + (size_t)n * lda * 4)
         lo = ws + (inv_ws_bytes(n, dtype) + rcopy_bytes) / sizeof(T);
     Ctx<T> c{A, lda, ws, info, dtype, xf, st, lo};
@@ -1153,7 +1249,7 @@ int trtri_impl(const T* L, int64_t n, int64_t ldl, T* W, int64_t ldw, T* tmp, in
 // leading dimensions; with padded ones the drivers fall back to the mma.sync 3xTF32 kernel).
 extern "C" size_t dcgp_potrf_workspace(int64_t n, int dtype) {
     if (n <= 0) return 0;
-    return inv_ws_bytes(n, dtype) + (dtype == DCGP_F32 ? (size_t)n * n * 4 + 2 * NB * NB * 4 : 0);
+    return inv_ws_bytes(n, dtype) + (dtype == DCGP_F32 ? (size_t)n * n * 4 + 3 * NB * NB * 4 : 0);
 }
 
 extern "C" int dcgp_potrf(void* A, int64_t n, int64_t lda, int* info, void* workspace, size_t workspace_bytes,

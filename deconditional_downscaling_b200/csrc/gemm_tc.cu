@@ -25,7 +25,7 @@
 // Shapes this kernel does not take (tiny problems, split-K candidates, unaligned leading
 // dimensions, 3xTF32 without remainder matrices) stay on the mma.sync kernel in gemm.cu.
 #include "common.cuh"
-#include <cuda.h>
+#include "tc.cuh"
 #include <cstdlib>
 
 namespace {
@@ -34,7 +34,7 @@ constexpr int TM = 128, TK = 32;  // CTA tile rows; TK floats = one 128-byte swi
 constexpr int STAGES = 4;
 constexpr int A_BYTES = TM * TK * 4;  // 16 KB
 constexpr int EPI_WARPS = 8;
-constexpr int NTHREADS_TC = 64 + 32 * EPI_WARPS;  // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-9 epilogue
+constexpr int NTHREADS_TC = 96 + 32 * EPI_WARPS;  // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-9 epilogue, warp 10 L2 prefetch
 constexpr int STG_PITCH = 33;                     // epilogue transpose buffers: 32 x 33 floats per warp
 constexpr int STG_BYTES = 32 * STG_PITCH * 4;
 constexpr int GROUP_M = 16;
@@ -56,62 +56,6 @@ struct TcParams {
     int64_t lower_off;  // lower: keep tiles with col0 <= row0 + TM - 1 + lower_off
     int64_t clo_cols;   // Clo is written for columns < clo_cols only (0 = all)
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(smem)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_c),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-
-// shared-memory matrix descriptor, 128-byte swizzle, sm_100 version bit set
-// layout: 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms, MN-major 32-bit data)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                              uint32_t layout) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-    d |= (uint64_t)layout << 61;
-    return d;
-}
 
 // tile index -> (tile row, tile column), grouped for L2 reuse
 __device__ __forceinline__ void tile_coord(const TcParams& p, int t, int& tm, int& tn) {
@@ -238,6 +182,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 ++lt;
             }
         }
+    } else if (warp == 2 + EPI_WARPS) {
+        // ===== with beta != 0: pull the C tile of the tile whose MMAs are starting into L2, one tile ahead of the
+        // epilogue, which cannot keep enough loads in flight by itself to cover DRAM latency =====
+        if (p.beta != 0.f) {
+            constexpr int LPR = TN * 4 / 128;  // 128-byte lines per tile row
+            uint32_t lt = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                int tm, tn;
+                tile_coord(p, t, tm, tn);
+                const int64_t m0 = (int64_t)tm * TM, n0 = (int64_t)tn * TN;
+                if (p.lower && n0 > m0 + TM - 1 + p.lower_off) continue;
+                if (lt > 0) mbar_wait(&tmem_full[(lt - 1) & 1u], ((lt - 1) >> 1) & 1u);
+                for (int e = lane; e < TM * LPR; e += 32) {
+                    const int64_t row = m0 + e / LPR, col = n0 + (e % LPR) * 32;
+                    if (row < p.m && col < p.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.C + row * p.ldc + col));
+                }
+                ++lt;
+            }
+        }
     } else {
         // ===== epilogue: warps 2..9; TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 =====
         const int q = warp & 3, h = (warp - 2) >> 2;
@@ -253,20 +216,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (p.lower && n0 > m0 + TM - 1 + p.lower_off) continue;
             const uint32_t buf = lt & 1u;
             const int64_t rbase = m0 + q * 32;
+            // old C is fetched one chunk ahead: the loads do not depend on the accumulator and stay in flight
+            // across the tcgen05.ld / transpose / store work of the previous chunk
+            float4 old[8], nxt[8];
+            auto fetch = [&](int ch, float4 (&dst)[8]) {
+                const int c0 = h * (TN / 2) + ch * 32;
+                if (p.beta != 0.f && vec && (n0 + c0 + 32 <= p.n)) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int64_t row = rbase + i * 4 + rsub;
+                        dst[i] = (row < p.m) ? *reinterpret_cast<const float4*>(p.C + row * p.ldc + n0 + c0 + c4)
+                                             : make_float4(0, 0, 0, 0);
+                    }
+                }
+            };
+            fetch(0, nxt);
 #pragma unroll 1
             for (int ch = 0; ch < TN / 64; ++ch) {
                 const int c0 = h * (TN / 2) + ch * 32;
                 const int64_t col = n0 + c0 + c4;
                 const bool fast = vec && (n0 + c0 + 32 <= p.n);
-                // old C first: these loads do not depend on the accumulator
-                float4 old[8];
-                if (p.beta != 0.f && fast) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int64_t row = rbase + i * 4 + rsub;
-                        old[i] = (row < p.m) ? *reinterpret_cast<const float4*>(p.C + row * p.ldc + col) : make_float4(0, 0, 0, 0);
-                    }
-                }
+                for (int i = 0; i < 8; ++i) old[i] = nxt[i];
+                if (ch + 1 < TN / 64) fetch(ch + 1, nxt);
                 if (ch == 0) {
                     mbar_wait(&tmem_full[buf], (lt >> 1) & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -416,7 +388,10 @@ int launch_tc(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMa
     p.tiles_m = (int)((p.m + TM - 1) / TM);
     p.tiles_n = (int)((p.n + TN - 1) / TN);
     const int64_t nt = (int64_t)p.tiles_m * p.tiles_n;
-    const unsigned grid = (unsigned)(nt < num_sms() ? nt : num_sms());
+    // one SM is left to the serial lane of the look-ahead factorisation / solves (single-CTA kernels that must
+    // not queue behind a persistent grid occupying every SM)
+    const int64_t cap = num_sms() > 8 ? num_sms() - 1 : num_sms();
+    const unsigned grid = (unsigned)(nt < cap ? nt : cap);
     gemm_tc_kernel<TN><<<grid, NTHREADS_TC, smem_tc<TN>(), st>>>(mapA, mapB, mapAlo, mapBlo, p);
     DCGP_CHECK_LAUNCH();
     return 0;

@@ -13,7 +13,7 @@ host = bench.minibatches(wl, shard, 5, seed=99)
 devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
 rec, on = [], [False]
 names = [n for n in ("gemm", "potrf_", "trsm_", "potrs_", "gram", "gram_bwd", "gram_bagsum", "gram_bagsum_bwd",
-                     "gram_bag_blocksum", "gram_bag_blocksum_bwd", "bag_sum", "whitened_kl", "logdet_chol") if hasattr(ops, n)]
+                     "gram_bag_blocksum", "gram_bag_blocksum_bwd", "bag_sum", "whitened_kl", "logdet_chol", "gemm_x3", "trtri", "split_lo", "solve_plan") if hasattr(ops, n)]
 for name in names:
     orig = getattr(ops, name)
     def wrapped(*a, _o=orig, _n=name, **k):
