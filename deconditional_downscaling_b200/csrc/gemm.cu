@@ -442,6 +442,14 @@ extern "C" int dcgp_gemm_ex(int transa, int transb, int64_t m, int64_t n, int64_
                           (cudaStream_t)stream, Alo, Blo, Clo);
 }
 
+// C (lower triangle) = alpha * op(A) op(A)^T + beta * C;  trans = 0: A is n x k, trans = 1: A is k x n
+extern "C" int dcgp_syrk(int trans, int64_t n, int64_t k, double alpha, const void* A, int64_t lda, double beta, void* C,
+                         int64_t ldc, int dtype, int flags, void* stream) {
+    return dcgp_gemm_impl(trans ? 1 : 0, trans ? 0 : 1, n, n, k, alpha, A, lda, A, lda, beta, C, ldc, dtype,
+                          (flags & (DCGP_GEMM_TF32X3 | DCGP_GEMM_NO_TCGEN05 | DCGP_GEMM_NO_SPLITK)) | DCGP_GEMM_LOWER,
+                          (cudaStream_t)stream, nullptr, nullptr, nullptr);
+}
+
 extern "C" int dcgp_gemm(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A,
                          int64_t lda, const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype,
                          int flags, void* stream) {

@@ -473,6 +473,94 @@ extern "C" int dcgp_gram(const dcgp_kernel_spec* spec, const void* x1, int64_t n
     return -12;
 }
 
+int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
+                   const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype, int flags,
+                   cudaStream_t st, const void* Alo, const void* Blo, void* Clo);
+
+namespace {
+// out[r, :] += (diag_const + diag_dev[0]) * W[r, :]: the nugget term of (K + c I) W for a row chunk
+template <typename T>
+__global__ void nugget_rows_kernel(T* __restrict__ out, int64_t ldo, const T* __restrict__ W, int64_t ldw, int64_t rows,
+                                   int64_t m, const T* __restrict__ diag_dev, T diag_const) {
+    const T c = diag_const + (diag_dev ? diag_dev[0] : T(0));
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < rows * m; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / m, j = e - r * m;
+        out[r * ldo + j] += c * W[r * ldw + j];
+    }
+}
+// Gram row panels: one panel when the whole matrix is small (<= 1 GiB: a single wide GEMM fills the machine
+// best), else 512 MiB panels - the full matrix (34 GB at N = 65536 in FP64) is never resident
+int64_t gm_rows(int64_t n1, int64_t n2, int dtype) {
+    const int64_t es = dtype == DCGP_F64 ? 8 : 4;
+    if (n1 * n2 * es <= (1ll << 30)) return n1;
+    int64_t rows = (512ll << 20) / (n2 * es);
+    rows = (rows / 128) * 128;
+    if (rows < 128) rows = 128;
+    return rows < n1 ? rows : n1;
+}
+}  // namespace
+
+// out = (k(x1, x2) [+ (diag_const + *diag_dev) I when SAME]) W without ever holding the Gram matrix in HBM as a
+// whole once it is large: row panels are generated into the workspace and consumed by the tensor-core GEMM.
+extern "C" size_t dcgp_gram_matmul_workspace(int64_t n1, int64_t n2, int dtype) {
+    if (n1 <= 0 || n2 <= 0) return 0;
+    return (size_t)gm_rows(n1, n2, dtype) * n2 * (dtype == DCGP_F64 ? 8 : 4);
+}
+
+extern "C" int dcgp_gram_matmul(const dcgp_kernel_spec* spec, const void* x1, int64_t n1, int64_t ldx1, const void* x2,
+                                int64_t n2, int64_t ldx2, const void* diag_dev, double diag_const, const void* W, int64_t m,
+                                int64_t ldw, void* out, int64_t ldo, void* workspace, size_t workspace_bytes, int dtype,
+                                int flags, void* stream) {
+    DevSpec sp;
+    if (make_dev_spec(spec, &sp)) return -1;
+    if (!x1 || n1 < 0) return -2;
+    if (!x2 || n2 < 0) return -5;
+    if (!W || m < 0 || ldw < m) return -10;
+    if (!out || ldo < m) return -13;
+    if (dtype != DCGP_F64 && dtype != DCGP_F32) return -17;
+    if (n1 == 0 || m == 0) return 0;
+    const int same = (flags & DCGP_GRAM_SAME) ? 1 : 0;
+    if (same && n1 != n2) return -6;
+    if (n2 == 0) return -6;
+    if (!workspace || workspace_bytes < dcgp_gram_matmul_workspace(n1, n2, dtype)) return -15;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t es = dtype == DCGP_F64 ? 8 : 4, rows = gm_rows(n1, n2, dtype);
+    const int gflags = flags & (DCGP_GEMM_TF32X3 | DCGP_GEMM_NO_TCGEN05);
+    if (rows == n1) {
+        // single panel: the symmetric Gram path (nugget applied on the diagonal by the generator itself)
+        int rc = dtype == DCGP_F64 ? launch_gram_fwd<double, double>(sp, x1, n1, ldx1, x2, n2, ldx2, workspace, n2, diag_dev,
+                                                                     diag_const, same, st)
+                                   : launch_gram_fwd<float, float>(sp, x1, n1, ldx1, x2, n2, ldx2, workspace, n2, diag_dev,
+                                                                   diag_const, same, st);
+        if (rc) return rc;
+        return dcgp_gemm_impl(0, 0, n1, m, n2, 1.0, workspace, n2, W, ldw, 0.0, out, ldo, dtype, gflags, st, nullptr, nullptr,
+                              nullptr);
+    }
+    for (int64_t r0 = 0; r0 < n1; r0 += rows) {
+        const int64_t nr = (n1 - r0 < rows) ? n1 - r0 : rows;
+        const char* xp = (const char*)x1 + r0 * ldx1 * es;
+        int rc = dtype == DCGP_F64
+                     ? launch_gram_fwd<double, double>(sp, xp, nr, ldx1, x2, n2, ldx2, workspace, n2, nullptr, 0.0, 0, st)
+                     : launch_gram_fwd<float, float>(sp, xp, nr, ldx1, x2, n2, ldx2, workspace, n2, nullptr, 0.0, 0, st);
+        if (rc) return rc;
+        char* op = (char*)out + r0 * ldo * es;
+        rc = dcgp_gemm_impl(0, 0, nr, m, n2, 1.0, workspace, n2, W, ldw, 0.0, op, ldo, dtype, gflags, st, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+        if (same && (diag_dev || diag_const != 0.0)) {
+            const char* wp = (const char*)W + r0 * ldw * es;
+            const unsigned grid = (unsigned)((nr * m + 255) / 256 < 4096 ? (nr * m + 255) / 256 : 4096);
+            if (dtype == DCGP_F64)
+                nugget_rows_kernel<double><<<grid, 256, 0, st>>>((double*)op, ldo, (const double*)wp, ldw, nr, m,
+                                                                 (const double*)diag_dev, diag_const);
+            else
+                nugget_rows_kernel<float><<<grid, 256, 0, st>>>((float*)op, ldo, (const float*)wp, ldw, nr, m,
+                                                                (const float*)diag_dev, (float)diag_const);
+            DCGP_CHECK_LAUNCH();
+        }
+    }
+    return 0;
+}
+
 extern "C" int dcgp_gram_bwd(const dcgp_kernel_spec* spec, const void* x1, int64_t n1, int64_t ldx1, const void* x2,
                              int64_t n2, int64_t ldx2, const void* G, int64_t ldg, void* dls, void* dos, void* dx1,
                              int64_t lddx1, int dtype, int flags, void* stream) {

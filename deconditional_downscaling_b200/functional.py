@@ -380,8 +380,7 @@ class _KernelMatmulFn(Function):
 
     @staticmethod
     def forward(ctx, meta, x1, x2, W, diag_dev, *hyp):
-        K = ops.gram(_spec(meta, hyp), x1, x2, diag_dev=diag_dev, diag_const=meta.diag_const)
-        out = ops.gemm(K, W)
+        out = ops.gram_matmul(_spec(meta, hyp), x1, x2, W.detach(), diag_dev=diag_dev, diag_const=meta.diag_const)
         ctx.meta, ctx.same = meta, x2 is None
         ctx.save_for_backward(x1, x2 if x2 is not None else x1, W, diag_dev if diag_dev is not None else W.new_zeros(1), *hyp)
         ctx.has_diag = diag_dev is not None
@@ -396,10 +395,9 @@ class _KernelMatmulFn(Function):
         spec = _spec(meta, hyp)
         gW = None
         if need[3]:
-            K = ops.gram(spec, x1, None if same else x2, diag_dev=diag_dev if ctx.has_diag else None,
-                         diag_const=meta.diag_const)
-            gW = ops.gemm(K, gO, transa=True)
-            del K
+            # K^T gO: the Gram matrix is symmetric when x2 is x1, otherwise k(x2, x1) is its transpose
+            gW = ops.gram_matmul(spec, x1, None, gO, diag_dev=diag_dev if ctx.has_diag else None, diag_const=meta.diag_const) \
+                if same else ops.gram_matmul(spec, x2, x1, gO)
         dx1 = dx2 = None
         hg = [None] * len(hyp)
         if need[1] or need[2] or any(need[5:]):

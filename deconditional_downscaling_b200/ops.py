@@ -134,6 +134,41 @@ def gram(spec: FlatSpec, x1, x2=None, diag_dev=None, diag_const=0.0, out=None):
     return K
 
 
+def gram_matmul(spec: FlatSpec, x1, x2, W, diag_dev=None, diag_const=0.0):
+    """(k(x1, x2) [+ nugget when x2 is None]) @ W with the Gram matrix held only as bounded row panels."""
+    same = x2 is None
+    x1 = _rowmajor(x1)
+    x2 = x1 if same else _rowmajor(x2)
+    W = _rowmajor(W)
+    _req(x1, x2, W, diag_dev)
+    n1, n2, m = x1.size(0), x2.size(0), W.size(1)
+    if W.size(0) != n2:
+        raise ValueError(f"gram_matmul: W has {W.size(0)} rows, the Gram matrix {n2} columns")
+    out = torch.empty(n1, m, dtype=x1.dtype, device=x1.device)
+    lib = _lib.load()
+    ws = _workspace(lib.dcgp_gram_matmul_workspace(n1, n2, _dt(x1)), x1.device)
+    cs = spec.c_spec()
+    flags = (GRAM_SAME if same else 0) | _x3(x1, n1 * n2 * m <= X3_GEMM_LIMIT)
+    rc = lib.dcgp_gram_matmul(ctypes.byref(cs), _ptr(x1), n1, _ld(x1), _ptr(x2), n2, _ld(x2), _ptr(diag_dev), float(diag_const),
+                              _ptr(W), m, _ld(W), _ptr(out), _ld(out), _ptr(ws), ws.numel(), _dt(x1), flags, _stream())
+    check(rc, "dcgp_gram_matmul")
+    return out
+
+
+def syrk(A, trans=False, alpha=1.0, beta=0.0, C=None):
+    """Lower triangle of alpha * op(A) op(A)^T + beta * C (the strict upper triangle of C is left untouched)."""
+    A = _rowmajor(A)
+    _req(A, C)
+    n, k = (A.size(1), A.size(0)) if trans else (A.size(0), A.size(1))
+    if C is None:
+        C = torch.zeros(n, n, dtype=A.dtype, device=A.device)
+        beta = 0.0
+    rc = _lib.load().dcgp_syrk(int(trans), n, k, float(alpha), _ptr(A), _ld(A), float(beta), _ptr(C), _ld(C), _dt(A),
+                               _x3(A, n * n * k <= X3_GEMM_LIMIT), _stream())
+    check(rc, "dcgp_syrk")
+    return C
+
+
 def gram_bwd(spec: FlatSpec, x1, x2, G, need_dx1=False):
     """Returns (dls [ncomp, MAX_DIMS], dos [ncomp], dx1 or None)."""
     same = x2 is None

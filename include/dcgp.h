@@ -96,6 +96,15 @@ DCGP_API int dcgp_gram(const dcgp_kernel_spec* spec, const void* x1, int64_t n1,
               int64_t ldx2, void* K, int64_t ldk, const void* diag_dev, double diag_const, int dtype, int flags,
               void* stream);
 
+/* out = (k(x1, x2) [+ (diag_const + *diag_dev) I with DCGP_GRAM_SAME]) W, W is n2 x m: the fused K W of
+ * SURVEY.md section 8a row 6 (src/kernels/cme_aggregate_kernel.py:58-70 forms K R by materialising K).  The
+ * Gram matrix exists only as row panels in the workspace (a single panel up to 1 GiB, 512 MiB panels beyond). */
+DCGP_API size_t dcgp_gram_matmul_workspace(int64_t n1, int64_t n2, int dtype);
+DCGP_API int dcgp_gram_matmul(const dcgp_kernel_spec* spec, const void* x1, int64_t n1, int64_t ldx1, const void* x2,
+                     int64_t n2, int64_t ldx2, const void* diag_dev, double diag_const, const void* W, int64_t m,
+                     int64_t ldw, void* out, int64_t ldo, void* workspace, size_t workspace_bytes, int dtype, int flags,
+                     void* stream);
+
 /* Backward of dcgp_gram for a dense upstream gradient G (n1 x n2):
  *   dls[c*DCGP_MAX_DIMS + k] += sum_ij G_ij dK_ij/dl_{c,k}
  *   dos[c]                   += sum_ij G_ij dK_ij/dos_c
@@ -117,6 +126,12 @@ DCGP_API int dcgp_gram_bwd(const dcgp_kernel_spec* spec, const void* x1, int64_t
  * src/variational/variational_strategy.py:44-65. */
 DCGP_API int dcgp_gemm(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
               const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype, int flags, void* stream);
+
+/* C (lower triangle only) = alpha * op(A) op(A)^T + beta * C; trans = 0: A is n x k, trans = 1: A is k x n.
+ * The trailing updates of the factorisation and the A^T A / U^T U terms of the ELBO
+ * (src/likelihoods/cmp_likelihood.py:61-64) are of this form. */
+DCGP_API int dcgp_syrk(int trans, int64_t n, int64_t k, double alpha, const void* A, int64_t lda, double beta, void* C,
+              int64_t ldc, int dtype, int flags, void* stream);
 
 /* 3xTF32 with the tensor core's own operand rounding: tcgen05.mma kind::tf32 reads an FP32 operand
  * truncated to TF32 (x_hi); dcgp_split_lo writes what it drops, x_lo = x - x_hi.  dcgp_gemm_ex takes

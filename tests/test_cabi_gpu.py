@@ -397,3 +397,35 @@ def test_split_matmul_whitening_matches_float64_solve():
     assert rel(K32.grad, K64.grad) < 5e-6
     sym = lambda g: 0.5 * (g + g.t())
     assert rel(sym(A2.grad), sym(Kzz.grad)) < 1e-4
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 2e-3)])
+def test_gram_matmul_equals_gram_then_gemm(dtype, tol):
+    """dcgp_gram_matmul (row panels through the workspace) == materialised Gram @ W, with and without the
+    nugget, for same and cross inputs, ragged sizes."""
+    from deconditional_downscaling_b200 import ops
+    from deconditional_downscaling_b200.exact import rbf_spec
+    torch.manual_seed(2)
+    spec = rbf_spec(3, dtype, "cuda")
+    x = torch.randn(1111, 3, dtype=dtype, device="cuda")
+    y = torch.randn(777, 3, dtype=dtype, device="cuda")
+    W1 = torch.randn(1111, 65, dtype=dtype, device="cuda")
+    W2 = torch.randn(777, 200, dtype=dtype, device="cuda")
+    dd = torch.tensor([0.3], dtype=dtype, device="cuda")
+    rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm()).item()
+    ref = ops.gram(spec, x, None, diag_dev=dd, diag_const=0.2).double() @ W1.double()
+    assert rel(ops.gram_matmul(spec, x, None, W1, diag_dev=dd, diag_const=0.2), ref) < tol
+    ref = ops.gram(spec, x, y).double() @ W2.double()
+    assert rel(ops.gram_matmul(spec, x, y, W2), ref) < tol
+
+
+def test_syrk_lower_triangle():
+    from deconditional_downscaling_b200 import ops
+    torch.manual_seed(4)
+    A = torch.randn(300, 500, dtype=torch.float64, device="cuda")
+    C0 = torch.randn(300, 300, dtype=torch.float64, device="cuda")
+    C = ops.syrk(A, alpha=-1.0, beta=1.0, C=C0.clone())
+    ref = C0 - A @ A.t()
+    assert torch.allclose(C.tril(), ref.tril(), rtol=1e-12, atol=1e-10)
+    Ct = ops.syrk(A, trans=True)
+    assert torch.allclose(Ct.tril(), (A.t() @ A).tril(), rtol=1e-12, atol=1e-10)

@@ -151,3 +151,16 @@ def test_row_block_sharded_kernel_matmul_equals_unsharded():
                                                km.raw_outputscale.detach().cpu(), None)]), x.cpu()) @ W.cpu()
     assert ((torch.cat(parts) - full).norm() / full.norm()).item() < 1e-13
     assert ((full.cpu() - ref).norm() / ref.norm()).item() < 1e-10
+
+
+def test_gram_matmul_multi_panel_matches_single_products():
+    """Above 1 GiB the Gram matrix is produced in 512 MiB row panels; (K + c I) W must not change."""
+    o = ops()
+    torch.manual_seed(9)
+    dt = torch.float64
+    n, m = 12000, 24
+    x = torch.randn(n, 3, dtype=dt, device=DEV)
+    W = torch.randn(n, m, dtype=dt, device=DEV)
+    got = o.gram_matmul(rbf(3, dt), x, None, W, diag_const=0.37)
+    ref = torch.cat([o.gemm(o.gram(rbf(3, dt), x[i:i + 3000], x), W) for i in range(0, n, 3000)]) + 0.37 * W
+    assert ((got - ref).norm() / ref.norm()).item() < 1e-13
