@@ -49,6 +49,8 @@ _SIGNATURES = {
     "dcgp_gram_matmul": (c_int, [POINTER(KernelSpec), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
                                  c_double, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_size_t, c_int, c_int,
                                  c_void_p]),
+    "dcgp_vbagg_ell": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_int, c_void_p]),
     "dcgp_potrf_workspace": (c_size_t, [c_int64, c_int]),
     "dcgp_potrf": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "dcgp_trsm_workspace": (c_size_t, [c_int64, c_int64, c_int]),

@@ -705,3 +705,62 @@ extern "C" int dcgp_whitened_kl(const void* m, const void* Ls, int64_t M, int64_
     DCGP_CHECK_LAUNCH();
     return 0;
 }
+
+namespace {
+// Bag-level expected log-likelihood of the aggregate-observation model and its adjoints in one pass:
+//   ell = -1/2 sum_a [ (z_a^2 - 2 z_a S_a / n_a + (T_a + S_a^2) / n_a^2) n_a / s2 + log(2 pi s2 / n_a) ]
+//   d ell / d S_a = (z_a - S_a / n_a) / s2,   d ell / d T_a = -1 / (2 n_a s2),
+//   d ell / d s2  = -1/2 sum_a [ 1 / s2 - q_a n_a / s2^2 ]           (q_a = the bracket's first factor)
+template <typename T>
+__global__ void __launch_bounds__(256) vbagg_ell_kernel(const T* __restrict__ z, const T* __restrict__ S,
+                                                        const T* __restrict__ Tq, const int64_t* __restrict__ offsets,
+                                                        int64_t n_bags, const T* __restrict__ noise, T* __restrict__ ell,
+                                                        T* __restrict__ dS, T* __restrict__ dT, T* __restrict__ dnoise) {
+    __shared__ T red[2][8];
+    const T s2 = noise[0];
+    T acc = T(0), accn = T(0);
+    for (int64_t a = threadIdx.x; a < n_bags; a += 256) {
+        const T n = (T)(offsets[a + 1] - offsets[a]);
+        const T q = z[a] * z[a] - T(2) * z[a] * S[a] / n + (Tq[a] + S[a] * S[a]) / (n * n);
+        acc += q * n / s2 + t_log<T>(T(6.283185307179586476925286766559) * s2 / n);
+        accn += T(1) / s2 - q * n / (s2 * s2);
+        if (dS) dS[a] = (z[a] - S[a] / n) / s2;
+        if (dT) dT[a] = T(-0.5) / (n * s2);
+    }
+    acc = warp_sum(acc);
+    accn = warp_sum(accn);
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = acc;
+        red[1][threadIdx.x >> 5] = accn;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T t = T(0), tn = T(0);
+        for (int w = 0; w < 8; ++w) {
+            t += red[0][w];
+            tn += red[1][w];
+        }
+        ell[0] = T(-0.5) * t;
+        if (dnoise) dnoise[0] = T(-0.5) * tn;
+    }
+}
+}  // namespace
+
+extern "C" int dcgp_vbagg_ell(const void* z, const void* S, const void* T, const int64_t* offsets, int64_t n_bags,
+                              const void* noise, void* ell, void* dS, void* dT, void* dnoise, int dtype, void* stream) {
+    if (!z || !S || !T || !offsets) return -1;
+    if (!noise) return -6;
+    if (!ell) return -7;
+    if (n_bags < 0) return -5;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == DCGP_F64)
+        vbagg_ell_kernel<double><<<1, 256, 0, st>>>((const double*)z, (const double*)S, (const double*)T, offsets, n_bags,
+                                                    (const double*)noise, (double*)ell, (double*)dS, (double*)dT, (double*)dnoise);
+    else if (dtype == DCGP_F32)
+        vbagg_ell_kernel<float><<<1, 256, 0, st>>>((const float*)z, (const float*)S, (const float*)T, offsets, n_bags,
+                                                   (const float*)noise, (float*)ell, (float*)dS, (float*)dT, (float*)dnoise);
+    else
+        return -11;
+    DCGP_CHECK_LAUNCH();
+    return 0;
+}

@@ -495,6 +495,26 @@ class _WhitenedKLFn(Function):
         return g * dm, g * dLs
 
 
+class _VbaggEllFn(Function):
+    @staticmethod
+    def forward(ctx, z, S, T, offsets, noise):
+        ell, dS, dT, dn = ops.vbagg_ell(z.detach(), S.detach(), T.detach(), offsets, noise.detach())
+        ctx.save_for_backward(dS, dT, dn)
+        ctx.noise_shape = noise.shape
+        return ell
+
+    @staticmethod
+    def backward(ctx, g):
+        dS, dT, dn = ctx.saved_tensors
+        return None, g * dS, g * dT, None, (g * dn).reshape(ctx.noise_shape)
+
+
+def vbagg_ell(z, S, T, offsets, noise):
+    """sum_a E_q log N(z_a | mean_a f, noise / n_a) from the per-bag sums of the posterior mean (S) and
+    covariance (T); bags are the contiguous row ranges `offsets`."""
+    return _VbaggEllFn.apply(z, S, T, offsets, noise)
+
+
 def whitened_kl(variational_mean, chol_variational_covar):
     """KL(N(m, tril(Ls) tril(Ls)^T) || N(0, I)) in one pass; the lower mask of
     CholeskyVariationalDistribution is applied inside the kernel."""

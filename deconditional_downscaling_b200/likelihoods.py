@@ -161,10 +161,4 @@ class VBaggGaussianLikelihood(GaussianLikelihood):
             S = F.bag_sum(variational_dist.mean, offsets)
             rows = F.bag_sum(variational_dist.covariance_matrix, offsets)          # n_bags x N
             T = F.bag_sum(rows.t().contiguous(), offsets).diagonal()
-        sizes = torch.Tensor(list(bags_sizes)).to(z.device).to(z.dtype) if not torch.is_tensor(bags_sizes) \
-            else bags_sizes.to(z.device).to(z.dtype)
-        noise = self.noise.to(z.dtype)
-        first = z.pow(2) - 2 * z * S / sizes + (T + S.pow(2)) / sizes.pow(2)
-        first = first * (sizes / noise)
-        second = torch.log(2 * np.pi * noise / sizes)
-        return -0.5 * torch.sum(first + second)
+        return F.vbagg_ell(z, S, T, offsets, self.noise.to(z.dtype))

@@ -395,6 +395,19 @@ def whitened_kl(m, Ls, need_grad=False):
     return out[0], dm, dLs
 
 
+def vbagg_ell(z, S, T, offsets, noise):
+    """Returns (ell, dS, dT, dnoise) of the bag-level expected log-likelihood (dcgp_vbagg_ell)."""
+    z, S, T = z.contiguous(), S.contiguous(), T.contiguous()
+    noise = noise.reshape(1).contiguous()
+    _req(z, S, T, noise)
+    n = z.numel()
+    ell = torch.empty(1, dtype=z.dtype, device=z.device)
+    dS, dT, dn = torch.empty_like(S), torch.empty_like(T), torch.empty_like(noise)
+    check(_lib.load().dcgp_vbagg_ell(_ptr(z), _ptr(S), _ptr(T), _ptr(offsets), n, _ptr(noise), _ptr(ell), _ptr(dS), _ptr(dT),
+                                     _ptr(dn), _dt(z), _stream()), "dcgp_vbagg_ell")
+    return ell[0], dS, dT, dn
+
+
 def rff_features(x, W, lengthscale):
     """Phi = [cos(x W / l), sin(x W / l)]; x: N x d (active dims only), W: d x D."""
     x, W = _rowmajor(x), _rowmajor(W)

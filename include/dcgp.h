@@ -225,6 +225,13 @@ DCGP_API int dcgp_rff_features_bwd(const void* x, int64_t n, int64_t ldx, int d,
                                    const void* lengthscale, const void* dphi, int64_t ldg, void* dx, int64_t lddx,
                                    void* dls, int dtype, void* stream);
 
+/* VBagg expected log-likelihood from the per-bag statistics S_a = 1_a^T mu_q, T_a = 1_a^T Sigma_q 1_a (produced by
+ * dcgp_gram_bagsum / dcgp_gram_bag_blocksum and the whitening products) and its adjoints dS, dT, dnoise (any of
+ * them may be NULL) in one launch: src/likelihoods/vbagg_gaussian_likelihood.py:78-111 without the dense
+ * covariance of :74 and the per-bag python loops of :75, :99-101.  noise / ell / dnoise are device scalars. */
+DCGP_API int dcgp_vbagg_ell(const void* z, const void* S, const void* T, const int64_t* offsets, int64_t n_bags,
+                   const void* noise, void* ell, void* dS, void* dT, void* dnoise, int dtype, void* stream);
+
 /* ---- whitened KL ---------------------------------------------------------------
  * out[0] = 0.5 * (||tril(Ls)||_F^2 + ||m||^2 - M - sum_i log Ls_ii^2) in one pass over Ls
  * (src/mlls/bag_variational_elbo.py:49 -> variational_strategy.kl_divergence()).
