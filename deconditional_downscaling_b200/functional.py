@@ -16,6 +16,10 @@ from . import ops
 from .ops import FlatSpec
 
 
+class CachingError(RuntimeError):
+    """gpytorch.utils.errors.CachingError."""
+
+
 class NotPSDError(RuntimeError):
     """Raised when a Cholesky factorisation meets a non-positive pivot (same
     name and role as gpytorch.utils.errors.NotPSDError, which the reference

@@ -23,6 +23,7 @@ from torch.nn.functional import softplus
 
 from . import functional as F
 from .functional import KernelMeta
+from .constraints import Positive
 from .module import Module
 
 
@@ -302,6 +303,7 @@ class Kernel(Module):
         if self.has_lengthscale:
             nd = 1 if ard_num_dims is None else ard_num_dims
             self.register_parameter("raw_lengthscale", nn.Parameter(torch.zeros(1, nd)))
+            self.raw_lengthscale_constraint = Positive()
 
     @property
     def lengthscale(self):
@@ -380,6 +382,7 @@ class ScaleKernel(Kernel):
         super().__init__(**kwargs)
         self.base_kernel = base_kernel
         self.register_parameter("raw_outputscale", nn.Parameter(torch.tensor(0.0)))
+        self.raw_outputscale_constraint = Positive()
 
     @property
     def outputscale(self):

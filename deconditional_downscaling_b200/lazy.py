@@ -56,6 +56,93 @@ class DenseMatrix:
         return DenseMatrix(self.tensor.to(*a, **k))
 
 
+class DiagLazyTensor(DenseMatrix):
+    """Diagonal matrix given by its diagonal (gpytorch.lazy.DiagLazyTensor as used by src/kernels/delta_kernel.py:11
+    and src/models/bagged_gp.py:78)."""
+
+    def __init__(self, diag):
+        self._diag = diag
+
+    @property
+    def tensor(self):
+        return torch.diag_embed(self._diag)
+
+    @property
+    def shape(self):
+        return torch.Size([self._diag.numel(), self._diag.numel()])
+
+    def size(self, i=None):
+        return self.shape if i is None else self.shape[i]
+
+    def diag(self):
+        return self._diag
+
+    def matmul(self, W):
+        return self._diag.unsqueeze(-1) * W if W.dim() == 2 else self._diag * W
+
+    __matmul__ = matmul
+
+
+class SumLazyTensor(DenseMatrix):
+    """Sum of matrix-likes, evaluated on demand (src/variational/variational_strategy.py:64-66)."""
+
+    def __init__(self, *terms):
+        self.terms = [lazify(t) for t in terms]
+
+    @property
+    def tensor(self):
+        out = self.terms[0].evaluate()
+        for t in self.terms[1:]:
+            out = out + t.evaluate()
+        return out
+
+    @property
+    def shape(self):
+        return self.terms[0].shape
+
+    def diag(self):
+        out = self.terms[0].diag()
+        for t in self.terms[1:]:
+            out = out + t.diag()
+        return out
+
+
+class MatmulLazyTensor(DenseMatrix):
+    """Product of two matrix-likes, evaluated on demand on the tensor cores."""
+
+    def __init__(self, left, right):
+        self.left, self.right = lazify(left), lazify(right)
+
+    @property
+    def tensor(self):
+        return F.matmul(self.left.evaluate(), self.right.evaluate())
+
+    @property
+    def shape(self):
+        return torch.Size([self.left.shape[0], self.right.shape[1]])
+
+    def diag(self):
+        return (self.left.evaluate() * self.right.evaluate().t()).sum(-1)
+
+
+class RootLazyTensor(DenseMatrix):
+    """R R^T given its root (low-rank roots of the RFF kernels, src/kernels/rff_kernel.py:104-110)."""
+
+    def __init__(self, root):
+        self.root = delazify(root)
+
+    @property
+    def tensor(self):
+        return F.matmul(self.root, self.root, transb=True)
+
+    @property
+    def shape(self):
+        return torch.Size([self.root.size(0), self.root.size(0)])
+
+    def diag(self):
+        return (self.root * self.root).sum(-1)
+
+
 class LazyCovariance:
     """Covariance known through callables: dense() and diag() (posterior covariances that are
     only materialised when somebody asks, e.g. the 2000-point NLL chunks of

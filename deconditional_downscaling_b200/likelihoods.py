@@ -13,6 +13,7 @@ from torch.nn.functional import softplus
 from . import functional as F
 from .distributions import MultivariateNormal
 from .lazy import DenseMatrix, delazify
+from .constraints import GreaterThan
 from .module import Module
 
 
@@ -20,6 +21,7 @@ class HomoskedasticNoise(Module):
     def __init__(self):
         super().__init__()
         self.register_parameter("raw_noise", nn.Parameter(torch.zeros(1)))
+        self.raw_noise_constraint = GreaterThan(1e-4)
 
     @property
     def noise(self):
@@ -35,7 +37,11 @@ class HomoskedasticNoise(Module):
         return DenseMatrix(torch.diag_embed(self.noise.expand(n)))
 
 
-class GaussianLikelihood(Module):
+class Likelihood(Module):
+    """gpytorch.likelihoods.Likelihood base."""
+
+
+class GaussianLikelihood(Likelihood):
     def __init__(self, noise_prior=None, noise_constraint=None, batch_shape=None, **kwargs):
         super().__init__()
         self.noise_covar = HomoskedasticNoise()

@@ -4,5 +4,6 @@ from .variational_gp import VariationalGP
 from .exact_cmp import ExactCMP
 from .variational_cmp import VariationalCMP
 from .cmp import CMP
+from .bagged_gp import BaggedGP
 
-__all__ = ["ExactGP", "VariationalGP", "ExactCMP", "VariationalCMP", "CMP"]
+__all__ = ["ExactGP", "VariationalGP", "ExactCMP", "VariationalCMP", "CMP", "BaggedGP"]

@@ -35,3 +35,24 @@ class ApproximateGP(GP):
         if inputs.dim() == 1:
             inputs = inputs.unsqueeze(-1)
         return self.variational_strategy(inputs, prior=prior, **kwargs)
+
+
+class DefaultPredictionStrategy:
+    """gpytorch.models.exact_prediction_strategies.DefaultPredictionStrategy as the reference's strategies use it
+    (a holder of the training prior, labels and likelihood; cmp_prediction_strategy.py:31-36).  The models of this
+    package compute their posteriors themselves (ExactCMP.predict, ExactGP.__call__), so this is only the base
+    object a subclass written against gpytorch can build on."""
+
+    def __init__(self, train_inputs, train_prior_dist, train_labels, likelihood, root=None, inv_root=None):
+        self.train_inputs, self.train_prior_dist = train_inputs, train_prior_dist
+        self.train_labels, self.likelihood = train_labels, likelihood
+        self._memoize_cache = {}
+
+    @property
+    def lik_train_train_covar(self):
+        mvn = self.likelihood(self.train_prior_dist, self.train_inputs)
+        return mvn.lazy_covariance_matrix
+
+    @property
+    def num_train(self):
+        return self.train_labels.numel()

@@ -8,6 +8,8 @@ from ..kernels import _as_2d
 from ..lazy import LazyCovariance
 from .base import ExactGPBase
 from .cmp import CMP
+from ..kernels import CMEAggregateKernel
+from ..means import CMEAggregateMean
 
 
 class ExactCMPPredictionStrategy:
@@ -64,15 +66,21 @@ class ExactCMP(ExactGPBase, CMP):
         if use_individuals_noise:
             self._init_noise_kernel()
         self.lbda = lbda
-        self.mean_module = None
-        self.covar_module = None
-        self.individuals_prediction_strategy = None
         # The reference factors Lambda here on the CPU and moves R in `.to()`; libdcgp has no CPU
         # path, so the (gradient-free) initial factorisation happens at first use on the device
-        # (see _ensure_cme_modules), once data and hyper-parameters both live there.
+        # (see _ensure_cme_modules), once data and hyper-parameters both live there.  The two CME
+        # modules exist from the start - un-factored - so that state_dict() has the reference's
+        # `mean_module.*` / `covar_module.*` entries before the first step as well.
+        with torch.no_grad():
+            mean0 = individuals_mean(_as_2d(train_individuals))
+        self.mean_module = CMEAggregateMean(bag_kernel=bag_kernel, bags_values=extended_train_bags,
+                                            individuals_mean=mean0, root_inv_bags_covar=None)
+        self.covar_module = CMEAggregateKernel(bag_kernel=bag_kernel, bags_values=extended_train_bags,
+                                               individuals_covar=None, root_inv_bags_covar=None)
+        self.individuals_prediction_strategy = None
 
     def _ensure_cme_modules(self):
-        if self.mean_module is None:
+        if self.mean_module.root_inv_bags_covar is None:
             self._init_cmp_mean_covar_modules(self.train_individuals, self.extended_train_bags)
 
     def _clear_cache(self):
@@ -131,8 +139,9 @@ class ExactCMP(ExactGPBase, CMP):
     def _apply(self, fn):
         out = super()._apply(fn)
         # device / dtype changed: Lambda^{-1} is re-factored lazily where the data now lives
-        self.mean_module = None
-        self.covar_module = None
+        self.mean_module.root_inv_bags_covar = None
+        self.covar_module.root_inv_bags_covar = None
+        self.covar_module.individuals_covar = None
         self.individuals_prediction_strategy = None
         return out
 
