@@ -129,7 +129,7 @@ def test_state_dict_wire_format_matches_reference_checkpoints():
         fake = {k: torch.full(s, 0.25) if s else torch.tensor(0.25) for k, s in ref[name].items()}
         module.load_state_dict(fake)
         assert all(torch.all(v == 0.25) for v in module.state_dict().values() if v.is_floating_point())
-    lik = mine["cmp_likelihood"]
+    lik = L.CMPLikelihood(use_individuals_noise=True)
     assert float(lik.noise_covar.raw_noise_constraint.transform(torch.zeros(1))) == pytest.approx(math_softplus0() + 1e-4)
 
 
