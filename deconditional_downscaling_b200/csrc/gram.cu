@@ -34,8 +34,8 @@ __device__ __forceinline__ T eval_pair(const DevSpec& sp, const T* os, const T (
     return val;
 }
 
-// accumulate the adjoints of one pair: g multiplies dK/dtheta, gs multiplies dK/da
-template <typename T, int NC, int DPC>
+// accumulate the adjoints of one pair: g multiplies dK/dtheta, gs multiplies dK/da (only when DX)
+template <typename T, int NC, int DPC, bool DX = true, bool FAST = false>
 __device__ __forceinline__ void accum_pair(const DevSpec& sp, const T* os, const T (&a)[NC * DPC],
                                            const T (&b)[NC * DPC], T g, T gs, T (&gl)[NC * DPC], T (&go)[NC],
                                            T (&ga)[NC * DPC]) {
@@ -49,14 +49,15 @@ __device__ __forceinline__ void accum_pair(const DevSpec& sp, const T* os, const
             acc = fma(u[j], u[j], acc);
         }
         T phi, w;
-        kernel_phi_w<T>(sp.kind[c], acc, phi, w);
+        if (FAST) kernel_phi_w_fast<T>(sp.kind[c], acc, phi, w);
+        else kernel_phi_w<T>(sp.kind[c], acc, phi, w);
         go[c] = fma(g, phi, go[c]);
         const T ow = os[c] * w;
         const T gow = g * ow, gsow = -gs * ow;
 #pragma unroll
         for (int j = 0; j < DPC; ++j) {
             gl[c * DPC + j] = fma(gow * u[j], u[j], gl[c * DPC + j]);
-            ga[c * DPC + j] = fma(gsow, u[j], ga[c * DPC + j]);
+            if (DX) ga[c * DPC + j] = fma(gsow, u[j], ga[c * DPC + j]);
         }
     }
 }
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(256) gram_fwd_kernel(const __grid_constant__ D
 // ---------------------------------------------------------------------------------------
 // backward, dense upstream gradient G (n1 x n2)
 // ---------------------------------------------------------------------------------------
-template <typename T, int NC, int DPC, int RW>
+template <typename T, int NC, int DPC, int RW, bool DX>
 __global__ void __launch_bounds__(256) gram_bwd_kernel(const __grid_constant__ DevSpec sp, const T* __restrict__ x1,
                                                        int64_t n1, int64_t ldx1, const T* __restrict__ x2, int64_t n2,
                                                        int64_t ldx2, const T* __restrict__ G, int64_t ldg,
@@ -164,46 +165,112 @@ __global__ void __launch_bounds__(256) gram_bwd_kernel(const __grid_constant__ D
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t row0 = ((int64_t)blockIdx.y * 8 + warp) * RW;
-    if (row0 >= n1) return;
-    T a[RW][TD], gx[RW][TD], gl[TD], go[NC];
-#pragma unroll
-    for (int r = 0; r < RW; ++r)
-#pragma unroll
-        for (int k = 0; k < TD; ++k) {
-            a[r][k] = (row0 + r < n1) ? x1[(row0 + r) * ldx1 + sp.col[k]] * sv.inv_ls[k] : T(0);
-            gx[r][k] = T(0);
-        }
+    T gl[TD], go[NC];
 #pragma unroll
     for (int k = 0; k < TD; ++k) gl[k] = T(0);
 #pragma unroll
     for (int c = 0; c < NC; ++c) go[c] = T(0);
-
-    for (int cc = lane; cc < ncols; cc += 32) {
-        const int64_t col = col0 + cc;
-        T b[TD];
-#pragma unroll
-        for (int k = 0; k < TD; ++k) b[k] = s2[k * cblk + cc];
-#pragma unroll
-        for (int r = 0; r < RW; ++r) {
-            const int64_t row = row0 + r;
-            if (row < n1) {
-                const T g = G[row * ldg + col];
-                const T gs = same ? g + G[col * ldg + row] : g;  // both argument slots for d/dx
-                accum_pair<T, NC, DPC>(sp, sv.os, a[r], b, g, gs, gl, go, gx[r]);
-            }
-        }
-    }
-    commit_theta<T, NC, DPC>(sp, sv, gl, go, dls, dos, lane);
-    if (dx1) {
+    // a CTA walks its column block down the rows (grid.y is a few waves, not n1 / 8 RW): the hyper-parameter
+    // adjoints stay in registers across the walk and reach memory as ONE atomic per value and CTA - with one
+    // per warp the ~10 shared addresses serialised hundreds of thousands of atomics
+    for (int64_t row0 = ((int64_t)blockIdx.y * 8 + warp) * RW; row0 < n1; row0 += (int64_t)gridDim.y * 8 * RW) {
+        T a[RW][TD], gx[RW][TD];
 #pragma unroll
         for (int r = 0; r < RW; ++r)
 #pragma unroll
             for (int k = 0; k < TD; ++k) {
-                T v = warp_sum(gx[r][k]);
-                if (lane == 0 && row0 + r < n1 && (k / DPC) < sp.n_comp && (k % DPC) < sp.ndims[k / DPC])
-                    atomicAdd(&dx1[(row0 + r) * lddx1 + sp.col[k]], v * sv.inv_ls[k]);
+                a[r][k] = (row0 + r < n1) ? x1[(row0 + r) * ldx1 + sp.col[k]] * sv.inv_ls[k] : T(0);
+                gx[r][k] = T(0);
             }
+        constexpr int VEC = 16 / sizeof(T);  // columns per lane and step: one 16-byte load of G per row
+        constexpr bool FAST = sizeof(T) == 4;
+        const bool vec = ((ldg % VEC) == 0) && ((reinterpret_cast<uintptr_t>(G) & 15) == 0) && (ncols % VEC) == 0;
+        if (vec) {
+            for (int cc = lane * VEC; cc < ncols; cc += 32 * VEC) {
+                T gv[RW][VEC];
+#pragma unroll
+                for (int r = 0; r < RW; ++r) {
+                    if (row0 + r < n1) {
+                        if (VEC == 4) {
+                            const float4 t = *reinterpret_cast<const float4*>(G + (row0 + r) * ldg + col0 + cc);
+                            gv[r][0] = t.x; gv[r][1] = t.y; gv[r][VEC - 2] = t.z; gv[r][VEC - 1] = t.w;
+                        } else {
+                            const double2 t = *reinterpret_cast<const double2*>(G + (row0 + r) * ldg + col0 + cc);
+                            gv[r][0] = t.x; gv[r][VEC - 1] = t.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) gv[r][q] = T(0);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    T b[TD];
+#pragma unroll
+                    for (int k = 0; k < TD; ++k) b[k] = s2[k * cblk + cc + q];
+#pragma unroll
+                    for (int r = 0; r < RW; ++r) {
+                        const T g = gv[r][q];
+                        T gs = g;
+                        if (DX && same && row0 + r < n1) gs += G[(col0 + cc + q) * ldg + row0 + r];
+                        accum_pair<T, NC, DPC, DX, FAST>(sp, sv.os, a[r], b, g, gs, gl, go, gx[r]);
+                    }
+                }
+            }
+        } else {
+            for (int cc = lane; cc < ncols; cc += 32) {
+                const int64_t col = col0 + cc;
+                T b[TD];
+#pragma unroll
+                for (int k = 0; k < TD; ++k) b[k] = s2[k * cblk + cc];
+#pragma unroll
+                for (int r = 0; r < RW; ++r) {
+                    const int64_t row = row0 + r;
+                    if (row < n1) {
+                        const T g = G[row * ldg + col];
+                        // d/dx of k(x, x) collects both argument slots: needs G + G^T - a strided (transposed)
+                        // read, only paid when coordinate gradients are requested
+                        const T gs = (same && DX) ? g + G[col * ldg + row] : g;
+                        accum_pair<T, NC, DPC, DX, FAST>(sp, sv.os, a[r], b, g, gs, gl, go, gx[r]);
+                    }
+                }
+            }
+        }
+        if (DX) {
+#pragma unroll
+            for (int r = 0; r < RW; ++r)
+#pragma unroll
+                for (int k = 0; k < TD; ++k) {
+                    T v = warp_sum(gx[r][k]);
+                    if (lane == 0 && row0 + r < n1 && (k / DPC) < sp.n_comp && (k % DPC) < sp.ndims[k / DPC])
+                        atomicAdd(&dx1[(row0 + r) * lddx1 + sp.col[k]], v * sv.inv_ls[k]);
+                }
+        }
+    }
+    // block reduction of the hyper-parameter adjoints
+    __shared__ T red[8][TD + NC];
+#pragma unroll
+    for (int k = 0; k < TD; ++k) {
+        const T v = warp_sum(gl[k]);
+        if (lane == 0) red[warp][k] = v;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const T v = warp_sum(go[c]);
+        if (lane == 0) red[warp][TD + c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < TD + NC) {
+        T v = T(0);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        if (threadIdx.x < TD) {
+            const int c = threadIdx.x / DPC, j = threadIdx.x % DPC;
+            if (dls && c < sp.n_comp && j < sp.ndims[c]) atomicAdd(&dls[c * DCGP_MAX_DIMS + j], v * sv.inv_ls[threadIdx.x]);
+        } else {
+            const int c = threadIdx.x - TD;
+            if (dos && c < sp.n_comp) atomicAdd(&dos[c], v);
+        }
     }
 }
 
@@ -427,12 +494,25 @@ void launch_gram_bwd_one(const DevSpec& sp, const void* x1, int64_t n1, int64_t 
                          int same, cudaStream_t st) {
     const int cblk = 512;
     size_t smem = (size_t)NC * DPC * cblk * sizeof(T);
-    dim3 grid((unsigned)((n2 + cblk - 1) / cblk), (unsigned)((n1 + 8 * RW - 1) / (8 * RW)));
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(gram_bwd_kernel<T, NC, DPC, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gram_bwd_kernel<T, NC, DPC, RW><<<grid, 256, smem, st>>>(sp, (const T*)x1, n1, ldx1, (const T*)x2, n2, ldx2,
-                                                             (const T*)G, ldg, (T*)dls, (T*)dos, (T*)dx1, lddx1, same,
-                                                             cblk);
+    // column blocks x row walkers: about four CTAs per SM in total
+    const int64_t gx = (n2 + cblk - 1) / cblk, rows_max = (n1 + 8 * RW - 1) / (8 * RW);
+    int64_t gy = (4 * (int64_t)num_sms() + gx - 1) / gx;
+    if (gy > rows_max) gy = rows_max;
+    if (gy < 1) gy = 1;
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    if (dx1) {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(gram_bwd_kernel<T, NC, DPC, RW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        gram_bwd_kernel<T, NC, DPC, RW, true><<<grid, 256, smem, st>>>(sp, (const T*)x1, n1, ldx1, (const T*)x2, n2, ldx2,
+                                                                       (const T*)G, ldg, (T*)dls, (T*)dos, (T*)dx1, lddx1,
+                                                                       same, cblk);
+    } else {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(gram_bwd_kernel<T, NC, DPC, RW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        gram_bwd_kernel<T, NC, DPC, RW, false><<<grid, 256, smem, st>>>(sp, (const T*)x1, n1, ldx1, (const T*)x2, n2, ldx2,
+                                                                        (const T*)G, ldg, (T*)dls, (T*)dos, (T*)dx1, lddx1,
+                                                                        same, cblk);
+    }
 }
 
 template <typename T>
