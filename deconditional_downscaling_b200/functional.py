@@ -107,10 +107,47 @@ def matmul(A, B, transa=False, transb=False):
 
 
 # ---------------------------------------------------------------------- Cholesky & solves
+_DEFERRED = None   # list collecting the device `info` words of the factorisations of a deferred region
+
+
 def _raise_if_not_pd(info):
+    """LAPACK-style failure word -> NotPSDError.  Reading it synchronises the host with the stream; inside a
+    `deferred_pd_checks()` region the words are collected instead and examined once by `.check()`."""
+    if _DEFERRED is not None:
+        _DEFERRED.append(info)
+        return
     i = int(info.item())
     if i != 0:
         raise NotPSDError(f"Cholesky failed: leading minor {i} is not positive definite")
+
+
+class deferred_pd_checks:
+    """with deferred_pd_checks() as pending: ...; pending.check()
+
+    Every Cholesky in the region runs optimistically (no read-back, so the host keeps issuing work ahead of the
+    GPU); `check()` reads all failure words in one transfer and raises NotPSDError for the first failed
+    factorisation.  Results computed after a failed factorisation are garbage (NaN) and must be discarded by the
+    caller - training.ElboTrainer re-runs the step with immediate checks and jitter retries in that case."""
+
+    def __enter__(self):
+        global _DEFERRED
+        self._outer, self.infos = _DEFERRED, []
+        _DEFERRED = self.infos
+        return self
+
+    def __exit__(self, *exc):
+        global _DEFERRED
+        _DEFERRED = self._outer
+        return False
+
+    def check(self):
+        if not self.infos:
+            return
+        words = torch.cat([i.reshape(1) for i in self.infos]).tolist()
+        self.infos.clear()
+        for k, w in enumerate(words):
+            if w != 0:
+                raise NotPSDError(f"Cholesky #{k} of the region failed: leading minor {w} is not positive definite")
 
 
 class _CholeskyFn(Function):

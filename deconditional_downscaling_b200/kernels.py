@@ -299,6 +299,8 @@ class Kernel(Module):
         if active_dims is not None and not torch.is_tensor(active_dims):
             active_dims = torch.tensor(list(active_dims), dtype=torch.long)
         self.register_buffer("active_dims", active_dims)
+        # host copy: the column selection shapes every launch and must not cost a device read-back each time
+        self._active_dims_host = None if active_dims is None else [int(i) for i in active_dims.tolist()]
         self.ard_num_dims = ard_num_dims
         if self.has_lengthscale:
             nd = 1 if ard_num_dims is None else ard_num_dims
@@ -316,7 +318,9 @@ class Kernel(Module):
 
     def _dims(self, d, parent_dims, own=True):
         if own and self.active_dims is not None:
-            own = [int(i) for i in self.active_dims.tolist()]
+            if self._active_dims_host is None or len(self._active_dims_host) != self.active_dims.numel():
+                self._active_dims_host = [int(i) for i in self.active_dims.tolist()]   # e.g. after load_state_dict
+            own = self._active_dims_host
             return own if parent_dims is None else [parent_dims[i] for i in own]
         return list(range(d)) if parent_dims is None else list(parent_dims)
 

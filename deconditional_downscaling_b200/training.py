@@ -11,6 +11,7 @@ from typing import Dict, Optional
 import torch
 import torch.distributed as dist
 
+from . import functional as F
 from .likelihoods import CMPLikelihood, VBaggGaussianLikelihood
 from .mlls import BagVariationalELBO
 
@@ -50,10 +51,7 @@ class ElboTrainer:
         self.elbo = BagVariationalELBO(likelihood, model, num_data=num_data, beta=beta)
         self.params = list(model.parameters()) + list(likelihood.parameters())
         # q(u) must exist before the optimizer / flat buffer are laid out
-        vs = model.variational_strategy
-        if not bool(vs.variational_params_initialized.item()):
-            vs._variational_distribution.initialize_variational_distribution()
-            vs.variational_params_initialized.fill_(1)
+        model.variational_strategy.ensure_initialized()
         self.grads = FlatGrads(self.params)
         self.opt = torch.optim.Adam(self.params, lr=lr)
         model.train()
@@ -69,8 +67,17 @@ class ElboTrainer:
     def step(self, x, z, **kw):
         """One ELBO step on device-resident tensors; returns the (device) loss."""
         self.grads.zero()
-        loss = self.loss(x, z, **kw)
-        loss.backward()
+        try:
+            # optimistic pass: no host read-back between the factorisations, ONE check before the update
+            with F.deferred_pd_checks() as pending:
+                loss = self.loss(x, z, **kw)
+                loss.backward()
+            pending.check()
+        except F.NotPSDError:
+            # psd_safe_cholesky semantics (jitter retries, then NotPSDError) with immediate checks
+            self.grads.zero()
+            loss = self.loss(x, z, **kw)
+            loss.backward()
         self.grads.allreduce_mean()
         self.opt.step()
         return loss.detach()

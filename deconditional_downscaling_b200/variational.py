@@ -148,6 +148,17 @@ class VariationalStrategy(Module):
         vd = self._variational_distribution
         return F.whitened_kl(vd.variational_mean, vd.chol_variational_covar)
 
+    def ensure_initialized(self):
+        """First-call initialisation of q(u) (gpytorch _VariationalStrategy.__call__).  The flag is a device buffer
+        (it is part of the checkpoint); once seen set it is remembered on the host so that steady-state steps do
+        not synchronise on it."""
+        if getattr(self, "_initialized_host", False):
+            return
+        if not bool(self.variational_params_initialized.item()):
+            self._variational_distribution.initialize_variational_distribution()
+            self.variational_params_initialized.fill_(1)
+        self._initialized_host = True
+
     def _prior_modules(self):
         m = self.model
         if hasattr(m, "individuals_kernel"):       # VariationalCMP (src/models/variational_cmp.py:76-79)
@@ -157,9 +168,7 @@ class VariationalStrategy(Module):
     def __call__(self, x, prior=False, **kwargs):
         if prior:
             return self.model.forward(x, **kwargs)
-        if not bool(self.variational_params_initialized.item()):
-            self._variational_distribution.initialize_variational_distribution()
-            self.variational_params_initialized.fill_(1)
+        self.ensure_initialized()
         kernel, mean = self._prior_modules()
         vd = self._variational_distribution
         Z = self.inducing_points

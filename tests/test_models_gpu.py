@@ -265,3 +265,23 @@ def test_not_psd_raises_reference_compatible_error():
     A = -torch.eye(8, dtype=torch.float64, device=DEV)
     with pytest.raises(F.NotPSDError):
         F.psd_safe_cholesky(A)
+
+
+def test_deferred_pd_checks_collect_and_raise():
+    """Factorisations inside a deferred region do not read their failure word back; check() raises for the
+    first failed one, and ElboTrainer-style callers can then repeat the work with immediate checks."""
+    from deconditional_downscaling_b200 import functional as F
+    good = torch.eye(200, dtype=torch.float64, device=DEV) * 2.0
+    bad = good.clone()
+    bad[150, 150] = -1.0
+    with F.deferred_pd_checks() as pending:
+        F.cholesky(good)
+        F.cholesky(bad)          # no exception here
+        F.cholesky(good)
+    with pytest.raises(F.NotPSDError, match="#1"):
+        pending.check()
+    with pytest.raises(F.NotPSDError):
+        F.cholesky(bad)          # immediate mode unchanged
+    with F.deferred_pd_checks() as pending:
+        F.cholesky(good)
+    pending.check()
