@@ -79,30 +79,32 @@ def gram(meta: KernelMeta, hyp: Sequence[torch.Tensor], x1, x2=None, diag_dev=No
 # ---------------------------------------------------------------------- GEMM
 class _MatmulFn(Function):
     @staticmethod
-    def forward(ctx, A, B, ta, tb):
+    def forward(ctx, A, B, ta, tb, precise):
         ctx.ta, ctx.tb = ta, tb
+        ctx.mm = ops.gemm_x3 if precise else ops.gemm
         ctx.save_for_backward(A, B)
-        return ops.gemm(A, B, transa=ta, transb=tb)
+        return ctx.mm(A, B, transa=ta, transb=tb)
 
     @staticmethod
     def backward(ctx, gC):
         A, B = ctx.saved_tensors
-        ta, tb = ctx.ta, ctx.tb
+        ta, tb, mm = ctx.ta, ctx.tb, ctx.mm
         gC = gC.contiguous()
         gA = gB = None
         if ctx.needs_input_grad[0]:
-            gA = ops.gemm(B, gC, transa=tb, transb=True) if ta else ops.gemm(gC, B, transa=False, transb=not tb)
+            gA = mm(B, gC, transa=tb, transb=True) if ta else mm(gC, B, transa=False, transb=not tb)
         if ctx.needs_input_grad[1]:
-            gB = ops.gemm(gC, A, transa=True, transb=ta) if tb else ops.gemm(A, gC, transa=not ta, transb=False)
-        return gA, gB, None, None
+            gB = mm(gC, A, transa=True, transb=ta) if tb else mm(A, gC, transa=not ta, transb=False)
+        return gA, gB, None, None, None
 
 
-def matmul(A, B, transa=False, transb=False):
-    """op(A) @ op(B) on the tensor cores; 1-D B is treated as a column."""
+def matmul(A, B, transa=False, transb=False, precise=False):
+    """op(A) @ op(B) on the tensor cores; 1-D B is treated as a column.  `precise`: FP32 operands are multiplied
+    with 3xTF32 (~FP32 accuracy) whatever the size - for products whose result enters a cancellation."""
     vec = B.dim() == 1
     if vec:
         B = B.unsqueeze(-1)
-    out = _MatmulFn.apply(A, B, transa, transb)
+    out = _MatmulFn.apply(A, B, transa, transb, precise)
     return out.squeeze(-1) if vec else out
 
 

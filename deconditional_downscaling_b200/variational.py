@@ -92,39 +92,47 @@ class VariationalPosterior(MultivariateNormal):
     def loc(self, v):
         pass
 
+    @property
+    def D(self):
+        """L_S L_S^T - I (M x M), the middle matrix of Sigma_q = K_xx + 1e-4 I + A~^T (L_S L_S^T - I) A~
+        (variational_strategy.py:57-66).  Everything below is written on D - never as the difference of the
+        two large quadratic forms |L_S^T A~|^2 - |A~|^2, which cancels (L_S starts at I) and would expose the
+        truncation bias of single-pass TF32 products; D itself is formed with 3xTF32."""
+        def fn():
+            Ls = self.Ls
+            eye = torch.eye(Ls.size(0), dtype=Ls.dtype, device=Ls.device)
+            return F.matmul(Ls, Ls, transb=True, precise=True) - eye
+        return self._get("D", fn)
+
     def _variance(self):
         def fn():
             At = self.At
-            LsA = F.matmul(self.Ls, At, transa=True)
-            return self.kops.diag(self.x) + 1e-4 + (LsA * LsA).sum(0) - (At * At).sum(0)
+            return self.kops.diag(self.x) + 1e-4 + (F.matmul(self.D, At) * At).sum(0)
         return self._get("var", fn)
 
     def _dense_covar(self):
         def fn():
             At = self.At
-            LsA = F.matmul(self.Ls, At, transa=True)
-            return self.kops.gram(self.x, None, diag_const=1e-4) + F.matmul(LsA, LsA, transa=True) - F.matmul(At, At, transa=True)
+            return self.kops.gram(self.x, None, diag_const=1e-4) + F.matmul(At, F.matmul(self.D, At), transa=True)
         return self._get("cov", fn)
 
     # ---- reductions for the likelihoods ---------------------------------------------------------
     def quad_form(self, A):
         """A^T Sigma_q A for A (N x n) without forming Sigma_q:
-        A^T (K_xx + 1e-4 I) A + (L_S^T U)^T (L_S^T U) - U^T U,  U = A~ A  (SURVEY.md §8a row 13)."""
+        A^T (K_xx + 1e-4 I) A + U^T D U,  U = A~ A  (SURVEY.md §8a row 13)."""
         KA = self.kops.matmul(self.x, None, A, diag_const=1e-4)
         U = F.matmul(self.At, A)
-        LsU = F.matmul(self.Ls, U, transa=True)
-        return F.matmul(A, KA, transa=True) + F.matmul(LsU, LsU, transa=True) - F.matmul(U, U, transa=True)
+        return F.matmul(A, KA, transa=True) + F.matmul(U, F.matmul(self.D, U), transa=True)
 
     def bag_stats(self, offsets):
         """S_a = 1_a^T mu_q and T_a = 1_a^T Sigma_q 1_a for contiguous bags, from the bag-summed
         cross Gram (K_Zx is never formed): u_a = L_Z^{-1} (K_Zx 1_a),
-        T_a = 1_a^T K_xx 1_a + 1e-4 n_a + |L_S^T u_a|^2 - |u_a|^2  (SURVEY.md §8a row 15)."""
+        T_a = 1_a^T K_xx 1_a + 1e-4 n_a + u_a^T D u_a  (SURVEY.md §8a row 15)."""
         sizes = (offsets[1:] - offsets[:-1]).to(self.dtype)
         KbZ = self.kops.bagsum(self.Z, self.x, offsets)                    # n_bags x M
         Ub = self._whiten(KbZ.t().contiguous())                               # M x n_bags
         S = F.matmul(Ub, self.m.to(self.dtype), transa=True) + F.bag_sum(self.mean_module(self.x).to(self.dtype), offsets)
-        LsU = F.matmul(self.Ls, Ub, transa=True)
-        T = self.kops.bag_blocksum(self.x, offsets) + 1e-4 * sizes + (LsU * LsU).sum(0) - (Ub * Ub).sum(0)
+        T = self.kops.bag_blocksum(self.x, offsets) + 1e-4 * sizes + (F.matmul(self.D, Ub) * Ub).sum(0)
         return S, T
 
 

@@ -164,3 +164,47 @@ def test_gram_matmul_multi_panel_matches_single_products():
     got = o.gram_matmul(rbf(3, dt), x, None, W, diag_const=0.37)
     ref = torch.cat([o.gemm(o.gram(rbf(3, dt), x[i:i + 3000], x), W) for i in range(0, n, 3000)]) + 0.37 * W
     assert ((got - ref).norm() / ref.norm()).item() < 1e-13
+
+
+def test_evaluation_over_large_grid_is_chunk_invariant_and_matches_oracle():
+    """q(f) mean / variance over 120 000 prediction points (the evaluation path of the downscaling trainer):
+    chunked evaluation == one-shot evaluation, and a 3000-point slice matches the dense oracle formulas."""
+    from deconditional_downscaling_b200 import evaluation, kernels as K, means as Mn, models as M
+    torch.manual_seed(13)
+    dt = torch.float32
+    Mz, d, N = 256, 3, 120_000
+    km = K.ScaleKernel(K.RBFKernel(ard_num_dims=d))
+    model = M.VariationalGP(inducing_points=torch.randn(Mz, d), mean_module=Mn.ZeroMean(), covar_module=km).to(DEV).to(dt)
+    vd = model.variational_strategy._variational_distribution
+    with torch.no_grad():
+        vd.variational_mean.copy_(0.3 * torch.randn(Mz))
+        vd.chol_variational_covar.copy_(torch.eye(Mz) + 0.05 * torch.randn(Mz, Mz).tril())
+    model.variational_strategy.variational_params_initialized.fill_(1)
+    model.eval()
+    x = torch.randn(N, d, device=DEV, dtype=dt)
+    m1, v1 = evaluation.posterior_mean_variance(model, x, chunk=N)
+    m2, v2 = evaluation.posterior_mean_variance(model, x, chunk=17_000)
+    # FP32 models compute the wide products in single-pass TF32 (tolerance of that mode: 1e-3); the chunking
+    # changes tile shapes and summation order, not the algorithm
+    assert ((m1 - m2).norm() / m1.norm()).item() < 1e-3 and ((v1 - v2).norm() / v1.norm()).item() < 1e-3
+    assert torch.all(v1 > 0)
+    # oracle on a slice (float64, dense)
+    xs = x[:3000].double().cpu()
+    k = R.KernelSpec([R.Component("rbf", km.base_kernel.raw_lengthscale.detach().double().cpu().reshape(-1),
+                                  km.raw_outputscale.detach().double().cpu(), None)])
+    mu, Sig = R.svgp_q(k, model.variational_strategy.inducing_points.detach().double().cpu(), xs,
+                       vd.variational_mean.detach().double().cpu(), vd.chol_variational_covar.detach().double().cpu())
+    assert ((m1[:3000].double().cpu() - mu).norm() / mu.norm()).item() < 1e-3
+    assert ((v1[:3000].double().cpu() - Sig.diagonal()).norm() / Sig.diagonal().norm()).item() < 1e-3
+    # chunked NLL of the reference's metrics code on the exact-GP path
+    # (well separated points: the 2000 x 2000 FP32 posterior covariance of a chunk must stay positive definite;
+    # when it is not, the reference's metric is NaN by design, core/metrics.py:30-31)
+    xw = 4.0 * x[:4000]
+    nll = evaluation.chunked_nll(lambda xc: model(xc), xw, torch.zeros(4000, device=DEV, dtype=dt), chunk_size=2000)
+    assert math.isfinite(nll)
+    post = model(xw[:2000])
+    cov = post.covariance_matrix.double()
+    ref = -torch.distributions.MultivariateNormal(post.mean.double(), 0.5 * (cov + cov.t()), validate_args=False).log_prob(
+        torch.zeros(2000, device=DEV, dtype=torch.float64)) / 2000
+    nll0 = evaluation.chunked_nll(lambda xc: model(xc), xw[:2000], torch.zeros(2000, device=DEV, dtype=dt), chunk_size=2000)
+    assert abs(nll0 - ref.item()) < 1e-3 * abs(ref.item())
