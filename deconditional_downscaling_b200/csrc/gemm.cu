@@ -53,8 +53,14 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // parameter: 128 x 128 for problems that fill the machine, 64 x 64 for the many small, latency-bound
 // contractions inside the blocked factorisations (4x more CTAs, 1/4 of the per-CTA critical path).
 template <typename T> struct Tile;
+#ifndef DCGP_F64_BK
+#define DCGP_F64_BK 16
+#endif
+#ifndef DCGP_F64_STAGES
+#define DCGP_F64_STAGES 3
+#endif
 template <> struct Tile<double> {
-    static constexpr int BK = 16, PK = 20, STAGES = 3;
+    static constexpr int BK = DCGP_F64_BK, PK = DCGP_F64_BK + 4, STAGES = DCGP_F64_STAGES;
 };
 template <> struct Tile<float> {
     static constexpr int BK = 32, PK = 36, STAGES = 3;
@@ -163,6 +169,28 @@ __global__ void __launch_bounds__(256, (BM == 128 ? 1 : 2)) gemm_kernel(const __
         const T* as = As + buf * BM * PK + (wm * WM) * PK;
         const T* bs = Bs + buf * BN * PK + (wn * WN) * PK;
         if constexpr (sizeof(T) == 8) {
+#ifdef DCGP_F64_PREFETCH
+            // fragments of step ks + 1 are loaded before the DMMAs of step ks issue
+            double af[2][MT], bf[2][NT];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) af[0][i] = as[(i * 8 + g) * PK + t];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) bf[0][j] = bs[(j * 8 + g) * PK + t];
+#pragma unroll
+            for (int ks = 0; ks < BK / 4; ++ks) {
+                const int cur = ks & 1, nxt = cur ^ 1;
+                if (ks + 1 < BK / 4) {
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) af[nxt][i] = as[(i * 8 + g) * PK + (ks + 1) * 4 + t];
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) bf[nxt][j] = bs[(j * 8 + g) * PK + (ks + 1) * 4 + t];
+                }
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) mma_f64(acc[i][j], af[cur][i], bf[cur][j]);
+            }
+#else
 #pragma unroll
             for (int ks = 0; ks < BK / 4; ++ks) {
                 double af[MT], bf[NT];
@@ -175,6 +203,7 @@ __global__ void __launch_bounds__(256, (BM == 128 ? 1 : 2)) gemm_kernel(const __
 #pragma unroll
                     for (int j = 0; j < NT; ++j) mma_f64(acc[i][j], af[i], bf[j]);
             }
+#endif
         } else {
 #pragma unroll
             for (int ks = 0; ks < BK / 8; ++ks) {
