@@ -324,6 +324,7 @@ def run_ours(args):
                              "tolerance": 1e-3}
         if world == 1 and not args.no_exact:
             out["exact_cmp_n32k"] = run_exact(device, 4096 if args.small else 32768)
+            out["vbagg_1024bags"] = run_vbagg(device)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
@@ -382,6 +383,39 @@ def run_exact(device, N):
                          "frac": fl["potrf"] / ph["potrf"] / 1e12 / fp64_peak,
                          "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (best of 3)"},
             "potrf_info": int(res["info"].item()), "mll": float(res["mll"].item())}
+
+
+# ------------------------------------------------------------------ VBagg ELBO step at config-5 scale (N = 1 only)
+def run_vbagg(device, steps=10, warmup=3):
+    """1024 bags x 102 individuals per step (104 448 rows), M = 1024, d = 5, FP32: forward + backward + Adam.
+    The bag-summed cross Gram evaluates M x N_b kernel values per pass without storing K_Zx."""
+    from deconditional_downscaling_b200 import kernels as K, likelihoods as L, means as Mn, models as M
+    from deconditional_downscaling_b200.training import ElboTrainer
+    g = torch.Generator().manual_seed(5)
+    nb, per, Mz, d = 1024, 102, 1024, 5
+    sizes = [per] * nb
+    model = M.VariationalGP(inducing_points=torch.randn(Mz, d, generator=g), mean_module=Mn.ZeroMean(),
+                            covar_module=K.ScaleKernel(K.RBFKernel(ard_num_dims=d)))
+    lik = L.VBaggGaussianLikelihood()
+    model, lik = model.to(device), lik.to(device)
+    tr = ElboTrainer(model, lik, num_data=10240, beta=1.0, lr=0.01)
+    batches = [(torch.randn(nb * per, d, generator=g).to(device), torch.randn(nb, generator=g).to(device))
+               for _ in range(steps + warmup)]
+    for i in range(warmup):
+        tr.step(batches[i][0], batches[i][1], bags_sizes=sizes)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(warmup, warmup + steps):
+        loss = tr.step(batches[i][0], batches[i][1], bags_sizes=sizes)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / steps
+    evals = float(Mz) * nb * per
+    return {"metric": "vbagg_elbo_steps_per_s", "value": 1e3 / ms, "ms_per_step": ms, "bags_per_step": nb,
+            "individuals_per_step": nb * per, "inducing_points": Mz, "dtype": "f32 (f64 K_ZZ factor)",
+            "cross_gram_kernel_evals_per_step": evals, "final_loss": float(loss.item()),
+            "note": "bag-summed cross Gram forward + backward = 2 x M x N_b kernel evaluations per step, K_Zx never stored"}
 
 
 # ------------------------------------------------------------------ CPU arms (oracle port; the only place oracle/ runs)

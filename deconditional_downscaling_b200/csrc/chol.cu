@@ -21,6 +21,7 @@
 #include "tc.cuh"
 #include <cstdio>
 #include <cstdlib>
+#include <unordered_map>
 #include <vector>
 
 int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
@@ -670,7 +671,13 @@ struct LookAhead {
         return 0;
     }
 };
-thread_local LookAhead g_la;
+// One lane set per caller stream: factorisations issued from different streams (e.g. K_ZZ on a side stream while
+// Lambda factors on the main one) must not queue behind each other on shared internal streams.
+thread_local std::unordered_map<cudaStream_t, LookAhead> g_lanes;
+inline LookAhead& lanes_for(cudaStream_t st) {
+    if (g_lanes.size() >= 8 && g_lanes.find(st) == g_lanes.end()) return g_lanes.begin()->second;  // bounded; still correct
+    return g_lanes[st];
+}
 
 #ifdef DCGP_TRACE
 struct Trace {  // debug builds only: device timeline of the two lanes
@@ -725,7 +732,7 @@ inline int64_t la_panel(int dtype, int64_t nb) {
 // right of it in a single tcgen05 launch (lower tiles only, offset diagonal), then hands the chain lane a
 // private copy of the next block row so that the two lanes never touch the same memory.
 int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
-    LookAhead& x = g_la;
+    LookAhead& x = lanes_for(c.st);
     int rc = x.init();
     if (rc) return rc;
     static bool attr = false;
@@ -822,7 +829,7 @@ int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
 
 template <typename T>
 int chol_la(const Ctx<T>& c, int64_t j0, int64_t nb) {
-    LookAhead& x = g_la;
+    LookAhead& x = lanes_for(c.st);
     int rc = x.init();
     if (rc) return rc;
     const int64_t pw = c.la_pw, q = (nb + pw - 1) / pw, end = j0 + nb;
@@ -1075,7 +1082,7 @@ int ltrsm512_rec(const L5Ctx<T>& c, int trans, int64_t i0, int64_t nn) {
 // The recursion above serialises GEMMs whose 512..4096-row outputs cover a fraction of the SMs.
 template <typename T>
 int ltrsm512_la(const L5Ctx<T>& c, int trans) {
-    LookAhead& x = g_la;
+    LookAhead& x = lanes_for(c.st);
     int rc = x.init();
     if (rc) return rc;
     const int64_t n = c.n, q = (n + NBI - 1) / NBI;

@@ -17,6 +17,24 @@ from .lazy import LazyCovariance
 from .module import Module
 
 
+import os
+
+# opt-in (DCGP_SIDE_STREAM=1): overlap the K_ZZ factor with the caller's next work.  Measured on B200: 15.9 -> 15.2 ms
+# per VariationalCMP step when it works, but bimodal (some runs 21 ms: two serial chains and a persistent GEMM
+# grid compete for the one SM left free), so it stays off by default.
+SIDE_STREAM = os.environ.get("DCGP_SIDE_STREAM", "0") == "1"
+_SIDE = {}
+
+
+def _quiet_accumulate_grad_warning():
+    """The gradients of Z and of the kernel hyper-parameters arrive from two streams by design; autograd orders them
+    correctly and only warns about the extra synchronisation."""
+    fn = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+    if fn is not None and not _SIDE.get("_quiet"):
+        fn(False)
+        _SIDE["_quiet"] = True
+
+
 class CholeskyVariationalDistribution(Module):
     def __init__(self, num_inducing_points, batch_shape=None, mean_init_std=1e-3, **kwargs):
         super().__init__()
@@ -71,7 +89,30 @@ class VariationalPosterior(MultivariateNormal):
     def Wz(self):
         """L_Z^{-1} in float64 (FP32 models): the whitening products then run as 3xTF32 tensor-core GEMMs on
         an FP32 hi/lo pair of it instead of float64 triangular solves against 10^3 .. 10^4 columns."""
-        return self._get("Wz", lambda: F.chol_inverse(self.kops.gram(self.Z, None, diag_const=1e-3).double()))
+        W = self._get("Wz", lambda: F.chol_inverse(self.kops.gram(self.Z, None, diag_const=1e-3).double()))
+        side = self._c.pop("Wz_side", None)
+        if side is not None:                      # produced by prefetch(): order the consumer stream after it
+            main = torch.cuda.current_stream(W.device)
+            main.wait_stream(side)
+            W.record_stream(main)
+        return W
+
+    def prefetch(self):
+        """Start the K_ZZ factorisation + inversion on a side stream.  It is a chain of single-CTA kernels (about
+        1 ms at M = 1024) that is independent of the Lambda factorisation the caller issues next on the main
+        stream (VariationalCMP) - both are latency-bound, together they cost the longer of the two.  The autograd
+        engine runs the backward of these nodes on the same side stream."""
+        if self.dtype == torch.float64 or not self.x.is_cuda or "Wz" in self._c or not SIDE_STREAM:
+            return
+        dev = self.x.device
+        side = _SIDE.get(dev)
+        if side is None:
+            side = _SIDE[dev] = torch.cuda.Stream(device=dev)
+        _quiet_accumulate_grad_warning()
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self._c["Wz"] = F.chol_inverse(self.kops.gram(self.Z, None, diag_const=1e-3).double())
+        self._c["Wz_side"] = side
 
     def _whiten(self, K):
         """L_Z^{-1} K for K (M x cols) in the model dtype."""
@@ -181,4 +222,6 @@ class VariationalStrategy(Module):
         vd = self._variational_distribution
         Z = self.inducing_points
         x = _as_2d(x)
-        return VariationalPosterior(kernel, mean, Z.to(x.dtype), x, vd.variational_mean, vd.chol_variational_covar)
+        post = VariationalPosterior(kernel, mean, Z.to(x.dtype), x, vd.variational_mean, vd.chol_variational_covar)
+        post.prefetch()
+        return post
