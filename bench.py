@@ -302,7 +302,11 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma kind::tf32, TMA, TMEM): the direct dcgp_gemm "
                      "products of the timed steps that run as one launch of it each, CUDA events around every launch",
                      "achieved": fl_tc / t_tc / 1e12 if t_tc > 0 else None, "peak": tf32_peak, "unit": "TFLOP/s",
-                     "frac": (fl_tc / t_tc / 1e12) / tf32_peak if t_tc > 0 else None, "traffic": None,
+                     "frac": (fl_tc / t_tc / 1e12) / tf32_peak if t_tc > 0 else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step's most frequent large product
+                     # (K_xx[8192 x 8192] @ A[8192 x 1024], 335 MB compulsory) from the ncu --set full capture
+                     # profiles/r01_ncu_tcgemm_v2_8192x1024x8192_raw.csv
+                     "traffic": 425892096, "traffic_shape": "8192x1024x8192 NN",
                      "peak_source": f"{pk['source']}: sustained bf16 cuBLAS rate / 2 (TF32 issues at half the bf16 MMA rate)",
                      "launches": n_tc, "avg_launch_ms": 1e3 * t_tc / n_tc if n_tc else None,
                      "share_of_step": t_tc / t_dev if t_dev > 0 else None,

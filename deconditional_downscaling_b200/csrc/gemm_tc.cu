@@ -390,7 +390,8 @@ int launch_tc(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMa
     const int64_t nt = (int64_t)p.tiles_m * p.tiles_n;
     // one SM is left to the serial lane of the look-ahead factorisation / solves (single-CTA kernels that must
     // not queue behind a persistent grid occupying every SM)
-    const int64_t cap = num_sms() > 8 ? num_sms() - 1 : num_sms();
+    static const int reserve = getenv("DCGP_TC_RESERVE") ? atoi(getenv("DCGP_TC_RESERVE")) : 1;
+    const int64_t cap = num_sms() > 8 + reserve ? num_sms() - reserve : num_sms();
     const unsigned grid = (unsigned)(nt < cap ? nt : cap);
     gemm_tc_kernel<TN><<<grid, NTHREADS_TC, smem_tc<TN>(), st>>>(mapA, mapB, mapAlo, mapBlo, p);
     DCGP_CHECK_LAUNCH();
