@@ -981,7 +981,16 @@ int trsm128_impl(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t m,
 //   (b) two doubling levels (128 -> 256 -> 512), X21 = -X22 (L21 X11), batched over all blocks;
 //   (c) recursion on 512-row leaves: X_i = op(inv512_i) B_i (out of place) + deep-K updates.
 // ---------------------------------------------------------------------------------------------
-constexpr int NBI = 512;
+// Width of the inverted diagonal blocks.  512 by default; DCGP_NBI=1024 halves the number of steps in the serial
+// chain of a sweep but the wider leaf products and the extra doubling level eat the gain (measured on B200,
+// n = 8192, m = 1024: sweeps 0.82 -> 0.72 ms, plan build 0.38 -> 0.59 ms, errors 2x larger).
+// Chosen at every public entry point, so plans, workspaces and solves always agree.
+constexpr int NBI_MIN = 512;
+thread_local int64_t NBI = NBI_MIN;
+inline void pick_nbi(int64_t n) {
+    static const int64_t forced = getenv("DCGP_NBI") ? atoll(getenv("DCGP_NBI")) : 0;
+    NBI = (forced == 1024 && n >= 4096) ? 1024 : NBI_MIN;
+}
 
 template <typename T>
 struct L5Ctx {
@@ -1099,6 +1108,7 @@ int ltrsm512_la(const L5Ctx<T>& c, int trans) {
     DCGP_CU(cudaEventRecord(x.fork, c.st));
     DCGP_CU(cudaStreamWaitEvent(sa, x.fork, 0));
     DCGP_CU(cudaStreamWaitEvent(sb, x.fork, 0));
+    TRACE_BEGIN(c.st);
     for (int64_t s = 0; s < q; ++s) {
         const int64_t i = trans ? q - 1 - s : s;                    // block solved at this step
         const int64_t r = i * NBI, w = (n - r < NBI) ? n - r : NBI;
@@ -1108,16 +1118,20 @@ int ltrsm512_la(const L5Ctx<T>& c, int trans) {
         rc = dcgp_gemm_impl(trans, 0, w, c.m, w, 1.0, c.inv + i * NBI * NBI, NBI, c.B + r * c.ldb, c.ldb, 0.0, Xi, c.ldb,
                             c.dtype, c.xf, sa, lo ? c.invlo + i * NBI * NBI : nullptr, lo ? c.Blo + r * c.ldb : nullptr, Xilo);
         if (rc) return rc;
+        TRACE_MARK("A.leaf", s, sa);
         if (s == q - 1) break;
         DCGP_CU(cudaEventRecord(x.leaf[e], sa));
         if (s > 0) DCGP_CU(cudaStreamWaitEvent(sa, x.upd[ep], 0));
+        TRACE_MARK("A.waited", s, sa);
         if (!trans) {
             const int64_t r1 = r + NBI, w1 = (n - r1 < NBI) ? n - r1 : NBI, r2 = r1 + w1, nr = n - r2;
             rc = dcgp_gemm_impl(0, 0, w1, c.m, w, -1.0, c.L + r1 * c.ldl + r, c.ldl, Xi, c.ldb, 1.0, c.B + r1 * c.ldb, c.ldb,
                                 c.dtype, c.xf, sa, lo ? c.Llo + r1 * c.ldl + r : nullptr, Xilo, lo ? c.Blo + r1 * c.ldb : nullptr);
             if (rc) return rc;
+            TRACE_MARK("A.near", s, sa);
             if (nr <= 0) continue;
             DCGP_CU(cudaStreamWaitEvent(sb, x.leaf[e], 0));
+            TRACE_MARK("B.start", s, sb);
             rc = dcgp_gemm_impl(0, 0, nr, c.m, w, -1.0, c.L + r2 * c.ldl + r, c.ldl, Xi, c.ldb, 1.0, c.B + r2 * c.ldb, c.ldb,
                                 c.dtype, c.xf, sb, lo ? c.Llo + r2 * c.ldl + r : nullptr, Xilo, nullptr);
         } else {
@@ -1131,10 +1145,12 @@ int ltrsm512_la(const L5Ctx<T>& c, int trans) {
                                 lo ? c.Llo + r * c.ldl : nullptr, Xilo, nullptr);
         }
         if (rc) return rc;
+        TRACE_MARK("B.trail", s, sb);
         DCGP_CU(cudaEventRecord(x.upd[e], sb));
     }
     DCGP_CU(cudaEventRecord(x.join, sa));
     DCGP_CU(cudaStreamWaitEvent(c.st, x.join, 0));
+    TRACE_DUMP();
     return 0;
 }
 
@@ -1177,7 +1193,7 @@ int plan_build(const T* L, int64_t n, int64_t ldl, T* plan, int dtype, int xf, c
 template <typename T>
 int trsm_impl(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t m, int64_t ldb, T* ws, size_t ws_bytes,
               int dtype, int xf, cudaStream_t st, const T* plan = nullptr) {
-    const bool big = n >= 2 * NBI && m >= 64 &&
+    const bool big = n >= 2 * NBI_MIN && m >= 64 &&
                      ws_bytes >= (plan ? trsm512_work_bytes(n, ldb, dtype) : trsm512_ws_bytes(n, ldl, ldb, dtype));
     if (!big) {
         if (ws_bytes < inv_ws_bytes(n, dtype)) return -8;
@@ -1281,6 +1297,7 @@ extern "C" int dcgp_potrf(void* A, int64_t n, int64_t lda, int* info, void* work
 
 extern "C" size_t dcgp_trsm_workspace(int64_t n, int64_t m, int dtype) {
     if (n <= 0) return 0;
+    pick_nbi(n);
     const size_t small = inv_ws_bytes(n, dtype) + (dtype == DCGP_F32 ? ((size_t)n * n + (size_t)n * m) * 4 : 0);
     const size_t big = trsm512_ws_bytes(n, n, m, dtype);
     return small > big ? small : big;
@@ -1295,6 +1312,7 @@ extern "C" int dcgp_trsm(int trans, const void* L, int64_t n, int64_t ldl, void*
     if (!B || ldb < m) return -5;
     if (dtype != DCGP_F64 && dtype != DCGP_F32) return -10;
     if (!workspace || workspace_bytes < inv_ws_bytes(n, dtype)) return -8;
+    pick_nbi(n);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == DCGP_F64)
         return trsm_impl<double>(trans, (const double*)L, n, ldl, (double*)B, m, ldb, (double*)workspace,
@@ -1309,13 +1327,15 @@ extern "C" int dcgp_potrs(const void* L, int64_t n, int64_t ldl, void* B, int64_
 }
 
 extern "C" size_t dcgp_solve_plan_bytes(int64_t n, int64_t ldl, int dtype) {
-    if (n < 2 * NBI) return 0;  // small factors are solved on 128-wide blocks, nothing to prepare
+    if (n < 2 * NBI_MIN) return 0;  // small factors are solved on 128-wide blocks, nothing to prepare
+    pick_nbi(n);
     return plan_bytes_impl(n, ldl, dtype);
 }
 
 extern "C" int dcgp_solve_plan(const void* L, int64_t n, int64_t ldl, void* plan, size_t plan_bytes, int dtype, int flags,
                                void* stream) {
-    if (n < 2 * NBI) return 0;
+    if (n < 2 * NBI_MIN) return 0;
+    pick_nbi(n);
     if (!L || ldl < n) return -2;
     if (dtype != DCGP_F64 && dtype != DCGP_F32) return -6;
     if (!plan || plan_bytes < plan_bytes_impl(n, ldl, dtype)) return -5;
@@ -1328,7 +1348,8 @@ extern "C" int dcgp_solve_plan(const void* L, int64_t n, int64_t ldl, void* plan
 extern "C" int dcgp_trsm_planned(int trans, const void* L, int64_t n, int64_t ldl, const void* plan, size_t plan_bytes,
                                  void* B, int64_t m, int64_t ldb, void* workspace, size_t workspace_bytes, int dtype,
                                  int flags, void* stream) {
-    if (!plan || n < 2 * NBI || m < 64 || plan_bytes < plan_bytes_impl(n, ldl, dtype))
+    pick_nbi(n);
+    if (!plan || n < 2 * NBI_MIN || m < 64 || plan_bytes < plan_bytes_impl(n, ldl, dtype))
         return dcgp_trsm(trans, L, n, ldl, B, m, ldb, workspace, workspace_bytes, dtype, flags, stream);
     if (!L || ldl < n) return -2;
     if (!B || ldb < m) return -7;
