@@ -35,7 +35,7 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = TM * TK * 4;  // 16 KB
 constexpr int EPI_WARPS = 8;
 constexpr int NTHREADS_TC = 96 + 32 * EPI_WARPS;  // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-9 epilogue, warp 10 L2 prefetch
-constexpr int STG_PITCH = 33;                     // epilogue transpose buffers: 32 x 33 floats per warp
+constexpr int STG_PITCH = 32;                     // epilogue transpose buffers: 32 x 32 floats per warp (XOR-swizzled)
 constexpr int STG_BYTES = 32 * STG_PITCH * 4;
 constexpr int GROUP_M = 16;
 template <int TN> constexpr int stage_bytes() { return A_BYTES + TN * TK * 4; }
@@ -203,11 +203,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
     } else {
         // ===== epilogue: warps 2..9; TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 =====
+        // Per 32-column chunk: tcgen05.ld (thread = row) -> per-warp shared-memory transpose (32 x 32 floats, 16-byte
+        // chunks XOR-swizzled with the row: conflict-free 128-bit writes by rows and reads by row segments) -> 8 lanes
+        // cover one 128-byte row segment of C.  All global addressing is hoisted out of the chunk loop: with two
+        // epilogue warps per scheduler the loop is bound by its instruction count, not by bandwidth.
         const int q = warp & 3, h = (warp - 2) >> 2;
-        float* stg = stg_all + (size_t)(warp - 2) * 32 * STG_PITCH;
+        float4* stg4 = reinterpret_cast<float4*>(stg_all + (size_t)(warp - 2) * 32 * STG_PITCH);
         const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                          (!p.Clo || (reinterpret_cast<uintptr_t>(p.Clo) & 15) == 0);
         const int rsub = lane >> 3, c4 = (lane & 7) * 4;  // coalesced phase: 4 rows x 128 B per instruction
+        const float alpha = p.alpha, beta = p.beta;
+        const bool hasb = beta != 0.f;
+        const int64_t rs = 4 * p.ldc;  // row step of the coalesced phase
         uint32_t lt = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             int tm, tn;
@@ -216,25 +223,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (p.lower && n0 > m0 + TM - 1 + p.lower_off) continue;
             const uint32_t buf = lt & 1u;
             const int64_t rbase = m0 + q * 32;
+            const int64_t lrow0 = rbase + rsub;  // rows lrow0 + 4 i, i < 8, belong to this lane in the coalesced phase
+            const int64_t left = p.m - lrow0;
+            const int nrow = left <= 0 ? 0 : (left >= 29 ? 8 : (int)((left + 3) >> 2));
+            float* const crow = p.C + lrow0 * p.ldc + n0 + c4;
+            float* const lorow = p.Clo ? p.Clo + lrow0 * p.ldc + n0 + c4 : nullptr;
+            const int ncol_lo = p.Clo ? (p.clo_cols == 0 ? 0x7fffffff : (int)(p.clo_cols - n0 - c4)) : 0;  // Clo for c0 < ncol_lo
             // old C is fetched one chunk ahead: the loads do not depend on the accumulator and stay in flight
             // across the tcgen05.ld / transpose / store work of the previous chunk
             float4 old[8], nxt[8];
             auto fetch = [&](int ch, float4 (&dst)[8]) {
                 const int c0 = h * (TN / 2) + ch * 32;
-                if (p.beta != 0.f && vec && (n0 + c0 + 32 <= p.n)) {
+                if (hasb && vec && (n0 + c0 + 32 <= p.n)) {
+                    const float* src = crow + c0;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int64_t row = rbase + i * 4 + rsub;
-                        dst[i] = (row < p.m) ? *reinterpret_cast<const float4*>(p.C + row * p.ldc + n0 + c0 + c4)
-                                             : make_float4(0, 0, 0, 0);
-                    }
+                    for (int i = 0; i < 8; ++i)
+                        dst[i] = (i < nrow) ? *reinterpret_cast<const float4*>(src + i * rs) : make_float4(0, 0, 0, 0);
                 }
             };
             fetch(0, nxt);
 #pragma unroll 1
             for (int ch = 0; ch < TN / 64; ++ch) {
                 const int c0 = h * (TN / 2) + ch * 32;
-                const int64_t col = n0 + c0 + c4;
                 const bool fast = vec && (n0 + c0 + 32 <= p.n);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) old[i] = nxt[i];
@@ -262,47 +272,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
                 }
-                // transpose through shared memory: thread = row -> 8 lanes = one 128-byte row segment
+                // transpose: row `lane`, chunk c -> position c ^ (lane & 7)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) stg[lane * STG_PITCH + j] = p.alpha * __uint_as_float(r[j]);
+                for (int c = 0; c < 8; ++c)
+                    stg4[lane * 8 + (c ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
+                                                                    __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3]));
                 __syncwarp();
                 if (fast) {
+                    float* dst = crow + c0;
+                    const bool want_lo = c0 < ncol_lo;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int rr = i * 4 + rsub;
-                        const int64_t row = rbase + rr;
+                        const float4 sv = stg4[rr * 8 + ((lane & 7) ^ (rr & 7))];
                         float4 o;
-                        o.x = stg[rr * STG_PITCH + c4];
-                        o.y = stg[rr * STG_PITCH + c4 + 1];
-                        o.z = stg[rr * STG_PITCH + c4 + 2];
-                        o.w = stg[rr * STG_PITCH + c4 + 3];
-                        if (p.beta != 0.f) {
-                            o.x = fmaf(p.beta, old[i].x, o.x);
-                            o.y = fmaf(p.beta, old[i].y, o.y);
-                            o.z = fmaf(p.beta, old[i].z, o.z);
-                            o.w = fmaf(p.beta, old[i].w, o.w);
+                        if (hasb) {
+                            o.x = fmaf(beta, old[i].x, alpha * sv.x);
+                            o.y = fmaf(beta, old[i].y, alpha * sv.y);
+                            o.z = fmaf(beta, old[i].z, alpha * sv.z);
+                            o.w = fmaf(beta, old[i].w, alpha * sv.w);
+                        } else {
+                            o.x = alpha * sv.x; o.y = alpha * sv.y; o.z = alpha * sv.z; o.w = alpha * sv.w;
                         }
-                        if (row < p.m) {
-                            *reinterpret_cast<float4*>(p.C + row * p.ldc + col) = o;
-                            if (p.Clo && (p.clo_cols == 0 || col < p.clo_cols)) {
+                        if (i < nrow) {
+                            *reinterpret_cast<float4*>(dst + i * rs) = o;
+                            if (want_lo) {
                                 float4 l;
                                 l.x = o.x - __uint_as_float(__float_as_uint(o.x) & 0xFFFFE000u);
                                 l.y = o.y - __uint_as_float(__float_as_uint(o.y) & 0xFFFFE000u);
                                 l.z = o.z - __uint_as_float(__float_as_uint(o.z) & 0xFFFFE000u);
                                 l.w = o.w - __uint_as_float(__float_as_uint(o.w) & 0xFFFFE000u);
-                                *reinterpret_cast<float4*>(p.Clo + row * p.ldc + col) = l;
+                                *reinterpret_cast<float4*>(lorow + c0 + i * rs) = l;
                             }
                         }
                     }
                 } else {
                     // ragged / unaligned edge: one row per iteration, one column per lane
+                    const float* stg = reinterpret_cast<const float*>(stg4);
                     const int64_t cc = n0 + c0 + lane;
                     for (int rr = 0; rr < 32; ++rr) {
                         const int64_t row = rbase + rr;
                         if (row < p.m && cc < p.n) {
-                            float v = stg[rr * STG_PITCH + lane];
+                            float v = alpha * stg[rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))];
                             float* dst = p.C + row * p.ldc + cc;
-                            if (p.beta != 0.f) v = fmaf(p.beta, *dst, v);
+                            if (hasb) v = fmaf(beta, *dst, v);
                             *dst = v;
                             if (p.Clo && (p.clo_cols == 0 || cc < p.clo_cols)) p.Clo[row * p.ldc + cc] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
                         }
