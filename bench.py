@@ -297,8 +297,8 @@ def run_ours(args):
         "e2e": {"value": world * K_ / t_e2e, "unit": "minibatch ELBO steps/s (whole job)",
                 "h2d_bytes_per_step": batch_bytes(host[0]), "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "final_loss": final_loss,
-        # dominant throughput kernel (profiles/r01_launches_bench_step_v9_summary.csv: gemm_tc_kernel 39% of the
-        # kernel time of a step; the single-CTA potrf_step_kernel chain, 24%, is latency- not roofline-bound)
+        # dominant throughput kernel (profiles/r01_launches_bench_step_v15_summary.csv: gemm_tc_kernel 51% of the
+        # kernel time of a step; the single-CTA potrf_step_kernel chain, 25%, is latency- not roofline-bound)
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma kind::tf32, TMA, TMEM): the direct dcgp_gemm "
                      "products of the timed steps that run as one launch of it each, CUDA events around every launch",
                      "achieved": fl_tc / t_tc / 1e12 if t_tc > 0 else None, "peak": tf32_peak, "unit": "TFLOP/s",
