@@ -52,61 +52,95 @@ template <> __device__ __forceinline__ float fast_rsqrt<float>(float d) {
     return y * fmaf(-0.5f * d, y * y, 1.5f);
 }
 template <> __device__ __forceinline__ double fast_rsqrt<double>(double d) {
+    // seed: 2 ulp of FP32 (2.4e-7); each Newton step squares the relative error (x 1.5): 8.6e-14, then 1.1e-26
     double y = (double)rsqrtf((float)d);
-    y = y * fma(-0.5 * d, y * y, 1.5);
     y = y * fma(-0.5 * d, y * y, 1.5);
     return y * fma(-0.5 * d, y * y, 1.5);
 }
 
-// Leaf factorisation in shared memory, right-looking over 16-wide sub-panels:
-//   (1) warp 0 factors the 16x16 diagonal block in registers (one row per lane, shuffles broadcast
-//       the pivot row); pivots use fast_rsqrt, reciprocal diagonals go to rinv[];
+// (1) of block_potrf, executed by ONE warp: factor the pw x pw diagonal sub-block at p0 in registers.  A single warp
+// is latency-bound on instruction count, so the loop is predicate-free: lanes / columns outside the valid block
+// behave as an identity padding and every lane updates all of its registers (entries above the diagonal are junk
+// that is never stored).
+template <typename T>
+__device__ __forceinline__ void diag_step(T* S, T* rinv, int p0, int pw, int* info, int64_t j0) {
+    const int lane = threadIdx.x & 31;
+    const int r = lane;  // row within the sub-block
+    T row[SB];
+    T myinv = T(0);
+    int bad = 0;
+#pragma unroll
+    for (int c = 0; c < SB; ++c) row[c] = (r < pw && c <= r) ? S[(p0 + r) * SP + p0 + c] : ((r == c) ? T(1) : T(0));
+#pragma unroll
+    for (int c = 0; c < SB; ++c) {
+        const T d = __shfl_sync(0xffffffffu, row[c], c);  // pivot (already updated)
+        if (!(d > T(0)) && bad == 0) bad = c + 1;
+        const T y = fast_rsqrt<T>(d);
+        const T scaled = row[c] * y;
+        row[c] = (r == c) ? d * y : scaled;
+        if (r == c) myinv = y;
+        const T lrc = row[c];
+#pragma unroll
+        for (int k = c + 1; k < SB; ++k) {
+            const T lkc = __shfl_sync(0xffffffffu, row[c], k);  // L[k][c]
+            row[k] = fma(-lrc, lkc, row[k]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < SB; ++c)
+        if (r < pw && c <= r) S[(p0 + r) * SP + p0 + c] = row[c];
+    if (r < pw) rinv[p0 + r] = myinv;
+    if (lane == 0 && bad != 0 && bad <= pw && info && *info == 0) *info = (int)(j0 + p0 + bad);
+}
+
+// rank-pw update of the trailing lower triangle on the tensor cores: each participating warp takes 8x8 (DMMA) /
+// 16x8 (3xTF32) output tiles, K = 16, operands read straight from the tile.  Column tiles [nj0, nj1) only;
+// the tiles are dealt to warps wfirst .. wfirst + nwarps - 1.
+template <typename T>
+__device__ __forceinline__ void trailing_update(T* S, int nb, int p0, int pw, int nj0, int nj1, int wfirst, int nwarps) {
+    constexpr int TR = WarpTile<T>::ROWS, TC = WarpTile<T>::COLS, NA = WarpTile<T>::NACC;
+    const int warp = threadIdx.x >> 5;
+    if (warp < wfirst || warp >= wfirst + nwarps) return;
+    const int t0 = p0 + pw, rr = nb - t0;
+    const int ntr = (rr + TR - 1) / TR, ntc = (rr + TC - 1) / TC;
+    if (nj1 > ntc) nj1 = ntc;
+    const int ncol = nj1 - nj0;
+    if (ncol <= 0) return;
+    for (int e = warp - wfirst; e < ntr * ncol; e += nwarps) {
+        const int mi = e / ncol, nj = nj0 + (e - mi * ncol);
+        const int row0 = t0 + mi * TR, col0 = t0 + nj * TC;
+        if (col0 > row0 + TR - 1) continue;  // tile entirely above the diagonal
+        T acc[4] = {T(0), T(0), T(0), T(0)};
+        warp_tile_mma(
+            acc, SB, [&](int rl, int k) { return (row0 + rl < nb && k < pw) ? S[(row0 + rl) * SP + p0 + k] : T(0); },
+            [&](int k, int cl) { return (col0 + cl < nb && k < pw) ? S[(col0 + cl) * SP + p0 + k] : T(0); });
+#pragma unroll
+        for (int q = 0; q < NA; ++q) {
+            int rl, cl;
+            warp_tile_coord<T>(q, rl, cl);
+            const int row = row0 + rl, col = col0 + cl;
+            if (row < nb && col <= row) S[row * SP + col] -= acc[q];
+        }
+    }
+}
+
+// Right-looking factorisation over 16-wide sub-panels with an in-tile look-ahead:
+//   (1) warp 0 factors the 16x16 diagonal block (diag_step);
 //   (2) every thread owning a row below solves its 16 entries against that block (division-free);
-//   (3) the trailing lower triangle gets a rank-16 update in 4x4 register tiles.
-// Three barriers per sub-panel (24 per leaf) instead of three per column.
-// ---------------------------------------------------------------------------------------------
+//   (3a) the NEXT sub-panel's 16 columns get their rank-16 update first (all warps, short);
+//   (3b) warp 0 factors the next diagonal block while warps 1..15 update the rest of the trailing triangle.
+// Three barriers per sub-panel; the serial pivot chain of (1) is hidden behind (3b) whenever that is longer.
 template <typename T>
 __device__ void block_potrf(T* S, T* rinv, int nb, int* info, int64_t j0) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    constexpr int TC = WarpTile<T>::COLS, NJ_NEXT = SB / TC, NW = NTHREADS / 32;
 #ifdef DCGP_LEAF_TIMING
     long long acc1 = 0, acc2 = 0, acc3 = 0, tq = clock64();
 #endif
+    if (warp == 0) diag_step<T>(S, rinv, 0, min(SB, nb), info, j0);
+    __syncthreads();
     for (int p0 = 0; p0 < nb; p0 += SB) {
         const int pw = min(SB, nb - p0);
-        // (1) diagonal sub-block.  A single warp is latency-bound on instruction count, so the loop is
-        // predicate-free: lanes / columns outside the valid block behave as an identity padding and
-        // every lane updates all of its registers (entries above the diagonal are junk that is never
-        // stored).
-        if (warp == 0) {
-            const int r = lane;  // row within the sub-block
-            T row[SB];
-            T myinv = T(0);
-            int bad = 0;
-#pragma unroll
-            for (int c = 0; c < SB; ++c)
-                row[c] = (r < pw && c <= r) ? S[(p0 + r) * SP + p0 + c] : ((r == c) ? T(1) : T(0));
-#pragma unroll
-            for (int c = 0; c < SB; ++c) {
-                const T d = __shfl_sync(0xffffffffu, row[c], c);  // pivot (already updated)
-                if (!(d > T(0)) && bad == 0) bad = c + 1;
-                const T y = fast_rsqrt<T>(d);
-                const T scaled = row[c] * y;
-                row[c] = (r == c) ? d * y : scaled;
-                if (r == c) myinv = y;
-                const T lrc = row[c];
-#pragma unroll
-                for (int k = c + 1; k < SB; ++k) {
-                    const T lkc = __shfl_sync(0xffffffffu, row[c], k);  // L[k][c]
-                    row[k] = fma(-lrc, lkc, row[k]);
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < SB; ++c)
-                if (r < pw && c <= r) S[(p0 + r) * SP + p0 + c] = row[c];
-            if (r < pw) rinv[p0 + r] = myinv;
-            if (lane == 0 && bad != 0 && bad <= pw && info && *info == 0) *info = (int)(j0 + p0 + bad);
-        }
-        __syncthreads();
 #ifdef DCGP_LEAF_TIMING
         { long long t = clock64(); acc1 += t - tq; tq = t; }
 #endif
@@ -133,38 +167,21 @@ __device__ void block_potrf(T* S, T* rinv, int nb, int* info, int64_t j0) {
 #ifdef DCGP_LEAF_TIMING
         { long long t = clock64(); acc2 += t - tq; tq = t; }
 #endif
-        // (3) rank-pw update of the trailing lower triangle on the tensor cores: each warp takes
-        // 8x8 (DMMA) / 16x8 (3xTF32) output tiles, K = 16, operands read straight from the tile.
         const int t0 = p0 + pw;
-        const int rr = nb - t0;
-        {
-            constexpr int TR = WarpTile<T>::ROWS, TC = WarpTile<T>::COLS, NA = WarpTile<T>::NACC;
-            const int ntr = (rr + TR - 1) / TR, ntc = (rr + TC - 1) / TC;
-            for (int e = warp; e < ntr * ntc; e += NTHREADS / 32) {
-                const int mi = e / ntc, nj = e - mi * ntc;
-                const int row0 = t0 + mi * TR, col0 = t0 + nj * TC;
-                if (col0 > row0 + TR - 1) continue;  // tile entirely above the diagonal
-                T acc[4] = {T(0), T(0), T(0), T(0)};
-                warp_tile_mma(
-                    acc, SB,
-                    [&](int rl, int k) { return (row0 + rl < nb && k < pw) ? S[(row0 + rl) * SP + p0 + k] : T(0); },
-                    [&](int k, int cl) { return (col0 + cl < nb && k < pw) ? S[(col0 + cl) * SP + p0 + k] : T(0); });
-#pragma unroll
-                for (int q = 0; q < NA; ++q) {
-                    int rl, cl;
-                    warp_tile_coord<T>(q, rl, cl);
-                    const int row = row0 + rl, col = col0 + cl;
-                    if (row < nb && col <= row) S[row * SP + col] -= acc[q];
-                }
-            }
-        }
+        if (t0 >= nb) break;
+        // (3a) the next sub-panel's columns
+        trailing_update<T>(S, nb, p0, pw, 0, NJ_NEXT, 0, NW);
+        __syncthreads();
+        // (3b) next pivots || rest of the trailing update
+        if (warp == 0) diag_step<T>(S, rinv, t0, min(SB, nb - t0), info, j0);
+        else trailing_update<T>(S, nb, p0, pw, NJ_NEXT, 1 << 30, 1, NW - 1);
         __syncthreads();
 #ifdef DCGP_LEAF_TIMING
         { long long t = clock64(); acc3 += t - tq; tq = t; }
 #endif
     }
 #ifdef DCGP_LEAF_TIMING
-    if (tid == 0) printf("  potrf steps: diag %lld  panel %lld  trailing %lld\n", acc1, acc2, acc3);
+    if (tid == 0) printf("  potrf steps: (first diag) %lld  panel %lld  trailing+next diag %lld\n", acc1, acc2, acc3);
 #endif
 }
 
