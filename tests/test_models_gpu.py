@@ -285,3 +285,49 @@ def test_deferred_pd_checks_collect_and_raise():
     with F.deferred_pd_checks() as pending:
         F.cholesky(good)
     pending.check()
+
+
+def _small_vcmp_trainer(lbda, seed=0):
+    from deconditional_downscaling_b200 import kernels as K, likelihoods as L, means as Mn, models as M
+    from deconditional_downscaling_b200.training import ElboTrainer
+    torch.manual_seed(seed)
+    Mz, d, r, Nb, nb = 48, 3, 2, 600, 40
+    k = K.ScaleKernel(K.RBFKernel(ard_num_dims=d))
+    l = K.ScaleKernel(K.RBFKernel(ard_num_dims=r))
+    model = M.VariationalCMP(inducing_points=torch.randn(Mz, d), individuals_mean=Mn.ZeroMean(), individuals_kernel=k,
+                             bag_kernel=l, lbda=lbda, use_individuals_noise=True)
+    lik = L.CMPLikelihood(use_individuals_noise=True)
+    model, lik = model.to(DEV), lik.to(DEV)
+    tr = ElboTrainer(model, lik, num_data=nb, beta=1.0, lr=0.01)
+    batch = dict(x=torch.randn(Nb, d, device=DEV), z=torch.randn(nb, device=DEV), bags_values=torch.randn(nb, r, device=DEV),
+                 extended_bags_values=torch.randn(Nb, r, device=DEV))
+    return tr, batch
+
+
+def test_trainer_step_failure_raises_and_leaves_parameters_untouched():
+    """A step whose Lambda is not positive definite: the optimistic (deferred-check) pass fails, the eager pass
+    retries with jitter and raises NotPSDError like the reference's psd_safe_cholesky; no update is applied."""
+    from deconditional_downscaling_b200 import functional as F
+    tr, b = _small_vcmp_trainer(lbda=-5.0)      # l(y~, y~) - 5 N I is negative definite: no jitter can repair it
+    before = [p.detach().clone() for p in tr.params]
+    with pytest.raises(F.NotPSDError):
+        tr.step(b["x"], b["z"], bags_values=b["bags_values"], extended_bags_values=b["extended_bags_values"])
+    assert all(torch.equal(p.detach(), q) for p, q in zip(tr.params, before))
+    assert F._DEFERRED is None                   # the deferred region was left cleanly
+
+
+def test_side_stream_prefetch_gives_identical_step(monkeypatch):
+    """The optional side-stream K_ZZ factorisation (DCGP_SIDE_STREAM=1) only reorders work: loss and updated
+    parameters match the single-stream step."""
+    from deconditional_downscaling_b200 import variational
+    out = []
+    for side in (False, True):
+        monkeypatch.setattr(variational, "SIDE_STREAM", side)
+        tr, b = _small_vcmp_trainer(lbda=1e-3, seed=3)
+        losses = [tr.step(b["x"], b["z"], bags_values=b["bags_values"], extended_bags_values=b["extended_bags_values"]).item()
+                  for _ in range(3)]
+        torch.cuda.synchronize()
+        out.append((losses, [p.detach().clone() for p in tr.params]))
+    (l0, p0), (l1, p1) = out
+    assert all(abs(a - c) <= 1e-5 * max(1.0, abs(a)) for a, c in zip(l0, l1))
+    assert all(torch.allclose(a, c, rtol=1e-4, atol=1e-5) for a, c in zip(p0, p1))
