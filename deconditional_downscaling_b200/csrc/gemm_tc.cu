@@ -8,7 +8,8 @@
 //   * the FP32 accumulators live in TMEM, double-buffered (2 x TN columns), so the MMAs of tile i+1 run
 //     while warps 2..9 drain tile i: tcgen05.ld (32 lanes x 32 columns), a per-warp shared-memory
 //     transpose so that global traffic is 128-byte-line coalesced, alpha/beta, optional TF32 remainder
-//     output for the 3xTF32 consumers of C.
+//     output for the 3xTF32 consumers of C;
+//   * 3xTF32 (A_lo B + A B_lo + A B from pre-split remainder matrices) as three MMA groups per k-tile.
 // Tiles are ordered in groups of 16 tile-rows (column-major inside a group) so that the ~148 tiles in
 // flight share operand panels in L2.
 //
@@ -38,9 +39,14 @@ constexpr int NTHREADS_TC = 96 + 32 * EPI_WARPS;  // warp 0 TMA, warp 1 MMA (+TM
 constexpr int STG_PITCH = 32;                     // epilogue transpose buffers: 32 x 32 floats per warp (XOR-swizzled)
 constexpr int STG_BYTES = 32 * STG_PITCH * 4;
 constexpr int GROUP_M = 16;
-template <int TN> constexpr int stage_bytes() { return A_BYTES + TN * TK * 4; }
-template <int TN> constexpr size_t smem_tc() {
-    return (size_t)STAGES * stage_bytes<TN>() + (size_t)EPI_WARPS * STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+// FAT (3xTF32): one stage holds {A, A_lo, B, B_lo} of a real k-tile and feeds three MMA groups, so every operand
+// tile crosses L2 -> shared memory once instead of twice (3 stages of 64 KB for 128-wide tiles, 2 of 96 KB for
+// 256-wide ones).  3xTF32 products are bound by the per-SM operand streaming rate, not by the tensor pipe:
+// measured on B200, potrs 8192 x 1024 1.98 -> 1.73 ms, 8192 x 8192 7.58 -> 6.96 ms.
+template <int TN, bool FAT> constexpr int n_stages() { return FAT ? (TN == 128 ? 3 : 2) : STAGES; }
+template <int TN, bool FAT> constexpr int stage_bytes() { return (FAT ? 2 : 1) * (A_BYTES + TN * TK * 4); }
+template <int TN, bool FAT> constexpr size_t smem_tc() {
+    return (size_t)n_stages<TN, FAT>() * stage_bytes<TN, FAT>() + (size_t)EPI_WARPS * STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 }
 
 struct TcParams {
@@ -67,12 +73,14 @@ __device__ __forceinline__ void tile_coord(const TcParams& p, int t, int& tm, in
     tn = r / gsz;
 }
 
-template <int TN>
+template <int TN, bool FAT>
 __global__ void __launch_bounds__(NTHREADS_TC, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapBlo,
                const __grid_constant__ TcParams p) {
-    constexpr int STAGE_BYTES = stage_bytes<TN>();
+    constexpr int STAGE_BYTES = stage_bytes<TN, FAT>();
+    constexpr int STAGES = n_stages<TN, FAT>();
+    constexpr int B_BYTES = TN * TK * 4;
     constexpr int TMEM_COLS = 2 * TN;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -87,7 +95,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int nkt = (int)((p.k + TK - 1) / TK);
     // 3xTF32: the tensor core reads FP32 operands truncated to TF32 (x_hi); with x_lo = x - x_hi given as
     // separate matrices, A B ~= A_lo B_hi + A_hi B_lo + A_hi B_hi, accumulated in the same TMEM tile.
-    const int nv = p.x3 ? 3 * nkt : nkt;  // virtual k-tiles per output tile
+    const int nv = (p.x3 && !FAT) ? 3 * nkt : nkt;  // pipeline steps per output tile
     const int ntiles = p.tiles_m * p.tiles_n;
 
     if (threadIdx.x == 0) {
@@ -125,22 +133,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(&empty[s], ph ^ 1u);
                     unsigned char* sa = tiles + (size_t)s * STAGE_BYTES;
-                    unsigned char* sb = sa + A_BYTES;
                     mbar_expect_tx(&full[s], STAGE_BYTES);
-                    const int kt = p.x3 ? v / 3 : v;
-                    const int sel = p.x3 ? v % 3 : 2;  // 0: A_lo B, 1: A B_lo, 2: A B
-                    const CUtensorMap* ma = (sel == 0) ? &mapAlo : &mapA;
-                    const CUtensorMap* mb = (sel == 1) ? &mapBlo : &mapB;
-                    const int k0 = kt * TK;
-                    if (!p.a_mn) {
-                        tma_load_2d(sa, ma, &full[s], k0, m0);
+                    auto load_a = [&](unsigned char* dst, const CUtensorMap* ma, int k0) {
+                        if (!p.a_mn) {
+                            tma_load_2d(dst, ma, &full[s], k0, m0);
+                        } else {
+                            for (int c = 0; c < TM / 32; ++c) tma_load_2d(dst + c * 4096, ma, &full[s], m0 + 32 * c, k0);
+                        }
+                    };
+                    auto load_b = [&](unsigned char* dst, const CUtensorMap* mb, int k0) {
+                        if (!p.b_mn) {
+                            tma_load_2d(dst, mb, &full[s], k0, n0);
+                        } else {
+                            for (int c = 0; c < TN / 32; ++c) tma_load_2d(dst + c * 4096, mb, &full[s], n0 + 32 * c, k0);
+                        }
+                    };
+                    if constexpr (FAT) {
+                        const int k0 = v * TK;  // stage layout: A | A_lo | B | B_lo
+                        load_a(sa, &mapA, k0);
+                        load_a(sa + A_BYTES, &mapAlo, k0);
+                        load_b(sa + 2 * A_BYTES, &mapB, k0);
+                        load_b(sa + 2 * A_BYTES + B_BYTES, &mapBlo, k0);
                     } else {
-                        for (int c = 0; c < TM / 32; ++c) tma_load_2d(sa + c * 4096, ma, &full[s], m0 + 32 * c, k0);
-                    }
-                    if (!p.b_mn) {
-                        tma_load_2d(sb, mb, &full[s], k0, n0);
-                    } else {
-                        for (int c = 0; c < TN / 32; ++c) tma_load_2d(sb + c * 4096, mb, &full[s], n0 + 32 * c, k0);
+                        const int kt = p.x3 ? v / 3 : v;
+                        const int sel = p.x3 ? v % 3 : 2;  // 0: A_lo B, 1: A B_lo, 2: A B
+                        load_a(sa, (sel == 0) ? &mapAlo : &mapA, kt * TK);
+                        load_b(sa + A_BYTES, (sel == 1) ? &mapBlo : &mapB, kt * TK);
                     }
                 }
             }
@@ -165,16 +183,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(&full[s], ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t sa = smem_u32(tiles + (size_t)s * STAGE_BYTES);
-                    const uint32_t sb = sa + A_BYTES;
-#pragma unroll
-                    for (int kk = 0; kk < TK / 8; ++kk) {
-                        // MN-major 32-bit operands use the 32-byte-atom flavour of the 128-byte swizzle:
-                        // atoms of 4 k-rows x 128 B (SBO = 512 B), 32-float chunks 4096 B apart (LBO)
+                    const uint32_t s0 = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+                    // MN-major 32-bit operands use the 32-byte-atom flavour of the 128-byte swizzle:
+                    // atoms of 4 k-rows x 128 B (SBO = 512 B), 32-float chunks 4096 B apart (LBO)
+                    auto group = [&](uint32_t sa, uint32_t sb, bool first) {
                         const uint32_t lbo = 4096, sbo = 512, kadv = 1024;
-                        const uint64_t ad = p.a_mn ? make_desc(sa + kk * kadv, lbo, sbo, 1) : make_desc(sa + kk * 32, 16, 1024, 2);
-                        const uint64_t bd = p.b_mn ? make_desc(sb + kk * kadv, lbo, sbo, 1) : make_desc(sb + kk * 32, 16, 1024, 2);
-                        umma_tf32(tacc, ad, bd, idesc, (v > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+                        for (int kk = 0; kk < TK / 8; ++kk) {
+                            const uint64_t ad = p.a_mn ? make_desc(sa + kk * kadv, lbo, sbo, 1) : make_desc(sa + kk * 32, 16, 1024, 2);
+                            const uint64_t bd = p.b_mn ? make_desc(sb + kk * kadv, lbo, sbo, 1) : make_desc(sb + kk * 32, 16, 1024, 2);
+                            umma_tf32(tacc, ad, bd, idesc, (first && kk == 0) ? 0u : 1u);
+                        }
+                    };
+                    if constexpr (FAT) {
+                        const uint32_t a = s0, alo = s0 + A_BYTES, b = s0 + 2 * A_BYTES, blo = b + B_BYTES;
+                        group(alo, b, v == 0);
+                        group(a, blo, false);
+                        group(a, b, false);
+                    } else {
+                        group(s0, s0 + A_BYTES, v == 0);
                     }
                     umma_commit(&empty[s]);  // frees the stage once the MMAs above have read it
                 }
@@ -389,12 +416,12 @@ int dcgp_split_lo_impl(const void* src, void* dst, int64_t rows, int64_t cols, i
     return 0;
 }
 
-template <int TN>
+template <int TN, bool FAT>
 int launch_tc(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapAlo, const CUtensorMap& mapBlo,
               TcParams& p, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc<TN>());
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<TN, FAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc<TN, FAT>());
         if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
         attr = true;
     }
@@ -406,7 +433,7 @@ int launch_tc(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMa
     static const int reserve = getenv("DCGP_TC_RESERVE") ? atoi(getenv("DCGP_TC_RESERVE")) : 1;
     const int64_t cap = num_sms() > 8 + reserve ? num_sms() - reserve : num_sms();
     const unsigned grid = (unsigned)(nt < cap ? nt : cap);
-    gemm_tc_kernel<TN><<<grid, NTHREADS_TC, smem_tc<TN>(), st>>>(mapA, mapB, mapAlo, mapBlo, p);
+    gemm_tc_kernel<TN, FAT><<<grid, NTHREADS_TC, smem_tc<TN, FAT>(), st>>>(mapA, mapB, mapAlo, mapBlo, p);
     DCGP_CHECK_LAUNCH();
     return 0;
 }
@@ -454,7 +481,14 @@ int dcgp_gemm_tc_ex(int transa, int transb, int64_t m, int64_t n, int64_t k, dou
     p.x3 = x3;
     p.lower_off = lower_off;
     p.clo_cols = clo_cols;
-    return tn == 128 ? launch_tc<128>(mapA, mapB, mapAlo, mapBlo, p, st) : launch_tc<256>(mapA, mapB, mapAlo, mapBlo, p, st);
+    if (tn == 128) {
+        static const int fat = getenv("DCGP_TC_FAT") ? atoi(getenv("DCGP_TC_FAT")) : 2;  // 0: off, 1: narrow tiles, 2: all
+        return (x3 && fat) ? launch_tc<128, true>(mapA, mapB, mapAlo, mapBlo, p, st)
+                           : launch_tc<128, false>(mapA, mapB, mapAlo, mapBlo, p, st);
+    }
+    static const int fatw = getenv("DCGP_TC_FAT") ? atoi(getenv("DCGP_TC_FAT")) : 2;
+    if (x3 && fatw >= 2) return launch_tc<256, true>(mapA, mapB, mapAlo, mapBlo, p, st);
+    return launch_tc<256, false>(mapA, mapB, mapAlo, mapBlo, p, st);
 }
 
 int dcgp_gemm_tc_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
