@@ -267,7 +267,7 @@ def run_ours(args):
     n_gemm, t_gemm, fl_gemm, gemm_by = probe.summary()
     n_tc, t_tc, fl_tc = probe.tcgen05_products()
     # ---- end-to-end arm: pinned host -> device copies and loss read-back inside the timed region
-    for i in range(min(W_, 2)):
+    for i in range(W_):
         trainer.step_from_host(host[i], device)
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

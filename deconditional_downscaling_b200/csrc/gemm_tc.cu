@@ -9,7 +9,10 @@
 //     while warps 2..9 drain tile i: tcgen05.ld (32 lanes x 32 columns), a per-warp shared-memory
 //     transpose so that global traffic is 128-byte-line coalesced, alpha/beta, optional TF32 remainder
 //     output for the 3xTF32 consumers of C;
-//   * 3xTF32 (A_lo B + A B_lo + A B from pre-split remainder matrices) as three MMA groups per k-tile.
+//   * 3xTF32 (A_lo B + A B_lo + A B from pre-split remainder matrices) as three MMA groups per k-tile;
+//   * optional thread-block clusters of two CTAs on vertically adjacent tiles: each CTA fetches half of the shared
+//     B tile and TMA-multicasts it to both (operand traffic per CTA -1/3), stages are released to both producers
+//     with a multicast tcgen05.commit.
 // Tiles are ordered in groups of 16 tile-rows (column-major inside a group) so that the ~148 tiles in
 // flight share operand panels in L2.
 //
@@ -63,17 +66,45 @@ struct TcParams {
     int64_t clo_cols;   // Clo is written for columns < clo_cols only (0 = all)
 };
 
-// tile index -> (tile row, tile column), grouped for L2 reuse
-__device__ __forceinline__ void tile_coord(const TcParams& p, int t, int& tm, int& tn) {
-    const int per_group = GROUP_M * p.tiles_n;
-    const int g = t / per_group, first = g * GROUP_M;
-    const int gsz = min(GROUP_M, p.tiles_m - first);
-    const int r = t - g * per_group;
-    tm = first + r % gsz;
-    tn = r / gsz;
+// index -> (row, column) over a rows x cols grid, in groups of `group` rows (column-major inside a group) so that
+// the CTAs in flight share operand panels in L2
+__device__ __forceinline__ void grouped_coord(int t, int rows, int cols, int group, int& r, int& c) {
+    const int per_group = group * cols;
+    const int g = t / per_group, first = g * group;
+    const int gsz = min(group, rows - first);
+    const int q = t - g * per_group;
+    r = first + q % gsz;
+    c = q / gsz;
 }
 
-template <int TN, bool FAT>
+// i-th work item of this CTA: 0 = no more work, 1 = compute, 2 = nothing to do (every role skips it alike).
+// CL = 1: tiles are dealt round-robin to CTAs.  CL = 2: clusters of two CTAs take vertically adjacent tile pairs
+// (rank r gets tile row 2 pair + r) that share the B tile; a pair is skipped only when both tiles lie above the
+// (offset) diagonal, `store` tells whether this CTA's own tile is wanted.
+template <int TN, int CL>
+__device__ __forceinline__ int work_item(const TcParams& p, int i, uint32_t rank, int& tm, int& tn, bool& store) {
+    if constexpr (CL == 1) {
+        const int t = blockIdx.x + i * gridDim.x;
+        if (t >= p.tiles_m * p.tiles_n) return 0;
+        grouped_coord(t, p.tiles_m, p.tiles_n, GROUP_M, tm, tn);
+        store = !(p.lower && (int64_t)tn * TN > (int64_t)tm * TM + TM - 1 + p.lower_off);
+        return store ? 1 : 2;
+    } else {
+        const int rows = (p.tiles_m + 1) / 2;
+        const int t = (int)(blockIdx.x >> 1) + i * (int)(gridDim.x >> 1);
+        if (t >= rows * p.tiles_n) return 0;
+        int pr;
+        grouped_coord(t, rows, p.tiles_n, GROUP_M / 2, pr, tn);
+        tm = 2 * pr + (int)rank;
+        store = !(p.lower && (int64_t)tn * TN > (int64_t)tm * TM + TM - 1 + p.lower_off);
+        const bool pair = !(p.lower && (int64_t)tn * TN > (int64_t)(2 * pr + 1) * TM + TM - 1 + p.lower_off);
+        return pair ? 1 : 2;
+    }
+}
+
+// mapB / mapBlo: for CL = 2 and a K-major B their box holds TN / 2 rows (each CTA of the pair fetches one half
+// of the shared B tile and multicasts it to both)
+template <int TN, bool FAT, int CL>
 __global__ void __launch_bounds__(NTHREADS_TC, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapBlo,
@@ -96,12 +127,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // 3xTF32: the tensor core reads FP32 operands truncated to TF32 (x_hi); with x_lo = x - x_hi given as
     // separate matrices, A B ~= A_lo B_hi + A_hi B_lo + A_hi B_hi, accumulated in the same TMEM tile.
     const int nv = (p.x3 && !FAT) ? 3 * nkt : nkt;  // pipeline steps per output tile
-    const int ntiles = p.tiles_m * p.tiles_n;
+    const uint32_t rank = (CL == 2) ? cluster_ctarank() : 0u;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], CL);  // every CTA that writes into this stage waits for every CTA that reads it
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 1);
@@ -116,6 +147,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (CL == 2) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
@@ -123,11 +155,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (lane == 0) {
             // ===== TMA producer =====
             uint32_t it = 0;  // virtual k-tiles issued so far (ring position carries across tiles)
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (int i = 0;; ++i) {
                 int tm, tn;
-                tile_coord(p, t, tm, tn);
+                bool store;
+                const int st = work_item<TN, CL>(p, i, rank, tm, tn, store);
+                if (st == 0) break;
+                if (st == 2) continue;
                 const int m0 = tm * TM, n0 = tn * TN;
-                if (p.lower && n0 > m0 + TM - 1 + p.lower_off) continue;
                 for (int v = 0; v < nv; ++v, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1u;
@@ -142,7 +176,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         }
                     };
                     auto load_b = [&](unsigned char* dst, const CUtensorMap* mb, int k0) {
-                        if (!p.b_mn) {
+                        if constexpr (CL == 2) {
+                            // this CTA's half of the shared B tile, delivered to both CTAs of the pair
+                            if (!p.b_mn) {
+                                tma_load_2d_mc(dst + rank * (TN / 2) * 128, mb, &full[s], k0, n0 + (int)rank * (TN / 2), 3);
+                            } else {
+                                for (int c = (int)rank * (TN / 64); c < ((int)rank + 1) * (TN / 64); ++c)
+                                    tma_load_2d_mc(dst + c * 4096, mb, &full[s], n0 + 32 * c, k0, 3);
+                            }
+                        } else if (!p.b_mn) {
                             tma_load_2d(dst, mb, &full[s], k0, n0);
                         } else {
                             for (int c = 0; c < TN / 32; ++c) tma_load_2d(dst + c * 4096, mb, &full[s], n0 + 32 * c, k0);
@@ -170,10 +212,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                                    ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             uint32_t it = 0, lt = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (int i = 0;; ++i) {
                 int tm, tn;
-                tile_coord(p, t, tm, tn);
-                if (p.lower && tn * TN > tm * TM + TM - 1 + p.lower_off) continue;
+                bool store;
+                const int st = work_item<TN, CL>(p, i, rank, tm, tn, store);
+                if (st == 0) break;
+                if (st == 2) continue;
                 const uint32_t buf = lt & 1u;
                 mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -203,7 +247,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     } else {
                         group(s0, s0 + A_BYTES, v == 0);
                     }
-                    umma_commit(&empty[s]);  // frees the stage once the MMAs above have read it
+                    // frees the stage once the MMAs above have read it (in both CTAs for a multicast pair)
+                    if constexpr (CL == 2) umma_commit_mc(&empty[s], 3);
+                    else umma_commit(&empty[s]);
                 }
                 umma_commit(&tmem_full[buf]);  // accumulator complete
                 ++lt;
@@ -215,12 +261,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (p.beta != 0.f) {
             constexpr int LPR = TN * 4 / 128;  // 128-byte lines per tile row
             uint32_t lt = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (int i = 0;; ++i) {
                 int tm, tn;
-                tile_coord(p, t, tm, tn);
+                bool store;
+                const int st = work_item<TN, CL>(p, i, rank, tm, tn, store);
+                if (st == 0) break;
+                if (st == 2) continue;
                 const int64_t m0 = (int64_t)tm * TM, n0 = (int64_t)tn * TN;
-                if (p.lower && n0 > m0 + TM - 1 + p.lower_off) continue;
                 if (lt > 0) mbar_wait(&tmem_full[(lt - 1) & 1u], ((lt - 1) >> 1) & 1u);
+                if (!store) {
+                    ++lt;
+                    continue;
+                }
                 for (int e = lane; e < TM * LPR; e += 32) {
                     const int64_t row = m0 + e / LPR, col = n0 + (e % LPR) * 32;
                     if (row < p.m && col < p.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.C + row * p.ldc + col));
@@ -243,12 +295,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const bool hasb = beta != 0.f;
         const int64_t rs = 4 * p.ldc;  // row step of the coalesced phase
         uint32_t lt = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (int i = 0;; ++i) {
             int tm, tn;
-            tile_coord(p, t, tm, tn);
+            bool store;
+            const int st = work_item<TN, CL>(p, i, rank, tm, tn, store);
+            if (st == 0) break;
+            if (st == 2) continue;
             const int64_t m0 = (int64_t)tm * TM, n0 = (int64_t)tn * TN;
-            if (p.lower && n0 > m0 + TM - 1 + p.lower_off) continue;
             const uint32_t buf = lt & 1u;
+            if (!store) {
+                // partner-only tile of a pair (above the diagonal): accumulated for lock-step, never written
+                mbar_wait(&tmem_full[buf], (lt >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+                ++lt;
+                continue;
+            }
             const int64_t rbase = m0 + q * 32;
             const int64_t lrow0 = rbase + rsub;  // rows lrow0 + 4 i, i < 8, belong to this lane in the coalesced phase
             const int64_t left = p.m - lrow0;
@@ -355,6 +418,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (CL == 2) cluster_sync_all();  // no CTA leaves while its peer can still signal or write into it
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
@@ -416,24 +480,43 @@ int dcgp_split_lo_impl(const void* src, void* dst, int64_t rows, int64_t cols, i
     return 0;
 }
 
-template <int TN, bool FAT>
+template <int TN, bool FAT, int CL>
 int launch_tc(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapAlo, const CUtensorMap& mapBlo,
               TcParams& p, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<TN, FAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc<TN, FAT>());
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<TN, FAT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem_tc<TN, FAT>());
         if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
         attr = true;
     }
     p.tiles_m = (int)((p.m + TM - 1) / TM);
     p.tiles_n = (int)((p.n + TN - 1) / TN);
-    const int64_t nt = (int64_t)p.tiles_m * p.tiles_n;
+    // work items: tiles, or vertically adjacent tile pairs for the multicast clusters
+    const int64_t items = (CL == 2 ? (int64_t)((p.tiles_m + 1) / 2) : (int64_t)p.tiles_m) * p.tiles_n;
     // one SM is left to the serial lane of the look-ahead factorisation / solves (single-CTA kernels that must
     // not queue behind a persistent grid occupying every SM)
     static const int reserve = getenv("DCGP_TC_RESERVE") ? atoi(getenv("DCGP_TC_RESERVE")) : 1;
-    const int64_t cap = num_sms() > 8 + reserve ? num_sms() - reserve : num_sms();
-    const unsigned grid = (unsigned)(nt < cap ? nt : cap);
-    gemm_tc_kernel<TN, FAT><<<grid, NTHREADS_TC, smem_tc<TN, FAT>(), st>>>(mapA, mapB, mapAlo, mapBlo, p);
+    const int64_t cap = (num_sms() > 8 + reserve ? num_sms() - reserve : num_sms()) / CL;
+    const unsigned grid = (unsigned)(items < cap ? items : cap) * CL;
+    if constexpr (CL == 1) {
+        gemm_tc_kernel<TN, FAT, CL><<<grid, NTHREADS_TC, smem_tc<TN, FAT>(), st>>>(mapA, mapB, mapAlo, mapBlo, p);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(NTHREADS_TC);
+        cfg.dynamicSmemBytes = smem_tc<TN, FAT>();
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<TN, FAT, CL>, mapA, mapB, mapAlo, mapBlo, p);
+        if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
+    }
     DCGP_CHECK_LAUNCH();
     return 0;
 }
@@ -453,6 +536,11 @@ int dcgp_gemm_tc_ex(int transa, int transb, int64_t m, int64_t n, int64_t k, dou
     // narrow tiles when the wide ones would not fill one wave of SMs
     const int64_t wide = ((m + TM - 1) / TM) * ((n + 255) / 256);
     const int tn = (2 * wide <= num_sms()) ? 128 : 256;
+    // multicast pairs (two CTAs share every B tile) once there is more than a wave of wide tiles
+    static const int cl_on = getenv("DCGP_TC_CLUSTER") ? atoi(getenv("DCGP_TC_CLUSTER")) : 2;
+    // (measured on B200 at 8192^3: NN 650 -> 675, TN 597 -> 648 TF/s, but NT 692 -> 670: mode 1 = always, 2 = only when
+    // B is MN-major, i.e. not transposed)
+    const int cl = (cl_on && (cl_on == 1 || !transb) && tn == 256 && wide >= num_sms() && m >= 2 * TM) ? 2 : 1;
     CUtensorMap mapA, mapB, mapAlo, mapBlo;
     // op(A)[m, k]: notrans -> A is m x k (K-major); trans -> A is k x m (MN-major)
     // op(B)[k, n]: trans -> B is n x k (K-major); notrans -> B is k x n (MN-major)
@@ -461,7 +549,7 @@ int dcgp_gemm_tc_ex(int transa, int transb, int64_t m, int64_t n, int64_t k, dou
                       : make_map(mp, X, m, k, lda, TK, TM, CU_TENSOR_MAP_SWIZZLE_128B);
     };
     auto mk_b = [&](CUtensorMap* mp, const void* X) {
-        return transb ? make_map(mp, X, n, k, ldb, TK, tn, CU_TENSOR_MAP_SWIZZLE_128B)
+        return transb ? make_map(mp, X, n, k, ldb, TK, tn / cl, CU_TENSOR_MAP_SWIZZLE_128B)
                       : make_map(mp, X, k, n, ldb, 32, TK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     };
     if (mk_a(&mapA, A) || mk_b(&mapB, B)) return 1;
@@ -481,14 +569,15 @@ int dcgp_gemm_tc_ex(int transa, int transb, int64_t m, int64_t n, int64_t k, dou
     p.x3 = x3;
     p.lower_off = lower_off;
     p.clo_cols = clo_cols;
-    if (tn == 128) {
-        static const int fat = getenv("DCGP_TC_FAT") ? atoi(getenv("DCGP_TC_FAT")) : 2;  // 0: off, 1: narrow tiles, 2: all
-        return (x3 && fat) ? launch_tc<128, true>(mapA, mapB, mapAlo, mapBlo, p, st)
-                           : launch_tc<128, false>(mapA, mapB, mapAlo, mapBlo, p, st);
-    }
-    static const int fatw = getenv("DCGP_TC_FAT") ? atoi(getenv("DCGP_TC_FAT")) : 2;
-    if (x3 && fatw >= 2) return launch_tc<256, true>(mapA, mapB, mapAlo, mapBlo, p, st);
-    return launch_tc<256, false>(mapA, mapB, mapAlo, mapBlo, p, st);
+    static const int fat = getenv("DCGP_TC_FAT") ? atoi(getenv("DCGP_TC_FAT")) : 2;  // 0: off, 1: narrow tiles, 2: all
+    if (tn == 128)
+        return (x3 && fat) ? launch_tc<128, true, 1>(mapA, mapB, mapAlo, mapBlo, p, st)
+                           : launch_tc<128, false, 1>(mapA, mapB, mapAlo, mapBlo, p, st);
+    if (cl == 2)
+        return (x3 && fat >= 2) ? launch_tc<256, true, 2>(mapA, mapB, mapAlo, mapBlo, p, st)
+                                : launch_tc<256, false, 2>(mapA, mapB, mapAlo, mapBlo, p, st);
+    return (x3 && fat >= 2) ? launch_tc<256, true, 1>(mapA, mapB, mapAlo, mapBlo, p, st)
+                            : launch_tc<256, false, 1>(mapA, mapB, mapAlo, mapBlo, p, st);
 }
 
 int dcgp_gemm_tc_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,

@@ -84,6 +84,18 @@ class ElboTrainer:
 
     def step_from_host(self, host_batch: Dict[str, torch.Tensor], device):
         """End-to-end step: pinned host tensors -> device, step, loss back to the host."""
-        dev = {k: (v.to(device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host_batch.items()}
+        # persistent device staging buffers (one per input name and shape): no allocator traffic per step
+        stage = self.__dict__.setdefault("_stage", {})
+        dev = {}
+        for k, v in host_batch.items():
+            if not torch.is_tensor(v):
+                dev[k] = v
+                continue
+            key = (k, tuple(v.shape), v.dtype)
+            buf = stage.get(key)
+            if buf is None:
+                buf = stage[key] = torch.empty(v.shape, dtype=v.dtype, device=device)
+            buf.copy_(v, non_blocking=True)
+            dev[k] = buf
         x, z = dev.pop("x"), dev.pop("z")
         return float(self.step(x, z, **dev).item())
