@@ -208,3 +208,30 @@ def test_evaluation_over_large_grid_is_chunk_invariant_and_matches_oracle():
         torch.zeros(2000, device=DEV, dtype=torch.float64)) / 2000
     nll0 = evaluation.chunked_nll(lambda xc: model(xc), xw[:2000], torch.zeros(2000, device=DEV, dtype=dt), chunk_size=2000)
     assert abs(nll0 - ref.item()) < 1e-3 * abs(ref.item())
+
+
+@pytest.mark.parametrize("transa,m,n,k", [(False, 5037, 9005, 777), (True, 4993, 8200, 1031), (False, 385, 40000, 200)])
+def test_cluster_multicast_gemm_ragged_shapes(transa, m, n, k):
+    """Non-transposed B with more than a wave of wide tiles runs on two-CTA clusters with multicast B tiles: ragged
+    M / N / K, an odd number of tile rows (the second CTA of the last pair has no tile), beta and lower-only."""
+    o = ops()
+    torch.manual_seed(m)
+    A = torch.randn((k, m) if transa else (m, k), device=DEV)
+    B = torch.randn(k, n, device=DEV)
+    C0 = torch.randn(m, n, device=DEV)
+    ref = (A.t() if transa else A).double() @ B.double()
+    o.TF32_MODE = "fast"
+    try:
+        C = o.gemm(A, B, transa=transa)
+        assert ((C.double() - ref).norm() / ref.norm()).item() < 2e-3
+        C = o.gemm(A, B, transa=transa, alpha=-0.5, beta=1.0, C=C0.clone())
+        full = C0.double() - 0.5 * ref
+        assert ((C.double() - full).norm() / full.norm()).item() < 2e-3
+    finally:
+        o.TF32_MODE = "auto"
+    X = o.gemm_x3(A, B, transa=transa)                       # fat 3xTF32 stages on clusters
+    assert ((X.double() - ref).norm() / ref.norm()).item() < 1e-5
+    if m <= n:
+        Cl = o.gemm(A, B[:, :m].contiguous(), transa=transa, alpha=1.0, beta=1.0, C=C0[:, :m].clone(), lower=True)
+        want = (C0[:, :m].double() + ref[:, :m]).tril()
+        assert ((Cl.double().tril() - want).norm() / want.norm()).item() < 2e-3
