@@ -1180,9 +1180,11 @@ size_t plan_bytes_impl(int64_t n, int64_t ldl, int dtype) {
     return 2 * nbig * NBI * NBI * es + (dtype == DCGP_F32 ? (size_t)n * ldl * 4 : 0);
 }
 
-size_t trsm512_work_bytes(int64_t n, int64_t m_ld, int dtype) {  // X (+ remainders of X and of B)
-    const size_t es = dtype == DCGP_F64 ? 8 : 4;
-    return (size_t)n * m_ld * es * (dtype == DCGP_F32 ? 3 : 1);
+// X (+ FP32: remainders of X and of B, and a copy of B with a TMA-compatible leading dimension - a multiple of
+// 4 floats - for right-hand sides whose own layout is not)
+size_t trsm512_work_bytes(int64_t n, int64_t m_ld, int dtype) {
+    if (dtype == DCGP_F64) return (size_t)n * m_ld * 8;
+    return (size_t)n * ((m_ld + 3) & ~(int64_t)3) * 4 * 4;
 }
 
 size_t trsm512_ws_bytes(int64_t n, int64_t ldl, int64_t m_ld, int dtype) {
@@ -1210,7 +1212,7 @@ int plan_build(const T* L, int64_t n, int64_t ldl, T* plan, int dtype, int xf, c
 template <typename T>
 int trsm_impl(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t m, int64_t ldb, T* ws, size_t ws_bytes,
               int dtype, int xf, cudaStream_t st, const T* plan = nullptr) {
-    const bool big = n >= 2 * NBI_MIN && m >= 64 &&
+    const bool big = n >= 2 * NBI_MIN && m >= 16 &&
                      ws_bytes >= (plan ? trsm512_work_bytes(n, ldb, dtype) : trsm512_ws_bytes(n, ldl, ldb, dtype));
     if (!big) {
         if (ws_bytes < inv_ws_bytes(n, dtype)) return -8;
@@ -1228,19 +1230,35 @@ int trsm_impl(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t m, in
         ws += plan_bytes_impl(n, ldl, dtype) / sizeof(T);
     }
     const T* inv = plan;
+    // FP32 3xTF32 runs on the tcgen05 kernel, whose TMA maps need 16-byte aligned rows: right-hand sides with another
+    // layout (e.g. 50 or 81 columns, packed) are solved in a padded copy
+    T* Bw = B;
+    int64_t ldw = ldb;
+    const bool pad = sizeof(T) == 4 && xf && ((ldb & 3) || (reinterpret_cast<uintptr_t>(B) & 15));
+    if (pad) ldw = (m + 3) & ~(int64_t)3;
     T* X = ws;
-    L5Ctx<T> c{L, ldl, B, m, ldb, const_cast<T*>(inv), X, dtype, xf, st, nullptr, nullptr, n};
+    if (pad) {
+        Bw = X + 3 * (size_t)n * ldw;
+        cudaError_t e = cudaMemcpy2DAsync(Bw, (size_t)ldw * sizeof(T), B, (size_t)ldb * sizeof(T), (size_t)m * sizeof(T),
+                                          (size_t)n, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
+    }
+    L5Ctx<T> c{L, ldl, Bw, m, ldw, const_cast<T*>(inv), X, dtype, xf, st, nullptr, nullptr, n};
     if (sizeof(T) == 4 && xf) {
         c.invlo = inv + nbig * NBI * NBI;
         c.Llo = c.invlo + nbig * NBI * NBI;
-        c.Xlo = X + (size_t)n * ldb;
-        c.Blo = c.Xlo + (size_t)n * ldb;
+        c.Xlo = X + (size_t)n * ldw;
+        c.Blo = c.Xlo + (size_t)n * ldw;
     }
     static const int use_la = getenv("DCGP_TRSM_LA") ? atoi(getenv("DCGP_TRSM_LA")) : 1;
-    for (int sweep = (trans == 1 ? 1 : 0); sweep <= (trans == 0 ? 0 : 1); ++sweep) {
+    const int last = (trans == 0 ? 0 : 1);
+    for (int sweep = (trans == 1 ? 1 : 0); sweep <= last; ++sweep) {
         rc = (use_la && nbig >= 4) ? ltrsm512_la(c, sweep) : ltrsm512_rec(c, sweep, 0, n);
         if (rc) return rc;
-        cudaError_t e = cudaMemcpy2DAsync(B, (size_t)ldb * sizeof(T), X, (size_t)ldb * sizeof(T), (size_t)m * sizeof(T),
+        // the solved rows become the right-hand side of the next sweep / the result
+        T* dst = (sweep == last) ? B : Bw;
+        const int64_t ldd = (sweep == last) ? ldb : ldw;
+        cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)ldd * sizeof(T), X, (size_t)ldw * sizeof(T), (size_t)m * sizeof(T),
                                           (size_t)n, cudaMemcpyDeviceToDevice, st);
         if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
     }
@@ -1366,7 +1384,7 @@ extern "C" int dcgp_trsm_planned(int trans, const void* L, int64_t n, int64_t ld
                                  void* B, int64_t m, int64_t ldb, void* workspace, size_t workspace_bytes, int dtype,
                                  int flags, void* stream) {
     pick_nbi(n);
-    if (!plan || n < 2 * NBI_MIN || m < 64 || plan_bytes < plan_bytes_impl(n, ldl, dtype))
+    if (!plan || n < 2 * NBI_MIN || m < 16 || plan_bytes < plan_bytes_impl(n, ldl, dtype))
         return dcgp_trsm(trans, L, n, ldl, B, m, ldb, workspace, workspace_bytes, dtype, flags, stream);
     if (!L || ldl < n) return -2;
     if (!B || ldb < m) return -7;

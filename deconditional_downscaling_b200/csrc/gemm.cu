@@ -412,8 +412,10 @@ int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, doub
         // the mma.sync kernel below
         const bool x3 = (flags & DCGP_GEMM_TF32X3) != 0;
         const int64_t tc_tiles = ((m + 127) / 128) * ((n + 127) / 128);  // narrow (128 x 128) tiles
-        if (!(flags & (DCGP_GEMM_NO_TCGEN05 | DCGP_GEMM_INPLACE)) && m >= 128 && n >= 128 && k >= 64 && (!x3 || (Alo && Blo)) &&
-            tc_tiles >= (x3 ? 4 : 32)) {
+        // (3xTF32 with remainder operands: the mma.sync alternative is ~4x slower, so even a mostly empty 128-wide
+        // tile column - a few dozen right-hand sides - is worth it; TMA zero-fills the missing columns)
+        if (!(flags & (DCGP_GEMM_NO_TCGEN05 | DCGP_GEMM_INPLACE)) && m >= 128 && n >= ((x3 && Alo && Blo) ? 32 : 128) && k >= 64 &&
+            (!x3 || (Alo && Blo)) && tc_tiles >= (x3 ? 4 : 32)) {
             const int rc = dcgp_gemm_tc_impl(transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, flags,
                                              x3 ? Alo : nullptr, x3 ? Blo : nullptr, Clo, st);
             if (rc <= 0) return rc;
