@@ -734,7 +734,7 @@ inline int64_t la_panel(int dtype, int64_t nb) {
     int64_t pw;
     if (force[i] >= 0) pw = force[i];
     else if (i == 1) pw = nb <= 8192 ? 128 : (nb <= 16384 ? 256 : 512);      // measured on B200 (tools/potrf_sweep.py)
-    else pw = nb <= 4096 ? 128 : (nb <= 8192 ? 512 : 1024);
+    else pw = nb <= 5120 ? 128 : (nb <= 7168 ? 256 : (nb <= 12288 ? 512 : 1024));
     return (pw > 0 && nb > 2 * pw) ? pw : 0;
 }
 
