@@ -1132,8 +1132,10 @@ int ltrsm512_la(const L5Ctx<T>& c, int trans) {
         const int e = (int)(s & 3), ep = (int)((s + 3) & 3);
         T* Xi = c.X + r * c.ldb;
         T* Xilo = lo ? c.Xlo + r * c.ldb : nullptr;
+        // (the inverted block is lower triangular, its transpose upper: the tcgen05 kernel skips the zero k-tiles)
         rc = dcgp_gemm_impl(trans, 0, w, c.m, w, 1.0, c.inv + i * NBI * NBI, NBI, c.B + r * c.ldb, c.ldb, 0.0, Xi, c.ldb,
-                            c.dtype, c.xf, sa, lo ? c.invlo + i * NBI * NBI : nullptr, lo ? c.Blo + r * c.ldb : nullptr, Xilo);
+                            c.dtype, c.xf | (trans ? DCGP_GEMM_A_UPPER : DCGP_GEMM_A_LOWER), sa,
+                            lo ? c.invlo + i * NBI * NBI : nullptr, lo ? c.Blo + r * c.ldb : nullptr, Xilo);
         if (rc) return rc;
         TRACE_MARK("A.leaf", s, sa);
         if (s == q - 1) break;

@@ -64,6 +64,7 @@ struct TcParams {
     int tiles_m, tiles_n;
     int64_t lower_off;  // lower: keep tiles with col0 <= row0 + TM - 1 + lower_off
     int64_t clo_cols;   // Clo is written for columns < clo_cols only (0 = all)
+    int a_tri;          // op(A) triangular: 1 lower (k <= row), 2 upper (k >= row) - k-tiles of zeros are skipped
 };
 
 // index -> (row, column) over a rows x cols grid, in groups of `group` rows (column-major inside a group) so that
@@ -104,6 +105,14 @@ __device__ __forceinline__ int work_item(const TcParams& p, int i, uint32_t rank
 
 // mapB / mapBlo: for CL = 2 and a K-major B their box holds TN / 2 rows (each CTA of the pair fetches one half
 // of the shared B tile and multicasts it to both)
+// real k-tiles [kt0, kt1) that can hold non-zeros of op(A) for tile row tm
+__device__ __forceinline__ void k_range(const TcParams& p, int tm, int nkt, int& kt0, int& kt1) {
+    kt0 = 0;
+    kt1 = nkt;
+    if (p.a_tri == 1) kt1 = min(nkt, ((tm + 1) * TM + TK - 1) / TK);
+    if (p.a_tri == 2) kt0 = min(nkt - 1, (tm * TM) / TK);
+}
+
 template <int TN, bool FAT, int CL>
 __global__ void __launch_bounds__(NTHREADS_TC, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -126,7 +135,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int nkt = (int)((p.k + TK - 1) / TK);
     // 3xTF32: the tensor core reads FP32 operands truncated to TF32 (x_hi); with x_lo = x - x_hi given as
     // separate matrices, A B ~= A_lo B_hi + A_hi B_lo + A_hi B_hi, accumulated in the same TMEM tile.
-    const int nv = (p.x3 && !FAT) ? 3 * nkt : nkt;  // pipeline steps per output tile
     const uint32_t rank = (CL == 2) ? cluster_ctarank() : 0u;
 
     if (threadIdx.x == 0) {
@@ -162,7 +170,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (st == 0) break;
                 if (st == 2) continue;
                 const int m0 = tm * TM, n0 = tn * TN;
-                for (int v = 0; v < nv; ++v, ++it) {
+                int kt0, kt1;
+                k_range(p, tm, nkt, kt0, kt1);
+                const int nvt = (p.x3 && !FAT) ? 3 * (kt1 - kt0) : (kt1 - kt0);
+                for (int v = 0; v < nvt; ++v, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(&empty[s], ph ^ 1u);
@@ -191,13 +202,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         }
                     };
                     if constexpr (FAT) {
-                        const int k0 = v * TK;  // stage layout: A | A_lo | B | B_lo
+                        const int k0 = (kt0 + v) * TK;  // stage layout: A | A_lo | B | B_lo
                         load_a(sa, &mapA, k0);
                         load_a(sa + A_BYTES, &mapAlo, k0);
                         load_b(sa + 2 * A_BYTES, &mapB, k0);
                         load_b(sa + 2 * A_BYTES + B_BYTES, &mapBlo, k0);
                     } else {
-                        const int kt = p.x3 ? v / 3 : v;
+                        const int kt = kt0 + (p.x3 ? v / 3 : v);
                         const int sel = p.x3 ? v % 3 : 2;  // 0: A_lo B, 1: A B_lo, 2: A B
                         load_a(sa, (sel == 0) ? &mapAlo : &mapA, kt * TK);
                         load_b(sa + A_BYTES, (sel == 1) ? &mapBlo : &mapB, kt * TK);
@@ -222,7 +233,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tacc = tmem_base + buf * TN;
-                for (int v = 0; v < nv; ++v, ++it) {
+                int kt0, kt1;
+                k_range(p, tm, nkt, kt0, kt1);
+                const int nvt = (p.x3 && !FAT) ? 3 * (kt1 - kt0) : (kt1 - kt0);
+                for (int v = 0; v < nvt; ++v, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(&full[s], ph);
@@ -540,7 +554,8 @@ int dcgp_gemm_tc_ex(int transa, int transb, int64_t m, int64_t n, int64_t k, dou
     static const int cl_on = getenv("DCGP_TC_CLUSTER") ? atoi(getenv("DCGP_TC_CLUSTER")) : 2;
     // (measured on B200 at 8192^3: NN 650 -> 675, TN 597 -> 648 TF/s, but NT 692 -> 670: mode 1 = always, 2 = only when
     // B is MN-major, i.e. not transposed)
-    const int cl = (cl_on && (cl_on == 1 || !transb) && tn == 256 && wide >= num_sms() && m >= 2 * TM) ? 2 : 1;
+    const int cl = (cl_on && (cl_on == 1 || !transb) && tn == 256 && wide >= num_sms() && m >= 2 * TM &&
+                    !(flags & (DCGP_GEMM_A_LOWER | DCGP_GEMM_A_UPPER))) ? 2 : 1;  // pairs must share their k-range
     CUtensorMap mapA, mapB, mapAlo, mapBlo;
     // op(A)[m, k]: notrans -> A is m x k (K-major); trans -> A is k x m (MN-major)
     // op(B)[k, n]: trans -> B is n x k (K-major); notrans -> B is k x n (MN-major)
@@ -569,6 +584,7 @@ int dcgp_gemm_tc_ex(int transa, int transb, int64_t m, int64_t n, int64_t k, dou
     p.x3 = x3;
     p.lower_off = lower_off;
     p.clo_cols = clo_cols;
+    p.a_tri = (flags & DCGP_GEMM_A_LOWER) ? 1 : ((flags & DCGP_GEMM_A_UPPER) ? 2 : 0);
     static const int fat = getenv("DCGP_TC_FAT") ? atoi(getenv("DCGP_TC_FAT")) : 2;  // 0: off, 1: narrow tiles, 2: all
     if (tn == 128)
         return (x3 && fat) ? launch_tc<128, true, 1>(mapA, mapB, mapAlo, mapBlo, p, st)

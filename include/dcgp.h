@@ -58,6 +58,8 @@ extern "C" {
 #define DCGP_GEMM_LOWER 1       /* only tiles touching the lower triangle of C are computed/written */
 #define DCGP_GEMM_NO_SPLITK 2   /* C aliases an input (in-place): the K loop is never split across CTAs */
 #define DCGP_GEMM_INPLACE 16    /* C aliases A (then n <= 128) or B (then m <= 128): single tile along that dimension */
+#define DCGP_GEMM_A_LOWER 32  /* op(A) is lower triangular (zero for k > row): k-tiles past the diagonal are skipped */
+#define DCGP_GEMM_A_UPPER 64  /* op(A) is upper triangular (zero for k < row) */
 #define DCGP_GEMM_NO_TCGEN05 8  /* F32 only: keep the contraction on the mma.sync kernel (A/B testing) */
 #define DCGP_GEMM_TF32X3 4      /* F32 only: error-compensated 3xTF32 (~FP32 accuracy) instead of single-pass
                                    TF32; also honoured in the flags of dcgp_potrf / dcgp_trsm / dcgp_potrs */
