@@ -181,7 +181,7 @@ class GemmProbe:
 
 
 # ------------------------------------------------------------------ our arm
-def build_trainer(wl, device, dtype=torch.float32):
+def build_trainer(wl, device, dtype=torch.float32, cuda_graph=False):
     from deconditional_downscaling_b200 import kernels as K, likelihoods as L, means as Mn, models as M
     from deconditional_downscaling_b200.training import ElboTrainer
     inv_sp1 = math.log(math.e - 1.0)
@@ -202,7 +202,7 @@ def build_trainer(wl, device, dtype=torch.float32):
         vd.variational_mean.zero_()
         vd.chol_variational_covar.copy_(torch.eye(wl["M"]))
     model.variational_strategy.variational_params_initialized.fill_(1)
-    return ElboTrainer(model, lik, num_data=wl["n_bags_total"], beta=wl["beta"], lr=wl["lr"])
+    return ElboTrainer(model, lik, num_data=wl["n_bags_total"], beta=wl["beta"], lr=wl["lr"], cuda_graph=cuda_graph)
 
 
 def run_ours(args):
@@ -218,27 +218,58 @@ def run_ours(args):
     wl = SMALL if args.small else WL
     from deconditional_downscaling_b200 import ops, _lib
     lib = _lib.load()
-    trainer = build_trainer(wl, device)
     shard = make_shard(wl, rank % wl["shards"])
-    K_, W_ = args.steps, args.warmup
+    K_, W_ = args.steps, max(args.warmup, 3)
     host = minibatches(wl, shard, K_ + W_, seed=99 + rank)
     host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
     devb = [{k: v.to(device) for k, v in b.items()} for b in host]
-
-    def dev_step(i):
-        b = dict(devb[i])
-        return trainer.step(b.pop("x"), b.pop("z"), **b)
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(step_fn):
+        """W_ warm-up steps, then K_ steps between events on the current stream; max over ranks."""
+        first = None
+        for i in range(W_):
+            l_ = step_fn(i)
+            if i == 0:
+                first = float(l_.item()) if torch.is_tensor(l_) else float(l_)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(W_, W_ + K_):
+            last = step_fn(i)
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), first, (float(last.item()) if torch.is_tensor(last) else float(last))
+
+    # ---- eager pass with CUDA events around every tensor-core contraction call: the roofline numbers.  (Events cannot
+    # be recorded around individual kernels of a graph replay, so the same steps are issued eagerly once.)
     probe = GemmProbe(ops)
     probe.install()
-    # ---- device-resident arm -------------------------------------------------------------
-    first_loss = None
-    for i in range(W_):
+    eager = build_trainer(wl, device)
+
+    def eager_step(i):
+        b = dict(devb[i])
+        probe.on = i >= W_
+        return eager.step(b.pop("x"), b.pop("z"), **b)
+    t_eager, _, _ = timed(eager_step)
+    probe.on = False
+    del eager
+    torch.cuda.empty_cache()
+
+    # ---- device-resident arm: the step as a user of the package runs it (CUDA-graph replay unless --no-graph) ---------
+    trainer = build_trainer(wl, device, cuda_graph=not args.no_graph)
+
+    def dev_step(i):
+        b = dict(devb[i])
+        return trainer.step(b.pop("x"), b.pop("z"), **b)
+    for i in range(W_):          # warm-up here (capture happens on the third call), timed region below
         l_ = dev_step(i)
         if i == 0:
             first_loss = float(l_.item())   # ELBO of minibatch 0 at the initial parameters (parity check below)
@@ -248,16 +279,14 @@ def run_ours(args):
         clocks.start()
         time.sleep(0.25)
     sync_all()
-    l0 = lib.dcgp_launch_count()
-    probe.on = True
+    l0 = lib.dcgp_launch_count() + trainer.launches_replayed
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(W_, W_ + K_):
         loss = dev_step(i)
     e1.record()
     sync_all()
-    probe.on = False
-    launches = lib.dcgp_launch_count() - l0
+    launches = lib.dcgp_launch_count() + trainer.launches_replayed - l0
     t_dev = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
@@ -292,11 +321,14 @@ def run_ours(args):
                    "cme_individuals_per_step_per_gpu": wl["individuals_per_step"], "inducing_points": wl["M"],
                    "d": wl["d"], "r": wl["r"], "lbda": wl["lbda"], "likelihood": "CMPLikelihood(use_individuals_noise=True)",
                    "step": "forward + backward + flat-gradient all-reduce + Adam", "parallelism": f"dp{world}",
+                   "step_mode": "eager" if args.no_graph else "CUDA-graph replay of forward + backward + all-reduce (captured once, "
+                                "third warm-up step), factorisation check, eager Adam",
                    "l2": "per-step working set (Lambda 8192^2 f32 = 268 MB plus K_xx) exceeds the 126 MB L2; "
                          "a fresh minibatch every step"},
         "e2e": {"value": world * K_ / t_e2e, "unit": "minibatch ELBO steps/s (whole job)",
                 "h2d_bytes_per_step": batch_bytes(host[0]), "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "final_loss": final_loss,
+        "value_eager": world * K_ / t_eager,
         # dominant throughput kernel (profiles/r01_launches_bench_step_v15_summary.csv: gemm_tc_kernel 51% of the
         # kernel time of a step; the single-CTA potrf_step_kernel chain, 25%, is latency- not roofline-bound)
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma kind::tf32, TMA, TMEM): the direct dcgp_gemm "
@@ -309,12 +341,13 @@ def run_ours(args):
                      "traffic": 425892096, "traffic_shape": "8192x1024x8192 NN",
                      "peak_source": f"{pk['source']}: sustained bf16 cuBLAS rate / 2 (TF32 issues at half the bf16 MMA rate)",
                      "launches": n_tc, "avg_launch_ms": 1e3 * t_tc / n_tc if n_tc else None,
-                     "share_of_step": t_tc / t_dev if t_dev > 0 else None,
+                     "share_of_step": t_tc / t_eager if t_eager > 0 else None,
                      "path": {"what": "all tensor-core contractions of the step (dcgp_gemm, and the GEMMs inside dcgp_potrf / "
                               "dcgp_trsm_planned incl. their serial leaf chains): algorithmic flops / event time",
                               "achieved": fl_gemm / t_gemm / 1e12 if t_gemm > 0 else None,
                               "frac": (fl_gemm / t_gemm / 1e12) / tf32_peak if t_gemm > 0 else None,
-                              "calls": n_gemm, "share_of_step": t_gemm / t_dev if t_dev > 0 else None, "by_call": gemm_by}},
+                              "calls": n_gemm, "share_of_step": t_gemm / t_eager if t_eager > 0 else None, "by_call": gemm_by,
+                              "measured_on": "the eager issue of the same steps (value_eager)"}},
         "allreduce_bytes_per_step": trainer.grads.nbytes,
     }
     if rank == 0:
@@ -472,6 +505,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--small", action="store_true", help="reduced sizes (smoke / CI)")

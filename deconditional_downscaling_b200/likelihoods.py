@@ -133,9 +133,27 @@ class CMPLikelihood(GaussianLikelihood):
         return -0.5 * (n * torch.log(2 * math.pi * noise) + ((err * err).sum() + covar_term) / noise)
 
 
+_OFFSETS = {}
+
+
 def bag_offsets(bags_sizes, device):
-    sizes = torch.as_tensor(bags_sizes, dtype=torch.int64)
-    return torch.cat([torch.zeros(1, dtype=torch.int64), sizes.cumsum(0)]).to(device)
+    """int64 device array of n_bags + 1 row offsets of contiguous bags.  Lists are memoised (a trainer passes the same
+    sizes every step; the upload is a pageable host-to-device copy, which also has no place inside a CUDA graph)."""
+    if torch.is_tensor(bags_sizes):
+        sizes = bags_sizes.to(dtype=torch.int64, device="cpu")
+        key = None
+    else:
+        key = (tuple(int(s) for s in bags_sizes), str(device))
+        hit = _OFFSETS.get(key)
+        if hit is not None:
+            return hit
+        sizes = torch.tensor(key[0], dtype=torch.int64)
+    out = torch.cat([torch.zeros(1, dtype=torch.int64), sizes.cumsum(0)]).to(device)
+    if key is not None:
+        if len(_OFFSETS) > 64:
+            _OFFSETS.clear()
+        _OFFSETS[key] = out
+    return out
 
 
 class VBaggGaussianLikelihood(GaussianLikelihood):

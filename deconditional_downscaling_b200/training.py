@@ -46,7 +46,7 @@ class FlatGrads:
 class ElboTrainer:
     """VariationalCMP (+CMPLikelihood) or VariationalGP (+VBaggGaussianLikelihood) ELBO steps."""
 
-    def __init__(self, model, likelihood, num_data, beta=1.0, lr=0.01):
+    def __init__(self, model, likelihood, num_data, beta=1.0, lr=0.01, cuda_graph=False):
         self.model, self.likelihood = model, likelihood
         self.elbo = BagVariationalELBO(likelihood, model, num_data=num_data, beta=beta)
         self.params = list(model.parameters()) + list(likelihood.parameters())
@@ -56,6 +56,11 @@ class ElboTrainer:
         self.opt = torch.optim.Adam(self.params, lr=lr)
         model.train()
         likelihood.train()
+        # CUDA-graph mode: forward + backward + gradient all-reduce of a minibatch SHAPE are captured once (third call
+        # with that shape) and replayed; the optimizer runs outside the graph, after the factorisation checks
+        self.cuda_graph = cuda_graph
+        self._graphs, self._graph_calls, self._capture_stream = {}, {}, None
+        self.launches_replayed = 0   # libdcgp kernel launches executed through graph replays (host counters do not see them)
 
     def loss(self, x, z, **kw):
         q = self.model(x)
@@ -64,23 +69,105 @@ class ElboTrainer:
                                                             extended_bags_values=kw["extended_bags_values"])
         return -self.elbo(variational_dist_f=q, target=z, **kw)
 
-    def step(self, x, z, **kw):
-        """One ELBO step on device-resident tensors; returns the (device) loss."""
+    def _backward_pass(self, x, z, kw):
+        """zero grads -> loss -> backward -> all-reduce, optimistic about the factorisations; returns (loss, pending)."""
         self.grads.zero()
-        try:
-            # optimistic pass: no host read-back between the factorisations, ONE check before the update
-            with F.deferred_pd_checks() as pending:
-                loss = self.loss(x, z, **kw)
-                loss.backward()
-            pending.check()
-        except F.NotPSDError:
-            # psd_safe_cholesky semantics (jitter retries, then NotPSDError) with immediate checks
-            self.grads.zero()
+        with F.deferred_pd_checks() as pending:
             loss = self.loss(x, z, **kw)
             loss.backward()
         self.grads.allreduce_mean()
-        self.opt.step()
+        return loss.detach(), pending
+
+    def _checked_pass(self, x, z, kw):
+        """psd_safe_cholesky semantics (jitter retries, then NotPSDError) with immediate checks."""
+        self.grads.zero()
+        loss = self.loss(x, z, **kw)
+        loss.backward()
+        self.grads.allreduce_mean()
         return loss.detach()
+
+    def step(self, x, z, **kw):
+        """One ELBO step on device-resident tensors; returns the (device) loss."""
+        if self.cuda_graph:
+            return self._graph_step(x, z, kw)
+        # optimistic pass: no host read-back between the factorisations, ONE check before the update
+        return self._eager_step(x, z, kw)
+
+    # ---- CUDA-graph mode ---------------------------------------------------------------------------------
+    def _graph_step(self, x, z, kw):
+        """Everything of graph mode - eager warm-up steps, capture, replays, optimizer - runs on ONE dedicated stream:
+        autograd's gradient-accumulation nodes are bound to the stream they were first used on, and a node bound to the
+        default stream cannot take part in a capture."""
+        dev = x.device
+        if self._capture_stream is None:
+            self._capture_stream = torch.cuda.Stream(device=dev)
+        s, cur = self._capture_stream, torch.cuda.current_stream(dev)
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):
+            out = self._graph_step_on_stream(x, z, kw)
+        cur.wait_stream(s)
+        return out
+
+    def _eager_step(self, x, z, kw):
+        try:
+            loss, pending = self._backward_pass(x, z, kw)
+            pending.check()
+        except F.NotPSDError:
+            loss = self._checked_pass(x, z, kw)
+        self.opt.step()
+        return loss
+
+    def _graph_step_on_stream(self, x, z, kw):
+        tensors = {"x": x, "z": z, **{k: v for k, v in kw.items() if torch.is_tensor(v)}}
+        others = {k: v for k, v in kw.items() if not torch.is_tensor(v)}
+        key = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(tensors.items())) + \
+            tuple((k, tuple(v) if isinstance(v, (list, tuple)) else v) for k, v in sorted(others.items()))
+        entry = self._graphs.get(key)
+        if entry is None:
+            n = self._graph_calls[key] = self._graph_calls.get(key, 0) + 1
+            if n <= 2:   # eager warm-up: kernel attributes, look-ahead lanes, allocator
+                return self._eager_step(x, z, kw)
+            try:
+                entry = self._capture(tensors, others)
+            except RuntimeError as err:   # e.g. autograd state bound to another stream by earlier eager use
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the ELBO step failed ({str(err).splitlines()[0]}); staying eager")
+                torch.cuda.synchronize(x.device)
+                entry = False
+            self._graphs[key] = entry
+        if entry is False:
+            return self._eager_step(x, z, kw)
+        static, graph, loss, infos, launches = entry
+        for k, v in tensors.items():
+            if v is not static[k]:
+                static[k].copy_(v, non_blocking=True)
+        graph.replay()
+        self.launches_replayed += launches
+        out = loss.clone()
+        if infos is not None and bool(infos.any().item()):
+            # a factorisation failed inside the replay: repeat the pass eagerly (retries with jitter or raises)
+            out = self._checked_pass(tensors["x"], tensors["z"], {**{k: v for k, v in tensors.items() if k not in ("x", "z")}, **others})
+        self.opt.step()
+        return out
+
+    def _capture(self, tensors, others):
+        """Called on the capture stream."""
+        from . import _lib
+        dev = tensors["x"].device
+        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if quiet is not None:
+            quiet(False)
+        static = {k: v.clone() for k, v in tensors.items()}
+        kw = {**{k: v for k, v in static.items() if k not in ("x", "z")}, **others}
+        torch.cuda.synchronize(dev)
+        lib = _lib.load()
+        graph = torch.cuda.CUDAGraph()
+        n0 = lib.dcgp_launch_count()
+        with torch.cuda.graph(graph, stream=self._capture_stream):
+            loss, pending = self._backward_pass(static["x"], static["z"], kw)
+            infos = torch.cat([i.reshape(1) for i in pending.infos]) if pending.infos else None
+        launches = int(lib.dcgp_launch_count() - n0)
+        return static, graph, loss, infos, launches
 
     def step_from_host(self, host_batch: Dict[str, torch.Tensor], device):
         """End-to-end step: pinned host tensors -> device, step, loss back to the host."""
