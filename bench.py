@@ -364,8 +364,18 @@ def run_ours(args):
             out["vbagg_1024bags"] = run_vbagg(device)
         print(json.dumps(out), flush=True)
     if world > 1:
+        # Orderly end of a multi-rank run: everyone has finished its device work, the graphs that hold captured NCCL
+        # all-reduces are dropped first, and the process leaves without the communicator teardown (which was seen to
+        # block for minutes after graph capture, long after rank 0 had printed its line).
+        sync_all()
+        trainer.close()
+        del trainer
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # ------------------------------------------------------------------ ExactCMP N = 32k composite (N = 1 only)

@@ -169,6 +169,16 @@ class ElboTrainer:
         launches = int(lib.dcgp_launch_count() - n0)
         return static, graph, loss, infos, launches
 
+    def close(self):
+        """Drop the captured graphs (and the NCCL work recorded in them).  Call before
+        `torch.distributed.destroy_process_group()`: tearing a communicator down while graphs that hold
+        its collectives are alive can block at process exit."""
+        if self._capture_stream is not None:
+            self._capture_stream.synchronize()
+        self._graphs.clear()
+        self._graph_calls.clear()
+        self.cuda_graph = False
+
     def step_from_host(self, host_batch: Dict[str, torch.Tensor], device):
         """End-to-end step: pinned host tensors -> device, step, loss back to the host."""
         # persistent device staging buffers (one per input name and shape): no allocator traffic per step
