@@ -78,7 +78,8 @@ from progress.bar import Bar
 import matplotlib.pyplot as plt          # imported unconditionally by the runners, used only under --plot
 import gpytorch
 from gpytorch.kernels import RBFKernel, ScaleKernel
-from src.models import ExactCMP, VariationalCMP, VBaggGaussianLikelihood if False else VariationalCMP
+from src.models import ExactCMP, VariationalCMP
+from src.likelihoods import CMPLikelihood, VBaggGaussianLikelihood
 from src.utils import Registry
 import helper                            # a sibling module: the script's directory is on sys.path
 
