@@ -508,9 +508,10 @@ int launch_tc(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMa
     p.tiles_n = (int)((p.n + TN - 1) / TN);
     // work items: tiles, or vertically adjacent tile pairs for the multicast clusters
     const int64_t items = (CL == 2 ? (int64_t)((p.tiles_m + 1) / 2) : (int64_t)p.tiles_m) * p.tiles_n;
-    // one SM is left to the serial lane of the look-ahead factorisation / solves (single-CTA kernels that must
-    // not queue behind a persistent grid occupying every SM)
-    static const int reserve = getenv("DCGP_TC_RESERVE") ? atoi(getenv("DCGP_TC_RESERVE")) : 1;
+    // two SMs are left to the serial lanes (the single-CTA chain of the look-ahead factorisation / solves, and the
+    // K_ZZ chain a captured ELBO step runs beside it): their kernels must not queue behind a persistent grid
+    // occupying every SM
+    static const int reserve = getenv("DCGP_TC_RESERVE") ? atoi(getenv("DCGP_TC_RESERVE")) : 2;
     const int64_t cap = (num_sms() > 8 + reserve ? num_sms() - reserve : num_sms()) / CL;
     const unsigned grid = (unsigned)(items < cap ? items : cap) * CL;
     if constexpr (CL == 1) {

@@ -45,6 +45,15 @@ def rbf_spec(d, dtype, device, lengthscale=1.0, outputscale=math.log(2.0)):
                         [torch.full((1,), outputscale, dtype=dtype, device=device)])
 
 
+def padded(rows, cols, dtype, device, mult=4):
+    """rows x cols view of a buffer whose row stride is rounded up to `mult` elements (16 B in FP32): the tall-skinny
+    N x n operands here have n = number of bags, rarely a multiple of 4, and TMA (tcgen05 GEMM) / 16-byte cp.async
+    (FP64 GEMM) need aligned rows - an unaligned W sends K W to the scalar-load mma.sync kernel (measured at N = 32768,
+    n = 327, FP32: 13.8 ms = 51 TF/s)."""
+    ld = -(-cols // mult) * mult
+    return torch.empty(rows, ld, dtype=dtype, device=device)[:, :cols]
+
+
 def exact_cmp_phases(x, ext, y, z, xs, lbda, timer=None, k_spec=None, l_spec=None, noise=math.log(2.0) + 1e-4):
     """Runs Gram(K), Gram(Lambda), potrf, potrs, K W, Q / MLL and the posterior on xs.
     Returns dict(mll, logdet, post_mean, post_var, info)."""
@@ -64,11 +73,11 @@ def exact_cmp_phases(x, ext, y, z, xs, lbda, timer=None, k_spec=None, l_spec=Non
     with timer.phase("potrf"):
         info = ops.potrf_(Lam)
     with timer.phase("gram_B"):
-        W = ops.gram(l_spec, ext, y)                     # l(y~, y), N x n
+        W = ops.gram(l_spec, ext, y, out=padded(N, n, dt, dev))   # l(y~, y), N x n
     with timer.phase("potrs"):
         ops.potrs_(Lam, W)                              # W = Lambda^{-1} l(y~, y)
     with timer.phase("KW"):
-        KW = ops.gemm(K, W)
+        KW = ops.gemm(K, W, C=padded(N, n, dt, dev))
     with timer.phase("Q_mll"):
         Q = ops.gemm(W, KW, transa=True)
         Q.diagonal().add_(noise)
@@ -81,7 +90,7 @@ def exact_cmp_phases(x, ext, y, z, xs, lbda, timer=None, k_spec=None, l_spec=Non
     del K
     with timer.phase("posterior"):
         Ks = ops.gram(k_spec, xs, x)                     # k(x*, x)
-        C = ops.gemm(Ks, W)                             # N* x n
+        C = ops.gemm(Ks, W, C=padded(xs.size(0), n, dt, dev))   # N* x n
         del Ks
         mean = ops.gemm(C, alpha).squeeze(-1)
         Vt = C.t().contiguous()

@@ -12,6 +12,7 @@ import torch
 import torch.distributed as dist
 
 from . import functional as F
+from . import variational
 from .likelihoods import CMPLikelihood, VBaggGaussianLikelihood
 from .mlls import BagVariationalELBO
 
@@ -103,7 +104,8 @@ class ElboTrainer:
             self._capture_stream = torch.cuda.Stream(device=dev)
         s, cur = self._capture_stream, torch.cuda.current_stream(dev)
         s.wait_stream(cur)
-        with torch.cuda.stream(s):
+        # the captured schedule also overlaps the K_ZZ factor with the Lambda factorisation (variational.prefetch)
+        with torch.cuda.stream(s), variational.side_stream_scope():
             out = self._graph_step_on_stream(x, z, kw)
         cur.wait_stream(s)
         return out
