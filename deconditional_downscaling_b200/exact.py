@@ -47,9 +47,11 @@ def rbf_spec(d, dtype, device, lengthscale=1.0, outputscale=math.log(2.0)):
 
 def padded(rows, cols, dtype, device, mult=4):
     """rows x cols view of a buffer whose row stride is rounded up to `mult` elements (16 B in FP32): the tall-skinny
-    N x n operands here have n = number of bags, rarely a multiple of 4, and TMA (tcgen05 GEMM) / 16-byte cp.async
-    (FP64 GEMM) need aligned rows - an unaligned W sends K W to the scalar-load mma.sync kernel (measured at N = 32768,
+    N x n operands here have n = number of bags, rarely a multiple of 4, and TMA (tcgen05 GEMM) needs 16-byte
+    aligned rows - an unaligned W sends K W to the scalar-load mma.sync kernel (measured at N = 32768,
     n = 327, FP32: 13.8 ms = 51 TF/s)."""
+    if dtype != torch.float32:      # FP64: no gain for the products, and the FP64 solves are faster on contiguous W
+        mult = 1                    # (N = 8192, n = 81: potrs 1.9 ms contiguous, 5.9 ms with ld = 84)
     ld = -(-cols // mult) * mult
     return torch.empty(rows, ld, dtype=dtype, device=device)[:, :cols]
 

@@ -27,6 +27,8 @@ import os
 # chains and a persistent GEMM grid compete for the SMs left free); "0": never.
 SIDE_STREAM = os.environ.get("DCGP_SIDE_STREAM", "auto")
 _SCOPE = [0]
+# prefetch() also whitens K_Zx and forms D on the side stream (A/B on B200 in DESIGN.md)
+SIDE_WHITEN = os.environ.get("DCGP_SIDE_WHITEN", "0") == "1"
 
 
 def side_stream_active():
@@ -91,9 +93,21 @@ class VariationalPosterior(MultivariateNormal):
 
     # ---- cached pieces -------------------------------------------------------------------
     def _get(self, key, fn):
+        self._join_side()
         if key not in self._c:
             self._c[key] = fn()
         return self._c[key]
+
+    def _join_side(self):
+        """First use of anything after prefetch(): order the consumer stream after the side stream."""
+        side = self._c.pop("_side", None)
+        if side is not None:
+            main = torch.cuda.current_stream(self.x.device)
+            main.wait_stream(side)
+            for key in self._c.pop("_side_keys", ()):
+                v = self._c.get(key)
+                if torch.is_tensor(v):
+                    v.record_stream(main)
 
     @property
     def dtype(self):
@@ -112,13 +126,7 @@ class VariationalPosterior(MultivariateNormal):
     def Wz(self):
         """L_Z^{-1} in float64 (FP32 models): the whitening products then run as 3xTF32 tensor-core GEMMs on
         an FP32 hi/lo pair of it instead of float64 triangular solves against 10^3 .. 10^4 columns."""
-        W = self._get("Wz", lambda: F.chol_inverse(self.kops.gram(self.Z, None, diag_const=1e-3).double()))
-        side = self._c.pop("Wz_side", None)
-        if side is not None:                      # produced by prefetch(): order the consumer stream after it
-            main = torch.cuda.current_stream(W.device)
-            main.wait_stream(side)
-            W.record_stream(main)
-        return W
+        return self._get("Wz", lambda: F.chol_inverse(self.kops.gram(self.Z, None, diag_const=1e-3).double()))
 
     def prefetch(self):
         """Start the K_ZZ factorisation + inversion on a side stream.  It is a chain of single-CTA kernels (about
@@ -134,8 +142,15 @@ class VariationalPosterior(MultivariateNormal):
         _quiet_accumulate_grad_warning()
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
+            keys = ["Wz"]
             self._c["Wz"] = F.chol_inverse(self.kops.gram(self.Z, None, diag_const=1e-3).double())
-        self._c["Wz_side"] = side
+            if SIDE_WHITEN:
+                # ... and what follows from it without the CME solve: A~ = L_Z^{-1} K_Zx and D = L_S L_S^T - I.  Their
+                # backward nodes run on the side stream as well, next to the second big solve of the backward pass.
+                self._c["At"] = self._whiten(self.kops.gram(self.Z, self.x))
+                self.D
+                keys += ["At", "Ls", "D"]
+        self._c["_side"], self._c["_side_keys"] = side, keys
 
     def _whiten(self, K):
         """L_Z^{-1} K for K (M x cols) in the model dtype."""
