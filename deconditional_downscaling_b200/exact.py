@@ -50,8 +50,8 @@ def padded(rows, cols, dtype, device, mult=4):
     N x n operands here have n = number of bags, rarely a multiple of 4, and TMA (tcgen05 GEMM) needs 16-byte
     aligned rows - an unaligned W sends K W to the scalar-load mma.sync kernel (measured at N = 32768,
     n = 327, FP32: 13.8 ms = 51 TF/s)."""
-    if dtype != torch.float32:      # FP64: no gain for the products, and the FP64 solves are faster on contiguous W
-        mult = 1                    # (N = 8192, n = 81: potrs 1.9 ms contiguous, 5.9 ms with ld = 84)
+    if dtype != torch.float32:      # FP64 (DMMA kernel, cp.async loads): measured no gain from aligned rows
+        mult = 1
     ld = -(-cols // mult) * mult
     return torch.empty(rows, ld, dtype=dtype, device=device)[:, :cols]
 

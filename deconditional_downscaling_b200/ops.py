@@ -28,6 +28,7 @@ KINDS = {"rbf": _lib.KIND_RBF, "matern32": _lib.KIND_MATERN32, "matern12": _lib.
 TF32_MODE = "auto"
 USE_TCGEN05 = True   # False keeps FP32 contractions on the mma.sync kernel (A/B comparisons)
 X3_GEMM_LIMIT = 512 ** 3
+TC_ALIGN_MIN = 1 << 33   # FP32 products with m n k at least this large get 16-byte aligned operand rows (see _tma_rows)
 X3_SOLVE_LIMIT = 1 << 62  # dcgp_trsm / dcgp_potrs: always compensated in "auto"
 X3_POTRF_LIMIT = 1 << 62  # dcgp_potrf
 
@@ -188,6 +189,17 @@ def gram_bwd(spec: FlatSpec, x1, x2, G, need_dx1=False):
     return dls, dos, dx1
 
 
+def _tma_rows(t):
+    """t itself if its rows start on 16-byte boundaries, else a copy laid out with the row stride rounded up to 4 floats.
+    TMA cannot address unaligned rows, so e.g. an N x 327 operand would send a large product to the scalar-load
+    mma.sync kernel (N = 32768: 51 instead of 390 TF/s); the O(rows x cols) copy is noise next to such a product."""
+    if (_ld(t) & 3) == 0 and (t.data_ptr() & 15) == 0:
+        return t
+    buf = torch.empty(t.size(0), -(-t.size(1) // 4) * 4, dtype=t.dtype, device=t.device)[:, :t.size(1)]
+    buf.copy_(t)
+    return buf
+
+
 def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, C=None, lower=False, no_splitk=False):
     """C = alpha * op(A) @ op(B) + beta * C."""
     A, B = _rowmajor(A), _rowmajor(B)
@@ -196,6 +208,8 @@ def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, C=None, lower=Fa
     k2, n = (B.size(1), B.size(0)) if transb else (B.size(0), B.size(1))
     if k != k2:
         raise ValueError(f"gemm inner dims differ: {k} vs {k2}")
+    if A.dtype == torch.float32 and USE_TCGEN05 and m * n * k >= TC_ALIGN_MIN:
+        A, B = _tma_rows(A), _tma_rows(B)
     if C is None:
         C = torch.empty(m, n, dtype=A.dtype, device=A.device)
         beta = 0.0
@@ -278,7 +292,9 @@ def _solve(trans, L, B, plan):
     _req(L, B)
     n, m = B.size(0), B.size(1)
     lib = _lib.load()
-    ws = _workspace(lib.dcgp_trsm_workspace(n, m, _dt(L)), L.device)
+    # sized for B's row stride: the 512-block sweeps work in B's layout (a view with ld > m would otherwise drop to the
+    # 128-block path: FP64 n = 8192, m = 81, ld = 84 took 5.9 instead of 1.9 ms)
+    ws = _workspace(lib.dcgp_trsm_workspace(n, max(m, _ld(B)), _dt(L)), L.device)
     flags = _x3(L, n <= X3_SOLVE_LIMIT)
     if plan is not None:
         rc = lib.dcgp_trsm_planned(trans, _ptr(L), n, _ld(L), _ptr(plan), plan.numel(), _ptr(B), m, _ld(B), _ptr(ws), ws.numel(),

@@ -162,7 +162,9 @@ DCGP_API int dcgp_potrf(void* A, int64_t n, int64_t lda, int* info, void* worksp
 /* dcgp_trsm: solves op(L) X = B in place (B is n x m row-major), L lower triangular,
  * trans = 0: L X = B, trans = 1: L^T X = B.  Replaces TriangularLazyTensor.inv_matmul /
  * torch.triangular_solve (src/variational/variational_strategy.py:44) and, chained,
- * cholesky_solve behind LazyTensor.inv_matmul (cmp_prediction_strategy.py:60,164). */
+ * cholesky_solve behind LazyTensor.inv_matmul (cmp_prediction_strategy.py:60,164).
+ * Workspace: pass max(m, ldb) as m when B is a strided view (the blocked sweeps keep B's row stride; a workspace sized for
+ * a narrower B is still accepted but takes the slower 128-block path). */
 DCGP_API size_t dcgp_trsm_workspace(int64_t n, int64_t m, int dtype);
 DCGP_API int dcgp_trsm(int trans, const void* L, int64_t n, int64_t ldl, void* B, int64_t m, int64_t ldb, void* workspace,
               size_t workspace_bytes, int dtype, int flags, void* stream);

@@ -65,6 +65,32 @@ def test_gemm_linearity_full_size():
     assert ((lhs - rhs).norm() / rhs.norm()).item() < 2e-3
 
 
+@pytest.mark.parametrize("transa,transb", [(False, False), (True, False), (False, True)])
+def test_large_products_with_unaligned_rows_take_aligned_copies(transa, transb):
+    """An N x 327 FP32 operand (rows not 16-byte aligned, as W = Lambda^{-1} l(y~, y) with 327 bags) in a product large
+    enough for the tcgen05 kernel: ops.gemm re-lays the operand on aligned rows; result vs FP64 at TF32 tolerance,
+    operands untouched, result contiguous."""
+    o = ops()
+    torch.manual_seed(2)
+    N, n = 8192, 327
+    K = torch.randn(N, N, device=DEV)
+    W = torch.randn(N, n, device=DEV)
+    A = W if transa else K                       # op(A) is n x N (transa) or N x N
+    B = torch.randn(n, N, device=DEV)[:, :N] if transb else W
+    if transb:                                   # op(B) = B^T: N x n from an n x N matrix with aligned rows; unaligned A instead
+        A = torch.randn(N, N + 1, device=DEV)[:, :N] if not transa else W
+    W0 = W.clone()
+    C = o.gemm(A, B, transa=transa, transb=transb)
+    a = A.double().t() if transa else A.double()
+    b = B.double().t() if transb else B.double()
+    ref = a @ b
+    assert C.is_contiguous() and C.shape == ref.shape
+    assert ((C.double() - ref).norm() / ref.norm()).item() < 2e-3
+    assert torch.equal(W, W0)
+    assert o._tma_rows(W) is not W and o._tma_rows(K) is K
+    assert (o._ld(o._tma_rows(W)) & 3) == 0 and torch.equal(o._tma_rows(W), W)
+
+
 def test_exact_cmp_composite_matches_oracle_port():
     """Gram + Cholesky + solve + posterior composite (config 4 shape, N = 3000) vs the CPU port, FP64 1e-6."""
     from deconditional_downscaling_b200 import exact
