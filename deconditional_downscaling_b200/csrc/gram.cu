@@ -84,21 +84,20 @@ __global__ void __launch_bounds__(256) gram_fwd_kernel(const __grid_constant__ D
                                                        int64_t n1, int64_t ldx1, const T* __restrict__ x2, int64_t n2,
                                                        int64_t ldx2, TO* __restrict__ K, int64_t ldk,
                                                        const T* __restrict__ diag_dev, T diag_const, int same,
-                                                       int vec_ok) {
+                                                       int vec_ok, int row_tiles) {
+    // One CTA owns a 128-column (FP32; 64 in FP64) block and walks `row_tiles` 64-row tiles down it: the scaled x2
+    // coordinates of its columns stay in registers and the per-CTA set-up (kernel spec, strided x2 gather) is paid once
+    // per row_tiles x 64 x TCOLS outputs instead of once per 64 x TCOLS.
     constexpr int TD = NC * DPC;
     constexpr int VEC = 16 / sizeof(TO);
     constexpr int TCOLS = 32 * VEC;
     constexpr int TROWS = 64;
     __shared__ SpecVals<T> sv;
-    __shared__ T s1[TROWS][TD];
+    __shared__ T s1[2][TROWS][TD];
     load_spec_vals<T>(sp, &sv);
     __syncthreads();
-    const int64_t row0 = (int64_t)blockIdx.y * TROWS;
+    const int64_t rowbase = (int64_t)blockIdx.y * TROWS * row_tiles;
     const int64_t col0 = (int64_t)blockIdx.x * TCOLS;
-    for (int e = threadIdx.x; e < TROWS * TD; e += 256) {
-        int r = e / TD, k = e % TD;
-        s1[r][k] = (row0 + r < n1) ? x1[(row0 + r) * ldx1 + sp.col[k]] * sv.inv_ls[k] : T(0);
-    }
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     T b[VEC][TD];
 #pragma unroll
@@ -109,6 +108,16 @@ __global__ void __launch_bounds__(256) gram_fwd_kernel(const __grid_constant__ D
     }
     T dadd = T(0);
     if (same) dadd = diag_const + (diag_dev ? diag_dev[0] : T(0));
+    for (int t = 0; t < row_tiles; ++t) {
+    const int64_t row0 = rowbase + (int64_t)t * TROWS;
+    if (row0 >= n1) break;                       // uniform over the CTA
+    // double-buffered row coordinates: one barrier per tile (a thread refills buffer t & 1 only after the barrier of
+    // tile t - 1, which every thread passes after it has finished reading that buffer for tile t - 2)
+    T (*s1t)[TD] = s1[t & 1];
+    for (int e = threadIdx.x; e < TROWS * TD; e += 256) {
+        int r = e / TD, k = e % TD;
+        s1t[r][k] = (row0 + r < n1) ? x1[(row0 + r) * ldx1 + sp.col[k]] * sv.inv_ls[k] : T(0);
+    }
     __syncthreads();
 #pragma unroll 2
     for (int rr = 0; rr < TROWS / 8; ++rr) {
@@ -117,7 +126,7 @@ __global__ void __launch_bounds__(256) gram_fwd_kernel(const __grid_constant__ D
         if (row >= n1) break;
         T a[TD];
 #pragma unroll
-        for (int k = 0; k < TD; ++k) a[k] = s1[r][k];
+        for (int k = 0; k < TD; ++k) a[k] = s1t[r][k];
         TO out[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
@@ -139,6 +148,7 @@ __global__ void __launch_bounds__(256) gram_fwd_kernel(const __grid_constant__ D
             for (int v = 0; v < VEC; ++v)
                 if (c + v < n2) dst[v] = out[v];
         }
+    }
     }
 }
 
@@ -476,12 +486,17 @@ int launch_gram_fwd(const DevSpec& sp, const void* x1, int64_t n1, int64_t ldx1,
                     int64_t ldx2, void* K, int64_t ldk, const void* diag_dev, double diag_const, int same,
                     cudaStream_t st) {
     constexpr int VEC = 16 / sizeof(TO);
-    dim3 grid((unsigned)((n2 + 32 * VEC - 1) / (32 * VEC)), (unsigned)((n1 + 63) / 64));
+    // row tiles per CTA (DCGP_GRAM_RT, default 8), fewer when the grid would drop under ~8 CTAs per SM
+    static const int rt_max = getenv("DCGP_GRAM_RT") ? atoi(getenv("DCGP_GRAM_RT")) : 8;
+    const int64_t gx = (n2 + 32 * VEC - 1) / (32 * VEC), tiles_y = (n1 + 63) / 64;
+    int64_t rt = rt_max < 1 ? 1 : rt_max;
+    while (rt > 1 && gx * ((tiles_y + rt - 1) / rt) < (int64_t)num_sms() * 8) rt >>= 1;
+    dim3 grid((unsigned)gx, (unsigned)((tiles_y + rt - 1) / rt));
     int vec_ok = ((reinterpret_cast<uintptr_t>(K) % 16) == 0) && ((ldk * sizeof(TO)) % 16 == 0);
 #define CALL(NCV, DPCV)                                                                                      \
     gram_fwd_kernel<T, TO, NCV, DPCV><<<grid, 256, 0, st>>>(sp, (const T*)x1, n1, ldx1, (const T*)x2, n2, ldx2, \
                                                             (TO*)K, ldk, (const T*)diag_dev, (T)diag_const, same, \
-                                                            vec_ok);
+                                                            vec_ok, (int)rt);
     DCGP_DISPATCH_LAYOUT(sp, CALL);
 #undef CALL
     DCGP_CHECK_LAUNCH();
