@@ -43,14 +43,11 @@ class MultivariateNormal:
         return self.loc.shape[-1:]
 
     def log_prob(self, value):
-        """-0.5 [(v-mu)^T S^{-1} (v-mu) + log det S + k log 2pi], Cholesky-based (on the GPU when
-        the tensors live there; the CPU branch serves `.cpu()`-ed posteriors of the plotting code)."""
+        """-0.5 [(v-mu)^T S^{-1} (v-mu) + log det S + k log 2pi] through the libdcgp Cholesky and triangular solve.
+        GPU only, like every other computation of the package: a posterior moved with `.cpu()` (the plotting code of the
+        runners does that for `.mean` / `.confidence_region()`) raises here instead of factorising on the host."""
         diff = value - self.loc
         S = self.covariance_matrix
-        if S.is_cuda:
-            L = F.psd_safe_cholesky(S)
-            half = F.trsm(L, diff, trans=False)
-            return -0.5 * ((half * half).sum() + F.logdet_from_chol(L) + diff.numel() * math.log(2 * math.pi))
-        L = torch.linalg.cholesky(S)
-        half = torch.linalg.solve_triangular(L, diff.unsqueeze(-1), upper=False)
-        return -0.5 * ((half * half).sum() + 2 * L.diagonal().log().sum() + diff.numel() * math.log(2 * math.pi))
+        L = F.psd_safe_cholesky(S)
+        half = F.trsm(L, diff, trans=False)
+        return -0.5 * ((half * half).sum() + F.logdet_from_chol(L) + diff.numel() * math.log(2 * math.pi))
