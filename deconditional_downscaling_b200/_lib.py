@@ -8,7 +8,8 @@ import os
 from ctypes import POINTER, Structure, c_double, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdcgp.so")
+# DCGP_LIB selects another build of the same library (e.g. the -DDCGP_LEAF_TIMING one of tools/leaf_timing.py)
+LIB_PATH = os.environ.get("DCGP_LIB") or os.path.join(_HERE, "lib", "libdcgp.so")
 
 F64, F32 = 0, 1
 KIND_RBF, KIND_MATERN32, KIND_MATERN12, KIND_MATERN52 = 0, 1, 2, 3

@@ -124,13 +124,82 @@ __device__ __forceinline__ void trailing_update(T* S, int nb, int p0, int pw, in
     }
 }
 
+// ---- inverse riding along with the factorisation (FINV) ------------------------------------------------------
+// X = L^{-1} is wanted next to L (the panel solves of the callers are products with it).  Row c of L^{-T} is the
+// solution y of  y L^T = e_c  - the very operation step (2) of block_potrf applies to the rows below the pivots.  With
+// FINV the unit rows e_c ride along as extra rows of the tile: they live in the unused upper part, shifted by one
+// column, in the layout block_trtri produces ( X(i, c), i >= c  <->  S[c][i + 1] ), get their 16 columns solved in
+// step (2) by threads the rows below leave idle, and their rank-16 updates in step (3b) by warps 1..15, which wait
+// there for warp 0's pivot chain anyway (B200, one 128-block: pivots 2.4 us per sub-panel, block_trtri 17.6 us per
+// leaf = 31 % of a link of the look-ahead chain; profiles/r01_leaf_timing_v31.txt).  Entries left of the diagonal of an
+// extra row are identically zero and are neither loaded nor stored (that storage belongs to L).
+template <typename T>
+__device__ __forceinline__ void inv_rows_init(T* S, int nb) {   // called by warps 1 .. 15 (warp 0 is in diag_step)
+    for (int e = (int)threadIdx.x - 32; e < NB * NB; e += NTHREADS - 32) {
+        const int c = e >> 7, k = e & (NB - 1);
+        if (c < nb && k < nb && k >= c) S[c * SP + k + 1] = (k == c) ? T(1) : T(0);
+    }
+}
+
+// step (2) for extra row c < p0 + pw: y[p0 .. p0+pw) = residual * L_d^{-T}
+template <typename T>
+__device__ __forceinline__ void inv_rows_panel(T* S, const T* rinv, int p0, int pw) {
+    const int c = NTHREADS - 1 - (int)threadIdx.x;   // from the top: the rows below use the low thread ids
+    if (c >= p0 + pw) return;
+    T x[SB];
+#pragma unroll
+    for (int kk = 0; kk < SB; ++kk) x[kk] = (kk < pw && p0 + kk >= c) ? S[c * SP + p0 + kk + 1] : T(0);
+#pragma unroll
+    for (int kk = 0; kk < SB; ++kk) {
+        if (kk < pw) {
+            T s = x[kk];
+#pragma unroll
+            for (int k = 0; k < SB; ++k)
+                if (k < kk) s = fma(-x[k], S[(p0 + kk) * SP + p0 + k], s);
+            x[kk] = s * rinv[p0 + kk];
+        }
+    }
+#pragma unroll
+    for (int kk = 0; kk < SB; ++kk)
+        if (kk < pw && p0 + kk >= c) S[c * SP + p0 + kk + 1] = x[kk];
+}
+
+// step (3) for the extra rows [0, t0), t0 = p0 + pw: residual[c][k] -= sum_kk y[c][p0 + kk] L[k][p0 + kk], k in [t0, nb)
+template <typename T>
+__device__ __forceinline__ void inv_rows_update(T* S, int nb, int p0, int pw, int wfirst, int nwarps) {
+    constexpr int TR = WarpTile<T>::ROWS, TC = WarpTile<T>::COLS, NA = WarpTile<T>::NACC;
+    const int warp = threadIdx.x >> 5;
+    if (warp < wfirst || warp >= wfirst + nwarps) return;
+    const int t0 = p0 + pw;
+    const int ntr = (t0 + TR - 1) / TR, ntc = (nb - t0 + TC - 1) / TC;
+    for (int e = warp - wfirst; e < ntr * ntc; e += nwarps) {
+        const int mi = e / ntc, nj = e - mi * ntc;
+        const int row0 = mi * TR, col0 = t0 + nj * TC;
+        T acc[4] = {T(0), T(0), T(0), T(0)};
+        warp_tile_mma(
+            acc, SB,
+            [&](int rl, int k) {
+                const int c = row0 + rl;
+                return (c < t0 && k < pw && p0 + k >= c) ? S[c * SP + p0 + k + 1] : T(0);
+            },
+            [&](int k, int cl) { return (col0 + cl < nb && k < pw) ? S[(col0 + cl) * SP + p0 + k] : T(0); });
+#pragma unroll
+        for (int q = 0; q < NA; ++q) {
+            int rl, cl;
+            warp_tile_coord<T>(q, rl, cl);
+            const int c = row0 + rl, col = col0 + cl;
+            if (c < t0 && col < nb) S[c * SP + col + 1] -= acc[q];
+        }
+    }
+}
+
 // Right-looking factorisation over 16-wide sub-panels with an in-tile look-ahead:
 //   (1) warp 0 factors the 16x16 diagonal block (diag_step);
 //   (2) every thread owning a row below solves its 16 entries against that block (division-free);
 //   (3a) the NEXT sub-panel's 16 columns get their rank-16 update first (all warps, short);
 //   (3b) warp 0 factors the next diagonal block while warps 1..15 update the rest of the trailing triangle.
 // Three barriers per sub-panel; the serial pivot chain of (1) is hidden behind (3b) whenever that is longer.
-template <typename T>
+template <typename T, bool FINV = false>
 __device__ void block_potrf(T* S, T* rinv, int nb, int* info, int64_t j0) {
     const int tid = threadIdx.x, warp = tid >> 5;
     constexpr int TC = WarpTile<T>::COLS, NJ_NEXT = SB / TC, NW = NTHREADS / 32;
@@ -138,6 +207,7 @@ __device__ void block_potrf(T* S, T* rinv, int nb, int* info, int64_t j0) {
     long long acc1 = 0, acc2 = 0, acc3 = 0, tq = clock64();
 #endif
     if (warp == 0) diag_step<T>(S, rinv, 0, min(SB, nb), info, j0);
+    else if (FINV) inv_rows_init<T>(S, nb);
     __syncthreads();
     for (int p0 = 0; p0 < nb; p0 += SB) {
         const int pw = min(SB, nb - p0);
@@ -163,6 +233,7 @@ __device__ void block_potrf(T* S, T* rinv, int nb, int* info, int64_t j0) {
             for (int c = 0; c < SB; ++c)
                 if (c < pw) S[i * SP + p0 + c] = x[c];
         }
+        if (FINV) inv_rows_panel<T>(S, rinv, p0, pw);
         __syncthreads();
 #ifdef DCGP_LEAF_TIMING
         { long long t = clock64(); acc2 += t - tq; tq = t; }
@@ -172,9 +243,12 @@ __device__ void block_potrf(T* S, T* rinv, int nb, int* info, int64_t j0) {
         // (3a) the next sub-panel's columns
         trailing_update<T>(S, nb, p0, pw, 0, NJ_NEXT, 0, NW);
         __syncthreads();
-        // (3b) next pivots || rest of the trailing update
+        // (3b) next pivots || rest of the trailing update (|| the extra rows of the inverse)
         if (warp == 0) diag_step<T>(S, rinv, t0, min(SB, nb - t0), info, j0);
-        else trailing_update<T>(S, nb, p0, pw, NJ_NEXT, 1 << 30, 1, NW - 1);
+        else {
+            trailing_update<T>(S, nb, p0, pw, NJ_NEXT, 1 << 30, 1, NW - 1);
+            if (FINV) inv_rows_update<T>(S, nb, p0, pw, 1, NW - 1);
+        }
         __syncthreads();
 #ifdef DCGP_LEAF_TIMING
         { long long t = clock64(); acc3 += t - tq; tq = t; }
@@ -197,6 +271,9 @@ __device__ void block_potrf(T* S, T* rinv, int nb, int* info, int64_t j0) {
 template <typename T>
 __device__ void block_trtri(T* S, const T* rinv, int nb) {
     const int tid = threadIdx.x;
+#ifdef DCGP_LEAF_TIMING
+    long long tA = 0, tB = 0, tC = 0, tq = clock64(), t0c;
+#endif
     for (int e = tid; e < nb; e += NTHREADS) {
         const int d0 = (e / SB) * SB, c = e;  // column c of the sub-block starting at d0
         const int dw = min(SB, nb - d0);
@@ -219,6 +296,9 @@ __device__ void block_trtri(T* S, const T* rinv, int nb) {
             if (r < dw && d0 + r >= c) XX(d0 + r, c) = x[r];
     }
     __syncthreads();
+#ifdef DCGP_LEAF_TIMING
+    { long long t = clock64(); t0c = t - tq; tq = t; }
+#endif
     for (int b = SB; b < nb; b *= 2) {
         const int npairs = (nb + 2 * b - 1) / (2 * b);
         // step A: T = L21 X11 -> parked at XX(i, c), i in half 2, c in half 1 (tensor-core tiles)
@@ -242,6 +322,9 @@ __device__ void block_trtri(T* S, const T* rinv, int nb) {
             }
         }
         __syncthreads();
+#ifdef DCGP_LEAF_TIMING
+        { long long t = clock64(); tA += t - tq; tq = t; }
+#endif
         // step B: X21 = -X22 T  -> written over the (dead) L21 block in the lower triangle
         for (int e = warp; e < npairs * tpr * tpc; e += NTHREADS / 32) {
             const int pr = e / (tpr * tpc), tt = e - pr * tpr * tpc;
@@ -265,6 +348,9 @@ __device__ void block_trtri(T* S, const T* rinv, int nb) {
             }
         }
         __syncthreads();
+#ifdef DCGP_LEAF_TIMING
+        { long long t = clock64(); tB += t - tq; tq = t; }
+#endif
         // step C: move X21 into the overlay
         for (int e = tid; e < npairs * b * b; e += NTHREADS) {
             const int pr = e / (b * b), tt = e - pr * b * b;
@@ -272,7 +358,13 @@ __device__ void block_trtri(T* S, const T* rinv, int nb) {
             if (i < nb) XX(i, c) = S[i * SP + c];
         }
         __syncthreads();
+#ifdef DCGP_LEAF_TIMING
+        { long long t = clock64(); tC += t - tq; tq = t; }
+#endif
     }
+#ifdef DCGP_LEAF_TIMING
+    if (tid == 0) printf("  trtri: level0 %lld  A %lld  B %lld  C %lld\n", t0c, tA, tB, tC);
+#endif
 }
 
 template <typename T>
@@ -307,7 +399,7 @@ __device__ void load_lower(T* S, T* rinv, const T* A, int64_t lda, int nb, bool 
     }
 }
 
-template <typename T>
+template <typename T, bool FINV = false>
 __global__ void __launch_bounds__(NTHREADS) potrf_diag_kernel(T* __restrict__ A, int64_t lda, int nb,
                                                               T* __restrict__ inv, int* info, int64_t j0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -321,7 +413,7 @@ __global__ void __launch_bounds__(NTHREADS) potrf_diag_kernel(T* __restrict__ A,
 #ifdef DCGP_LEAF_TIMING
     long long t1 = clock64();
 #endif
-    block_potrf<T>(S, rinv, nb, info, j0);
+    block_potrf<T, FINV>(S, rinv, nb, info, j0);
 #ifdef DCGP_LEAF_TIMING
     long long t2 = clock64();
 #endif
@@ -334,7 +426,7 @@ __global__ void __launch_bounds__(NTHREADS) potrf_diag_kernel(T* __restrict__ A,
 #ifdef DCGP_LEAF_TIMING
     long long t3 = clock64();
 #endif
-    block_trtri<T>(S, rinv, nb);
+    if (!FINV) block_trtri<T>(S, rinv, nb);   // FINV: the inverse already sits in the overlay
 #ifdef DCGP_LEAF_TIMING
     long long t4 = clock64();
 #endif
@@ -389,6 +481,7 @@ __device__ __forceinline__ void issue_128(uint32_t tmem_d, uint32_t a_addr, uint
         : "r"(taddr));                                                                                               \
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
 
+template <bool FINV>
 __global__ void __launch_bounds__(NTHREADS) potrf_step_kernel(float* __restrict__ A, int64_t lda, int nb,
                                                               float* __restrict__ inv, int* info, int64_t j0,
                                                               const float* __restrict__ R, const float* __restrict__ invp) {
@@ -506,20 +599,27 @@ __global__ void __launch_bounds__(NTHREADS) potrf_step_kernel(float* __restrict_
 #ifdef DCGP_LEAF_TIMING
     long long tq3 = clock64();
 #endif
-    block_potrf<float>(S, rinv, nb, info, j0);
+    block_potrf<float, FINV>(S, rinv, nb, info, j0);
 #ifdef DCGP_LEAF_TIMING
     long long tq4 = clock64();
 #endif
     for (int i = warp; i < nb; i += NTHREADS / 32)
         for (int k = lane; k <= i; k += 32) A[(int64_t)i * lda + k] = S[i * SP + k];
     __syncthreads();
-    block_trtri<float>(S, rinv, nb);
+#ifdef DCGP_LEAF_TIMING
+    long long tq5 = clock64();
+#endif
+    if (!FINV) block_trtri<float>(S, rinv, nb);
+#ifdef DCGP_LEAF_TIMING
+    long long tq6 = clock64();
+#endif
     store_inverse<float>(S, nb, inv, NB);
 #ifdef DCGP_LEAF_TIMING
     __syncthreads();
     if (tid == 0 && j0 == 256)
         printf("step kernel: load %lld  P %lld  syrk %lld  potrf %lld  rest %lld\n", tq1 - tq0, tq2 - tq1, tq3 - tq2, tq4 - tq3,
                clock64() - tq4);
+    if (tid == 0) printf("  tail: storeL %lld  trtri %lld  storeinv %lld\n", tq5 - tq4, tq6 - tq5, clock64() - tq6);
 #endif
 }
 
@@ -563,6 +663,13 @@ __global__ void __launch_bounds__(256) logdet_kernel(const T* __restrict__ L, in
 
 template <typename T>
 constexpr size_t leaf_smem() { return (size_t)NB * SP * sizeof(T); }
+
+// DCGP_LEAF_FINV=1: the leaves compute the inverse of their factor inside the factorisation loop (see inv_rows_*)
+// instead of a block_trtri pass after it.  Off by default until it has been measured on the GPU.
+inline bool leaf_finv() {
+    static const bool on = getenv("DCGP_LEAF_FINV") && atoi(getenv("DCGP_LEAF_FINV")) != 0;
+    return on;
+}
 
 template <typename T>
 int set_smem_attr(const void* fn) {
@@ -622,8 +729,12 @@ inline int64_t la_panel(int dtype, int64_t nb);
 template <typename T>
 int chol_rec(const Ctx<T>& c, int64_t j0, int64_t nb) {
     if (nb <= NB) {
-        potrf_diag_kernel<T><<<1, NTHREADS, leaf_smem<T>(), c.st>>>(c.A + j0 * c.lda + j0, c.lda, (int)nb,
-                                                                    c.ws + (j0 / NB) * NB * NB, c.info, j0);
+        if (leaf_finv())
+            potrf_diag_kernel<T, true><<<1, NTHREADS, leaf_smem<T>(), c.st>>>(c.A + j0 * c.lda + j0, c.lda, (int)nb,
+                                                                              c.ws + (j0 / NB) * NB * NB, c.info, j0);
+        else
+            potrf_diag_kernel<T, false><<<1, NTHREADS, leaf_smem<T>(), c.st>>>(c.A + j0 * c.lda + j0, c.lda, (int)nb,
+                                                                               c.ws + (j0 / NB) * NB * NB, c.info, j0);
         DCGP_CHECK_LAUNCH();
         return 0;
     }
@@ -754,8 +865,10 @@ int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
     if (rc) return rc;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(potrf_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(potrf_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)STEP_SMEM);
+        if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
+        e = cudaFuncSetAttribute(potrf_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM);
         if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
         attr = true;
     }
@@ -775,8 +888,12 @@ int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
     DCGP_CU(cudaStreamWaitEvent(sa, x.fork, 0));
     DCGP_CU(cudaStreamWaitEvent(sb, x.fork, 0));
     TRACE_BEGIN(c.st);
-    potrf_diag_kernel<float><<<1, NTHREADS, leaf_smem<float>(), sa>>>(c.A + j0 * c.lda + j0, c.lda, NB, c.ws + (j0 / NB) * NB * NB,
-                                                                       c.info, j0);
+    if (leaf_finv())
+        potrf_diag_kernel<float, true><<<1, NTHREADS, leaf_smem<float>(), sa>>>(c.A + j0 * c.lda + j0, c.lda, NB,
+                                                                                 c.ws + (j0 / NB) * NB * NB, c.info, j0);
+    else
+        potrf_diag_kernel<float, false><<<1, NTHREADS, leaf_smem<float>(), sa>>>(c.A + j0 * c.lda + j0, c.lda, NB,
+                                                                                  c.ws + (j0 / NB) * NB * NB, c.info, j0);
     DCGP_CHECK_LAUNCH();
     for (int64_t j = 0; j + 1 < q; ++j) {
         const int64_t bj = j0 + j * NB;
@@ -830,9 +947,14 @@ int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
         // ---- chain lane: block j+1 (its inputs were completed by the bulk update of panel j-1)
         if (j > 0) DCGP_CU(cudaStreamWaitEvent(sa, x.upd[ep], 0));
         TRACE_MARK("A.waited", j, sa);
-        potrf_step_kernel<<<1, NTHREADS, STEP_SMEM, sa>>>(c.A + b1 * c.lda + b1, c.lda, (int)w1,
-                                                                           c.ws + (b1 / NB) * NB * NB, c.info, b1,
-                                                                           rcopy + (size_t)(j & 1) * NB * NB, invj);
+        if (leaf_finv())
+            potrf_step_kernel<true><<<1, NTHREADS, STEP_SMEM, sa>>>(c.A + b1 * c.lda + b1, c.lda, (int)w1,
+                                                                    c.ws + (b1 / NB) * NB * NB, c.info, b1,
+                                                                    rcopy + (size_t)(j & 1) * NB * NB, invj);
+        else
+            potrf_step_kernel<false><<<1, NTHREADS, STEP_SMEM, sa>>>(c.A + b1 * c.lda + b1, c.lda, (int)w1,
+                                                                     c.ws + (b1 / NB) * NB * NB, c.info, b1,
+                                                                     rcopy + (size_t)(j & 1) * NB * NB, invj);
         DCGP_CHECK_LAUNCH();
     }
     // join both lanes: the last panel solve on the bulk lane has no later consumer on the chain lane
@@ -915,8 +1037,12 @@ size_t inv_ws_bytes(int64_t n, int dtype) {
 
 template <typename T>
 int potrf_impl(T* A, int64_t n, int64_t lda, int* info, T* ws, size_t ws_bytes, int dtype, int xf, cudaStream_t st) {
-    int rc = set_smem_attr<T>((const void*)potrf_diag_kernel<T>);
+    int rc = set_smem_attr<T>((const void*)potrf_diag_kernel<T, false>);
     if (rc) return rc;
+    if (leaf_finv()) {
+        rc = set_smem_attr<T>((const void*)potrf_diag_kernel<T, true>);
+        if (rc) return rc;
+    }
     T* lo = nullptr;
     const size_t rcopy_bytes = 3 * NB * NB * 4;  // two block-row copies + remainders of one inverted block
     if (sizeof(T) == 4 && xf && n > 2 * NB && ws_bytes >= inv_ws_bytes(n, dtype) + rcopy_bytes + (size_t)n * lda * 4)
