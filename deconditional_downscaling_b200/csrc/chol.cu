@@ -62,7 +62,10 @@ template <> __device__ __forceinline__ double fast_rsqrt<double>(double d) {
 // is latency-bound on instruction count, so the loop is predicate-free: lanes / columns outside the valid block
 // behave as an identity padding and every lane updates all of its registers (entries above the diagonal are junk
 // that is never stored).
-template <typename T>
+// PIV2 (experimental, DCGP_LEAF_PIV2=1): the pivot of column c+1 is broadcast from `row[c+1] - lrc^2` of lane c+1's own
+// registers - for that lane the exchanged factor L[c+1][c] of the general update IS its lrc - which takes one of the two
+// dependent shuffles out of every column step of the chain.  Bitwise the same values as the plain order.
+template <typename T, bool PIV2 = false>
 __device__ __forceinline__ void diag_step(T* S, T* rinv, int p0, int pw, int* info, int64_t j0) {
     const int lane = threadIdx.x & 31;
     const int r = lane;  // row within the sub-block
@@ -71,15 +74,17 @@ __device__ __forceinline__ void diag_step(T* S, T* rinv, int p0, int pw, int* in
     int bad = 0;
 #pragma unroll
     for (int c = 0; c < SB; ++c) row[c] = (r < pw && c <= r) ? S[(p0 + r) * SP + p0 + c] : ((r == c) ? T(1) : T(0));
+    T dnext = PIV2 ? __shfl_sync(0xffffffffu, row[0], 0) : T(0);
 #pragma unroll
     for (int c = 0; c < SB; ++c) {
-        const T d = __shfl_sync(0xffffffffu, row[c], c);  // pivot (already updated)
+        const T d = PIV2 ? dnext : __shfl_sync(0xffffffffu, row[c], c);  // pivot (already updated)
         if (!(d > T(0)) && bad == 0) bad = c + 1;
         const T y = fast_rsqrt<T>(d);
         const T scaled = row[c] * y;
         row[c] = (r == c) ? d * y : scaled;
         if (r == c) myinv = y;
         const T lrc = row[c];
+        if (PIV2 && c + 1 < SB) dnext = __shfl_sync(0xffffffffu, fma(-lrc, lrc, row[c + 1]), c + 1);
 #pragma unroll
         for (int k = c + 1; k < SB; ++k) {
             const T lkc = __shfl_sync(0xffffffffu, row[c], k);  // L[k][c]
@@ -199,14 +204,15 @@ __device__ __forceinline__ void inv_rows_update(T* S, int nb, int p0, int pw, in
 //   (3a) the NEXT sub-panel's 16 columns get their rank-16 update first (all warps, short);
 //   (3b) warp 0 factors the next diagonal block while warps 1..15 update the rest of the trailing triangle.
 // Three barriers per sub-panel; the serial pivot chain of (1) is hidden behind (3b) whenever that is longer.
-template <typename T, bool FINV = false>
+template <typename T, int MODE = 0>   // MODE bit 0: FINV (inverse rides along), bit 1: PIV2 (short pivot chain)
 __device__ void block_potrf(T* S, T* rinv, int nb, int* info, int64_t j0) {
+    constexpr bool FINV = (MODE & 1) != 0, PIV2 = (MODE & 2) != 0;
     const int tid = threadIdx.x, warp = tid >> 5;
     constexpr int TC = WarpTile<T>::COLS, NJ_NEXT = SB / TC, NW = NTHREADS / 32;
 #ifdef DCGP_LEAF_TIMING
     long long acc1 = 0, acc2 = 0, acc3 = 0, tq = clock64();
 #endif
-    if (warp == 0) diag_step<T>(S, rinv, 0, min(SB, nb), info, j0);
+    if (warp == 0) diag_step<T, PIV2>(S, rinv, 0, min(SB, nb), info, j0);
     else if (FINV) inv_rows_init<T>(S, nb);
     __syncthreads();
     for (int p0 = 0; p0 < nb; p0 += SB) {
@@ -244,7 +250,7 @@ __device__ void block_potrf(T* S, T* rinv, int nb, int* info, int64_t j0) {
         trailing_update<T>(S, nb, p0, pw, 0, NJ_NEXT, 0, NW);
         __syncthreads();
         // (3b) next pivots || rest of the trailing update (|| the extra rows of the inverse)
-        if (warp == 0) diag_step<T>(S, rinv, t0, min(SB, nb - t0), info, j0);
+        if (warp == 0) diag_step<T, PIV2>(S, rinv, t0, min(SB, nb - t0), info, j0);
         else {
             trailing_update<T>(S, nb, p0, pw, NJ_NEXT, 1 << 30, 1, NW - 1);
             if (FINV) inv_rows_update<T>(S, nb, p0, pw, 1, NW - 1);
@@ -399,7 +405,7 @@ __device__ void load_lower(T* S, T* rinv, const T* A, int64_t lda, int nb, bool 
     }
 }
 
-template <typename T, bool FINV = false>
+template <typename T, int MODE = 0>
 __global__ void __launch_bounds__(NTHREADS) potrf_diag_kernel(T* __restrict__ A, int64_t lda, int nb,
                                                               T* __restrict__ inv, int* info, int64_t j0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -413,7 +419,7 @@ __global__ void __launch_bounds__(NTHREADS) potrf_diag_kernel(T* __restrict__ A,
 #ifdef DCGP_LEAF_TIMING
     long long t1 = clock64();
 #endif
-    block_potrf<T, FINV>(S, rinv, nb, info, j0);
+    block_potrf<T, MODE>(S, rinv, nb, info, j0);
 #ifdef DCGP_LEAF_TIMING
     long long t2 = clock64();
 #endif
@@ -426,7 +432,7 @@ __global__ void __launch_bounds__(NTHREADS) potrf_diag_kernel(T* __restrict__ A,
 #ifdef DCGP_LEAF_TIMING
     long long t3 = clock64();
 #endif
-    if (!FINV) block_trtri<T>(S, rinv, nb);   // FINV: the inverse already sits in the overlay
+    if (!(MODE & 1)) block_trtri<T>(S, rinv, nb);   // FINV: the inverse already sits in the overlay
 #ifdef DCGP_LEAF_TIMING
     long long t4 = clock64();
 #endif
@@ -481,7 +487,7 @@ __device__ __forceinline__ void issue_128(uint32_t tmem_d, uint32_t a_addr, uint
         : "r"(taddr));                                                                                               \
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
 
-template <bool FINV>
+template <int MODE>
 __global__ void __launch_bounds__(NTHREADS) potrf_step_kernel(float* __restrict__ A, int64_t lda, int nb,
                                                               float* __restrict__ inv, int* info, int64_t j0,
                                                               const float* __restrict__ R, const float* __restrict__ invp) {
@@ -599,7 +605,7 @@ __global__ void __launch_bounds__(NTHREADS) potrf_step_kernel(float* __restrict_
 #ifdef DCGP_LEAF_TIMING
     long long tq3 = clock64();
 #endif
-    block_potrf<float, FINV>(S, rinv, nb, info, j0);
+    block_potrf<float, MODE>(S, rinv, nb, info, j0);
 #ifdef DCGP_LEAF_TIMING
     long long tq4 = clock64();
 #endif
@@ -609,7 +615,7 @@ __global__ void __launch_bounds__(NTHREADS) potrf_step_kernel(float* __restrict_
 #ifdef DCGP_LEAF_TIMING
     long long tq5 = clock64();
 #endif
-    if (!FINV) block_trtri<float>(S, rinv, nb);
+    if (!(MODE & 1)) block_trtri<float>(S, rinv, nb);
 #ifdef DCGP_LEAF_TIMING
     long long tq6 = clock64();
 #endif
@@ -664,12 +670,22 @@ __global__ void __launch_bounds__(256) logdet_kernel(const T* __restrict__ L, in
 template <typename T>
 constexpr size_t leaf_smem() { return (size_t)NB * SP * sizeof(T); }
 
-// DCGP_LEAF_FINV=1: the leaves compute the inverse of their factor inside the factorisation loop (see inv_rows_*)
-// instead of a block_trtri pass after it.  Off by default until it has been measured on the GPU.
-inline bool leaf_finv() {
-    static const bool on = getenv("DCGP_LEAF_FINV") && atoi(getenv("DCGP_LEAF_FINV")) != 0;
-    return on;
+// Experimental leaf variants, off by default until measured on the GPU (MODE of block_potrf):
+//   DCGP_LEAF_FINV=1  the leaves build the inverse of their factor inside the factorisation loop (inv_rows_*) instead of a
+//                     block_trtri pass after it;
+//   DCGP_LEAF_PIV2=1  short pivot chain in diag_step.
+inline int leaf_mode() {
+    static const int mode = ((getenv("DCGP_LEAF_FINV") && atoi(getenv("DCGP_LEAF_FINV")) != 0) ? 1 : 0) |
+                            ((getenv("DCGP_LEAF_PIV2") && atoi(getenv("DCGP_LEAF_PIV2")) != 0) ? 2 : 0);
+    return mode;
 }
+#define DCGP_LEAF_DISPATCH(CALL) \
+    switch (leaf_mode()) {       \
+        case 1: CALL(1); break;  \
+        case 2: CALL(2); break;  \
+        case 3: CALL(3); break;  \
+        default: CALL(0); break; \
+    }
 
 template <typename T>
 int set_smem_attr(const void* fn) {
@@ -729,12 +745,11 @@ inline int64_t la_panel(int dtype, int64_t nb);
 template <typename T>
 int chol_rec(const Ctx<T>& c, int64_t j0, int64_t nb) {
     if (nb <= NB) {
-        if (leaf_finv())
-            potrf_diag_kernel<T, true><<<1, NTHREADS, leaf_smem<T>(), c.st>>>(c.A + j0 * c.lda + j0, c.lda, (int)nb,
-                                                                              c.ws + (j0 / NB) * NB * NB, c.info, j0);
-        else
-            potrf_diag_kernel<T, false><<<1, NTHREADS, leaf_smem<T>(), c.st>>>(c.A + j0 * c.lda + j0, c.lda, (int)nb,
-                                                                               c.ws + (j0 / NB) * NB * NB, c.info, j0);
+#define CALL(M)                                                                                              \
+    potrf_diag_kernel<T, M><<<1, NTHREADS, leaf_smem<T>(), c.st>>>(c.A + j0 * c.lda + j0, c.lda, (int)nb,      \
+                                                                   c.ws + (j0 / NB) * NB * NB, c.info, j0)
+        DCGP_LEAF_DISPATCH(CALL);
+#undef CALL
         DCGP_CHECK_LAUNCH();
         return 0;
     }
@@ -865,10 +880,10 @@ int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
     if (rc) return rc;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(potrf_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)STEP_SMEM);
-        if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
-        e = cudaFuncSetAttribute(potrf_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM);
+        cudaError_t e = cudaSuccess;
+#define CALL(M) e = cudaFuncSetAttribute(potrf_step_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM)
+        DCGP_LEAF_DISPATCH(CALL);
+#undef CALL
         if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
         attr = true;
     }
@@ -888,12 +903,11 @@ int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
     DCGP_CU(cudaStreamWaitEvent(sa, x.fork, 0));
     DCGP_CU(cudaStreamWaitEvent(sb, x.fork, 0));
     TRACE_BEGIN(c.st);
-    if (leaf_finv())
-        potrf_diag_kernel<float, true><<<1, NTHREADS, leaf_smem<float>(), sa>>>(c.A + j0 * c.lda + j0, c.lda, NB,
-                                                                                 c.ws + (j0 / NB) * NB * NB, c.info, j0);
-    else
-        potrf_diag_kernel<float, false><<<1, NTHREADS, leaf_smem<float>(), sa>>>(c.A + j0 * c.lda + j0, c.lda, NB,
-                                                                                  c.ws + (j0 / NB) * NB * NB, c.info, j0);
+#define CALL(M)                                                                                                 \
+    potrf_diag_kernel<float, M><<<1, NTHREADS, leaf_smem<float>(), sa>>>(c.A + j0 * c.lda + j0, c.lda, NB,        \
+                                                                         c.ws + (j0 / NB) * NB * NB, c.info, j0)
+    DCGP_LEAF_DISPATCH(CALL);
+#undef CALL
     DCGP_CHECK_LAUNCH();
     for (int64_t j = 0; j + 1 < q; ++j) {
         const int64_t bj = j0 + j * NB;
@@ -947,14 +961,12 @@ int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
         // ---- chain lane: block j+1 (its inputs were completed by the bulk update of panel j-1)
         if (j > 0) DCGP_CU(cudaStreamWaitEvent(sa, x.upd[ep], 0));
         TRACE_MARK("A.waited", j, sa);
-        if (leaf_finv())
-            potrf_step_kernel<true><<<1, NTHREADS, STEP_SMEM, sa>>>(c.A + b1 * c.lda + b1, c.lda, (int)w1,
-                                                                    c.ws + (b1 / NB) * NB * NB, c.info, b1,
-                                                                    rcopy + (size_t)(j & 1) * NB * NB, invj);
-        else
-            potrf_step_kernel<false><<<1, NTHREADS, STEP_SMEM, sa>>>(c.A + b1 * c.lda + b1, c.lda, (int)w1,
-                                                                     c.ws + (b1 / NB) * NB * NB, c.info, b1,
-                                                                     rcopy + (size_t)(j & 1) * NB * NB, invj);
+#define CALL(M)                                                                                                  \
+    potrf_step_kernel<M><<<1, NTHREADS, STEP_SMEM, sa>>>(c.A + b1 * c.lda + b1, c.lda, (int)w1,                    \
+                                                         c.ws + (b1 / NB) * NB * NB, c.info, b1,                   \
+                                                         rcopy + (size_t)(j & 1) * NB * NB, invj)
+        DCGP_LEAF_DISPATCH(CALL);
+#undef CALL
         DCGP_CHECK_LAUNCH();
     }
     // join both lanes: the last panel solve on the bulk lane has no later consumer on the chain lane
@@ -1037,12 +1049,11 @@ size_t inv_ws_bytes(int64_t n, int dtype) {
 
 template <typename T>
 int potrf_impl(T* A, int64_t n, int64_t lda, int* info, T* ws, size_t ws_bytes, int dtype, int xf, cudaStream_t st) {
-    int rc = set_smem_attr<T>((const void*)potrf_diag_kernel<T, false>);
+    int rc = 0;
+#define CALL(M) rc = set_smem_attr<T>((const void*)potrf_diag_kernel<T, M>)
+    DCGP_LEAF_DISPATCH(CALL);
+#undef CALL
     if (rc) return rc;
-    if (leaf_finv()) {
-        rc = set_smem_attr<T>((const void*)potrf_diag_kernel<T, true>);
-        if (rc) return rc;
-    }
     T* lo = nullptr;
     const size_t rcopy_bytes = 3 * NB * NB * 4;  // two block-row copies + remainders of one inverted block
     if (sizeof(T) == 4 && xf && n > 2 * NB && ws_bytes >= inv_ws_bytes(n, dtype) + rcopy_bytes + (size_t)n * lda * 4)

@@ -74,3 +74,47 @@ def test_fused_leaf_gives_factor_and_inverse(nb):
     assert np.isfinite(L).all() and np.isfinite(X).all()
     assert np.abs(L - ref).max() < 1e-12 * np.abs(ref).max()
     assert np.abs(X @ ref - np.eye(nb)).max() < 1e-12
+
+
+def diag_step_lanes(block, pw, piv2):
+    """diag_step of csrc/chol.cu lane by lane (lane r holds row r of the 16 x 16 block; entries above the diagonal are
+    junk that is never stored): `piv2` broadcasts the next pivot from `row[c+1] - lrc^2` of lane c+1 instead of the
+    generally updated row[c+1] (DCGP_LEAF_PIV2).  Returns the factor and the inverse pivots."""
+    lanes = 32
+    row = np.zeros((lanes, SB))
+    for r in range(lanes):
+        for c in range(SB):
+            row[r, c] = block[r, c] if (r < pw and c <= r) else (1.0 if r == c else 0.0)
+    myinv = np.zeros(lanes)
+    dnext = row[0, 0]
+    for c in range(SB):
+        d = dnext if piv2 else row[c, c]                      # shuffle from lane c
+        y = 1.0 / np.sqrt(d)
+        scaled = row[:, c] * y
+        for r in range(lanes):
+            row[r, c] = d * y if r == c else scaled[r]
+        myinv[c] = y
+        lrc = row[:, c].copy()
+        if piv2 and c + 1 < SB:
+            own = -lrc * lrc + row[:, c + 1]
+            dnext = own[c + 1]                                # shuffle from lane c + 1
+        for k in range(c + 1, SB):
+            lkc = row[k, c]                                   # shuffle of row[c] from lane k
+            row[:, k] = -lrc * lkc + row[:, k]
+    L = np.zeros((pw, pw))
+    for r in range(pw):
+        L[r, :r + 1] = row[r, :r + 1]
+    return L, myinv[:pw]
+
+
+@pytest.mark.parametrize("pw", [16, 9, 1])
+def test_short_pivot_chain_is_the_same_arithmetic(pw):
+    rng = np.random.default_rng(pw)
+    M = rng.standard_normal((pw, pw))
+    A = M @ M.T + pw * np.eye(pw)
+    blk = np.zeros((32, SB))
+    blk[:pw, :pw] = np.tril(A)
+    L0, i0 = diag_step_lanes(blk, pw, False)
+    L1, i1 = diag_step_lanes(blk, pw, True)
+    assert np.array_equal(L0, L1) and np.array_equal(i0, i1)          # bitwise: same operands, same order
+    assert np.abs(L0 - np.linalg.cholesky(A)).max() < 1e-12 * np.abs(A).max()

@@ -1,5 +1,5 @@
 """DCGP_LEAF_FINV=1 (the leaves of the factorisation build the inverse of their factor inside the pivot loop instead of a
-separate block_trtri pass; csrc/chol.cu, inv_rows_*).  The switch is read once per process, so the checks run in a
+separate block_trtri pass; csrc/chol.cu, inv_rows_*) and DCGP_LEAF_PIV2=1 (short pivot chain in diag_step).  The switch is read once per process, so the checks run in a
 subprocess.  EXPERIMENTAL: written when no GPU time was left in round 1 (the tile algorithm is checked by
 tests/test_leaf_finv_cpu.py on a host emulation; the default path's SASS is byte-identical to the validated build), hence
 opt-in:  DCGP_TEST_EXPERIMENTAL=1 python -m pytest tests/test_leaf_finv_gpu.py -m gpu"""
@@ -42,7 +42,10 @@ print("ok")
 '''
 
 
-def test_factorisation_with_fused_leaf_inverse_matches_lapack():
-    r = subprocess.run([sys.executable, "-c", CHECK, ROOT], env={**os.environ, "DCGP_LEAF_FINV": "1"},
+@pytest.mark.parametrize("finv,piv2", [("1", "0"), ("0", "1"), ("1", "1")])
+def test_factorisation_with_experimental_leaves_matches_lapack(finv, piv2):
+    """DCGP_LEAF_FINV (inverse rides along with the factorisation) and DCGP_LEAF_PIV2 (short pivot chain), alone and
+    together: factors against LAPACK, solves and inverses through the blocks the leaves produced."""
+    r = subprocess.run([sys.executable, "-c", CHECK, ROOT], env={**os.environ, "DCGP_LEAF_FINV": finv, "DCGP_LEAF_PIV2": piv2},
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-3000:]
