@@ -429,6 +429,10 @@ def run_exact(device, N):
                          "achieved": fl["potrf"] / ph["potrf"] / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": fl["potrf"] / ph["potrf"] / 1e12 / fp64_peak,
                          "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (best of 3)"},
+            # the Gram build is bound by the N^2 * 8 bytes it writes; FP64 exp (about 25 DFMA per entry) is the co-bound
+            "gram_roofline": {"bound": "hbm", "kernel": "gram_fwd_kernel<double>", "achieved": N * N * 8 / ph["gram_K"] / 1e9,
+                              "peak": peaks()["hbm_gbs"], "unit": "GB/s",
+                              "frac": N * N * 8 / ph["gram_K"] / 1e9 / peaks()["hbm_gbs"], "peak_source": peaks()["source"]},
             "potrf_info": int(res["info"].item()), "mll": float(res["mll"].item())}
 
 
