@@ -87,3 +87,22 @@ def test_row_block_sharded_product_two_ranks():
     for r in range(2):
         res, ref = out[r]
         torch.testing.assert_close(res, ref, rtol=1e-13, atol=1e-13)
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
+    """bench.py --impl reference launched as the driver launches it for N > 1: rank 0 alone runs the CPU arm and prints
+    the JSON line, the other ranks leave with exit code 0 and no output."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(root, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--small", "--steps", "1", "--warmup", "0"],
+                       cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["metric"] == "elbo_steps_per_s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
