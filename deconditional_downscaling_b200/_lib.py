@@ -82,6 +82,8 @@ _SIGNATURES = {
                                       c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "dcgp_whitened_kl": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                  c_void_p]),
+    "dcgp_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double,
+                               c_double, c_double, c_void_p, c_int, c_int, c_int, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

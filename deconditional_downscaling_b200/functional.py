@@ -110,6 +110,39 @@ def matmul(A, B, transa=False, transb=False, precise=False):
 
 # ---------------------------------------------------------------------- Cholesky & solves
 _DEFERRED = None   # list collecting the device `info` words of the factorisations of a deferred region
+_POOL = None       # InfoPool handing out those words from one buffer (trainer steps), or None
+
+
+class InfoPool:
+    """One device buffer of int32 failure words: every factorisation of a deferred region writes its LAPACK-style
+    `info` into the next slot, so that the whole step's status is ONE tensor - the veto argument of the device-side
+    optimiser update, the payload of the cross-rank MAX all-reduce and a single host read."""
+
+    def __init__(self, device, capacity=64):
+        self.buf = torch.zeros(capacity, dtype=torch.int32, device=device)
+        self.used = 0
+
+    def reset(self):
+        self.used = 0
+
+    def next(self):
+        if self.used >= self.buf.numel():
+            raise RuntimeError("InfoPool exhausted: more factorisations in one step than slots")
+        slot = self.buf[self.used:self.used + 1]
+        self.used += 1
+        return slot
+
+    def words(self):
+        return self.buf[:self.used]
+
+    def any_failed(self):
+        """The one host read-back of a step."""
+        return self.used > 0 and bool(self.words().cpu().any())
+
+
+def _info_slot():
+    """Where the next factorisation reports: a pool slot inside a pooled deferred region, else a fresh word."""
+    return _POOL.next() if _POOL is not None else None
 
 
 def _raise_if_not_pd(info):
@@ -129,17 +162,21 @@ class deferred_pd_checks:
     Every Cholesky in the region runs optimistically (no read-back, so the host keeps issuing work ahead of the
     GPU); `check()` reads all failure words in one transfer and raises NotPSDError for the first failed
     factorisation.  Results computed after a failed factorisation are garbage (NaN) and must be discarded by the
-    caller - training.ElboTrainer re-runs the step with immediate checks and jitter retries in that case."""
+    caller - training.ElboTrainer vetoes the update on the device and re-runs the step with immediate checks and
+    jitter retries in that case.  With `pool` the words live in that InfoPool instead of separate tensors."""
+
+    def __init__(self, pool=None):
+        self.pool = pool
 
     def __enter__(self):
-        global _DEFERRED
-        self._outer, self.infos = _DEFERRED, []
-        _DEFERRED = self.infos
+        global _DEFERRED, _POOL
+        self._outer, self._outer_pool, self.infos = _DEFERRED, _POOL, []
+        _DEFERRED, _POOL = self.infos, self.pool
         return self
 
     def __exit__(self, *exc):
-        global _DEFERRED
-        _DEFERRED = self._outer
+        global _DEFERRED, _POOL
+        _DEFERRED, _POOL = self._outer, self._outer_pool
         return False
 
     def check(self):
@@ -156,7 +193,7 @@ class _CholeskyFn(Function):
     @staticmethod
     def forward(ctx, A, check):
         L = A.detach().clone(memory_format=torch.contiguous_format)
-        info = ops.potrf_(L)
+        info = ops.potrf_(L, info=_info_slot())
         if check:
             _raise_if_not_pd(info)
         L = L.tril_()
@@ -251,7 +288,7 @@ class _GaussianTermsFn(Function):
     @staticmethod
     def forward(ctx, C, e, G):
         L = C.detach().clone(memory_format=torch.contiguous_format)
-        info = ops.potrf_(L)
+        info = ops.potrf_(L, info=_info_slot())
         _raise_if_not_pd(info)
         L = L.tril_()
         W = ops.trtri(L)
@@ -300,7 +337,7 @@ class _CholInverseFn(Function):
     @staticmethod
     def forward(ctx, A):
         L = A.detach().clone(memory_format=torch.contiguous_format)
-        info = ops.potrf_(L)
+        info = ops.potrf_(L, info=_info_slot())
         _raise_if_not_pd(info)
         L = L.tril_()
         W = ops.trtri(L)
@@ -411,7 +448,7 @@ def kernel_factor(meta, hyp, x, check=True):
     """Cholesky factor of k(x,x) + diag_const*I (no autograd: consumed by kernel_solve)."""
     with torch.no_grad():
         L = ops.gram(_spec(meta, hyp), x, None, diag_const=meta.diag_const)
-        info = ops.potrf_(L)
+        info = ops.potrf_(L, info=_info_slot())
         if check:
             _raise_if_not_pd(info)
         L._dcgp_plan = ops.solve_plan(L)

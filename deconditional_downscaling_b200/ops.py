@@ -49,19 +49,34 @@ def _dt(t: torch.Tensor) -> int:
 
 
 def _req(*tensors):
+    """CUDA tensors only (no CPU fallback), all on the CURRENT device: the launchers pass the current device's stream
+    and libdcgp keeps per-device state (kernel attributes, look-ahead lanes) for the device that is current at the
+    call - a tensor living elsewhere would be launched on the wrong device."""
+    cur = None
     for t in tensors:
         if t is None:
             continue
         if not t.is_cuda:
             raise _lib.DcgpError("libdcgp ops need CUDA tensors (there is no CPU fallback)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise _lib.DcgpError(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: "
+                                 "wrap the call in `with torch.cuda.device(t.device)`")
+
+
+def _same_dtype(what, *tensors):
+    dts = {t.dtype for t in tensors if t is not None}
+    if len(dts) > 1:
+        raise TypeError(f"{what}: operands must share one dtype, got {sorted(str(d) for d in dts)}")
 
 
 def _ptr(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _rowmajor(t: torch.Tensor) -> torch.Tensor:
@@ -204,6 +219,7 @@ def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, C=None, lower=Fa
     """C = alpha * op(A) @ op(B) + beta * C."""
     A, B = _rowmajor(A), _rowmajor(B)
     _req(A, B, C)
+    _same_dtype("gemm", A, B, C)
     m, k = (A.size(1), A.size(0)) if transa else (A.size(0), A.size(1))
     k2, n = (B.size(1), B.size(0)) if transb else (B.size(0), B.size(1))
     if k != k2:
@@ -236,6 +252,7 @@ def gemm_x3(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, C=None, Alo=N
     are computed here unless the caller already holds them)."""
     A, B = _rowmajor(A), _rowmajor(B)
     _req(A, B, C)
+    _same_dtype("gemm_x3", A, B, C, Alo, Blo)
     if A.dtype != torch.float32:
         return gemm(A, B, transa=transa, transb=transb, alpha=alpha, beta=beta, C=C)
     m, k = (A.size(1), A.size(0)) if transa else (A.size(0), A.size(1))
@@ -290,6 +307,7 @@ def _solve(trans, L, B, plan):
     L = _rowmajor(L)
     _inplace_ok(B)
     _req(L, B)
+    _same_dtype("triangular solve", L, B)
     n, m = B.size(0), B.size(1)
     lib = _lib.load()
     # sized for B's row stride: the 512-block sweeps work in B's layout (a view with ld > m would otherwise drop to the
@@ -447,3 +465,22 @@ def rff_features_bwd(x, W, lengthscale, dphi, need_dx=True):
                                             _ptr(dx), _ld(dx) if need_dx else 0, _ptr(dls), _dt(x), _stream()),
           "dcgp_rff_features_bwd")
     return dx, dls
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, grad_scale=1.0, veto=None, zero_grads=False):
+    """Fused multi-tensor Adam over flat buffers (dcgp_adam_step); `step` is a device float64 counter, `veto` optional
+    device int32 words (non-zero -> the update is skipped on the device)."""
+    _req(params, grads, exp_avg, exp_avg_sq, step, veto)
+    if not (params.dtype == grads.dtype == exp_avg.dtype == exp_avg_sq.dtype):
+        raise TypeError("adam_step: parameter, gradient and moment buffers must share one dtype")
+    if step.dtype != torch.float64 or (veto is not None and veto.dtype != torch.int32):
+        raise TypeError("adam_step: step must be float64 and veto int32")
+    for t in (params, grads, exp_avg, exp_avg_sq):
+        if not t.is_contiguous() or t.numel() != params.numel():
+            raise ValueError("adam_step needs contiguous flat buffers of one length")
+    with torch.cuda.device(params.device):
+        rc = _lib.load().dcgp_adam_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(step), params.numel(),
+                                        float(lr), float(beta1), float(beta2), float(eps), float(grad_scale), _ptr(veto),
+                                        0 if veto is None else veto.numel(), 1 if zero_grads else 0, _dt(params),
+                                        _stream(params.device))
+    check(rc, "dcgp_adam_step")

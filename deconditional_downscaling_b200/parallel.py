@@ -35,18 +35,28 @@ def sharded_rows_matmul(panel_fn: Callable[[int, int], torch.Tensor], n_rows: in
     return torch.cat([recv[r][: h - l] for r, (l, h) in enumerate(sizes)], dim=0)
 
 
-def sharded_kernel_matmul(kernel, x1: torch.Tensor, x2: Optional[torch.Tensor], W: torch.Tensor, group=None):
-    """k(x1, x2) @ W with x1's rows sharded over the ranks (x2 None means x2 = x1).  Every rank holds
-    x1, x2 and W (they are O(N d) / O(N n)); only Gram tiles are distributed."""
+def kernel_matmul_panel(kops, x1, x2, Wm, lo, hi, diag_const=0.0):
+    """Rows [lo, hi) of (k(x1, x2) [+ diagonal terms when x2 is None]) @ Wm.  A row block of a self-product is a
+    CROSS product for the Gram kernel (x1[lo:hi] against all of x1), which knows no diagonal: the delta-kernel scale
+    (ScaleKernel(DeltaKernel), src/models/cmp.py:61-62) and the nugget are added here on the block's own rows, so
+    the result does not depend on the number of ranks."""
+    if x2 is None and lo == 0 and hi == x1.size(0):
+        return kops.matmul(x1, None, Wm, diag_const=diag_const)
+    out = kops.matmul(x1[lo:hi], x1 if x2 is None else x2, Wm)
+    if x2 is None:
+        dd = kops._delta_scale()
+        if dd is not None or diag_const:
+            out = out + ((dd if dd is not None else 0.0) + diag_const) * Wm[lo:hi]
+    return out
+
+
+def sharded_kernel_matmul(kernel, x1: torch.Tensor, x2: Optional[torch.Tensor], W: torch.Tensor, group=None, diag_const=0.0):
+    """(k(x1, x2) [+ delta terms + diag_const I when x2 is None]) @ W with x1's rows sharded over the ranks.  Every
+    rank holds x1, x2 and W (they are O(N d) / O(N n)); only Gram tiles are distributed."""
     x1 = x1 if x1.dim() == 2 else x1.unsqueeze(-1)
-    x2f = x1 if x2 is None else (x2 if x2.dim() == 2 else x2.unsqueeze(-1))
+    x2f = None if x2 is None else (x2 if x2.dim() == 2 else x2.unsqueeze(-1))
     kops = kernel.ops(x1)
     Wm = W if W.dim() == 2 else W.unsqueeze(-1)
-
-    def panel(lo, hi):
-        if x2 is None and lo == 0 and hi == x1.size(0):
-            return kops.matmul(x1, None, Wm)
-        return kops.matmul(x1[lo:hi], x2f, Wm)
-
-    out = sharded_rows_matmul(panel, x1.size(0), Wm.size(1), x1.dtype, x1.device, group)
+    out = sharded_rows_matmul(lambda lo, hi: kernel_matmul_panel(kops, x1, x2f, Wm, lo, hi, diag_const), x1.size(0),
+                              Wm.size(1), x1.dtype, x1.device, group)
     return out.squeeze(-1) if W.dim() == 1 else out

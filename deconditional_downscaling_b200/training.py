@@ -5,8 +5,20 @@
 experiments/swiss_roll/models/vbagg.py:88-101): q = model(x) -> ELBO -> backward -> Adam,
 plus - when torch.distributed is initialised - ONE NCCL all-reduce of the flat gradient
 buffer (every rank draws its own minibatch; gradients are averaged).
+
+Step protocol (`DataParallelStepper`, the same on every rank, no rank-local control flow between collectives):
+  1. optimistic pass: forward + backward with every Cholesky failure word written into one device pool
+     (functional.InfoPool) - no host read-back;
+  2. MAX all-reduce of the pool (a few dozen ints): afterwards every rank holds the union of all ranks' failures;
+  3. SUM all-reduce of the flat gradient buffer - always, by every rank;
+  4. fused device-side Adam over the flat parameter buffer, predicated on the pool (dcgp_adam_step `veto`): if any
+     rank failed, no rank updates;
+  5. ONE host read of the pool; if it is non-zero EVERY rank repeats the minibatch with immediate checks and
+     psd_safe_cholesky's jitter retries (collectively: a rank whose retry fails reports it through a second flag
+     all-reduce and all ranks raise NotPSDError together).
+Steps 1-4 are what `cuda_graph=True` captures and replays.
 """
-from typing import Dict, Optional
+from typing import Dict, Iterable, List, Optional
 
 import torch
 import torch.distributed as dist
@@ -17,6 +29,10 @@ from .likelihoods import CMPLikelihood, VBaggGaussianLikelihood
 from .mlls import BagVariationalELBO
 
 
+def _world():
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
 class FlatGrads:
     """All parameter gradients as views into one contiguous buffer, so the data-parallel
     exchange is a single collective (payload ~ M^2 + M d + M + O(10) values)."""
@@ -25,6 +41,8 @@ class FlatGrads:
         self.params = [p for p in params if p.requires_grad]
         total = sum(p.numel() for p in self.params)
         dtype = self.params[0].dtype
+        if any(p.dtype != dtype for p in self.params):
+            raise TypeError("FlatGrads needs parameters of one dtype (move the model with .to(dtype) first)")
         self.flat = torch.zeros(total, dtype=dtype, device=self.params[0].device)
         off = 0
         for p in self.params:
@@ -34,31 +52,176 @@ class FlatGrads:
     def zero(self):
         self.flat.zero_()
 
-    def allreduce_mean(self):
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    def allreduce_sum(self):
+        if _world() > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.div_(dist.get_world_size())
+
+    def allreduce_mean(self):
+        if _world() > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(_world())
 
     @property
     def nbytes(self):
         return self.flat.numel() * self.flat.element_size()
 
 
-class ElboTrainer:
+class FlatParams(FlatGrads):
+    """FlatGrads + the parameters themselves re-laid as views of one buffer (same order), so the optimiser update is
+    one launch over two flat arrays and the initial rank-0 broadcast one collective."""
+
+    def __init__(self, params):
+        super().__init__(params)
+        self.values = torch.empty_like(self.flat)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                view = self.values[off:off + p.numel()].view_as(p)
+                view.copy_(p)
+                p.data = view
+                off += p.numel()
+
+
+def sync_module_state(modules: Iterable[torch.nn.Module], flat_params: Optional[torch.Tensor] = None, src: int = 0):
+    """Broadcast parameters and buffers from rank `src`: replicas must start identical (q(u)'s mean is initialised
+    with 1e-3 * randn and RFF frequencies are drawn lazily - both per process)."""
+    if _world() == 1:
+        return
+    if flat_params is not None:
+        dist.broadcast(flat_params, src)
+    else:
+        for m in modules:
+            for p in m.parameters():
+                dist.broadcast(p.data, src)
+    for m in modules:
+        for b in m.buffers():
+            if b.numel():
+                dist.broadcast(b, src)
+
+
+def materialize_lazy_buffers(model):
+    """RFF kernels draw their frequency buffers at first evaluation (kernels.RFFKernel._terms); do it now so that
+    they exist on every rank before the broadcast."""
+    vs = getattr(model, "variational_strategy", None)
+    if vs is None:
+        return
+    kernel, _ = vs._prior_modules()
+    kernel._terms(vs.inducing_points.size(-1), None)
+
+
+class FusedAdam:
+    """torch.optim.Adam arithmetic (default betas / eps, no weight decay, no amsgrad) as ONE libdcgp launch over the
+    flat buffers, predicated on device failure words.  state_dict() is laid out like torch.optim.Adam's so that the
+    reference's checkpoints ('optimizer' entry of state.pt, experiments/*/models/*.py) keep their format."""
+
+    def __init__(self, flat: FlatParams, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        self.flat = flat
+        self.defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=0, amsgrad=False)
+        self.param_groups = [dict(self.defaults, params=flat.params)]
+        self.exp_avg = torch.zeros_like(flat.values)
+        self.exp_avg_sq = torch.zeros_like(flat.values)
+        self.step_count = torch.zeros(1, dtype=torch.float64, device=flat.values.device)
+
+    def step(self, veto: Optional[torch.Tensor] = None, grad_scale: float = 1.0, zero_grads: bool = False):
+        from . import ops
+        g = self.param_groups[0]
+        ops.adam_step(self.flat.values, self.flat.flat, self.exp_avg, self.exp_avg_sq, self.step_count, g["lr"],
+                      g["betas"][0], g["betas"][1], g["eps"], grad_scale, veto, zero_grads)
+
+    def zero_grad(self, set_to_none=False):
+        self.flat.zero()
+
+    def state_dict(self):
+        state, off = {}, 0
+        for i, p in enumerate(self.flat.params):
+            n = p.numel()
+            state[i] = {"step": self.step_count.clone().reshape(()).to(torch.float32),
+                        "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p).clone()}
+            off += n
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        group.update(maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
+                     params=list(range(len(self.flat.params))))
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        off = 0
+        for i, p in enumerate(self.flat.params):
+            n = p.numel()
+            st = sd["state"].get(i)
+            if st is not None:
+                self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                self.step_count.fill_(float(st["step"]))
+            off += n
+        for k in ("lr", "betas", "eps"):
+            if k in sd["param_groups"][0]:
+                self.param_groups[0][k] = sd["param_groups"][0][k]
+
+
+class DataParallelStepper:
+    """The rank-symmetric step protocol (module docstring).  Subclasses provide the compute:
+      optimistic_pass(batch) -> loss   forward + backward, failure words into self.pool (no host sync)
+      checked_pass(batch)    -> loss   forward + backward with immediate checks; raises F.NotPSDError
+      update(veto)                     optimiser update (veto: device int words or None)
+    and own `self.grads` (FlatGrads) and `self.pool` (F.InfoPool)."""
+
+    def exchange(self):
+        """Steps 2 + 3: failure words first (MAX), then the gradient (SUM) - both by every rank, unconditionally."""
+        if _world() > 1:
+            dist.all_reduce(self.pool.words(), op=dist.ReduceOp.MAX)
+            self.grads.allreduce_sum()
+
+    def device_step(self, batch):
+        """Steps 1-4: no host synchronisation inside; capturable in a CUDA graph."""
+        self.pool.reset()
+        loss = self.optimistic_pass(batch)
+        self.exchange()
+        self.update(self.pool.words())
+        return loss
+
+    def resolve(self, batch, loss):
+        """Step 5, after device_step or a replay of it."""
+        if not self.pool.any_failed():
+            return loss
+        return self.collective_checked_step(batch)
+
+    def collective_checked_step(self, batch):
+        self.grads.zero()
+        err, loss = None, None
+        try:
+            loss = self.checked_pass(batch)
+        except F.NotPSDError as e:
+            err = e
+        flag = torch.tensor([1 if err is not None else 0], dtype=torch.int32, device=self.grads.flat.device)
+        if _world() > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()):
+            self.grads.zero()
+            raise err if err is not None else F.NotPSDError("a Cholesky factorisation failed on another rank")
+        self.grads.allreduce_sum()
+        self.update(None)
+        return loss
+
+
+class ElboTrainer(DataParallelStepper):
     """VariationalCMP (+CMPLikelihood) or VariationalGP (+VBaggGaussianLikelihood) ELBO steps."""
 
     def __init__(self, model, likelihood, num_data, beta=1.0, lr=0.01, cuda_graph=False):
         self.model, self.likelihood = model, likelihood
         self.elbo = BagVariationalELBO(likelihood, model, num_data=num_data, beta=beta)
         self.params = list(model.parameters()) + list(likelihood.parameters())
-        # q(u) must exist before the optimizer / flat buffer are laid out
+        # q(u) and lazily drawn buffers must exist before the optimizer / flat buffers are laid out and broadcast
         model.variational_strategy.ensure_initialized()
-        self.grads = FlatGrads(self.params)
-        self.opt = torch.optim.Adam(self.params, lr=lr)
+        materialize_lazy_buffers(model)
+        self.grads = FlatParams(self.params)
+        sync_module_state([model, likelihood], self.grads.values)
+        self.opt = FusedAdam(self.grads, lr=lr)
+        self.pool = F.InfoPool(self.grads.flat.device)
         model.train()
         likelihood.train()
-        # CUDA-graph mode: forward + backward + gradient all-reduce of a minibatch SHAPE are captured once (third call
-        # with that shape) and replayed; the optimizer runs outside the graph, after the factorisation checks
+        # CUDA-graph mode: steps 1-4 of the protocol for a minibatch SHAPE are captured once (third call with that
+        # shape) and replayed
         self.cuda_graph = cuda_graph
         self._graphs, self._graph_calls, self._capture_stream = {}, {}, None
         self.launches_replayed = 0   # libdcgp kernel launches executed through graph replays (host counters do not see them)
@@ -70,33 +233,36 @@ class ElboTrainer:
                                                             extended_bags_values=kw["extended_bags_values"])
         return -self.elbo(variational_dist_f=q, target=z, **kw)
 
-    def _backward_pass(self, x, z, kw):
-        """zero grads -> loss -> backward -> all-reduce, optimistic about the factorisations; returns (loss, pending)."""
-        self.grads.zero()
-        with F.deferred_pd_checks() as pending:
-            loss = self.loss(x, z, **kw)
+    # ---- DataParallelStepper compute ---------------------------------------------------------------------
+    def optimistic_pass(self, batch):
+        with F.deferred_pd_checks(self.pool):
+            loss = self.loss(batch["x"], batch["z"], **batch["kw"])
             loss.backward()
-        self.grads.allreduce_mean()
-        return loss.detach(), pending
-
-    def _checked_pass(self, x, z, kw):
-        """psd_safe_cholesky semantics (jitter retries, then NotPSDError) with immediate checks."""
-        self.grads.zero()
-        loss = self.loss(x, z, **kw)
-        loss.backward()
-        self.grads.allreduce_mean()
         return loss.detach()
 
+    def checked_pass(self, batch):
+        loss = self.loss(batch["x"], batch["z"], **batch["kw"])
+        loss.backward()
+        return loss.detach()
+
+    def update(self, veto):
+        # gradients are averaged over the ranks inside the update; the buffer is left zeroed for the next pass
+        self.opt.step(veto=veto, grad_scale=1.0 / _world(), zero_grads=True)
+
+    # ---- public step ----------------------------------------------------------------------------------------
     def step(self, x, z, **kw):
         """One ELBO step on device-resident tensors; returns the (device) loss."""
         if self.cuda_graph:
             return self._graph_step(x, z, kw)
-        # optimistic pass: no host read-back between the factorisations, ONE check before the update
         return self._eager_step(x, z, kw)
+
+    def _eager_step(self, x, z, kw):
+        batch = {"x": x, "z": z, "kw": kw}
+        return self.resolve(batch, self.device_step(batch))
 
     # ---- CUDA-graph mode ---------------------------------------------------------------------------------
     def _graph_step(self, x, z, kw):
-        """Everything of graph mode - eager warm-up steps, capture, replays, optimizer - runs on ONE dedicated stream:
+        """Everything of graph mode - eager warm-up steps, capture, replays - runs on ONE dedicated stream:
         autograd's gradient-accumulation nodes are bound to the stream they were first used on, and a node bound to the
         default stream cannot take part in a capture."""
         dev = x.device
@@ -110,47 +276,28 @@ class ElboTrainer:
         cur.wait_stream(s)
         return out
 
-    def _eager_step(self, x, z, kw):
-        try:
-            loss, pending = self._backward_pass(x, z, kw)
-            pending.check()
-        except F.NotPSDError:
-            loss = self._checked_pass(x, z, kw)
-        self.opt.step()
-        return loss
-
     def _graph_step_on_stream(self, x, z, kw):
         tensors = {"x": x, "z": z, **{k: v for k, v in kw.items() if torch.is_tensor(v)}}
         others = {k: v for k, v in kw.items() if not torch.is_tensor(v)}
+        g = self.opt.param_groups[0]
         key = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(tensors.items())) + \
-            tuple((k, tuple(v) if isinstance(v, (list, tuple)) else v) for k, v in sorted(others.items()))
+            tuple((k, tuple(v) if isinstance(v, (list, tuple)) else v) for k, v in sorted(others.items())) + \
+            (("lr", g["lr"]),)        # the learning rate is a launch constant of the captured update
         entry = self._graphs.get(key)
         if entry is None:
             n = self._graph_calls[key] = self._graph_calls.get(key, 0) + 1
             if n <= 2:   # eager warm-up: kernel attributes, look-ahead lanes, allocator
                 return self._eager_step(x, z, kw)
-            try:
-                entry = self._capture(tensors, others)
-            except RuntimeError as err:   # e.g. autograd state bound to another stream by earlier eager use
-                import warnings
-                warnings.warn(f"CUDA-graph capture of the ELBO step failed ({str(err).splitlines()[0]}); staying eager")
-                torch.cuda.synchronize(x.device)
-                entry = False
-            self._graphs[key] = entry
-        if entry is False:
-            return self._eager_step(x, z, kw)
-        static, graph, loss, infos, launches = entry
+            # a failed capture is an error, not a silent fall-back to eager steps under the "graph" label
+            entry = self._graphs[key] = self._capture(tensors, others)
+        static, graph, loss, launches = entry
         for k, v in tensors.items():
             if v is not static[k]:
                 static[k].copy_(v, non_blocking=True)
         graph.replay()
         self.launches_replayed += launches
-        out = loss.clone()
-        if infos is not None and bool(infos.any().item()):
-            # a factorisation failed inside the replay: repeat the pass eagerly (retries with jitter or raises)
-            out = self._checked_pass(tensors["x"], tensors["z"], {**{k: v for k, v in tensors.items() if k not in ("x", "z")}, **others})
-        self.opt.step()
-        return out
+        batch = {"x": static["x"], "z": static["z"], "kw": {**{k: v for k, v in static.items() if k not in ("x", "z")}, **others}}
+        return self.resolve(batch, loss.clone())
 
     def _capture(self, tensors, others):
         """Called on the capture stream."""
@@ -160,16 +307,15 @@ class ElboTrainer:
         if quiet is not None:
             quiet(False)
         static = {k: v.clone() for k, v in tensors.items()}
-        kw = {**{k: v for k, v in static.items() if k not in ("x", "z")}, **others}
+        batch = {"x": static["x"], "z": static["z"], "kw": {**{k: v for k, v in static.items() if k not in ("x", "z")}, **others}}
         torch.cuda.synchronize(dev)
         lib = _lib.load()
         graph = torch.cuda.CUDAGraph()
         n0 = lib.dcgp_launch_count()
         with torch.cuda.graph(graph, stream=self._capture_stream):
-            loss, pending = self._backward_pass(static["x"], static["z"], kw)
-            infos = torch.cat([i.reshape(1) for i in pending.infos]) if pending.infos else None
+            loss = self.device_step(batch)
         launches = int(lib.dcgp_launch_count() - n0)
-        return static, graph, loss, infos, launches
+        return static, graph, loss, launches
 
     def close(self):
         """Drop the captured graphs (and the NCCL work recorded in them).  Call before

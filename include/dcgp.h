@@ -243,6 +243,18 @@ DCGP_API int dcgp_vbagg_ell(const void* z, const void* S, const void* T, const i
 DCGP_API int dcgp_whitened_kl(const void* m, const void* Ls, int64_t M, int64_t ldls, void* out, void* dm, void* dLs,
                      int64_t lddls, int dtype, void* stream);
 
+/* ---- optimiser update ------------------------------------------------------------
+ * One fused multi-tensor Adam update over flat buffers of n values (torch.optim.Adam arithmetic, no weight decay,
+ * no amsgrad): the `optimizer.step()` of experiments/downscaling/models/variational_cmp.py:183 and
+ * experiments/swiss_roll/models/variational_cmp.py:110.  `step` is a DEVICE double holding the number of updates
+ * applied so far (advanced here).  `veto` (optional): n_veto device ints - if any is non-zero (a failed
+ * factorisation of the step, see `info` of dcgp_potrf) nothing is changed, so the update can sit inside a captured
+ * CUDA graph with no host decision.  grads are scaled by grad_scale first (1 / world size after a SUM all-reduce)
+ * and zeroed afterwards when zero_grads != 0. */
+DCGP_API int dcgp_adam_step(void* params, void* grads, void* exp_avg, void* exp_avg_sq, void* step, int64_t n, double lr,
+                            double beta1, double beta2, double eps, double grad_scale, const int* veto, int n_veto,
+                            int zero_grads, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -433,3 +433,34 @@ def test_syrk_lower_triangle():
     assert torch.allclose(C.tril(), ref.tril(), rtol=1e-12, atol=1e-10)
     Ct = ops.syrk(A, trans=True)
     assert torch.allclose(Ct.tril(), (A.t() @ A).tril(), rtol=1e-12, atol=1e-10)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_adam_step_matches_torch_adam_and_honours_the_veto(dtype):
+    """dcgp_adam_step = torch.optim.Adam (defaults) on flat buffers; a non-zero veto word leaves parameters, moments and
+    the step counter untouched; grad_scale averages a summed gradient; zero_grads clears the buffer."""
+    from deconditional_downscaling_b200 import ops
+    torch.manual_seed(3)
+    n = 70001
+    p0 = torch.randn(n, dtype=dtype, device=DEV)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=0.01)
+    p, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    step = torch.zeros(1, dtype=torch.float64, device=DEV)
+    veto = torch.zeros(3, dtype=torch.int32, device=DEV)
+    for it in range(5):
+        g = torch.randn(n, dtype=dtype, device=DEV) * (10.0 ** (it - 2))
+        ref.grad = g.clone()
+        opt.step()
+        g2 = 2.0 * g                                     # as after a SUM all-reduce over two ranks
+        ops.adam_step(p, g2, m, v, step, 0.01, 0.9, 0.999, 1e-8, grad_scale=0.5, veto=veto, zero_grads=True)
+        assert g2.abs().max().item() == 0
+        tol = 1e-12 if dtype == torch.float64 else 2e-6
+        assert ((p - ref.detach()).abs().max() / ref.detach().abs().max()).item() < tol
+    assert step.item() == 5
+    before = (p.clone(), m.clone(), v.clone())
+    veto[1] = 7
+    g = torch.randn(n, dtype=dtype, device=DEV)
+    ops.adam_step(p, g, m, v, step, 0.01, 0.9, 0.999, 1e-8, veto=veto, zero_grads=True)
+    assert step.item() == 5 and torch.equal(p, before[0]) and torch.equal(m, before[1]) and torch.equal(v, before[2])
+    assert g.abs().max().item() > 0                      # a vetoed update does not clear the gradient either

@@ -179,6 +179,29 @@ def test_row_block_sharded_kernel_matmul_equals_unsharded():
     assert ((full.cpu() - ref).norm() / ref.norm()).item() < 1e-10
 
 
+def test_row_block_sharded_self_product_keeps_delta_and_nugget_terms():
+    """k = Scale(RBF) + Scale(Delta) (src/models/cmp.py:61-62) and a nugget: the row panels of a self-product are
+    cross products for the Gram kernel, so the diagonal terms are added per panel - the result must not depend on
+    the number of ranks (ranks emulated in one process)."""
+    from deconditional_downscaling_b200 import kernels as K
+    from deconditional_downscaling_b200.parallel import kernel_matmul_panel, row_block
+    torch.manual_seed(6)
+    dt = torch.float64
+    x = torch.randn(700, 3, dtype=dt, device=DEV)
+    W = torch.randn(700, 9, dtype=dt, device=DEV)
+    km = (K.ScaleKernel(K.RBFKernel(ard_num_dims=3)) + K.ScaleKernel(K.DeltaKernel())).to(DEV).double()
+    with torch.no_grad():
+        kops = km.ops(x)
+        full = kops.matmul(x, None, W, diag_const=0.3)
+        dense = kops.gram(x, None, diag_const=0.3) @ W
+        for world in (2, 3):
+            parts = [kernel_matmul_panel(kops, x, None, W, *row_block(700, r, world), diag_const=0.3) for r in range(world)]
+            assert ((torch.cat(parts) - full).norm() / full.norm()).item() < 1e-13
+    assert ((full - dense).norm() / dense.norm()).item() < 1e-12
+    delta_part = torch.nn.functional.softplus(km.kernels[1].raw_outputscale.detach()) + 0.3
+    assert delta_part.item() > 0.5          # the diagonal terms are a visible part of the product
+
+
 def test_gram_matmul_multi_panel_matches_single_products():
     """Above 1 GiB the Gram matrix is produced in 512 MiB row panels; (K + c I) W must not change."""
     o = ops()

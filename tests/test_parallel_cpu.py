@@ -106,3 +106,102 @@ def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["metric"] == "elbo_steps_per_s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# step protocol of training.DataParallelStepper (collective failure decision BEFORE any update, rank-0 broadcast of the
+# initial state) on two gloo ranks, with a toy compute in place of the CUDA kernels
+def _protocol_worker(rank, world, port, out, fail_rank, fail_step, retry_fails):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from deconditional_downscaling_b200 import functional as F
+    from deconditional_downscaling_b200.training import DataParallelStepper, FlatGrads, sync_module_state
+
+    class Toy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(100 + rank)                         # every rank starts DIFFERENT ...
+            self.w = torch.nn.Parameter(torch.randn(5, dtype=torch.float64))
+            self.register_buffer("freq", torch.randn(3, dtype=torch.float64))   # ... incl. a lazily drawn buffer
+
+    class Stepper(DataParallelStepper):
+        def __init__(self):
+            self.m = Toy()
+            sync_module_state([self.m])                           # ... and is made identical here
+            self.grads = FlatGrads([self.m.w])
+            self.pool = F.InfoPool("cpu")
+            self.opt = torch.optim.Adam([self.m.w], lr=0.1)
+            self.t, self.checked, self.updates = 0, 0, 0
+
+        def _loss(self, batch):
+            return ((self.m.w * batch).sum() - 1.0) ** 2 + self.m.freq.sum() * 0
+
+        def optimistic_pass(self, batch):
+            bad = rank == fail_rank and self.t == fail_step
+            self.pool.next().fill_(3 if bad else 0)
+            loss = self._loss(batch) * (float("nan") if bad else 1.0)    # a failed factorisation poisons the gradient
+            loss.backward()
+            return loss.detach()
+
+        def checked_pass(self, batch):
+            self.checked += 1
+            if retry_fails and rank == fail_rank:
+                raise F.NotPSDError("retry failed")
+            loss = self._loss(batch)
+            loss.backward()
+            return loss.detach()
+
+        def update(self, veto):
+            if veto is not None and bool(veto.any()):
+                return
+            self.grads.flat.div_(world)
+            self.opt.step()
+            self.updates += 1
+            self.grads.zero()
+
+    s = Stepper()
+    start = s.m.w.detach().clone(), s.m.freq.clone()
+    g = torch.Generator().manual_seed(7 + rank)
+    raised = False
+    for t in range(4):
+        s.t = t
+        batch = torch.randn(5, generator=g, dtype=torch.float64)
+        try:
+            s.resolve(batch, s.device_step(batch))
+        except F.NotPSDError:
+            raised = True
+            break
+    out[rank] = (start, s.m.w.detach().clone(), s.checked, s.updates, raised, bool(torch.isfinite(s.m.w).all()))
+    dist.destroy_process_group()
+
+
+def _run_protocol(fail_rank, fail_step, retry_fails):
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_protocol_worker, args=(2, _free_port(), out, fail_rank, fail_step, retry_fails), nprocs=2, join=True)
+    return out[0], out[1]
+
+
+def test_replicas_start_identical_and_stay_identical_through_a_one_rank_failure():
+    """(1) parameters AND buffers are broadcast from rank 0 at construction; (2) a factorisation failing on
+    ONE rank makes BOTH ranks repeat the step (no rank applies the poisoned gradient, no unmatched collective, no hang)
+    and the replicas hold identical finite parameters afterwards."""
+    r0, r1 = _run_protocol(fail_rank=1, fail_step=2, retry_fails=False)
+    (w0, f0), (w1, f1) = r0[0], r1[0]
+    assert torch.equal(w0, w1) and torch.equal(f0, f1)
+    assert torch.equal(r0[1], r1[1]) and r0[5] and r1[5]
+    assert (r0[2], r1[2]) == (1, 1)              # both ranks took the checked pass, exactly once
+    assert (r0[3], r1[3]) == (4, 4)              # 3 optimistic updates + 1 checked update each
+    assert not r0[4] and not r1[4]
+
+
+def test_without_failures_no_rank_takes_the_checked_pass():
+    r0, r1 = _run_protocol(fail_rank=-1, fail_step=-1, retry_fails=False)
+    assert (r0[2], r1[2]) == (0, 0) and (r0[3], r1[3]) == (4, 4) and torch.equal(r0[1], r1[1])
+
+
+def test_unrecoverable_failure_on_one_rank_raises_on_all_ranks():
+    r0, r1 = _run_protocol(fail_rank=1, fail_step=1, retry_fails=True)
+    assert r0[4] and r1[4]                        # NotPSDError everywhere, nobody left waiting in a collective
+    assert torch.equal(r0[1], r1[1])              # and nobody applied a half-exchanged update
+    assert (r0[3], r1[3]) == (1, 1)

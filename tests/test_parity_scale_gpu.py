@@ -1,0 +1,284 @@
+"""Parity of the path that the bench actually times, at the sizes where the Blackwell kernels engage
+(gemm_tc_kernel / potrf_step_kernel need m, n >= 128; the 60-individual goldens never reach them):
+
+  * BASELINE config 5, one VariationalCMP minibatch (N_b = 8192 CME individuals, n = 1024 bags, M = 1024 inducing
+    points, additive Matern + RBF bag kernel, individuals noise): GPU FP32 (TF32 tcgen05 products, 3xTF32
+    factorisations, FP64 K_ZZ island) and GPU FP64 against the FP64 CPU oracle (oracle/port.py, the reference's
+    algorithm with the explicit root R and chol(Sigma_q)) - loss, ELL, KL, EVERY gradient, q(f) mean and variance;
+  * BASELINE config 1, ExactCMP at the swiss-roll size (N = 5000, n = 50, d = 3, r = 1): fit loss, every gradient
+    (after update_cmp_estimate_parameters, i.e. with gradient through Lambda^{-1}), posterior mean AND variance,
+    log-det of Q + s2 I - with a non-zero ConstantMean so that CMEAggregateMean is exercised on a non-trivial mean;
+  * a mid-size VariationalCMP with a ConstantMean individuals mean.
+
+Tolerances (north_star): 1e-6 relative in FP64, 1e-3 relative in FP32/TF32 for ELBO, posterior mean / variance and
+log-det.  Gradients are not named by north_star; they are held to 1e-6 (FP64) and to the per-tensor normwise bounds
+written next to each assert in FP32.
+"""
+import math
+import os
+
+import pytest
+import torch
+from torch.nn.functional import softplus
+
+from oracle import port
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+INV_SP1 = math.log(math.e - 1.0)
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu().reshape(-1)
+    b = torch.as_tensor(b).detach().double().cpu().reshape(-1)
+    return ((a - b).norm() / b.norm().clamp_min(1e-300)).item()
+
+
+def maxrel(a, b):
+    """max |a - b| / max |b|: the bound for vectors whose small entries carry no information."""
+    a = torch.as_tensor(a).detach().double().cpu().reshape(-1)
+    b = torch.as_tensor(b).detach().double().cpu().reshape(-1)
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-300)).item()
+
+
+# ------------------------------------------------------------------------------------------ VariationalCMP
+def vcmp_inputs(Nb, nb, M, d=5, r=3, seed=11):
+    g = torch.Generator().manual_seed(seed)
+    dt = torch.float64
+    per = max(Nb // nb, 1)
+    x = torch.randn(Nb, d, generator=g, dtype=dt)
+    y = torch.randn(nb, r, generator=g, dtype=dt)
+    ext = y[torch.arange(Nb) % nb] + 0.3 * torch.randn(Nb, r, generator=g, dtype=dt)
+    w = torch.randn(d, generator=g, dtype=dt)
+    z = torch.sin(x @ w)[: nb * per].view(nb, per).mean(1) + 0.05 * torch.randn(nb, generator=g, dtype=dt)
+    p = port.make_vcmp_params(M, d, r, dtype=dt, seed=seed + 1)
+    # away from the initial values so that every term of the ELBO and of its gradient is alive
+    p["var_mean"] = 0.1 * torch.randn(M, generator=g, dtype=dt)
+    p["chol_var"] = torch.eye(M, dtype=dt) + (0.5 / math.sqrt(M)) * torch.randn(M, M, generator=g, dtype=dt).tril()
+    p["k_raw_ls"] = p["k_raw_ls"] + 0.2 * torch.randn(d, generator=g, dtype=dt)
+    p["l0_raw_ls"] = p["l0_raw_ls"] + 0.2 * torch.randn(2, generator=g, dtype=dt)
+    p["k_raw_os"] = torch.tensor(0.3, dtype=dt)
+    p["raw_noise"] = torch.tensor([-1.0], dtype=dt)
+    p["noise_kernel_raw_os"] = torch.tensor(-0.5, dtype=dt)
+    return dict(x=x, y=y, ext=ext, z=z), p
+
+
+def oracle_vcmp(inp, p, lbda, num_data, beta=1.0, mean_const=None):
+    """FP64 CPU oracle of one minibatch: -ELBO, its gradients, q(f) mean / variance."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    if mean_const is not None:
+        leaves["mean_const"] = torch.tensor([mean_const], dtype=torch.float64, requires_grad=True)
+    x, y, ext, z = inp["x"], inp["y"], inp["ext"], inp["z"]
+    if mean_const is None:
+        loss = port.vcmp_loss(leaves, x, ext, y, z, lbda, num_data, beta)
+    else:
+        k, l = port.vcmp_specs(leaves, ext.shape[1])
+        mu_x = leaves["mean_const"].expand(x.shape[0])
+        mu_q, Sigma_q = R.svgp_q(k, leaves["Z"], x, leaves["var_mean"], leaves["chol_var"], mu_x=mu_x)
+        Rt, B = R.elbo_computation_parameters(l, y, ext, lbda)
+        ell = R.cmp_ell_with_noise(z, mu_q, Sigma_q, Rt, B, softplus(leaves["noise_kernel_raw_os"]), leaves["raw_noise"])
+        loss = -R.bag_elbo(ell, R.whitened_kl(leaves["var_mean"], leaves["chol_var"]), z.numel(), num_data, beta)
+    loss.backward()
+    with torch.no_grad():
+        k, _ = port.vcmp_specs(p, ext.shape[1])
+        mu_x = None if mean_const is None else torch.full((x.shape[0],), mean_const, dtype=torch.float64)
+        mu_q, Sigma_q = R.svgp_q(k, p["Z"], x, p["var_mean"], p["chol_var"], mu_x=mu_x)
+        kl = R.whitened_kl(p["var_mean"], p["chol_var"])
+    return dict(loss=loss.detach(), grads={k: v.grad for k, v in leaves.items()}, q_mean=mu_q, q_var=Sigma_q.diagonal().clone(),
+                kl=kl)
+
+
+def gpu_vcmp(inp, p, lbda, num_data, dtype, beta=1.0, mean_const=None):
+    from deconditional_downscaling_b200 import kernels as K, likelihoods as L, means as Mn, mlls as E, models as M
+    d, r, Mz = inp["x"].shape[1], inp["ext"].shape[1], p["Z"].shape[0]
+    k = K.ScaleKernel(K.RBFKernel(ard_num_dims=d))
+    l = K.ScaleKernel(K.MaternKernel(nu=1.5, ard_num_dims=2, active_dims=[0, 1])) + \
+        K.ScaleKernel(K.RBFKernel(ard_num_dims=r - 2, active_dims=list(range(2, r))))
+    mean = Mn.ZeroMean() if mean_const is None else Mn.ConstantMean()
+    model = M.VariationalCMP(inducing_points=p["Z"].clone(), individuals_mean=mean, individuals_kernel=k, bag_kernel=l,
+                             lbda=lbda, use_individuals_noise=True)
+    lik = L.CMPLikelihood(use_individuals_noise=True)
+    model, lik = model.to(DEV).to(dtype), lik.to(DEV).to(dtype)
+    vd = model.variational_strategy._variational_distribution
+    names = {
+        "Z": model.variational_strategy.inducing_points, "var_mean": vd.variational_mean, "chol_var": vd.chol_variational_covar,
+        "k_raw_ls": k.base_kernel.raw_lengthscale, "k_raw_os": k.raw_outputscale,
+        "l0_raw_ls": l.kernels[0].base_kernel.raw_lengthscale, "l0_raw_os": l.kernels[0].raw_outputscale,
+        "l1_raw_ls": l.kernels[1].base_kernel.raw_lengthscale, "l1_raw_os": l.kernels[1].raw_outputscale,
+        "raw_noise": lik.noise_covar.raw_noise, "noise_kernel_raw_os": model.noise_kernel.raw_outputscale,
+    }
+    if mean_const is not None:
+        names["mean_const"] = mean.constant
+    with torch.no_grad():
+        for key, prm in names.items():
+            src = torch.tensor([mean_const]) if key == "mean_const" else p[key]
+            prm.copy_(src.reshape(prm.shape).to(prm))
+    model.variational_strategy.variational_params_initialized.fill_(1)
+    model.train()
+    lik.train()
+    to = lambda t: t.to(device=DEV, dtype=dtype)
+    elbo = E.BagVariationalELBO(lik, model, num_data=num_data, beta=beta)
+    q = model(to(inp["x"]))
+    kw = model.get_elbo_computation_parameters(bags_values=to(inp["y"]), extended_bags_values=to(inp["ext"]))
+    loss = -elbo(variational_dist_f=q, target=to(inp["z"]), **kw)
+    loss.backward()
+    with torch.no_grad():
+        q2 = model(to(inp["x"]))
+        out = dict(loss=loss.detach(), q_mean=q2.mean.clone(), q_var=q2.variance.clone(),
+                   kl=model.variational_strategy.kl_divergence().detach(),
+                   grads={key: (prm.grad if prm.grad is not None else torch.zeros_like(prm)) for key, prm in names.items()})
+    torch.cuda.synchronize()
+    return out
+
+
+def report(tag, got, ref):
+    lines = [f"{tag}: loss {rel(got['loss'], ref['loss']):.2e}  q_mean {rel(got['q_mean'], ref['q_mean']):.2e}  "
+             f"q_var {rel(got['q_var'], ref['q_var']):.2e} (max {maxrel(got['q_var'], ref['q_var']):.2e})  kl {rel(got['kl'], ref['kl']):.2e}"]
+    for key in sorted(ref["grads"]):
+        lines.append(f"    grad {key:22s} rel {rel(got['grads'][key], ref['grads'][key]):.2e}  |ref| {ref['grads'][key].norm().item():.3e}")
+    print("\n".join(lines))
+
+
+# per-tensor normwise gradient bounds of the FP32 / TF32 path (single-pass TF32 products carry 2^-11 = 4.9e-4 per
+# operand; 3xTF32 factorisations and solves; measured values are printed by `report`)
+GRAD_TOL_F32 = 3e-3
+
+
+@pytest.fixture(scope="module")
+def config5():
+    inp, p = vcmp_inputs(Nb=8192, nb=1024, M=1024)
+    return inp, p, oracle_vcmp(inp, p, lbda=1e-4, num_data=10240)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_variational_cmp_config5_minibatch_matches_fp64_oracle(config5, dtype):
+    inp, p, ref = config5
+    got = gpu_vcmp(inp, p, lbda=1e-4, num_data=10240, dtype=dtype)
+    report(f"config5 {dtype}", got, ref)
+    tol = 1e-6 if dtype == torch.float64 else 1e-3
+    assert rel(got["loss"], ref["loss"]) < tol
+    assert rel(got["kl"], ref["kl"]) < tol
+    assert rel(got["q_mean"], ref["q_mean"]) < tol
+    assert rel(got["q_var"], ref["q_var"]) < tol
+    assert maxrel(got["q_var"], ref["q_var"]) < (1e-6 if dtype == torch.float64 else 2e-3)
+    gtol = 1e-6 if dtype == torch.float64 else GRAD_TOL_F32
+    for key, g in ref["grads"].items():
+        assert rel(got["grads"][key], g) < gtol, f"gradient of {key}: {rel(got['grads'][key], g):.3e}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_variational_cmp_with_constant_mean_matches_fp64_oracle(dtype):
+    """individuals_mean = ConstantMean(0.3): mu(x) enters q(f).mean (variational_strategy.py:47-52) and the
+    residual z - A^T mu_q (cmp_likelihood.py:70); its gradient is checked too."""
+    inp, p = vcmp_inputs(Nb=2048, nb=256, M=256, seed=21)
+    ref = oracle_vcmp(inp, p, lbda=1e-3, num_data=2560, mean_const=0.3)
+    got = gpu_vcmp(inp, p, lbda=1e-3, num_data=2560, dtype=dtype, mean_const=0.3)
+    report(f"constant-mean {dtype}", got, ref)
+    tol = 1e-6 if dtype == torch.float64 else 1e-3
+    assert rel(got["loss"], ref["loss"]) < tol
+    assert rel(got["q_mean"], ref["q_mean"]) < tol
+    assert rel(got["q_var"], ref["q_var"]) < tol
+    gtol = 1e-6 if dtype == torch.float64 else GRAD_TOL_F32
+    for key, g in ref["grads"].items():
+        assert rel(got["grads"][key], g) < gtol, f"gradient of {key}: {rel(got['grads'][key], g):.3e}"
+
+
+# ------------------------------------------------------------------------------------------ ExactCMP, config 1
+def swiss_roll_like(N=5000, n=50, seed=42):
+    """Swiss-roll-shaped synthetic set of the reference's size (experiments/swiss_roll/config/exact_cmp.yaml:
+    N = 5000 individuals in n = 50 bags along the height, d = 3, r = 1), standardised like generation.py:15-58."""
+    g = torch.Generator().manual_seed(seed)
+    dt = torch.float64
+    t = 1.5 * math.pi * (1 + 2 * torch.rand(N, generator=g, dtype=dt))
+    h = 21 * torch.rand(N, generator=g, dtype=dt)
+    x = torch.stack([t * torch.cos(t), h, t * torch.sin(t)], 1)
+    x = (x - x.mean(0)) / x.std(0)
+    order = x[:, 1].argsort()
+    x = x[order]
+    t = t[order]
+    bag = torch.arange(N) * n // N                          # contiguous height bags
+    yb = torch.stack([x[bag == a, 1].mean() for a in range(n)]).unsqueeze(-1)
+    ext = yb[bag] + 0.05 * torch.randn(N, 1, generator=g, dtype=dt)
+    z = torch.stack([torch.sin(t[bag == a]).mean() for a in range(n)]) + 0.05 * torch.randn(n, generator=g, dtype=dt)
+    xs = x[torch.randperm(N, generator=g)[:1000]].contiguous()
+    return x, ext, yb, z, xs
+
+
+EXACT_P = dict(k_raw_ls=torch.tensor([0.4, 0.7, 0.5], dtype=torch.float64), k_raw_os=torch.tensor(0.2, dtype=torch.float64),
+               l_raw_ls=torch.tensor([INV_SP1], dtype=torch.float64), l_raw_os=torch.tensor(0.1, dtype=torch.float64),
+               raw_noise=torch.tensor([-2.0], dtype=torch.float64), mean_const=torch.tensor([0.25], dtype=torch.float64))
+
+
+@pytest.fixture(scope="module")
+def config1():
+    torch.set_num_threads(os.cpu_count() or 1)
+    x, ext, yb, z, xs = swiss_roll_like()
+    lbda = 0.01
+    leaves = {k: v.clone().requires_grad_(True) for k, v in EXACT_P.items()}
+    k = R.KernelSpec([R.Component("rbf", leaves["k_raw_ls"], leaves["k_raw_os"], None)])
+    l = R.KernelSpec([R.Component("rbf", leaves["l_raw_ls"], leaves["l_raw_os"], None)])
+    N = x.shape[0]
+    mu = leaves["mean_const"].expand(N)
+    # the epoch >= 2 fit step: gradient flows through Lambda^{-1} as well (src/models/cmp.py:70-85)
+    mu_, K, Rt = R.cmp_estimate_parameters(k, l, x, ext, lbda, mu=mu)
+    m, Q = R.cme_aggregate_prior(l, ext, yb, mu_, K, Rt)
+    loss = -R.exact_mll(m, Q, z, leaves["raw_noise"])
+    loss.backward()
+    with torch.no_grad():
+        noise = softplus(EXACT_P["raw_noise"]).reshape(()) + 1e-4
+        logdet = torch.linalg.slogdet(Q + noise * torch.eye(z.numel(), dtype=torch.float64))[1]
+        mean, cov = R.exact_cmp_posterior(k, l, x, ext, yb, z, xs, mu_, K, Rt, EXACT_P["raw_noise"],
+                                          mu_s=EXACT_P["mean_const"].expand(xs.shape[0]))
+    return dict(data=(x, ext, yb, z, xs), lbda=lbda, loss=loss.detach(), grads={k_: v.grad for k_, v in leaves.items()},
+                prior_mean=m.detach(), prior_covar=Q.detach(), logdet=logdet, post_mean=mean, post_var=cov.diagonal().clone())
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_exact_cmp_config1_fit_and_posterior_match_fp64_oracle(config1, dtype):
+    from deconditional_downscaling_b200 import functional as F, kernels as K, likelihoods as L, means as Mn, mlls as E, models as M
+    x, ext, yb, z, xs = config1["data"]
+    to = lambda t: t.to(device=DEV, dtype=dtype)
+    kern = K.ScaleKernel(K.RBFKernel(ard_num_dims=3))
+    bag = K.ScaleKernel(K.RBFKernel(ard_num_dims=1))
+    mean = Mn.ConstantMean()
+    model = M.ExactCMP(train_individuals=to(x), extended_train_bags=to(ext), train_bags=to(yb), train_aggregate_targets=to(z),
+                       individuals_mean=mean, individuals_kernel=kern, bag_kernel=bag, lbda=config1["lbda"],
+                       likelihood=L.GaussianLikelihood(), use_individuals_noise=False).to(DEV).to(dtype)
+    names = {"k_raw_ls": kern.base_kernel.raw_lengthscale, "k_raw_os": kern.raw_outputscale,
+             "l_raw_ls": bag.base_kernel.raw_lengthscale, "l_raw_os": bag.raw_outputscale,
+             "raw_noise": model.likelihood.noise_covar.raw_noise, "mean_const": mean.constant}
+    with torch.no_grad():
+        for key, prm in names.items():
+            prm.copy_(EXACT_P[key].reshape(prm.shape).to(prm))
+    model.train()
+    mll = E.ExactMarginalLogLikelihood(model.likelihood, model)
+    model.update_cmp_estimate_parameters()
+    out = model(model.train_bags)
+    loss = -mll(out, model.train_aggregate_targets)
+    loss.backward()
+    tol = 1e-6 if dtype == torch.float64 else 1e-3
+    errs = {"loss": rel(loss, config1["loss"]), "prior_mean": rel(out.mean, config1["prior_mean"]),
+            "prior_covar": rel(out.covariance_matrix, config1["prior_covar"])}
+    with torch.no_grad():
+        n = z.numel()
+        C = out.covariance_matrix.detach() + model.likelihood.noise.to(dtype) * torch.eye(n, dtype=dtype, device=DEV)
+        logdet = F.logdet_from_chol(F.psd_safe_cholesky(C))
+        errs["logdet"] = rel(logdet, config1["logdet"])
+    grads = {key: (prm.grad.clone() if prm.grad is not None else torch.zeros_like(prm)) for key, prm in names.items()}
+    model.zero_grad()
+    model.update_cmp_estimate_parameters()
+    with torch.no_grad():
+        post = model.predict(to(xs))
+        errs["post_mean"] = rel(post.mean, config1["post_mean"])
+        errs["post_var"] = rel(post.variance, config1["post_var"])
+        errs["post_var_max"] = maxrel(post.variance, config1["post_var"])
+    gerr = {key: rel(grads[key], config1["grads"][key]) for key in names}
+    print(f"config1 {dtype}: " + "  ".join(f"{k_} {v:.2e}" for k_, v in errs.items()))
+    print("    grads: " + "  ".join(f"{k_} {v:.2e}" for k_, v in gerr.items()))
+    for key in ("loss", "prior_mean", "prior_covar", "logdet", "post_mean", "post_var"):
+        assert errs[key] < tol, f"{key}: {errs[key]:.3e}"
+    gtol = 1e-6 if dtype == torch.float64 else GRAD_TOL_F32
+    for key, e in gerr.items():
+        assert e < gtol, f"gradient of {key}: {e:.3e}"
