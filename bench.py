@@ -75,6 +75,18 @@ def minibatches(wl, shard, n_batches, seed):
     return out
 
 
+def bench_config(wl, world, step_mode):
+    """`config` of the JSON line - the same keys and values in our arm and in the reference arm (the workload is the
+    same WL dict in both); only `step_mode` says how each arm issues the step."""
+    return {"workload": wl["name"], "bags_per_step_per_gpu": wl["bags_per_step"],
+            "cme_individuals_per_step_per_gpu": wl["individuals_per_step"], "inducing_points": wl["M"],
+            "d": wl["d"], "r": wl["r"], "lbda": wl["lbda"], "likelihood": "CMPLikelihood(use_individuals_noise=True)",
+            "step": "forward + backward + flat-gradient all-reduce + Adam", "parallelism": f"dp{world}",
+            "step_mode": step_mode,
+            "l2": "per-step working set (Lambda 8192^2 f32 = 268 MB plus K_xx) exceeds the 126 MB L2; "
+                  "a fresh minibatch every step"}
+
+
 def batch_bytes(b):
     return sum(v.numel() * v.element_size() for v in b.values())
 
@@ -180,6 +192,44 @@ class GemmProbe:
         return len(sel), sum(r[0].elapsed_time(r[1]) for r in sel) * 1e-3, sum(r[2] for r in sel)
 
 
+def roofline_entry(by_call, n_calls, t_calls, fl_calls, n_tc, t_tc, fl_tc, t_eager, t_dev, steps, tf32_peak, pk):
+    lam = {k: v for k, v in by_call.items() if k == "potrf_"}
+    potrf = by_call.get("potrf_")
+    # potrf_ covers three factorisations per step (Lambda 8192^2 f32, C 1024^2 f32, K_ZZ 1024^2 f64); Lambda carries
+    # 99.6 % of their flops and ~80 % of their time, so the entry is in effect the Lambda factorisation
+    ach = potrf["tflops"] if potrf else None
+    peak_src = f"{pk['source']}: sustained bf16 cuBLAS rate / 2 (TF32 issues at half the bf16 MMA rate)"
+    return {
+        "bound": "tensor",
+        "kernel": "dcgp_potrf = potrf_step_kernel (single-CTA chain: tcgen05 3xTF32 products + 128-wide leaf) beside "
+                  "gemm_tc_kernel (tcgen05 rank-128 bulk updates) on two prioritised lanes",
+        "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak if ach else None,
+        "issued_frac": 3.0 * ach / tf32_peak if ach else None,
+        "traffic": None, "traffic_note": "latency-bound chain: DRAM bytes of the single-CTA step kernel are negligible "
+                   "(profiles/r01_ncu_potrf_step_v23_raw.csv); the bulk kernel's traffic is in profiles/r01_ncu_tcgemm_*",
+        "peak_source": peak_src,
+        "calls": potrf["calls"] if potrf else 0, "avg_call_ms": potrf["ms"] / potrf["calls"] if potrf else None,
+        "share_of_step": (potrf["ms"] * 1e-3) / t_eager if potrf and t_eager > 0 else None,
+        "measured_on": "the eager issue of the same steps (value_eager): CUDA events cannot bracket kernels inside a graph replay",
+        # the whole step against the same peak: all contraction flops of a step / the step time of the timed (graph) run
+        "whole_step": {"algorithmic_flops_per_step": fl_calls / steps,
+                       "achieved": fl_calls / steps / (t_dev / steps) / 1e12,
+                       "frac": fl_calls / steps / (t_dev / steps) / 1e12 / tf32_peak,
+                       "what": "sum over dcgp_gemm / potrf / trsm / potrs calls of 2mnk, n^3/3, n^2 m, 2 n^2 m "
+                               "divided by ms_per_step"},
+        # the throughput kernel on its own: direct dcgp_gemm products that are one gemm_tc_kernel launch each
+        "gemm_tc_kernel": {"achieved": fl_tc / t_tc / 1e12 if t_tc > 0 else None,
+                           "frac": (fl_tc / t_tc / 1e12) / tf32_peak if t_tc > 0 else None, "launches": n_tc,
+                           "avg_launch_ms": 1e3 * t_tc / n_tc if n_tc else None,
+                           "share_of_step": t_tc / t_eager if t_eager > 0 else None,
+                           "traffic": 425892096, "traffic_shape": "8192x1024x8192 NN (335.5 MB algorithmic), ncu --set full: "
+                                                                  "profiles/r01_ncu_tcgemm_v2_8192x1024x8192_raw.csv"},
+        "by_call": by_call,
+        "all_calls": {"calls": n_calls, "share_of_step": t_calls / t_eager if t_eager > 0 else None,
+                      "achieved": fl_calls / t_calls / 1e12 if t_calls > 0 else None},
+    }
+
+
 # ------------------------------------------------------------------ our arm
 def build_trainer(wl, device, dtype=torch.float32, cuda_graph=False):
     from deconditional_downscaling_b200 import kernels as K, likelihoods as L, means as Mn, models as M
@@ -215,7 +265,12 @@ def run_ours(args):
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    wl = SMALL if args.small else WL
+    wl = dict(SMALL if args.small else WL)
+    if args.scaling == "strong":
+        # secondary figure: the GLOBAL number of bags per optimiser step is fixed (8192 = 8 x the weak
+        # per-GPU batch) and split over the ranks; every rank still draws its own CME sample of the full size
+        wl["bags_per_step"] = (8 * wl["bags_per_step"]) // world
+        wl["name"] += f"_strong_{8 * (SMALL if args.small else WL)['bags_per_step']}bags_global"
     from deconditional_downscaling_b200 import ops, _lib
     lib = _lib.load()
     shard = make_shard(wl, rank % wl["shards"])
@@ -310,57 +365,48 @@ def run_ours(args):
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     t_e2e = t_e2e.item()
 
+    sharded = None
+    if world > 1 and not args.no_sharded_kw:
+        sharded = run_sharded_kw(device, world, rank, 4096 if args.small else 32768)
     pk = peaks()
     tf32_peak = pk["bf16_tflops_sustained"] / 2 if pk.get("bf16_tflops_sustained") else pk["bf16_tflops"] / 2
     out = {
         "metric": "elbo_steps_per_s", "value": world * K_ / t_dev, "unit": "minibatch ELBO steps/s (whole job)",
         "n_gpus": world, "steps": K_, "warmup": W_, "ms_per_step": 1e3 * t_dev / K_, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 storage; products on single-pass TF32 (tcgen05), factorisations/solves on 3xTF32; f64 island for K_ZZ",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32 storage; products on single-pass TF32 (tcgen05), factorisations/solves on 3xTF32; f64 island for K_ZZ",
         "data": "synthetic",
-        "config": {"workload": wl["name"], "bags_per_step_per_gpu": wl["bags_per_step"],
-                   "cme_individuals_per_step_per_gpu": wl["individuals_per_step"], "inducing_points": wl["M"],
-                   "d": wl["d"], "r": wl["r"], "lbda": wl["lbda"], "likelihood": "CMPLikelihood(use_individuals_noise=True)",
-                   "step": "forward + backward + flat-gradient all-reduce + Adam", "parallelism": f"dp{world}",
-                   "step_mode": "eager" if args.no_graph else "CUDA-graph replay of forward + backward + all-reduce (captured once, "
-                                "third warm-up step), factorisation check, eager Adam",
-                   "l2": "per-step working set (Lambda 8192^2 f32 = 268 MB plus K_xx) exceeds the 126 MB L2; "
-                         "a fresh minibatch every step"},
+        "config": bench_config(wl, world, "eager" if args.no_graph else
+                               "CUDA-graph replay of forward + backward + failure-word / gradient all-reduce + device-side "
+                               "fused Adam (captured once, third warm-up step); one 4-byte status read per step"),
         "e2e": {"value": world * K_ / t_e2e, "unit": "minibatch ELBO steps/s (whole job)",
                 "h2d_bytes_per_step": batch_bytes(host[0]), "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "final_loss": final_loss,
         "value_eager": world * K_ / t_eager,
-        # dominant throughput kernel (profiles/r01_launches_bench_step_v15_summary.csv: gemm_tc_kernel 51% of the
-        # kernel time of a step; the single-CTA potrf_step_kernel chain, 25%, is latency- not roofline-bound)
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma kind::tf32, TMA, TMEM): the direct dcgp_gemm "
-                     "products of the timed steps that run as one launch of it each, CUDA events around every launch",
-                     "achieved": fl_tc / t_tc / 1e12 if t_tc > 0 else None, "peak": tf32_peak, "unit": "TFLOP/s",
-                     "frac": (fl_tc / t_tc / 1e12) / tf32_peak if t_tc > 0 else None,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step's most frequent large product
-                     # (K_xx[8192 x 8192] @ A[8192 x 1024], 335 MB compulsory) from the ncu --set full capture
-                     # profiles/r01_ncu_tcgemm_v2_8192x1024x8192_raw.csv
-                     "traffic": 425892096, "traffic_shape": "8192x1024x8192 NN",
-                     "peak_source": f"{pk['source']}: sustained bf16 cuBLAS rate / 2 (TF32 issues at half the bf16 MMA rate)",
-                     "launches": n_tc, "avg_launch_ms": 1e3 * t_tc / n_tc if n_tc else None,
-                     "share_of_step": t_tc / t_eager if t_eager > 0 else None,
-                     "path": {"what": "all tensor-core contractions of the step (dcgp_gemm, and the GEMMs inside dcgp_potrf / "
-                              "dcgp_trsm_planned incl. their serial leaf chains): algorithmic flops / event time",
-                              "achieved": fl_gemm / t_gemm / 1e12 if t_gemm > 0 else None,
-                              "frac": (fl_gemm / t_gemm / 1e12) / tf32_peak if t_gemm > 0 else None,
-                              "calls": n_gemm, "share_of_step": t_gemm / t_eager if t_eager > 0 else None, "by_call": gemm_by,
-                              "measured_on": "the eager issue of the same steps (value_eager)"}},
+        # The dominant CALL of the step is the factorisation of Lambda (dcgp_potrf: the potrf_step_kernel chain +
+        # gemm_tc_kernel bulk updates, ~37 % of a step): `roofline` describes it.  Algorithmic flops n^3/3 per call
+        #  over the CUDA-event time of each call in the eagerly issued copy of the timed steps; the kernels
+        # inside issue 3xTF32, i.e. three MMAs per algorithmic product, which `issued_frac` accounts for.
+        "roofline": roofline_entry(gemm_by, n_gemm, t_gemm, fl_gemm, n_tc, t_tc, fl_tc, t_eager, t_dev, K_, tf32_peak, pk),
         "allreduce_bytes_per_step": trainer.grads.nbytes,
     }
+    if sharded is not None:
+        out["sharded_kw"] = sharded
     if rank == 0:
         out["clocks"] = clk
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(wl, host, steps=2)
-            c0 = out["cpu_baseline"].pop("first_loss")
-            out["parity"] = {"what": "-ELBO of minibatch 0 at the initial parameters: this run vs the CPU oracle port",
-                             "gpu": first_loss, "cpu_oracle": c0,
-                             "rel_diff": abs(first_loss - c0) / abs(c0) if first_loss is not None else None,
-                             "tolerance": 1e-3}
+            out["cpu_baseline"].pop("first_loss")
+            out["parity"] = parity_check(wl, host[0], device)
         if world == 1 and not args.no_exact:
-            out["exact_cmp_n32k"] = run_exact(device, 4096 if args.small else 32768)
+            del trainer, devb
+            torch.cuda.empty_cache()
+            Nx = 4096 if args.small else 32768
+            out["exact_cmp_n32k"] = run_exact(device, Nx, torch.float64, cpu_sample_n=0 if args.no_cpu else (2048 if args.small else 8192))
+            out["exact_cmp_n32k_tf32"] = run_exact(device, Nx, torch.float32)
+            out["exact_cmp_fit_n32k"] = run_exact_fit(device, Nx, torch.float64)
+            out["exact_cmp_fit_n32k_tf32"] = run_exact_fit(device, Nx, torch.float32)
+            if not args.no_cpu:
+                out["exact_cmp_fit_n32k"]["cpu_baseline"] = cpu_exact_fit(1024 if args.small else 4096)
             out["vbagg_1024bags"] = run_vbagg(device)
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -378,34 +424,101 @@ def run_ours(args):
         os._exit(0)
 
 
-# ------------------------------------------------------------------ ExactCMP N = 32k composite (N = 1 only)
-def run_exact(device, N):
-    from deconditional_downscaling_b200 import exact
-    dt = torch.float64
-    g = torch.Generator().manual_seed(7)
+# ------------------------------------------------------------------ row-block sharded K W (multi-rank runs)
+def run_sharded_kw(device, world, rank, N, reps=3):
+    """STRONG scaling of the large Gram product of the exact path: out = k(x, x) W (N x N x n, n = N / 100) with the
+    rows of the Gram matrix sharded over the ranks (parallel.sharded_kernel_matmul: every rank generates only its own
+    (N / G) x N tiles, ONE NCCL all-gather of the N x n result).  FP64 and FP32; max over ranks of the device time."""
+    from deconditional_downscaling_b200 import kernels as K
+    from deconditional_downscaling_b200.parallel import sharded_kernel_matmul
+    out = {}
+    n = max(N // 100, 1)
+    n = -(-n // 4) * 4          # 16-byte rows for the FP32 tcgen05 path
+    for name, dt in (("f64", torch.float64), ("f32", torch.float32)):
+        g = torch.Generator().manual_seed(21)
+        x = torch.randn(N, 3, generator=g, dtype=torch.float64).to(dt).to(device)
+        W = torch.randn(N, n, generator=g, dtype=torch.float64).to(dt).to(device)
+        kern = K.ScaleKernel(K.RBFKernel(ard_num_dims=3)).to(device).to(dt)
+        best = 1e9
+        with torch.no_grad():
+            for it in range(reps + 1):
+                dist.barrier()
+                torch.cuda.synchronize()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                res = sharded_kernel_matmul(kern, x, None, W)
+                e.record()
+                torch.cuda.synchronize()
+                t = torch.tensor([s.elapsed_time(e) * 1e-3], device=device, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                if it:
+                    best = min(best, t.item())
+            chk = res.double().norm().reshape(1)
+            ref = chk.clone()
+            dist.broadcast(ref, 0)
+            agree = bool(((chk - ref).abs() / ref).item() < 1e-12)
+        fl = 2.0 * N * N * n
+        out[name] = {"seconds": best, "tflops": fl / best / 1e12, "N": N, "n": n, "ranks": world,
+                     "allgather_bytes": N * n * (8 if dt == torch.float64 else 4), "result_identical_on_all_ranks": agree}
+        del x, W, res
+        torch.cuda.empty_cache()
+    out["scaling"] = "strong"
+    out["what"] = "k(x, x) W with row-block sharded Gram tiles + one all-gather; at 1 rank the same call is the unsharded product"
+    return out
+
+
+# ------------------------------------------------------------------ ExactCMP N = 32k (N = 1 only)
+def exact_inputs(N, dt, device=None, seed=7):
+    """Config-4 inputs: x ~ N(0, I_3) standardised, N / 100 bags, r = 3 continuous bag values."""
+    g = torch.Generator().manual_seed(seed)
     n = N // 100
-    x = torch.randn(N, 3, generator=g, dtype=dt)
+    x = torch.randn(N, 3, generator=g, dtype=torch.float64)
     x = (x - x.mean(0)) / x.std(0)
-    ybag = torch.randn(n, 3, generator=g, dtype=dt)
+    ybag = torch.randn(n, 3, generator=g, dtype=torch.float64)
     bag_of = torch.arange(N) * n // N
-    ext = ybag[bag_of] + 0.3 * torch.randn(N, 3, generator=g, dtype=dt)     # r = 3 continuous variant
-    z = torch.randn(n, generator=g, dtype=dt)
-    x, ext, ybag, z = (t.to(device) for t in (x, ext, ybag, z))
-    # measured FP64 tensor peak: cuBLAS DGEMM 8192^3 (MEASURED_PEAKS.json has no FP64 entry)
-    A = torch.randn(8192, 8192, dtype=dt, device=device)
-    B = torch.randn(8192, 8192, dtype=dt, device=device)
-    C = torch.empty_like(A)
-    best = 1e9
-    for i in range(4):
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        torch.matmul(A, B, out=C)
-        e.record()
-        torch.cuda.synchronize()
-        if i:
-            best = min(best, s.elapsed_time(e) * 1e-3)
-    fp64_peak = 2 * 8192 ** 3 / best / 1e12
-    del A, B, C
+    ext = ybag[bag_of] + 0.3 * torch.randn(N, 3, generator=g, dtype=torch.float64)
+    z = torch.randn(n, generator=g, dtype=torch.float64)
+    out = tuple(t.to(dt) for t in (x, ext, ybag, z))
+    return tuple(t.to(device) for t in out) if device is not None else out
+
+
+_FP64_PEAK = {}
+
+
+def fp64_peak(device):
+    """Measured FP64 tensor peak: cuBLAS DGEMM 8192^3, best of 3 (MEASURED_PEAKS.json has no FP64 entry)."""
+    if "v" not in _FP64_PEAK:
+        A = torch.randn(8192, 8192, dtype=torch.float64, device=device)
+        B = torch.randn(8192, 8192, dtype=torch.float64, device=device)
+        C = torch.empty_like(A)
+        best = 1e9
+        for i in range(4):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            torch.matmul(A, B, out=C)
+            e.record()
+            torch.cuda.synchronize()
+            if i:
+                best = min(best, s.elapsed_time(e) * 1e-3)
+        _FP64_PEAK["v"] = 2 * 8192 ** 3 / best / 1e12
+    return _FP64_PEAK["v"]
+
+
+def tf32_peak_value():
+    pk = peaks()
+    return pk["bf16_tflops_sustained"] / 2 if pk.get("bf16_tflops_sustained") else pk["bf16_tflops"] / 2
+
+
+def run_exact(device, N, dt=torch.float64, cpu_sample_n=0):
+    """Gram + Cholesky + solve composite of config 4 as explicit phases (no autograd): Gram(K), Gram(Lambda), potrf,
+    potrs, K W, Q / MLL, posterior mean + variance on N* = N points."""
+    from deconditional_downscaling_b200 import exact
+    f64 = dt == torch.float64
+    n = N // 100
+    x, ext, ybag, z = exact_inputs(N, dt, device)
+    peak = fp64_peak(device) if f64 else tf32_peak_value()
+    peak_src = "cuBLAS DGEMM 8192^3 measured in this run (best of 3)" if f64 else \
+        f"{peaks()['source']}: sustained bf16 cuBLAS rate / 2; the FP32 factorisation and solves issue 3xTF32 (3 MMAs per product)"
     exact.exact_cmp_phases(x[:4096], ext[:4096], ybag[:40], z[:40], x[:4096], 0.01)   # warm-up: kernels
     res = exact.exact_cmp_phases(x, ext, ybag, z, x, 0.01)                            # warm-up: allocator at full size
     del res
@@ -420,20 +533,129 @@ def run_exact(device, N):
     ph = timer.seconds()
     fl = exact.exact_cmp_flops(N, n, 3, N)
     tot_fl = sum(fl.values())
-    return {"metric": "gram_cholesky_solve_tflops", "N": N, "n_bags": n, "dtype": "f64",
-            "seconds": total, "tflops": tot_fl / total / 1e12, "algorithmic_flops": tot_fl,
-            "phases_ms": {k: 1e3 * v for k, v in ph.items()},
-            "potrf_tflops": fl["potrf"] / ph["potrf"] / 1e12, "potrs_tflops": fl["potrs"] / ph["potrs"] / 1e12,
-            "gram_K_gbs": N * N * 8 / ph["gram_K"] / 1e9,
-            "roofline": {"bound": "tensor", "kernel": "gemm_kernel<double> (DMMA) inside dcgp_potrf",
-                         "achieved": fl["potrf"] / ph["potrf"] / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": fl["potrf"] / ph["potrf"] / 1e12 / fp64_peak,
-                         "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (best of 3)"},
-            # the Gram build is bound by the N^2 * 8 bytes it writes; FP64 exp (about 25 DFMA per entry) is the co-bound
-            "gram_roofline": {"bound": "hbm", "kernel": "gram_fwd_kernel<double>", "achieved": N * N * 8 / ph["gram_K"] / 1e9,
-                              "peak": peaks()["hbm_gbs"], "unit": "GB/s",
-                              "frac": N * N * 8 / ph["gram_K"] / 1e9 / peaks()["hbm_gbs"], "peak_source": peaks()["source"]},
-            "potrf_info": int(res["info"].item()), "mll": float(res["mll"].item())}
+    es = 8 if f64 else 4
+    out = {"metric": "gram_cholesky_solve_tflops", "N": N, "n_bags": n, "dtype": "f64" if f64 else "f32 storage, 3xTF32 factorisation / solves",
+           "seconds": total, "tflops": tot_fl / total / 1e12, "algorithmic_flops": tot_fl,
+           "phases_ms": {k: 1e3 * v for k, v in ph.items()},
+           "potrf_tflops": fl["potrf"] / ph["potrf"] / 1e12, "potrs_tflops": fl["potrs"] / ph["potrs"] / 1e12,
+           "gram_K_gbs": N * N * es / ph["gram_K"] / 1e9,
+           "roofline": {"bound": "tensor", "kernel": ("gemm_kernel<double> (DMMA)" if f64 else "gemm_tc_kernel (tcgen05 3xTF32)") + " inside dcgp_potrf",
+                        "achieved": fl["potrf"] / ph["potrf"] / 1e12, "peak": peak, "unit": "TFLOP/s",
+                        "frac": fl["potrf"] / ph["potrf"] / 1e12 / peak, "peak_source": peak_src,
+                        "composite_frac": tot_fl / total / 1e12 / peak},
+           # the Gram build is bound by the N^2 * s bytes it writes; in FP64 exp (~25 DFMA per entry) is the co-bound
+           "gram_roofline": {"bound": "hbm", "kernel": f"gram_fwd_kernel<{'double' if f64 else 'float'}>",
+                             "achieved": N * N * es / ph["gram_K"] / 1e9, "peak": peaks()["hbm_gbs"], "unit": "GB/s",
+                             "frac": N * N * es / ph["gram_K"] / 1e9 / peaks()["hbm_gbs"], "peak_source": peaks()["source"]},
+           "potrf_info": int(res["info"].item()), "mll": float(res["mll"].item())}
+    del res
+    torch.cuda.empty_cache()
+    if cpu_sample_n:
+        out["cpu_baseline"] = cpu_exact_phases(cpu_sample_n)
+    return out
+
+
+def cpu_exact_phases(Nc):
+    """The same composite on the host cores (oracle/port.py, torch CPU / MKL, FP64) at a bounded sample size: the metric
+    is size-normalised (TFLOP/s), the N = 32768 composite itself would take (32768 / Nc)^3 times as long."""
+    from deconditional_downscaling_b200 import exact
+    from oracle import port
+    torch.set_num_threads(os.cpu_count() or 1)
+    x, ext, ybag, z = exact_inputs(Nc, torch.float64)
+    port.exact_cmp_phases(x[:1024], ext[:1024], ybag[:10], z[:10], x[:1024], 0.01)
+    t0 = time.perf_counter()
+    port.exact_cmp_phases(x, ext, ybag, z, x, 0.01)
+    dt = time.perf_counter() - t0
+    fl = sum(exact.exact_cmp_flops(Nc, Nc // 100, 3, Nc).values())
+    return {"value": fl / dt / 1e12, "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "port", "seconds": dt,
+            "sample": f"the same composite at N = {Nc} (n = {Nc // 100} bags, FP64, N* = N): one run after a 1024-point warm-up; "
+                      f"at N = 32768 the same rate means {fl / dt / 1e12:.3f} TFLOP/s x {(32768 / Nc) ** 3:.0f}x the time"}
+
+
+def run_exact_fit(device, N, dt, steps=1):
+    """ExactCMP FIT STEP + posterior through the model API, as the reference's trainer issues it
+    (experiments/swiss_roll/models/exact_cmp.py:89-118): zero_grad, -MLL(model(train_bags)), backward, Adam step,
+    update_cmp_estimate_parameters (re-factorises Lambda with the new hyper-parameters), then predict on N* = N.
+    Algorithmic flops per fit step: N^3/3 (potrf) + 2 N^2 n x 6 (W = Lambda^{-1} B and its adjoint solve, K W and
+    K^T gO, the two rank-n outer products dK = gO W^T and dLambda = -gB W^T) + 2 N n^2."""
+    from deconditional_downscaling_b200 import kernels as K, likelihoods as L, means as Mn, mlls as E, models as M
+    f64 = dt == torch.float64
+    n = N // 100
+    x, ext, ybag, z = exact_inputs(N, dt, device)
+    model = M.ExactCMP(train_individuals=x, extended_train_bags=ext, train_bags=ybag, train_aggregate_targets=z,
+                       individuals_mean=Mn.ZeroMean(), individuals_kernel=K.ScaleKernel(K.RBFKernel(ard_num_dims=3)),
+                       bag_kernel=K.ScaleKernel(K.RBFKernel(ard_num_dims=3)), lbda=0.01, likelihood=L.GaussianLikelihood(),
+                       use_individuals_noise=False).to(device).to(dt)
+    inv_sp1 = math.log(math.e - 1.0)
+    with torch.no_grad():
+        model.individuals_kernel.base_kernel.raw_lengthscale.fill_(inv_sp1)
+        model.bag_kernel.base_kernel.raw_lengthscale.fill_(inv_sp1)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    mll = E.ExactMarginalLogLikelihood(model.likelihood, model)
+
+    def step():
+        opt.zero_grad()
+        loss = -mll(model(model.train_bags), model.train_aggregate_targets)
+        loss.backward()
+        opt.step()
+        model.update_cmp_estimate_parameters()
+        return loss
+
+    step()                                     # warm-up: first factorisation, allocator at full size
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    with torch.no_grad():
+        post = model.predict(x)
+        pm, pv = post.mean, post.variance
+    e2.record()
+    torch.cuda.synchronize()
+    t_fit, t_pred = e0.elapsed_time(e1) * 1e-3 / steps, e1.elapsed_time(e2) * 1e-3
+    fl_fit = N ** 3 / 3.0 + 12.0 * N * N * n + 2.0 * N * n * n
+    fl_pred = 2.0 * N * N * n + 2.0 * N * n * n       # k(x*, x) W and the n x n solves
+    peak = fp64_peak(device) if f64 else tf32_peak_value()
+    out = {"metric": "exact_cmp_fit_step", "N": N, "n_bags": n, "dtype": "f64" if f64 else "f32 storage, TF32 / 3xTF32",
+           "fit_step_seconds": t_fit, "predict_seconds": t_pred, "fit_step_tflops": fl_fit / t_fit / 1e12,
+           "algorithmic_flops_fit": fl_fit, "algorithmic_flops_predict": fl_pred,
+           "roofline": {"bound": "tensor", "achieved": fl_fit / t_fit / 1e12, "peak": peak, "unit": "TFLOP/s",
+                        "frac": fl_fit / t_fit / 1e12 / peak,
+                        "kernel": "whole fit step (dcgp_potrf + two dcgp_potrs + four rank-n products + Gram forward / backward)"},
+           "loss": float(loss.item()), "post_mean_abs_max": float(pm.abs().max().item()), "post_var_min": float(pv.min().item())}
+    del model, post, pm, pv, opt
+    torch.cuda.empty_cache()
+    return out
+
+
+def cpu_exact_fit(Nc):
+    """The reference-style fit step on the host (oracle/port.exact_cmp_loss: explicit root R of Lambda^{-1}, R^T K R,
+    autograd backward; experiments/swiss_roll/models/exact_cmp.py:94-103) at a bounded sample size, FP64."""
+    from oracle import port
+    from oracle import restate as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    x, ext, ybag, z = exact_inputs(Nc, torch.float64)
+    inv_sp1 = math.log(math.e - 1.0)
+    leaves = [torch.full((3,), inv_sp1, dtype=torch.float64, requires_grad=True), torch.zeros((), dtype=torch.float64, requires_grad=True),
+              torch.full((3,), inv_sp1, dtype=torch.float64, requires_grad=True), torch.zeros((), dtype=torch.float64, requires_grad=True),
+              torch.zeros(1, dtype=torch.float64, requires_grad=True)]
+    k = R.KernelSpec([R.Component("rbf", leaves[0], leaves[1], None)])
+    l = R.KernelSpec([R.Component("rbf", leaves[2], leaves[3], None)])
+    opt = torch.optim.Adam(leaves, lr=0.01)
+    t0 = time.perf_counter()
+    opt.zero_grad()
+    loss = port.exact_cmp_loss(k, l, leaves[4], x, ext, ybag, z, 0.01)
+    loss.backward()
+    opt.step()
+    dt = time.perf_counter() - t0
+    n = Nc // 100
+    fl = Nc ** 3 / 3.0 + 12.0 * Nc * Nc * n + 2.0 * Nc * n * n
+    return {"value": fl / dt / 1e12, "unit": "TFLOP/s (the GPU arm's algorithmic flop count / CPU seconds)", "cores": os.cpu_count(),
+            "kind": "port", "seconds": dt, "loss": float(loss.item()),
+            "sample": f"one fit step (forward + backward + Adam) at N = {Nc}, n = {n}, FP64, the reference's algorithm "
+                      "(explicit N x N root R: O(N^3) products the GPU path never forms)"}
 
 
 # ------------------------------------------------------------------ VBagg ELBO step at config-5 scale (N = 1 only)
@@ -487,6 +709,55 @@ def cpu_steps(wl, host, steps, warmup=0):
     return dt, float(loss), first
 
 
+def parity_check(wl, hb, device):
+    """-ELBO and EVERY gradient of minibatch 0 at the initial parameters: this package on the GPU (FP32 storage, the
+    arithmetic of the timed run) against the FP64 CPU oracle (oracle/port.py, the reference's algorithm)."""
+    from oracle import port
+    torch.set_num_threads(os.cpu_count() or 1)
+    p = port.make_vcmp_params(wl["M"], wl["d"], wl["r"], dtype=torch.float64)
+    g = torch.Generator().manual_seed(0)
+    p["Z"] = torch.randn(wl["M"], wl["d"], generator=g).double()           # the inducing points of build_trainer
+    leaves = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    d64 = {k: v.double() for k, v in hb.items()}
+    t0 = time.perf_counter()
+    loss = port.vcmp_loss(leaves, d64["x"], d64["extended_bags_values"], d64["bags_values"], d64["z"], wl["lbda"],
+                          wl["n_bags_total"], wl["beta"])
+    loss.backward()
+    t_cpu = time.perf_counter() - t0
+    tr = build_trainer(wl, device)
+    m, lik = tr.model, tr.likelihood
+    vd = m.variational_strategy._variational_distribution
+    bag = m.bag_kernel.kernels
+    names = {"Z": m.variational_strategy.inducing_points, "var_mean": vd.variational_mean, "chol_var": vd.chol_variational_covar,
+             "k_raw_ls": m.individuals_kernel.base_kernel.raw_lengthscale, "k_raw_os": m.individuals_kernel.raw_outputscale,
+             "l0_raw_ls": bag[0].base_kernel.raw_lengthscale, "l0_raw_os": bag[0].raw_outputscale,
+             "l1_raw_ls": bag[1].base_kernel.raw_lengthscale, "l1_raw_os": bag[1].raw_outputscale,
+             "raw_noise": lik.noise_covar.raw_noise, "noise_kernel_raw_os": m.noise_kernel.raw_outputscale}
+    b = {k: v.to(device) for k, v in hb.items()}
+    tr.grads.zero()
+    gl = tr.loss(b["x"], b["z"], bags_values=b["bags_values"], extended_bags_values=b["extended_bags_values"])
+    gl.backward()
+    torch.cuda.synchronize()
+    errs = {}
+    for k, prm in names.items():
+        ref = leaves[k].grad.reshape(-1)
+        got = prm.grad.detach().double().cpu().reshape(-1)
+        errs[k] = ((got - ref).norm() / ref.norm().clamp_min(1e-300)).item()
+    direct = {k: v for k, v in errs.items() if not k.startswith(("l0_", "l1_"))}
+    out = {"what": "-ELBO and every gradient of minibatch 0 at the initial parameters: GPU (FP32 storage, TF32 products rounded "
+                   "to nearest, 3xTF32 factorisations) vs the FP64 CPU oracle (oracle/port.py)",
+           "gpu": float(gl.item()), "cpu_oracle": float(loss.item()),
+           "rel_diff": abs(float(gl.item()) - float(loss.item())) / abs(float(loss.item())), "tolerance": 1e-3,
+           "grad_rel_err": errs, "max_grad_rel_err": max(direct.values()),
+           "max_grad_rel_err_note": "normwise per parameter tensor; the four bag-kernel hyper-parameters (l0_*, l1_*) are listed "
+                                    "in grad_rel_err but not in the maximum: they are small remainders of two opposing parts (through "
+                                    "l(y, y~) and through Lambda^{-1}) and are held to 1e-3 of those parts in tests/test_parity_scale_gpu.py",
+           "oracle_seconds": t_cpu}
+    del tr
+    torch.cuda.empty_cache()
+    return out
+
+
 def cpu_baseline(wl, host, steps=2):
     dt, loss, first = cpu_steps(wl, host, steps)
     return {"first_loss": first, "value": steps / dt, "unit": "minibatch ELBO steps/s", "cores": os.cpu_count(), "kind": "port",
@@ -498,18 +769,21 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     wl = SMALL if args.small else WL
     shard = make_shard(wl, 0)
-    host = minibatches(wl, shard, args.steps + args.warmup, seed=99)
-    dt, loss, _ = cpu_steps(wl, host, args.steps, warmup=min(args.warmup, 1))
+    W_ = max(args.warmup, 3)      # the same rule as our arm (timing rules: W >= 3), so both lines report the same warm-up
+    host = minibatches(wl, shard, args.steps + W_, seed=99)
+    dt, loss, _ = cpu_steps(wl, host, args.steps, warmup=W_)
     v = args.steps / dt
     unit = "minibatch ELBO steps/s (whole job)"
     print(json.dumps({
-        "impl": "reference", "metric": "elbo_steps_per_s", "value": v, "unit": unit, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "impl": "reference", "metric": "elbo_steps_per_s", "value": v, "unit": unit, "n_gpus": world,
+        "steps": args.steps, "warmup": W_, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 island for K_ZZ)", "data": "synthetic",
-        "config": {"workload": wl["name"], "note": "reference algorithm restated on torch CPU (oracle/port.py): gpytorch 1.4.0 "
-                   "is not installable offline, so the unmodified reference cannot run"},
+        "config": bench_config(wl, world, "reference algorithm restated on torch CPU (oracle/port.py), one process on rank 0 "
+                               "with all host threads: gpytorch 1.4.0 is not installable offline, so the unmodified "
+                               "reference cannot run; for N > 1 this is still ONE CPU process - compare at N = 1 only"),
         "cpu_baseline": {"value": v, "unit": unit, "cores": os.cpu_count(), "kind": "port",
                          "sample": f"{args.steps} full minibatch steps on rank 0 only"},
         "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "final_loss": loss}), flush=True)
@@ -525,6 +799,9 @@ def main():
     ap.add_argument("--small", action="store_true", help="reduced sizes (smoke / CI)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-exact", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the headline): fixed per-GPU minibatch; strong: 8192 bags per step globally, split over the ranks")
+    ap.add_argument("--no-sharded-kw", action="store_true", help="skip the row-block sharded K W measurement of multi-rank runs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "dcgp_gemm": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_double, c_void_p, c_int64, c_void_p, c_int64,
                           c_double, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "dcgp_split_lo": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "dcgp_round_tf32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "dcgp_gemm_ex": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_double, c_void_p, c_int64, c_void_p, c_void_p,
                              c_int64, c_void_p, c_double, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]),
     "dcgp_syrk": (c_int, [c_int, c_int64, c_int64, c_double, c_void_p, c_int64, c_double, c_void_p, c_int64, c_int, c_int,

@@ -62,10 +62,10 @@ template <> __device__ __forceinline__ double fast_rsqrt<double>(double d) {
 // is latency-bound on instruction count, so the loop is predicate-free: lanes / columns outside the valid block
 // behave as an identity padding and every lane updates all of its registers (entries above the diagonal are junk
 // that is never stored).
-// PIV2 (experimental, DCGP_LEAF_PIV2=1): the pivot of column c+1 is broadcast from `row[c+1] - lrc^2` of lane c+1's own
-// registers - for that lane the exchanged factor L[c+1][c] of the general update IS its lrc - which takes one of the two
-// dependent shuffles out of every column step of the chain.  Bitwise the same values as the plain order.
-template <typename T, bool PIV2 = false>
+// Measured in isolation on B200 (tools/leafbench.cu, cycles per 16 columns): this column-by-column form 3242 (FP32) /
+// 3962 (FP64); broadcasting the next pivot from lane c+1's own registers ("PIV2", round 1) 3663 / 3661 - no gain,
+// removed; the two-columns-per-round form below 1496 for FP32, but 3953 for FP64 (DFMA latency: kept column-wise).
+template <typename T>
 __device__ __forceinline__ void diag_step(T* S, T* rinv, int p0, int pw, int* info, int64_t j0) {
     const int lane = threadIdx.x & 31;
     const int r = lane;  // row within the sub-block
@@ -74,21 +74,74 @@ __device__ __forceinline__ void diag_step(T* S, T* rinv, int p0, int pw, int* in
     int bad = 0;
 #pragma unroll
     for (int c = 0; c < SB; ++c) row[c] = (r < pw && c <= r) ? S[(p0 + r) * SP + p0 + c] : ((r == c) ? T(1) : T(0));
-    T dnext = PIV2 ? __shfl_sync(0xffffffffu, row[0], 0) : T(0);
 #pragma unroll
     for (int c = 0; c < SB; ++c) {
-        const T d = PIV2 ? dnext : __shfl_sync(0xffffffffu, row[c], c);  // pivot (already updated)
+        const T d = __shfl_sync(0xffffffffu, row[c], c);  // pivot (already updated)
         if (!(d > T(0)) && bad == 0) bad = c + 1;
         const T y = fast_rsqrt<T>(d);
         const T scaled = row[c] * y;
         row[c] = (r == c) ? d * y : scaled;
         if (r == c) myinv = y;
         const T lrc = row[c];
-        if (PIV2 && c + 1 < SB) dnext = __shfl_sync(0xffffffffu, fma(-lrc, lrc, row[c + 1]), c + 1);
 #pragma unroll
         for (int k = c + 1; k < SB; ++k) {
             const T lkc = __shfl_sync(0xffffffffu, row[c], k);  // L[k][c]
             row[k] = fma(-lrc, lkc, row[k]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < SB; ++c)
+        if (r < pw && c <= r) S[(p0 + r) * SP + p0 + c] = row[c];
+    if (r < pw) rinv[p0 + r] = myinv;
+    if (lane == 0 && bad != 0 && bad <= pw && info && *info == 0) *info = (int)(j0 + p0 + bad);
+}
+
+// FP32: two columns per latency round.  With a = A[c][c], b = A[c+1][c], e = A[c+1][c+1] (all already updated),
+//   y1 = 1/sqrt(a) and yd = 1/sqrt(a e - b^2) are INDEPENDENT reciprocal square roots (the second pivot is
+//   (a e - b^2) / a, so 1/sqrt(pivot2) = sqrt(a) yd), and the two shuffle rounds of a column pair collapse into one.
+// The hardware seed is taken flush-to-zero (no denormal fix-up instructions around MUFU.RSQ; a pivot below 1e-38 is a
+// failed factorisation in FP32 anyway) and refined by one Newton step as before.
+__device__ __forceinline__ float rsqrt_ftz_newton(float d) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(d));
+    return y * fmaf(-0.5f * d, y * y, 1.5f);
+}
+template <>
+__device__ __forceinline__ void diag_step<float>(float* S, float* rinv, int p0, int pw, int* info, int64_t j0) {
+    const int lane = threadIdx.x & 31;
+    const int r = lane;
+    float row[SB];
+    float myinv = 0.f;
+    int bad = 0;
+#pragma unroll
+    for (int c = 0; c < SB; ++c) row[c] = (r < pw && c <= r) ? S[(p0 + r) * SP + p0 + c] : ((r == c) ? 1.f : 0.f);
+#pragma unroll
+    for (int c = 0; c < SB; c += 2) {
+        const float a = __shfl_sync(0xffffffffu, row[c], c);
+        const float b = __shfl_sync(0xffffffffu, row[c], c + 1);
+        const float e = __shfl_sync(0xffffffffu, row[c + 1], c + 1);
+        const float det = fmaf(a, e, -(b * b));
+        if (bad == 0) {
+            if (!(a > 0.f)) bad = c + 1;
+            else if (!(det > 0.f)) bad = c + 2;
+        }
+        const float y1 = rsqrt_ftz_newton(a);
+        const float yd = rsqrt_ftz_newton(det);
+        const float sa = a * y1;            // sqrt(a)
+        const float y2 = sa * yd;           // 1 / sqrt(e - b^2 / a)
+        const float l21 = b * y1;
+        const float l1 = (r == c) ? sa : row[c] * y1;
+        const float t = fmaf(-l1, l21, row[c + 1]);
+        const float l2 = (r == c + 1) ? (det * yd) * y1 : t * y2;   // sqrt(det / a) on the diagonal
+        row[c] = l1;
+        row[c + 1] = l2;
+        if (r == c) myinv = y1;
+        if (r == c + 1) myinv = y2;
+#pragma unroll
+        for (int k = c + 2; k < SB; ++k) {
+            const float lk1 = __shfl_sync(0xffffffffu, l1, k);
+            const float lk2 = __shfl_sync(0xffffffffu, l2, k);
+            row[k] = fmaf(-l2, lk2, fmaf(-l1, lk1, row[k]));
         }
     }
 #pragma unroll
@@ -204,15 +257,15 @@ __device__ __forceinline__ void inv_rows_update(T* S, int nb, int p0, int pw, in
 //   (3a) the NEXT sub-panel's 16 columns get their rank-16 update first (all warps, short);
 //   (3b) warp 0 factors the next diagonal block while warps 1..15 update the rest of the trailing triangle.
 // Three barriers per sub-panel; the serial pivot chain of (1) is hidden behind (3b) whenever that is longer.
-template <typename T, int MODE = 0>   // MODE bit 0: FINV (inverse rides along), bit 1: PIV2 (short pivot chain)
+template <typename T, int MODE = 0>   // MODE bit 0: FINV (the inverse rides along)
 __device__ void block_potrf(T* S, T* rinv, int nb, int* info, int64_t j0) {
-    constexpr bool FINV = (MODE & 1) != 0, PIV2 = (MODE & 2) != 0;
+    constexpr bool FINV = (MODE & 1) != 0;
     const int tid = threadIdx.x, warp = tid >> 5;
     constexpr int TC = WarpTile<T>::COLS, NJ_NEXT = SB / TC, NW = NTHREADS / 32;
 #ifdef DCGP_LEAF_TIMING
     long long acc1 = 0, acc2 = 0, acc3 = 0, tq = clock64();
 #endif
-    if (warp == 0) diag_step<T, PIV2>(S, rinv, 0, min(SB, nb), info, j0);
+    if (warp == 0) diag_step<T>(S, rinv, 0, min(SB, nb), info, j0);
     else if (FINV) inv_rows_init<T>(S, nb);
     __syncthreads();
     for (int p0 = 0; p0 < nb; p0 += SB) {
@@ -250,7 +303,7 @@ __device__ void block_potrf(T* S, T* rinv, int nb, int* info, int64_t j0) {
         trailing_update<T>(S, nb, p0, pw, 0, NJ_NEXT, 0, NW);
         __syncthreads();
         // (3b) next pivots || rest of the trailing update (|| the extra rows of the inverse)
-        if (warp == 0) diag_step<T, PIV2>(S, rinv, t0, min(SB, nb - t0), info, j0);
+        if (warp == 0) diag_step<T>(S, rinv, t0, min(SB, nb - t0), info, j0);
         else {
             trailing_update<T>(S, nb, p0, pw, NJ_NEXT, 1 << 30, 1, NW - 1);
             if (FINV) inv_rows_update<T>(S, nb, p0, pw, 1, NW - 1);
@@ -670,21 +723,17 @@ __global__ void __launch_bounds__(256) logdet_kernel(const T* __restrict__ L, in
 template <typename T>
 constexpr size_t leaf_smem() { return (size_t)NB * SP * sizeof(T); }
 
-// Experimental leaf variants, off by default until measured on the GPU (MODE of block_potrf):
-//   DCGP_LEAF_FINV=1  the leaves build the inverse of their factor inside the factorisation loop (inv_rows_*) instead of a
-//                     block_trtri pass after it;
-//   DCGP_LEAF_PIV2=1  short pivot chain in diag_step.
+// Leaf variant (MODE of block_potrf): DCGP_LEAF_FINV=0 restores the separate block_trtri pass after the factorisation
+// (round-1 default); with 1 (default since round 2: FP32 8192^2 factorisation 4.67 -> 4.22 ms, ELBO step 12.14 -> 11.53 ms,
+// profiles/r02_finv_ab.txt) the leaves build the inverse of their factor inside the pivot loop (inv_rows_*).
 inline int leaf_mode() {
-    static const int mode = ((getenv("DCGP_LEAF_FINV") && atoi(getenv("DCGP_LEAF_FINV")) != 0) ? 1 : 0) |
-                            ((getenv("DCGP_LEAF_PIV2") && atoi(getenv("DCGP_LEAF_PIV2")) != 0) ? 2 : 0);
+    static const int mode = (getenv("DCGP_LEAF_FINV") && atoi(getenv("DCGP_LEAF_FINV")) == 0) ? 0 : 1;
     return mode;
 }
 #define DCGP_LEAF_DISPATCH(CALL) \
     switch (leaf_mode()) {       \
-        case 1: CALL(1); break;  \
-        case 2: CALL(2); break;  \
-        case 3: CALL(3); break;  \
-        default: CALL(0); break; \
+        case 0: CALL(0); break;  \
+        default: CALL(1); break; \
     }
 
 template <typename T>
@@ -1161,6 +1210,10 @@ struct L5Ctx {
     int64_t n;
     T* Blo = nullptr;          // look-ahead sweep: remainders of the not yet solved rows of B
     const T* invlo = nullptr;  // ... and of the inverted diagonal blocks
+    // two-step look-ahead products of the plan (build_la2): block b's row of L times the inverted diagonal blocks of its
+    // two left neighbours (fwd), the inverted diagonal blocks of its two lower neighbours times their blocks in column b
+    // (bwd), and their TF32 remainders
+    const T *fwd = nullptr, *bwd = nullptr, *fwdlo = nullptr, *bwdlo = nullptr;
 };
 
 template <typename T>
@@ -1310,13 +1363,162 @@ int ltrsm512_la(const L5Ctx<T>& c, int trans) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two-step look-ahead sweep: ONE dependent GEMM per block on the chain lane.
+//
+// In ltrsm512_la the chain does two dependent products per 512-block, X_i = inv_i B_i and B_{i+1} -= L_{i+1,i} X_i
+// (measured on B200, n = 8192, m = 1024: ~45 us per block, 16 blocks per sweep, four sweeps per ELBO step - the chain,
+// not the flops, is what a solve costs).  Both products only need B_i, so with
+//     F_b = [ L_{b,b-2} inv_{b-2} | L_{b,b-1} inv_{b-1} ]              (prepared once per factor, build_la2)
+// block b becomes final through a single product over the two blocks before it,
+//     B_b -= F_b [ B_{b-2} ; B_{b-1} ]                                  (contiguous rows of B, K = 1024)
+// provided every block further left has already been applied - which the bulk lane does two steps behind:
+//     bulk(s):  X_s = inv_s B_s ;  B_{s+3 ...} -= L_{s+3 ..., s} X_s.
+// Writers of block b in time order: bulk(0 .. b-3), then chain(b-1) alone (it waits for bulk(b-3)), so the chain's
+// epilogue also leaves the final TF32 remainders of the block.  The transposed sweep mirrors this with
+//     G_b = [ inv_{b+1} L_{b+1,b} ; inv_{b+2} L_{b+2,b} ]               B_b -= G_b^T [ B_{b+1} ; B_{b+2} ].
+template <typename T>
+int ltrsm512_la2(const L5Ctx<T>& c, int trans) {
+    LookAhead& x = lanes_for(c.st);
+    int rc = x.init();
+    if (rc) return rc;
+    const int64_t n = c.n, q = (n + NBI - 1) / NBI;
+    const cudaStream_t sa = x.sh, sb = x.sb;
+    const bool lo = c.Llo && c.Xlo && c.Blo && c.invlo && c.fwdlo && c.bwdlo;
+    auto width = [&](int64_t i) { return (n - i * NBI < NBI) ? n - i * NBI : (int64_t)NBI; };
+    if (lo) {  // the first block of the sweep is final as given: its remainders are not produced by any epilogue
+        const int64_t i = trans ? q - 1 : 0;
+        rc = dcgp_split_lo_impl(c.B + i * NBI * c.ldb, c.Blo + i * NBI * c.ldb, width(i), c.m, c.ldb, c.ldb, c.st);
+        if (rc) return rc;
+    }
+    DCGP_CU(cudaEventRecord(x.fork, c.st));
+    DCGP_CU(cudaStreamWaitEvent(sa, x.fork, 0));
+    DCGP_CU(cudaStreamWaitEvent(sb, x.fork, 0));
+    TRACE_BEGIN(c.st);
+    for (int64_t s = 0; s < q; ++s) {
+        const int64_t i = trans ? q - 1 - s : s;  // block that is final at the start of this step
+        const int e = (int)(s & 3);
+        // ---- chain lane: make the next block final
+        if (s + 1 < q) {
+            if (s >= 2) DCGP_CU(cudaStreamWaitEvent(sa, x.upd[(int)((s - 2) & 3)], 0));
+            TRACE_MARK("A.waited", s, sa);
+            if (!trans) {
+                const int64_t b = i + 1, k0 = (i >= 1 ? i - 1 : 0) * NBI, kk = (i + 1) * NBI - k0;
+                rc = dcgp_gemm_impl(0, 0, width(b), c.m, kk, -1.0, c.fwd + b * 2 * NBI * NBI, 2 * NBI, c.B + k0 * c.ldb, c.ldb,
+                                    1.0, c.B + b * NBI * c.ldb, c.ldb, c.dtype, c.xf, sa,
+                                    lo ? c.fwdlo + b * 2 * NBI * NBI : nullptr, lo ? c.Blo + k0 * c.ldb : nullptr,
+                                    lo ? c.Blo + b * NBI * c.ldb : nullptr);
+            } else {
+                const int64_t b = i - 1, k0 = i * NBI, k1 = (i + 2 < q ? i + 2 : q), kk = (k1 * NBI < n ? k1 * NBI : n) - k0;
+                rc = dcgp_gemm_impl(1, 0, NBI, c.m, kk, -1.0, c.bwd + b * 2 * NBI * NBI, NBI, c.B + k0 * c.ldb, c.ldb, 1.0,
+                                    c.B + b * NBI * c.ldb, c.ldb, c.dtype, c.xf, sa,
+                                    lo ? c.bwdlo + b * 2 * NBI * NBI : nullptr, lo ? c.Blo + k0 * c.ldb : nullptr,
+                                    lo ? c.Blo + b * NBI * c.ldb : nullptr);
+            }
+            if (rc) return rc;
+            TRACE_MARK("A.leaf", s, sa);
+            DCGP_CU(cudaEventRecord(x.leaf[e], sa));
+        }
+        // ---- bulk lane: X_i, then everything three or more blocks away
+        if (s >= 1) DCGP_CU(cudaStreamWaitEvent(sb, x.leaf[(int)((s - 1) & 3)], 0));
+        TRACE_MARK("B.start", s, sb);
+        const int64_t r = i * NBI, w = width(i);
+        T* Xi = c.X + r * c.ldb;
+        T* Xilo = lo ? c.Xlo + r * c.ldb : nullptr;
+        rc = dcgp_gemm_impl(trans, 0, w, c.m, w, 1.0, c.inv + i * NBI * NBI, NBI, c.B + r * c.ldb, c.ldb, 0.0, Xi, c.ldb,
+                            c.dtype, c.xf | (trans ? DCGP_GEMM_A_UPPER : DCGP_GEMM_A_LOWER), sb,
+                            lo ? c.invlo + i * NBI * NBI : nullptr, lo ? c.Blo + r * c.ldb : nullptr, Xilo);
+        if (rc) return rc;
+        if (!trans) {
+            const int64_t r3 = (i + 3) * NBI;
+            if (r3 < n) {
+                rc = dcgp_gemm_impl(0, 0, n - r3, c.m, w, -1.0, c.L + r3 * c.ldl + r, c.ldl, Xi, c.ldb, 1.0, c.B + r3 * c.ldb,
+                                    c.ldb, c.dtype, c.xf, sb, lo ? c.Llo + r3 * c.ldl + r : nullptr, Xilo, nullptr);
+                if (rc) return rc;
+            }
+        } else {
+            const int64_t nr = (i - 2) * NBI;  // rows [0, nr) are three or more blocks above
+            if (nr > 0) {
+                rc = dcgp_gemm_impl(1, 0, nr, c.m, w, -1.0, c.L + r * c.ldl, c.ldl, Xi, c.ldb, 1.0, c.B, c.ldb, c.dtype, c.xf,
+                                    sb, lo ? c.Llo + r * c.ldl : nullptr, Xilo, nullptr);
+                if (rc) return rc;
+            }
+        }
+        TRACE_MARK("B.trail", s, sb);
+        DCGP_CU(cudaEventRecord(x.upd[e], sb));
+    }
+    DCGP_CU(cudaEventRecord(x.join, sa));
+    DCGP_CU(cudaStreamWaitEvent(c.st, x.join, 0));
+    DCGP_CU(cudaEventRecord(x.fork, sb));
+    DCGP_CU(cudaStreamWaitEvent(c.st, x.fork, 0));
+    TRACE_DUMP();
+    return 0;
+}
+
+// F_b (b = 1 .. q-1) and G_b (b = 0 .. q-2) of ltrsm512_la2 from the factor and its inverted diagonal blocks: up to four
+// 512^3 products per block, independent of each other, dealt to the two lanes.
+template <typename T>
+int build_la2(const T* L, int64_t n, int64_t ldl, const T* inv, const T* invlo, const T* Llo, T* fwd, T* bwd, T* fwdlo,
+              T* bwdlo, int dtype, int xf, cudaStream_t st) {
+    LookAhead& x = lanes_for(st);
+    int rc = x.init();
+    if (rc) return rc;
+    const int64_t q = (n + NBI - 1) / NBI;
+    auto width = [&](int64_t i) { return (n - i * NBI < NBI) ? n - i * NBI : (int64_t)NBI; };
+    const bool lo = invlo && Llo && fwdlo && bwdlo;
+    DCGP_CU(cudaEventRecord(x.fork, st));
+    DCGP_CU(cudaStreamWaitEvent(x.sh, x.fork, 0));
+    DCGP_CU(cudaStreamWaitEvent(x.sb, x.fork, 0));
+    int turn = 0;
+    for (int64_t b = 0; b < q; ++b) {
+        for (int64_t j = (b >= 2 ? b - 2 : 0); j < b; ++j) {   // F_b: columns of block j
+            const int64_t off = b * 2 * NBI * NBI + (j - (b >= 2 ? b - 2 : 0)) * NBI;
+            const int64_t ol = b * NBI * ldl + j * NBI;
+            rc = dcgp_gemm_impl(0, 0, width(b), NBI, NBI, 1.0, L + ol, ldl, inv + j * NBI * NBI, NBI, 0.0, fwd + off, 2 * NBI,
+                                dtype, xf, (turn++ & 1) ? x.sb : x.sh, lo ? Llo + ol : nullptr,
+                                lo ? invlo + j * NBI * NBI : nullptr, lo ? fwdlo + off : nullptr);
+            if (rc) return rc;
+        }
+        for (int64_t i = b + 1; i < q && i <= b + 2; ++i) {    // G_b: rows of block i
+            const int64_t off = b * 2 * NBI * NBI + (i - b - 1) * NBI * NBI;
+            const int64_t ol = i * NBI * ldl + b * NBI;
+            rc = dcgp_gemm_impl(0, 0, width(i), NBI, width(i), 1.0, inv + i * NBI * NBI, NBI, L + ol, ldl, 0.0, bwd + off, NBI,
+                                dtype, xf | DCGP_GEMM_A_LOWER, (turn++ & 1) ? x.sb : x.sh, lo ? invlo + i * NBI * NBI : nullptr,
+                                lo ? Llo + ol : nullptr, lo ? bwdlo + off : nullptr);
+            if (rc) return rc;
+        }
+    }
+    DCGP_CU(cudaEventRecord(x.join, x.sh));
+    DCGP_CU(cudaStreamWaitEvent(st, x.join, 0));
+    DCGP_CU(cudaEventRecord(x.fork, x.sb));
+    DCGP_CU(cudaStreamWaitEvent(st, x.fork, 0));
+    return 0;
+}
+
+// DCGP_TRSM_LA: 1 (default) = look-ahead sweeps with two dependent GEMMs per block (ltrsm512_la), 2 = the two-step
+// look-ahead sweeps above (one dependent GEMM per block, products prepared in the plan), 0 = recursive sweeps.
+// Measured on B200 (profiles/r02_trsm_la2.txt, n = 8192, m = 1024, FP32): planned potrs 1.45 ms (1) vs 1.58 ms (2), plan
+// build 0.32 vs 0.88 ms - the chain GEMM of mode 2 has twice the depth on the same 32 tiles, so a block costs what
+// the two shallower products cost; it needs a split-K tcgen05 kernel to pay off and stays opt-in until then.
+inline int trsm_la_mode() {
+    static const int mode = getenv("DCGP_TRSM_LA") ? atoi(getenv("DCGP_TRSM_LA")) : 1;
+    return mode;
+}
+
 // A solve plan holds everything about L that a sweep needs beyond L itself, so that several solves with
 // one factor (forward and adjoint of the same Lambda^{-1}) prepare it once:
 //   [inv512 blocks][their TF32 remainders (scratch of the inversion)][TF32 remainders of L]
+//   [DCGP_TRSM_LA=2 only: products F_b, G_b of ltrsm512_la2, 2 x nbig blocks of 2 NBI x NBI][FP32: their TF32 remainders]
 size_t plan_bytes_impl(int64_t n, int64_t ldl, int dtype) {
     const size_t es = dtype == DCGP_F64 ? 8 : 4;
     const size_t nbig = (size_t)(n + NBI - 1) / NBI;
-    return 2 * nbig * NBI * NBI * es + (dtype == DCGP_F32 ? (size_t)n * ldl * 4 : 0);
+    return 2 * nbig * NBI * NBI * es + (dtype == DCGP_F32 ? (size_t)n * ldl * 4 : 0) +
+           (trsm_la_mode() >= 2 ? (dtype == DCGP_F32 ? 2 : 1) * 2 * nbig * 2 * NBI * NBI * es : 0);
+}
+template <typename T>
+inline T* plan_la2(const T* plan, int64_t n, int64_t ldl, int dtype) {
+    const size_t nbig = (size_t)(n + NBI - 1) / NBI;
+    return const_cast<T*>(plan) + 2 * nbig * NBI * NBI + (dtype == DCGP_F32 ? (size_t)n * ldl : 0);
 }
 
 // X (+ FP32: remainders of X and of B, and a copy of B with a TMA-compatible leading dimension - a multiple of
@@ -1342,6 +1544,14 @@ int plan_build(const T* L, int64_t n, int64_t ldl, T* plan, int dtype, int xf, c
         rc = dcgp_split_lo_impl(inv, tmp, nbig * NBI, NBI, NBI, NBI, st);
         if (rc) return rc;
         rc = dcgp_split_lo_impl(L, tmp + nbig * NBI * NBI, n, n, ldl, ldl, st);
+        if (rc) return rc;
+    }
+    if (nbig >= 4 && trsm_la_mode() >= 2) {   // the sweeps that use them (trsm_impl)
+        const bool lo = sizeof(T) == 4 && xf;
+        T* fwd = plan_la2<T>(plan, n, ldl, dtype);
+        T* bwd = fwd + nbig * 2 * NBI * NBI;
+        rc = build_la2<T>(L, n, ldl, inv, lo ? tmp : nullptr, lo ? tmp + nbig * NBI * NBI : nullptr, fwd, bwd,
+                          lo ? bwd + nbig * 2 * NBI * NBI : nullptr, lo ? bwd + 2 * nbig * 2 * NBI * NBI : nullptr, dtype, xf, st);
     }
     return rc;
 }
@@ -1389,10 +1599,18 @@ int trsm_impl(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t m, in
         c.Xlo = X + (size_t)n * ldw;
         c.Blo = c.Xlo + (size_t)n * ldw;
     }
-    static const int use_la = getenv("DCGP_TRSM_LA") ? atoi(getenv("DCGP_TRSM_LA")) : 1;
+    if (nbig >= 4 && trsm_la_mode() >= 2) {
+        c.fwd = plan_la2<T>(plan, n, ldl, dtype);
+        c.bwd = c.fwd + nbig * 2 * NBI * NBI;
+        if (sizeof(T) == 4 && xf) {
+            c.fwdlo = c.bwd + nbig * 2 * NBI * NBI;
+            c.bwdlo = c.fwdlo + nbig * 2 * NBI * NBI;
+        }
+    }
+    const int use_la = trsm_la_mode();
     const int last = (trans == 0 ? 0 : 1);
     for (int sweep = (trans == 1 ? 1 : 0); sweep <= last; ++sweep) {
-        rc = (use_la && nbig >= 4) ? ltrsm512_la(c, sweep) : ltrsm512_rec(c, sweep, 0, n);
+        rc = (use_la && nbig >= 4) ? (use_la >= 2 ? ltrsm512_la2(c, sweep) : ltrsm512_la(c, sweep)) : ltrsm512_rec(c, sweep, 0, n);
         if (rc) return rc;
         // the solved rows become the right-hand side of the next sweep / the result
         T* dst = (sweep == last) ? B : Bw;

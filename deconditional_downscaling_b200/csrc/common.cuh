@@ -101,7 +101,35 @@ __device__ __forceinline__ void load_spec_vals(const DevSpec& sp, SpecVals<T>* s
     } while (0)
 
 template <typename T> __device__ __forceinline__ T t_exp(T x);
-template <> __device__ __forceinline__ double t_exp<double>(double x) { return exp(x); }
+// exp(x) for x <= 0 in FP64 (every stationary kernel here evaluates exp at -r^2/2 or -c r): <= 2 ulp (checked against
+// 200-bit arithmetic over [-700, 0], tests/test_fast_exp_cpu.py restates it), 0 below -700.  The Gram build is bound
+// by this function, not by the bytes it writes: the library exp() costs ~30 FP64 instructions per entry (special cases,
+// a two-step range reduction, degree-11 polynomial), against which 8 bytes of output at 6.5 TB/s leave room for ~25.
+//   x = (n / 4) ln 2 + t, |t| <= ln 2 / 8:  exp(x) = 2^(n >> 2) * 2^((n & 3) / 4) * P9(t)
+// (Cody-Waite reduction with ln 2 / 4 split so that n * hi is exact, a four-entry table held in registers, a degree-9
+// Taylor polynomial - the remainder 0.087^10 / 10! = 7e-18 - and the power of two applied to the exponent field).
+__device__ __forceinline__ double exp_nonpos(double x) {
+    const int n = __double2int_rn(x * 5.7707801635558535);
+    const double nd = (double)n;
+    double t = fma(-nd, 0.1732867918908596, x);       // 0x1.62e42f8000000p-3: 27 trailing zero bits
+    t = fma(-nd, 3.249126723472472e-09, t);
+    double p = 2.7557319223985893e-06;
+    p = fma(p, t, 2.48015873015873e-05);
+    p = fma(p, t, 0.0001984126984126984);
+    p = fma(p, t, 0.001388888888888889);
+    p = fma(p, t, 0.008333333333333333);
+    p = fma(p, t, 0.041666666666666664);
+    p = fma(p, t, 0.16666666666666666);
+    p = fma(p, t, 0.5);
+    p = fma(p, t, 1.0);
+    p = fma(p, t, 1.0);
+    const int idx = n & 3;
+    const double tab = idx == 0 ? 1.0 : (idx == 1 ? 1.189207115002721 : (idx == 2 ? 1.4142135623730951 : 1.681792830507429));
+    p *= tab;
+    const double r = __hiloint2double(__double2hiint(p) + ((n >> 2) << 20), __double2loint(p));
+    return x < -700.0 ? 0.0 : r;
+}
+template <> __device__ __forceinline__ double t_exp<double>(double x) { return exp_nonpos(x); }
 template <> __device__ __forceinline__ float t_exp<float>(float x) { return __expf(x); }
 template <typename T> __device__ __forceinline__ T t_sqrt(T x);
 template <> __device__ __forceinline__ double t_sqrt<double>(double x) { return sqrt(x); }

@@ -450,6 +450,18 @@ __global__ void split_lo_kernel(const float* __restrict__ src, float* __restrict
     }
 }
 
+// dst = x rounded to the nearest TF32 value (ties away from zero, cvt.rna): what a single-pass TF32 product should see
+__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int64_t cols,
+                                  int64_t lds, int64_t ldd) {
+    const int64_t total = rows * cols;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / cols, c = e % cols;
+        uint32_t v;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v) : "f"(src[r * lds + c]));
+        dst[r * ldd + c] = __uint_as_float(v);
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -490,6 +502,18 @@ int dcgp_split_lo_impl(const void* src, void* dst, int64_t rows, int64_t cols, i
     const int64_t total = rows * cols;
     unsigned grid = (unsigned)min((int64_t)(num_sms() * 16), (total + 255) / 256);
     split_lo_kernel<<<grid, 256, 0, st>>>((const float*)src, (float*)dst, rows, cols, lds, ldd);
+    DCGP_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dcgp_round_tf32(const void* src, void* dst, int64_t rows, int64_t cols, int64_t lds, int64_t ldd, void* stream) {
+    if (rows < 0 || cols < 0) return -3;
+    if (rows == 0 || cols == 0) return 0;
+    if (!src || !dst) return -1;
+    if (lds < cols || ldd < cols) return -5;
+    const int64_t total = rows * cols;
+    unsigned grid = (unsigned)min((int64_t)(num_sms() * 16), (total + 255) / 256);
+    round_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, (float*)dst, rows, cols, lds, ldd);
     DCGP_CHECK_LAUNCH();
     return 0;
 }

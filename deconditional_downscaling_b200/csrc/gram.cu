@@ -13,6 +13,7 @@
 // column chunk; hyper-parameter and input-coordinate adjoints are accumulated in registers,
 // reduced with warp shuffles and committed with one atomicAdd per warp and output value.
 #include "common.cuh"
+#include "mma.cuh"
 
 namespace {
 
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(256) gram_fwd_kernel(const __grid_constant__ D
                                                        int64_t n1, int64_t ldx1, const T* __restrict__ x2, int64_t n2,
                                                        int64_t ldx2, TO* __restrict__ K, int64_t ldk,
                                                        const T* __restrict__ diag_dev, T diag_const, int same,
-                                                       int vec_ok, int row_tiles) {
+                                                       int vec_ok, int row_tiles, int rna) {
     // One CTA owns a 128-column (FP32; 64 in FP64) block and walks `row_tiles` 64-row tiles down it: the scaled x2
     // coordinates of its columns stay in registers and the per-CTA set-up (kernel spec, strided x2 gather) is paid once
     // per row_tiles x 64 x TCOLS outputs instead of once per 64 x TCOLS.
@@ -132,6 +133,11 @@ __global__ void __launch_bounds__(256) gram_fwd_kernel(const __grid_constant__ D
         for (int v = 0; v < VEC; ++v) {
             T val = eval_pair<T, NC, DPC>(sp, sv.os, a, b[v]);
             if (same && row == col0 + tx * VEC + v) val += dadd;
+            if constexpr (sizeof(T) == 4 && sizeof(TO) == 4) {
+                // operand of a single-pass TF32 product: round to nearest here, so that the truncating operand read of
+                // tcgen05.mma sees an exactly representable value (unbiased instead of -3.5e-4 relative on average)
+                if (rna) val = __uint_as_float(to_tf32(val));
+            }
             out[v] = (TO)val;
         }
         const int64_t c = col0 + tx * VEC;
@@ -484,7 +490,7 @@ __global__ void __launch_bounds__(256) whitened_kl_kernel(const T* __restrict__ 
 template <typename T, typename TO>
 int launch_gram_fwd(const DevSpec& sp, const void* x1, int64_t n1, int64_t ldx1, const void* x2, int64_t n2,
                     int64_t ldx2, void* K, int64_t ldk, const void* diag_dev, double diag_const, int same,
-                    cudaStream_t st) {
+                    cudaStream_t st, int rna = 0) {
     constexpr int VEC = 16 / sizeof(TO);
     // row tiles per CTA (DCGP_GRAM_RT, default 8), fewer when the grid would drop under ~8 CTAs per SM
     static const int rt_max = getenv("DCGP_GRAM_RT") ? atoi(getenv("DCGP_GRAM_RT")) : 8;
@@ -496,7 +502,7 @@ int launch_gram_fwd(const DevSpec& sp, const void* x1, int64_t n1, int64_t ldx1,
 #define CALL(NCV, DPCV)                                                                                      \
     gram_fwd_kernel<T, TO, NCV, DPCV><<<grid, 256, 0, st>>>(sp, (const T*)x1, n1, ldx1, (const T*)x2, n2, ldx2, \
                                                             (TO*)K, ldk, (const T*)diag_dev, (T)diag_const, same, \
-                                                            vec_ok, (int)rt);
+                                                            vec_ok, (int)rt, rna);
     DCGP_DISPATCH_LAYOUT(sp, CALL);
 #undef CALL
     DCGP_CHECK_LAUNCH();
@@ -621,12 +627,14 @@ extern "C" int dcgp_gram_matmul(const dcgp_kernel_spec* spec, const void* x1, in
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t es = dtype == DCGP_F64 ? 8 : 4, rows = gm_rows(n1, n2, dtype);
     const int gflags = flags & (DCGP_GEMM_TF32X3 | DCGP_GEMM_NO_TCGEN05);
+    // the generated panels feed nothing but this product: single-pass TF32 gets them rounded to nearest at the source
+    const int rna = (dtype == DCGP_F32 && !(flags & DCGP_GEMM_TF32X3)) ? 1 : 0;
     if (rows == n1) {
         // single panel: the symmetric Gram path (nugget applied on the diagonal by the generator itself)
         int rc = dtype == DCGP_F64 ? launch_gram_fwd<double, double>(sp, x1, n1, ldx1, x2, n2, ldx2, workspace, n2, diag_dev,
                                                                      diag_const, same, st)
                                    : launch_gram_fwd<float, float>(sp, x1, n1, ldx1, x2, n2, ldx2, workspace, n2, diag_dev,
-                                                                   diag_const, same, st);
+                                                                   diag_const, same, st, rna);
         if (rc) return rc;
         return dcgp_gemm_impl(0, 0, n1, m, n2, 1.0, workspace, n2, W, ldw, 0.0, out, ldo, dtype, gflags, st, nullptr, nullptr,
                               nullptr);
@@ -636,7 +644,7 @@ extern "C" int dcgp_gram_matmul(const dcgp_kernel_spec* spec, const void* x1, in
         const char* xp = (const char*)x1 + r0 * ldx1 * es;
         int rc = dtype == DCGP_F64
                      ? launch_gram_fwd<double, double>(sp, xp, nr, ldx1, x2, n2, ldx2, workspace, n2, nullptr, 0.0, 0, st)
-                     : launch_gram_fwd<float, float>(sp, xp, nr, ldx1, x2, n2, ldx2, workspace, n2, nullptr, 0.0, 0, st);
+                     : launch_gram_fwd<float, float>(sp, xp, nr, ldx1, x2, n2, ldx2, workspace, n2, nullptr, 0.0, 0, st, rna);
         if (rc) return rc;
         char* op = (char*)out + r0 * ldo * es;
         rc = dcgp_gemm_impl(0, 0, nr, m, n2, 1.0, workspace, n2, W, ldw, 0.0, op, ldo, dtype, gflags, st, nullptr, nullptr, nullptr);

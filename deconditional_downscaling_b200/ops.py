@@ -6,6 +6,8 @@ O(N^2)/O(N^3) operation is a libdcgp kernel.  No function in this module has a
 CPU or pure-torch fallback: non-CUDA tensors raise.
 """
 import ctypes
+import os
+import weakref
 from typing import List, Optional, Sequence
 
 import torch
@@ -97,6 +99,51 @@ def _ld(t: torch.Tensor) -> int:
     return t.stride(0) if t.size(0) > 1 else max(t.size(1), 1)
 
 
+# ---- operands of single-pass TF32 products, rounded to nearest ------------------------------------------------
+# tcgen05.mma reads FP32 operands by truncation: on raw data every single-pass product comes out about 7e-4 too small
+# (measured: tests/test_parity_scale_gpu.py before this rounding - gradients of the config-5 minibatch 2e-3 .. 7e-3 off
+# the FP64 oracle after three or four chained products).  Rounding the operands to the nearest TF32 value first (what
+# cuBLAS TF32 does inside its kernels) makes the products unbiased.  A tensor is rounded once and the copy reused
+# while the tensor object is alive and unmodified (A = Lambda^{-1} B and A~ feed half a dozen products each).
+ROUND_TF32 = os.environ.get("DCGP_ROUND_TF32", "1") != "0"
+_RNA = {}
+
+
+def round_tf32(X):
+    """Copy of the FP32 matrix X with every value rounded to the nearest TF32 value (dcgp_round_tf32)."""
+    X = _rowmajor(X)
+    _req(X)
+    if X.dtype != torch.float32:
+        raise TypeError("round_tf32 is an FP32 operation")
+    # rows stay 16-byte aligned whatever the column count (TMA operand of the tcgen05 kernel)
+    out = torch.empty(X.size(0), -(-X.size(1) // 4) * 4, dtype=X.dtype, device=X.device)[:, :X.size(1)]
+    check(_lib.load().dcgp_round_tf32(_ptr(X), _ptr(out), X.size(0), X.size(1), _ld(X), _ld(out), _stream()), "dcgp_round_tf32")
+    return out
+
+
+def _rna(t):
+    """round_tf32(t), cached per tensor object (weak reference + version counter: a freed or modified tensor never
+    hits; a new view of the same memory simply misses)."""
+    if not ROUND_TF32:
+        return t
+    key = id(t)
+    hit = _RNA.get(key)
+    if hit is not None and hit[0]() is t and hit[1] == t._version:
+        return hit[2]
+    out = round_tf32(t)
+    if len(_RNA) > 256:
+        for k in [k for k, v in _RNA.items() if v[0]() is None]:
+            del _RNA[k]
+    _RNA[key] = (weakref.ref(t, lambda _, k=key: _RNA.pop(k, None)), t._version, out)
+    return out
+
+
+def _single_pass_tc(dtype, m, n, k, flags):
+    """Mirrors the dispatch of dcgp_gemm (csrc/gemm.cu): FP32, no 3xTF32, a shape the tcgen05 kernel takes."""
+    return (dtype == torch.float32 and USE_TCGEN05 and not (flags & (_lib.GEMM_TF32X3 | _lib.GEMM_NO_TCGEN05)) and m >= 128
+            and n >= 128 and k >= 64 and ((m + 127) // 128) * ((n + 127) // 128) >= 32)
+
+
 class FlatSpec:
     """Additive kernel = list of (kind, dims, lengthscale[nd], outputscale[]) with the
     hyper-parameters as device tensors (already softplus-transformed)."""
@@ -165,6 +212,8 @@ def gram_matmul(spec: FlatSpec, x1, x2, W, diag_dev=None, diag_const=0.0):
     ws = _workspace(lib.dcgp_gram_matmul_workspace(n1, n2, _dt(x1)), x1.device)
     cs = spec.c_spec()
     flags = (GRAM_SAME if same else 0) | _x3(x1, n1 * n2 * m <= X3_GEMM_LIMIT)
+    if _single_pass_tc(x1.dtype, n1, m, n2, flags):
+        W = _rna(W)      # the Gram panels are rounded by their generator (csrc/gram.cu)
     rc = lib.dcgp_gram_matmul(ctypes.byref(cs), _ptr(x1), n1, _ld(x1), _ptr(x2), n2, _ld(x2), _ptr(diag_dev), float(diag_const),
                               _ptr(W), m, _ld(W), _ptr(out), _ld(out), _ptr(ws), ws.numel(), _dt(x1), flags, _stream())
     check(rc, "dcgp_gram_matmul")
@@ -230,6 +279,8 @@ def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, C=None, lower=Fa
         C = torch.empty(m, n, dtype=A.dtype, device=A.device)
         beta = 0.0
     flags = (GEMM_LOWER if lower else 0) | (_lib.GEMM_NO_SPLITK if no_splitk else 0) | _x3(A, m * n * k <= X3_GEMM_LIMIT)
+    if _single_pass_tc(A.dtype, m, n, k, flags):
+        A, B = _rna(A), _rna(B)
     rc = _lib.load().dcgp_gemm(int(transa), int(transb), m, n, k, float(alpha), _ptr(A), _ld(A), _ptr(B), _ld(B),
                                float(beta), _ptr(C), _ld(C), _dt(A), flags, _stream())
     check(rc, "dcgp_gemm")

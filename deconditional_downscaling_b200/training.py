@@ -35,7 +35,12 @@ def _world():
 
 class FlatGrads:
     """All parameter gradients as views into one contiguous buffer, so the data-parallel
-    exchange is a single collective (payload ~ M^2 + M d + M + O(10) values)."""
+    exchange is a single collective (payload ~ M^2 + M d + M + O(10) values).
+
+    Layout: parameters in the given order, except that the LARGEST one (chol_variational_covar: M^2 of the
+    M^2 + M d + M + O(10) values) sits at the end - `overlap_largest()` then all-reduces that slice on a side stream
+    the moment autograd has finished accumulating it (a post-accumulate-grad hook), under the rest of the backward
+    pass, and the collective at the end of the step only carries the small head of the buffer."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
@@ -44,21 +49,60 @@ class FlatGrads:
         if any(p.dtype != dtype for p in self.params):
             raise TypeError("FlatGrads needs parameters of one dtype (move the model with .to(dtype) first)")
         self.flat = torch.zeros(total, dtype=dtype, device=self.params[0].device)
-        off = 0
-        for p in self.params:
+        self.big = max(self.params, key=lambda p: p.numel())
+        self.offset, off = {}, 0
+        for p in [q for q in self.params if q is not self.big] + [self.big]:
+            self.offset[id(p)] = off
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
+        self.early_enabled = False      # set by overlap_largest()
+        self._early_done, self._side, self._hook = False, None, None
+
+    def slice_of(self, p, buf=None):
+        off = self.offset[id(p)]
+        return (self.flat if buf is None else buf)[off:off + p.numel()]
 
     def zero(self):
         self.flat.zero_()
 
+    def overlap_largest(self):
+        """Install the early all-reduce of the largest gradient (multi-rank runs only)."""
+        if self._hook is not None or _world() == 1:
+            return
+        big, piece = self.big, self.slice_of(self.big)
+
+        def hook(_):
+            if not self.early_enabled or _world() == 1:
+                return
+            if piece.is_cuda:
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=piece.device)
+                self._side.wait_stream(torch.cuda.current_stream(piece.device))
+                with torch.cuda.stream(self._side):
+                    dist.all_reduce(piece, op=dist.ReduceOp.SUM)
+            else:
+                dist.all_reduce(piece, op=dist.ReduceOp.SUM)
+            self._early_done = True
+
+        self._hook = big.register_post_accumulate_grad_hook(hook)
+        self.early_enabled = True
+
     def allreduce_sum(self):
-        if _world() > 1:
+        if _world() == 1:
+            return
+        if self._early_done:        # the largest slice is already on its way (or done): only the head remains
+            self._early_done = False
+            head = self.flat[:self.offset[id(self.big)]]
+            if head.numel():
+                dist.all_reduce(head, op=dist.ReduceOp.SUM)
+            if self._side is not None:
+                torch.cuda.current_stream(self.flat.device).wait_stream(self._side)
+        else:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
 
     def allreduce_mean(self):
         if _world() > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.allreduce_sum()
             self.flat.div_(_world())
 
     @property
@@ -67,19 +111,17 @@ class FlatGrads:
 
 
 class FlatParams(FlatGrads):
-    """FlatGrads + the parameters themselves re-laid as views of one buffer (same order), so the optimiser update is
+    """FlatGrads + the parameters themselves re-laid as views of one buffer (same layout), so the optimiser update is
     one launch over two flat arrays and the initial rank-0 broadcast one collective."""
 
     def __init__(self, params):
         super().__init__(params)
         self.values = torch.empty_like(self.flat)
-        off = 0
         with torch.no_grad():
             for p in self.params:
-                view = self.values[off:off + p.numel()].view_as(p)
+                view = self.slice_of(p, self.values).view_as(p)
                 view.copy_(p)
                 p.data = view
-                off += p.numel()
 
 
 def sync_module_state(modules: Iterable[torch.nn.Module], flat_params: Optional[torch.Tensor] = None, src: int = 0):
@@ -132,28 +174,23 @@ class FusedAdam:
         self.flat.zero()
 
     def state_dict(self):
-        state, off = {}, 0
+        state = {}
         for i, p in enumerate(self.flat.params):
-            n = p.numel()
             state[i] = {"step": self.step_count.clone().reshape(()).to(torch.float32),
-                        "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
-                        "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p).clone()}
-            off += n
+                        "exp_avg": self.flat.slice_of(p, self.exp_avg).view_as(p).clone(),
+                        "exp_avg_sq": self.flat.slice_of(p, self.exp_avg_sq).view_as(p).clone()}
         group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
         group.update(maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
                      params=list(range(len(self.flat.params))))
         return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
-        off = 0
         for i, p in enumerate(self.flat.params):
-            n = p.numel()
             st = sd["state"].get(i)
             if st is not None:
-                self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
-                self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                self.flat.slice_of(p, self.exp_avg).copy_(st["exp_avg"].reshape(-1))
+                self.flat.slice_of(p, self.exp_avg_sq).copy_(st["exp_avg_sq"].reshape(-1))
                 self.step_count.fill_(float(st["step"]))
-            off += n
         for k in ("lr", "betas", "eps"):
             if k in sd["param_groups"][0]:
                 self.param_groups[0][k] = sd["param_groups"][0][k]
@@ -189,10 +226,13 @@ class DataParallelStepper:
     def collective_checked_step(self, batch):
         self.grads.zero()
         err, loss = None, None
+        early, self.grads.early_enabled = self.grads.early_enabled, False   # a rank may raise before the hook fires
         try:
             loss = self.checked_pass(batch)
         except F.NotPSDError as e:
             err = e
+        finally:
+            self.grads.early_enabled = early
         flag = torch.tensor([1 if err is not None else 0], dtype=torch.int32, device=self.grads.flat.device)
         if _world() > 1:
             dist.all_reduce(flag, op=dist.ReduceOp.MAX)
@@ -217,6 +257,7 @@ class ElboTrainer(DataParallelStepper):
         self.grads = FlatParams(self.params)
         sync_module_state([model, likelihood], self.grads.values)
         self.opt = FusedAdam(self.grads, lr=lr)
+        self.grads.overlap_largest()
         self.pool = F.InfoPool(self.grads.flat.device)
         model.train()
         likelihood.train()

@@ -117,16 +117,25 @@ class VariationalPosterior(MultivariateNormal):
     def Ls(self):
         return self._get("Ls", lambda: self.Ls_raw.to(self.dtype).tril())
 
+    def _Kzz64(self):
+        """K_ZZ + 1e-3 I of the float64 island (variational_strategy.py:35-44).  The reference evaluates the kernel in
+        the model dtype and casts the matrix; here the M x M matrix is EVALUATED in double from the (cast) inducing
+        points and hyper-parameters: its factor amplifies entry errors by cond(K_ZZ + 1e-3 I) ~ 1e5, which took the
+        gradients of Z and of the variational mean of FP32 models 3e-3 off the FP64 oracle
+        (tests/test_parity_scale_gpu.py); the cost is M^2 double-precision kernel evaluations."""
+        Zd = self.Z.double()
+        return self.kernel.ops(Zd).gram(Zd, None, diag_const=1e-3)
+
     @property
     def Lz(self):
         """chol(K_ZZ + 1e-3 I) in float64 (psd_safe_cholesky semantics)."""
-        return self._get("Lz", lambda: F.psd_safe_cholesky(self.kops.gram(self.Z, None, diag_const=1e-3).double()))
+        return self._get("Lz", lambda: F.psd_safe_cholesky(self._Kzz64()))
 
     @property
     def Wz(self):
         """L_Z^{-1} in float64 (FP32 models): the whitening products then run as 3xTF32 tensor-core GEMMs on
         an FP32 hi/lo pair of it instead of float64 triangular solves against 10^3 .. 10^4 columns."""
-        return self._get("Wz", lambda: F.chol_inverse(self.kops.gram(self.Z, None, diag_const=1e-3).double()))
+        return self._get("Wz", lambda: F.chol_inverse(self._Kzz64()))
 
     def prefetch(self):
         """Start the K_ZZ factorisation + inversion on a side stream.  It is a chain of single-CTA kernels (about
@@ -143,7 +152,7 @@ class VariationalPosterior(MultivariateNormal):
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             keys = ["Wz"]
-            self._c["Wz"] = F.chol_inverse(self.kops.gram(self.Z, None, diag_const=1e-3).double())
+            self._c["Wz"] = F.chol_inverse(self._Kzz64())
             if SIDE_WHITEN:
                 # ... and what follows from it without the CME solve: A~ = L_Z^{-1} K_Zx and D = L_S L_S^T - I.  Their
                 # backward nodes run on the side stream as well, next to the second big solve of the backward pass.

@@ -144,6 +144,12 @@ DCGP_API int dcgp_syrk(int trans, int64_t n, int64_t k, double alpha, const void
  * keeps that solve in double precision; here the factor and its inverse are FP64 and the product runs
  * on an FP32 hi/lo pair of the inverse). */
 DCGP_API int dcgp_split_lo(const void* src, void* dst, int64_t rows, int64_t cols, int64_t lds, int64_t ldd, void* stream);
+/* dst = src rounded to the nearest TF32 value (cvt.rna.tf32.f32), rows x cols FP32, row-major.  tcgen05.mma reads FP32
+ * operands by truncation (round toward zero): on raw data a single-pass TF32 product is biased by about -7e-4 relative
+ * (the mean of the two truncation errors) - three chained products already leave the 1e-3 tolerance.  Operands rounded
+ * to nearest first make the product unbiased, which is what cuBLAS TF32 - the reference's GPU path
+ * (torch.backends.cuda.matmul.allow_tf32) - does inside its kernels. */
+DCGP_API int dcgp_round_tf32(const void* src, void* dst, int64_t rows, int64_t cols, int64_t lds, int64_t ldd, void* stream);
 DCGP_API int dcgp_gemm_ex(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
                  const void* Alo, const void* B, int64_t ldb, const void* Blo, double beta, void* C, int64_t ldc,
                  void* Clo, int dtype, int flags, void* stream);

@@ -52,11 +52,14 @@ def vcmp_specs(p, r):
     return k, l
 
 
-def vcmp_loss(p, x, ext, y, z, lbda, num_data, beta=1.0, use_individuals_noise=True):
-    """-ELBO of one VariationalCMP minibatch, the reference's algorithm."""
+def vcmp_loss(p, x, ext, y, z, lbda, num_data, beta=1.0, use_individuals_noise=True, detach_root=False):
+    """-ELBO of one VariationalCMP minibatch, the reference's algorithm.  `detach_root` (tests only): no gradient
+    through the root of Lambda^{-1}, which isolates the part of the bag-kernel gradient that flows through l(y, y~)."""
     k, l = vcmp_specs(p, ext.shape[1])
     mu_q, Sigma_q = R.svgp_q(k, p["Z"], x, p["var_mean"], p["chol_var"])
     Rt, B = R.elbo_computation_parameters(l, y, ext, lbda)
+    if detach_root:
+        Rt = Rt.detach()
     n = z.numel()
     noise = softplus(p["raw_noise"]).reshape(()) + 1e-4
     agg = B @ Rt

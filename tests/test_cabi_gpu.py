@@ -359,7 +359,11 @@ def test_gaussian_terms_values_and_gradients(dtype, tol):
                                            # few / oddly laid out right-hand sides: 512-block sweeps from 16 columns, FP32
                                            # through a padded copy (rows must be 16-byte aligned for TMA)
                                            (torch.float32, 2300, 50, 1e-4), (torch.float32, 3000, 17, 1e-4),
-                                           (torch.float64, 2300, 33, 1e-11), (torch.float32, 2048, 7, 1e-4)])
+                                           (torch.float64, 2300, 33, 1e-11), (torch.float32, 2048, 7, 1e-4),
+                                           # two-step look-ahead sweeps (>= 4 blocks of 512): exactly 4 blocks, a last
+                                           # block of one row, of 511 rows, many blocks
+                                           (torch.float32, 2561, 100, 1e-4), (torch.float64, 3583, 200, 1e-11),
+                                           (torch.float32, 5000, 520, 1e-4), (torch.float64, 4096, 64, 1e-11)])
 def test_planned_solves_match_reference(dtype, n, m, tol):
     """dcgp_solve_plan + dcgp_trsm_planned (trans 0 / 1 / 2) against float64 triangular solves; a plan
     is reusable across calls and small factors (no plan) fall back to dcgp_trsm."""

@@ -1,4 +1,4 @@
-"""Host emulation of the tile algorithm behind DCGP_LEAF_FINV (csrc/chol.cu: block_potrf<T, true> with inv_rows_init /
+"""Host emulation of the tile algorithm of the leaves (DCGP_LEAF_FINV, default since round 2) (csrc/chol.cu: block_potrf<T, true> with inv_rows_init /
 inv_rows_panel / inv_rows_update): right-looking Cholesky over 16-wide sub-panels in a pitch-129 tile whose unused upper
 part carries the unit rows e_c, so that L^{-1} is complete when the last pivot is ( X(i, c) <-> S[c][i + 1] ).  Same
 index expressions and predicates as the kernel, executed sequentially; the tile starts filled with NaN, so any read of
@@ -76,45 +76,73 @@ def test_fused_leaf_gives_factor_and_inverse(nb):
     assert np.abs(X @ ref - np.eye(nb)).max() < 1e-12
 
 
-def diag_step_lanes(block, pw, piv2):
-    """diag_step of csrc/chol.cu lane by lane (lane r holds row r of the 16 x 16 block; entries above the diagonal are
-    junk that is never stored): `piv2` broadcasts the next pivot from `row[c+1] - lrc^2` of lane c+1 instead of the
-    generally updated row[c+1] (DCGP_LEAF_PIV2).  Returns the factor and the inverse pivots."""
+def diag_pair_lanes(block, pw, dtype=np.float64):
+    """FP32 diag_step of csrc/chol.cu lane by lane (lane r holds row r of the 16 x 16 block, identity padding outside
+    the valid pw x pw part): two columns per round, 1/sqrt(a) and 1/sqrt(a e - b^2) from the same three broadcasts,
+    second pivot's reciprocal root = sqrt(a) / sqrt(det).  Returns the factor, the inverse pivots and `bad`."""
     lanes = 32
-    row = np.zeros((lanes, SB))
+    row = np.zeros((lanes, SB), dtype=dtype)
     for r in range(lanes):
         for c in range(SB):
             row[r, c] = block[r, c] if (r < pw and c <= r) else (1.0 if r == c else 0.0)
-    myinv = np.zeros(lanes)
-    dnext = row[0, 0]
-    for c in range(SB):
-        d = dnext if piv2 else row[c, c]                      # shuffle from lane c
-        y = 1.0 / np.sqrt(d)
-        scaled = row[:, c] * y
-        for r in range(lanes):
-            row[r, c] = d * y if r == c else scaled[r]
-        myinv[c] = y
-        lrc = row[:, c].copy()
-        if piv2 and c + 1 < SB:
-            own = -lrc * lrc + row[:, c + 1]
-            dnext = own[c + 1]                                # shuffle from lane c + 1
-        for k in range(c + 1, SB):
-            lkc = row[k, c]                                   # shuffle of row[c] from lane k
-            row[:, k] = -lrc * lkc + row[:, k]
-    L = np.zeros((pw, pw))
+    myinv = np.zeros(lanes, dtype=dtype)
+    bad = 0
+    one = dtype(1.0)
+    for c in range(0, SB, 2):
+        a, b, e = row[c, c], row[c + 1, c], row[c + 1, c + 1]       # three shuffles
+        det = a * e - b * b
+        if bad == 0:
+            if not a > 0:
+                bad = c + 1
+            elif not det > 0:
+                bad = c + 2
+        y1, yd = one / np.sqrt(a), one / np.sqrt(det)
+        sa = a * y1
+        y2 = sa * yd
+        l21 = b * y1
+        l1 = row[:, c] * y1
+        l1[c] = sa
+        t = row[:, c + 1] - l1 * l21
+        l2 = t * y2
+        l2[c + 1] = (det * yd) * y1
+        row[:, c], row[:, c + 1] = l1, l2
+        myinv[c], myinv[c + 1] = y1, y2
+        for k in range(c + 2, SB):
+            row[:, k] = row[:, k] - l1 * l1[k] - l2 * l2[k]           # shuffles of l1, l2 from lane k
+    L = np.zeros((pw, pw), dtype=dtype)
     for r in range(pw):
         L[r, :r + 1] = row[r, :r + 1]
-    return L, myinv[:pw]
+    return L, myinv[:pw], bad
 
 
-@pytest.mark.parametrize("pw", [16, 9, 1])
-def test_short_pivot_chain_is_the_same_arithmetic(pw):
+@pytest.mark.parametrize("pw", [16, 15, 9, 2, 1])
+def test_two_columns_per_round_pivots_give_the_cholesky_factor(pw):
     rng = np.random.default_rng(pw)
     M = rng.standard_normal((pw, pw))
     A = M @ M.T + pw * np.eye(pw)
     blk = np.zeros((32, SB))
     blk[:pw, :pw] = np.tril(A)
-    L0, i0 = diag_step_lanes(blk, pw, False)
-    L1, i1 = diag_step_lanes(blk, pw, True)
-    assert np.array_equal(L0, L1) and np.array_equal(i0, i1)          # bitwise: same operands, same order
-    assert np.abs(L0 - np.linalg.cholesky(A)).max() < 1e-12 * np.abs(A).max()
+    L, inv, bad = diag_pair_lanes(blk, pw)
+    ref = np.linalg.cholesky(A)
+    assert bad == 0
+    assert np.abs(L - ref).max() < 1e-13 * np.abs(A).max()
+    assert np.abs(inv * np.diag(ref) - 1).max() < 1e-13
+    L32, _, _ = diag_pair_lanes(blk.astype(np.float32), pw, np.float32)
+    assert np.abs(L32 - ref).max() < 2e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("col", [0, 1, 6, 7, 15])
+def test_two_columns_per_round_pivots_report_the_first_bad_minor(col):
+    """LAPACK-style info: the first non-positive leading minor, whether it is the first or the second column of a pair."""
+    rng = np.random.default_rng(col)
+    M = rng.standard_normal((16, 16))
+    A = M @ M.T + 16 * np.eye(16)
+    L = np.linalg.cholesky(A)
+    L[col, col] = 0.0                      # A = L L^T is then singular exactly at leading minor col + 1
+    A = L @ L.T
+    A[col, col] -= 1e-3
+    blk = np.zeros((32, SB))
+    blk[:16, :16] = np.tril(A)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        _, _, bad = diag_pair_lanes(blk, 16)
+    assert bad == col + 1

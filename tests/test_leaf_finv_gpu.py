@@ -1,17 +1,13 @@
-"""DCGP_LEAF_FINV=1 (the leaves of the factorisation build the inverse of their factor inside the pivot loop instead of a
-separate block_trtri pass; csrc/chol.cu, inv_rows_*) and DCGP_LEAF_PIV2=1 (short pivot chain in diag_step).  The switch is read once per process, so the checks run in a
-subprocess.  EXPERIMENTAL: written when no GPU time was left in round 1 (the tile algorithm is checked by
-tests/test_leaf_finv_cpu.py on a host emulation; the default path's SASS is byte-identical to the validated build), hence
-opt-in:  DCGP_TEST_EXPERIMENTAL=1 python -m pytest tests/test_leaf_finv_gpu.py -m gpu"""
+"""The factorisation leaves build the inverse of their factor inside the pivot loop (csrc/chol.cu, inv_rows_*; default since
+round 2 after the B200 A/B in profiles/r02_finv_ab.txt).  DCGP_LEAF_FINV=0 keeps the round-1 variant (separate block_trtri
+pass) for A/B runs: this test keeps that switch honest.  The switch is read once per process, hence the subprocess."""
 import os
 import subprocess
 import sys
 
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DCGP_TEST_EXPERIMENTAL", "") in ("", "0"),
-                                 reason="experimental switch, not yet validated on a GPU: set DCGP_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 CHECK = r'''
@@ -20,7 +16,7 @@ sys.path.insert(0, sys.argv[1])
 from deconditional_downscaling_b200 import ops
 torch.manual_seed(0)
 for dt, tol in ((torch.float64, 1e-10), (torch.float32, 2e-5)):
-    for n in (7, 16, 100, 128, 129, 517, 1024, 2048, 4096):
+    for n in (7, 16, 100, 128, 129, 517, 2048):
         M = torch.randn(n, n, dtype=torch.float64, device="cuda")
         A = (M @ M.t() / n + torch.eye(n, dtype=torch.float64, device="cuda")).to(dt)
         L = A.clone()
@@ -42,10 +38,40 @@ print("ok")
 '''
 
 
-@pytest.mark.parametrize("finv,piv2", [("1", "0"), ("0", "1"), ("1", "1")])
-def test_factorisation_with_experimental_leaves_matches_lapack(finv, piv2):
-    """DCGP_LEAF_FINV (inverse rides along with the factorisation) and DCGP_LEAF_PIV2 (short pivot chain), alone and
-    together: factors against LAPACK, solves and inverses through the blocks the leaves produced."""
-    r = subprocess.run([sys.executable, "-c", CHECK, ROOT], env={**os.environ, "DCGP_LEAF_FINV": finv, "DCGP_LEAF_PIV2": piv2},
+def test_factorisation_with_legacy_leaves_matches_lapack():
+    """DCGP_LEAF_FINV=0: factors against LAPACK, solves and inverses through the blocks the leaves produced (the default
+    mode is what every other GPU test exercises)."""
+    r = subprocess.run([sys.executable, "-c", CHECK, ROOT], env={**os.environ, "DCGP_LEAF_FINV": "0"},
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-3000:]
+
+
+CHECK_LA2 = r'''
+import sys, torch
+sys.path.insert(0, sys.argv[1])
+from deconditional_downscaling_b200 import ops
+torch.manual_seed(1)
+for dt, tol in ((torch.float64, 1e-11), (torch.float32, 1e-4)):
+    for n, m in ((2048, 64), (2561, 100), (3583, 200), (5000, 520)):
+        M = torch.randn(n, n, dtype=torch.float64, device="cuda")
+        A = M @ M.t() / n + torch.eye(n, dtype=torch.float64, device="cuda")
+        L = torch.linalg.cholesky(A).to(dt).contiguous()
+        plan = ops.solve_plan(L)
+        B = torch.randn(n, m, dtype=dt, device="cuda")
+        Ld, Bd = L.double(), B.double()
+        rel = lambda a, b: ((a.double() - b).norm() / b.norm()).item()
+        assert rel(ops.trsm_(L, B.clone(), plan=plan), torch.linalg.solve_triangular(Ld, Bd, upper=False)) < tol, (dt, n, m, "N")
+        assert rel(ops.trsm_(L, B.clone(), trans=True, plan=plan), torch.linalg.solve_triangular(Ld.t(), Bd, upper=True)) < tol, (dt, n, m, "T")
+        assert rel(ops.potrs_(L, B.clone(), plan=plan), torch.cholesky_solve(Bd, Ld)) < 10 * tol, (dt, n, m, "potrs")
+        assert rel(ops.potrs_(L, B.clone()), torch.cholesky_solve(Bd, Ld)) < 10 * tol, (dt, n, m, "unplanned")
+print("ok")
+'''
+
+
+def test_two_step_lookahead_sweeps_match_lapack():
+    """DCGP_TRSM_LA=2 (opt-in, csrc/chol.cu ltrsm512_la2: one dependent GEMM per 512-block on the chain lane, products
+    with the inverted neighbour blocks prepared in the plan): exactly four blocks, ragged last blocks of 1 and 511 rows,
+    many blocks; planned and unplanned; forward, transposed and both sweeps."""
+    r = subprocess.run([sys.executable, "-c", CHECK_LA2, ROOT], env={**os.environ, "DCGP_TRSM_LA": "2"},
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-3000:]

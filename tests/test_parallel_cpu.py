@@ -58,7 +58,8 @@ def test_flat_grads_views_alias_parameter_grads():
     b = torch.nn.Parameter(torch.zeros(4))
     f = FlatGrads([a, b])
     (a.sum() * 2 + (b * torch.arange(4.0)).sum()).backward()
-    assert f.flat.tolist() == [2.0] * 6 + [0.0, 1.0, 2.0, 3.0]
+    assert f.slice_of(a).tolist() == [2.0] * 6 and f.slice_of(b).tolist() == [0.0, 1.0, 2.0, 3.0]
+    assert f.flat.tolist() == [0.0, 1.0, 2.0, 3.0] + [2.0] * 6          # the largest gradient sits at the end of the buffer
     f.zero()
     assert a.grad.abs().sum() == 0 and b.grad.abs().sum() == 0
     assert f.nbytes == 40
@@ -111,7 +112,7 @@ def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
 # ---------------------------------------------------------------------------------------------------------------
 # step protocol of training.DataParallelStepper (collective failure decision BEFORE any update, rank-0 broadcast of the
 # initial state) on two gloo ranks, with a toy compute in place of the CUDA kernels
-def _protocol_worker(rank, world, port, out, fail_rank, fail_step, retry_fails):
+def _protocol_worker(rank, world, port, out, fail_rank, fail_step, retry_fails, overlap=True):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from deconditional_downscaling_b200 import functional as F
@@ -122,19 +123,22 @@ def _protocol_worker(rank, world, port, out, fail_rank, fail_step, retry_fails):
             super().__init__()
             torch.manual_seed(100 + rank)                         # every rank starts DIFFERENT ...
             self.w = torch.nn.Parameter(torch.randn(5, dtype=torch.float64))
+            self.big = torch.nn.Parameter(torch.randn(4, 5, dtype=torch.float64))   # exchanged early, by the hook
             self.register_buffer("freq", torch.randn(3, dtype=torch.float64))   # ... incl. a lazily drawn buffer
 
     class Stepper(DataParallelStepper):
         def __init__(self):
             self.m = Toy()
             sync_module_state([self.m])                           # ... and is made identical here
-            self.grads = FlatGrads([self.m.w])
+            self.grads = FlatGrads([self.m.w, self.m.big])
+            if overlap:
+                self.grads.overlap_largest()
             self.pool = F.InfoPool("cpu")
-            self.opt = torch.optim.Adam([self.m.w], lr=0.1)
+            self.opt = torch.optim.Adam([self.m.w, self.m.big], lr=0.1)
             self.t, self.checked, self.updates = 0, 0, 0
 
         def _loss(self, batch):
-            return ((self.m.w * batch).sum() - 1.0) ** 2 + self.m.freq.sum() * 0
+            return ((self.m.w * batch).sum() - 1.0) ** 2 + ((self.m.big @ batch).sum() - 0.5) ** 2 + self.m.freq.sum() * 0
 
         def optimistic_pass(self, batch):
             bad = rank == fail_rank and self.t == fail_step
@@ -160,7 +164,7 @@ def _protocol_worker(rank, world, port, out, fail_rank, fail_step, retry_fails):
             self.grads.zero()
 
     s = Stepper()
-    start = s.m.w.detach().clone(), s.m.freq.clone()
+    start = torch.cat([s.m.w.detach().reshape(-1), s.m.big.detach().reshape(-1)]), s.m.freq.clone()
     g = torch.Generator().manual_seed(7 + rank)
     raised = False
     for t in range(4):
@@ -171,14 +175,15 @@ def _protocol_worker(rank, world, port, out, fail_rank, fail_step, retry_fails):
         except F.NotPSDError:
             raised = True
             break
-    out[rank] = (start, s.m.w.detach().clone(), s.checked, s.updates, raised, bool(torch.isfinite(s.m.w).all()))
+    final = torch.cat([s.m.w.detach().reshape(-1), s.m.big.detach().reshape(-1)])
+    out[rank] = (start, final, s.checked, s.updates, raised, bool(torch.isfinite(final).all()))
     dist.destroy_process_group()
 
 
-def _run_protocol(fail_rank, fail_step, retry_fails):
+def _run_protocol(fail_rank, fail_step, retry_fails, overlap=True):
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_protocol_worker, args=(2, _free_port(), out, fail_rank, fail_step, retry_fails), nprocs=2, join=True)
+    mp.spawn(_protocol_worker, args=(2, _free_port(), out, fail_rank, fail_step, retry_fails, overlap), nprocs=2, join=True)
     return out[0], out[1]
 
 
@@ -198,6 +203,17 @@ def test_replicas_start_identical_and_stay_identical_through_a_one_rank_failure(
 def test_without_failures_no_rank_takes_the_checked_pass():
     r0, r1 = _run_protocol(fail_rank=-1, fail_step=-1, retry_fails=False)
     assert (r0[2], r1[2]) == (0, 0) and (r0[3], r1[3]) == (4, 4) and torch.equal(r0[1], r1[1])
+
+
+def test_early_allreduce_of_the_largest_gradient_changes_nothing():
+    """FlatGrads.overlap_largest(): the big slice is exchanged by a post-accumulate-grad hook during the backward pass, the
+    end-of-step collective carries only the head - same parameters as one collective over the whole buffer, with and
+    without a failing rank (the checked pass runs with the hook disabled)."""
+    for fail in ((-1, -1), (1, 2)):
+        a0, a1 = _run_protocol(fail[0], fail[1], False, overlap=True)
+        b0, b1 = _run_protocol(fail[0], fail[1], False, overlap=False)
+        assert torch.equal(a0[1], a1[1]) and torch.equal(b0[1], b1[1])
+        torch.testing.assert_close(a0[1], b0[1], rtol=1e-14, atol=1e-15)
 
 
 def test_unrecoverable_failure_on_one_rank_raises_on_all_ranks():

@@ -30,3 +30,8 @@ for n, m in zip(v[::2], v[1::2]):
     out.append(f"potrs {t:.3f} ms err {((X.double() - ref).norm() / ref.norm()).item():.1e}")
     tc, _ = timed(lambda: B.clone())
     print(f"{sys.argv[1]} n={n} m={m}: " + " | ".join(out) + f" | (clone {tc:.3f} ms)", flush=True)
+    plan = ops.solve_plan(L)
+    if plan is not None:
+        tp, _ = timed(lambda: ops.solve_plan(L))
+        t2, X = timed(lambda: ops.potrs_(L, B.clone(), plan=plan))
+        print(f"    plan build {tp:.3f} ms | planned potrs {t2:.3f} ms err {((X.double() - ref).norm() / ref.norm()).item():.1e}", flush=True)
