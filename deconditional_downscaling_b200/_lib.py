@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("DCGP_LIB") or os.path.join(_HERE, "lib", "libdcgp.so"
 F64, F32 = 0, 1
 KIND_RBF, KIND_MATERN32, KIND_MATERN12, KIND_MATERN52 = 0, 1, 2, 3
 MAX_COMPONENTS, MAX_DIMS = 4, 8
-GRAM_SAME, GRAM_OUT_F64 = 1, 2
+GRAM_SAME, GRAM_OUT_F64, GRAM_NO_FUSE = 1, 2, 256
 GEMM_LOWER, GEMM_NO_SPLITK, GEMM_TF32X3, GEMM_NO_TCGEN05 = 1, 2, 4, 8
 
 

@@ -36,6 +36,9 @@ int dcgp_gemm_tc_ex(int transa, int transb, int64_t m, int64_t n, int64_t k, dou
                     const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int flags, const void* Alo, const void* Blo,
                     void* Clo, int64_t lower_off, int64_t clo_cols, cudaStream_t st);
 
+int dcgp_potrf_link_tm(float* A, int64_t lda, int nb, float* inv, float* invlo, int* info, int64_t j0, const float* R,
+                       const float* invp, cudaStream_t st);
+
 namespace {
 
 constexpr int NB = 128;     // leaf block size
@@ -47,10 +50,6 @@ constexpr int SB = 16;      // sub-panel width inside the leaf
 // 1/sqrt(d) without the IEEE sqrt / div subroutines (they dominate the serial pivot chain):
 // hardware rsqrt seed + Newton steps y <- y (1.5 - 0.5 d y^2).  d <= 0 or NaN yields NaN.
 template <typename T> __device__ __forceinline__ T fast_rsqrt(T d);
-template <> __device__ __forceinline__ float fast_rsqrt<float>(float d) {
-    float y = rsqrtf(d);
-    return y * fmaf(-0.5f * d, y * y, 1.5f);
-}
 template <> __device__ __forceinline__ double fast_rsqrt<double>(double d) {
     // seed: 2 ulp of FP32 (2.4e-7); each Newton step squares the relative error (x 1.5): 8.6e-14, then 1.1e-26
     double y = (double)rsqrtf((float)d);
@@ -802,6 +801,9 @@ int chol_rec(const Ctx<T>& c, int64_t j0, int64_t nb) {
         DCGP_CHECK_LAUNCH();
         return 0;
     }
+    // (Halving FP32 blocks above 4096 by the recursion first - two look-ahead factorisations with L2-resident trailing
+    // matrices around one deep-K solve and update - was measured on B200 with the TMEM link kernel: 8192^2 3.80 -> 4.34 ms,
+    // reconstruction error 1.8e-6 -> 2.2e-5; not kept.)
     if (c.la_pw >= 0) {
         const int64_t pw = c.la_pw ? c.la_pw : la_panel(c.dtype, nb);
         if (pw && nb > 2 * pw) {
@@ -865,11 +867,10 @@ struct LookAhead {
 };
 // One lane set per caller stream: factorisations issued from different streams (e.g. K_ZZ on a side stream while
 // Lambda factors on the main one) must not queue behind each other on shared internal streams.
+// (Unbounded: a lane set is two streams and fourteen events; sharing one between two caller streams - what a bounded map
+// did in round 1 for a ninth stream - would let two concurrent factorisations wait on each other's events.)
 thread_local std::unordered_map<cudaStream_t, LookAhead> g_lanes;
-inline LookAhead& lanes_for(cudaStream_t st) {
-    if (g_lanes.size() >= 8 && g_lanes.find(st) == g_lanes.end()) return g_lanes.begin()->second;  // bounded; still correct
-    return g_lanes[st];
-}
+inline LookAhead& lanes_for(cudaStream_t st) { return g_lanes[st]; }
 
 #ifdef DCGP_TRACE
 struct Trace {  // debug builds only: device timeline of the two lanes
@@ -952,12 +953,21 @@ int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
     DCGP_CU(cudaStreamWaitEvent(sa, x.fork, 0));
     DCGP_CU(cudaStreamWaitEvent(sb, x.fork, 0));
     TRACE_BEGIN(c.st);
+    // DCGP_LINK_TM (default 1): the links run on the TMEM-resident kernel of chol_tm.cu (tcgen05 rank-16 updates inside the
+    // leaf; B200: FP32 8192^2 factorisation 4.18 -> 3.81 ms, 1024^2 0.46 -> 0.36 ms, profiles/r02_link_tm.txt); 0 = the
+    // shared-memory potrf_step_kernel of round 1
+    static const int link_tm = getenv("DCGP_LINK_TM") ? atoi(getenv("DCGP_LINK_TM")) : 1;
+    if (link_tm) {
+        rc = dcgp_potrf_link_tm(c.A + j0 * c.lda + j0, c.lda, NB, c.ws + (j0 / NB) * NB * NB, nullptr, c.info, j0, nullptr, nullptr, sa);
+        if (rc) return rc;
+    } else {
 #define CALL(M)                                                                                                 \
     potrf_diag_kernel<float, M><<<1, NTHREADS, leaf_smem<float>(), sa>>>(c.A + j0 * c.lda + j0, c.lda, NB,        \
                                                                          c.ws + (j0 / NB) * NB * NB, c.info, j0)
-    DCGP_LEAF_DISPATCH(CALL);
+        DCGP_LEAF_DISPATCH(CALL);
 #undef CALL
-    DCGP_CHECK_LAUNCH();
+        DCGP_CHECK_LAUNCH();
+    }
     for (int64_t j = 0; j + 1 < q; ++j) {
         const int64_t bj = j0 + j * NB;
         const int64_t b1 = bj + NB, w1 = (end - b1 < NB) ? end - b1 : NB, r0 = b1 + w1, nr = end - r0;
@@ -1010,13 +1020,19 @@ int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
         // ---- chain lane: block j+1 (its inputs were completed by the bulk update of panel j-1)
         if (j > 0) DCGP_CU(cudaStreamWaitEvent(sa, x.upd[ep], 0));
         TRACE_MARK("A.waited", j, sa);
+        if (link_tm) {
+            rc = dcgp_potrf_link_tm(c.A + b1 * c.lda + b1, c.lda, (int)w1, c.ws + (b1 / NB) * NB * NB, nullptr, c.info, b1,
+                                    rcopy + (size_t)(j & 1) * NB * NB, invj, sa);
+            if (rc) return rc;
+        } else {
 #define CALL(M)                                                                                                  \
     potrf_step_kernel<M><<<1, NTHREADS, STEP_SMEM, sa>>>(c.A + b1 * c.lda + b1, c.lda, (int)w1,                    \
                                                          c.ws + (b1 / NB) * NB * NB, c.info, b1,                   \
                                                          rcopy + (size_t)(j & 1) * NB * NB, invj)
-        DCGP_LEAF_DISPATCH(CALL);
+            DCGP_LEAF_DISPATCH(CALL);
 #undef CALL
-        DCGP_CHECK_LAUNCH();
+            DCGP_CHECK_LAUNCH();
+        }
     }
     // join both lanes: the last panel solve on the bulk lane has no later consumer on the chain lane
     DCGP_CU(cudaEventRecord(x.join, sa));

@@ -101,35 +101,11 @@ __device__ __forceinline__ void load_spec_vals(const DevSpec& sp, SpecVals<T>* s
     } while (0)
 
 template <typename T> __device__ __forceinline__ T t_exp(T x);
-// exp(x) for x <= 0 in FP64 (every stationary kernel here evaluates exp at -r^2/2 or -c r): <= 2 ulp (checked against
-// 200-bit arithmetic over [-700, 0], tests/test_fast_exp_cpu.py restates it), 0 below -700.  The Gram build is bound
-// by this function, not by the bytes it writes: the library exp() costs ~30 FP64 instructions per entry (special cases,
-// a two-step range reduction, degree-11 polynomial), against which 8 bytes of output at 6.5 TB/s leave room for ~25.
-//   x = (n / 4) ln 2 + t, |t| <= ln 2 / 8:  exp(x) = 2^(n >> 2) * 2^((n & 3) / 4) * P9(t)
-// (Cody-Waite reduction with ln 2 / 4 split so that n * hi is exact, a four-entry table held in registers, a degree-9
-// Taylor polynomial - the remainder 0.087^10 / 10! = 7e-18 - and the power of two applied to the exponent field).
-__device__ __forceinline__ double exp_nonpos(double x) {
-    const int n = __double2int_rn(x * 5.7707801635558535);
-    const double nd = (double)n;
-    double t = fma(-nd, 0.1732867918908596, x);       // 0x1.62e42f8000000p-3: 27 trailing zero bits
-    t = fma(-nd, 3.249126723472472e-09, t);
-    double p = 2.7557319223985893e-06;
-    p = fma(p, t, 2.48015873015873e-05);
-    p = fma(p, t, 0.0001984126984126984);
-    p = fma(p, t, 0.001388888888888889);
-    p = fma(p, t, 0.008333333333333333);
-    p = fma(p, t, 0.041666666666666664);
-    p = fma(p, t, 0.16666666666666666);
-    p = fma(p, t, 0.5);
-    p = fma(p, t, 1.0);
-    p = fma(p, t, 1.0);
-    const int idx = n & 3;
-    const double tab = idx == 0 ? 1.0 : (idx == 1 ? 1.189207115002721 : (idx == 2 ? 1.4142135623730951 : 1.681792830507429));
-    p *= tab;
-    const double r = __hiloint2double(__double2hiint(p) + ((n >> 2) << 20), __double2loint(p));
-    return x < -700.0 ? 0.0 : r;
-}
-template <> __device__ __forceinline__ double t_exp<double>(double x) { return exp_nonpos(x); }
+// FP64 exp: the CUDA library function.  Round 2 tried a hand-written exp for non-positive arguments (Cody-Waite reduction
+// by ln 2 / 4, four-entry table, degree-9 polynomial, <= 2 ulp): the Gram build got SLOWER on B200, 2473 GB/s with
+// FP64 <-> integer conversions and 2651 GB/s with the magic-number shift and two Horner chains, against 3030 GB/s with
+// exp() (profiles/r02_gram_fp64_exp.txt) - removed.
+template <> __device__ __forceinline__ double t_exp<double>(double x) { return exp(x); }
 template <> __device__ __forceinline__ float t_exp<float>(float x) { return __expf(x); }
 template <typename T> __device__ __forceinline__ T t_sqrt(T x);
 template <> __device__ __forceinline__ double t_sqrt<double>(double x) { return sqrt(x); }
@@ -175,6 +151,24 @@ __device__ __forceinline__ void kernel_phi_w(int kind, T r2, T& phi, T& w) {
         phi = (T(1) + s + T(5.0 / 3.0) * r2) * e;
         w = T(5.0 / 3.0) * (T(1) + s) * e;
     }
+}
+
+// value of the additive kernel for one pair; a[] and b[] already scaled by 1/l
+template <typename T, int NC, int DPC>
+__device__ __forceinline__ T eval_pair(const DevSpec& sp, const T* os, const T (&a)[NC * DPC],
+                                       const T (&b)[NC * DPC]) {
+    T val = T(0);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        T acc = T(0);
+#pragma unroll
+        for (int j = 0; j < DPC; ++j) {
+            T d = a[c * DPC + j] - b[c * DPC + j];
+            acc = fma(d, d, acc);
+        }
+        val = fma(os[c], kernel_phi<T>(sp.kind[c], acc), val);
+    }
+    return val;
 }
 
 // Same as kernel_phi_w with hardware-approximate exp / sqrt (MUFU ex2, rsq: ~2 ulp) for FP32 adjoint kernels,

@@ -497,6 +497,13 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int
 
 }  // namespace
 
+// tensor map of a row-major FP32 matrix for other translation units (gram_mm.cu): swz 0 = SWIZZLE_128B (K-major
+// boxes), 1 = SWIZZLE_128B_ATOM_32B (MN-major 32-bit boxes)
+int dcgp_tmap_f32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, int swz) {
+    return make_map(map, base, rows, cols, ld, box_cols, box_rows,
+                    swz ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 int dcgp_split_lo_impl(const void* src, void* dst, int64_t rows, int64_t cols, int64_t lds, int64_t ldd, cudaStream_t st) {
     if (rows <= 0 || cols <= 0) return 0;
     const int64_t total = rows * cols;

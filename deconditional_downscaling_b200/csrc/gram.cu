@@ -17,24 +17,6 @@
 
 namespace {
 
-// value of the additive kernel for one pair; a[] and b[] already scaled by 1/l
-template <typename T, int NC, int DPC>
-__device__ __forceinline__ T eval_pair(const DevSpec& sp, const T* os, const T (&a)[NC * DPC],
-                                       const T (&b)[NC * DPC]) {
-    T val = T(0);
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        T acc = T(0);
-#pragma unroll
-        for (int j = 0; j < DPC; ++j) {
-            T d = a[c * DPC + j] - b[c * DPC + j];
-            acc = fma(d, d, acc);
-        }
-        val = fma(os[c], kernel_phi<T>(sp.kind[c], acc), val);
-    }
-    return val;
-}
-
 // accumulate the adjoints of one pair: g multiplies dK/dtheta, gs multiplies dK/da (only when DX)
 template <typename T, int NC, int DPC, bool DX = true, bool FAST = false>
 __device__ __forceinline__ void accum_pair(const DevSpec& sp, const T* os, const T (&a)[NC * DPC],
@@ -590,16 +572,34 @@ __global__ void nugget_rows_kernel(T* __restrict__ out, int64_t ldo, const T* __
     }
 }
 // Gram row panels: one panel when the whole matrix is small (<= 1 GiB: a single wide GEMM fills the machine
-// best), else 512 MiB panels - the full matrix (34 GB at N = 65536 in FP64) is never resident
+// best), else 2 GiB panels - the full matrix (34 GB at N = 65536 in FP64) is never resident.  (512 MiB panels, the
+// round-1 size, are 2048 rows at N = 32768 in FP64: with n = 327 right-hand sides that is 48 tiles of 128 x 128 on 148
+// SMs per panel, and K W took 57 ms against 33 ms for the materialised Gram + one GEMM; profiles/r02_bench_c6.json.)
 int64_t gm_rows(int64_t n1, int64_t n2, int dtype) {
     const int64_t es = dtype == DCGP_F64 ? 8 : 4;
     if (n1 * n2 * es <= (1ll << 30)) return n1;
-    int64_t rows = (512ll << 20) / (n2 * es);
+    int64_t rows = (2048ll << 20) / (n2 * es);
     rows = (rows / 128) * 128;
     if (rows < 128) rows = 128;
     return rows < n1 ? rows : n1;
 }
+// ... trimmed so that a panel's GEMM is a whole number of waves of 128 x 128 tiles (m right-hand sides): 8192 rows x 3 tile
+// columns are 192 tiles = 1.3 waves of 148 SMs, 6272 rows are 147 tiles (FP64, N = 32768, n = 327: K W 47.5 ms with 2 GiB
+// panels against 33 ms for one GEMM on the materialised matrix)
+int64_t gm_rows_for(int64_t n1, int64_t n2, int64_t m, int dtype) {
+    const int64_t cap = gm_rows(n1, n2, dtype);
+    if (cap >= n1) return n1;
+    const int64_t ct = (m + 127) / 128, sms = num_sms();
+    const int64_t waves = (cap / 128) * ct / sms;
+    if (waves < 1) return cap;
+    const int64_t rows = (waves * sms / ct) * 128;
+    return rows >= 128 ? rows : cap;
+}
 }  // namespace
+
+int dcgp_gram_matmul_fused_f32(const DevSpec& sp, const void* x1, int64_t n1, int64_t ldx1, const void* x2, int64_t n2,
+                               int64_t ldx2, const void* diag_dev, double diag_const, const void* W, int64_t m, int64_t ldw,
+                               void* out, int64_t ldo, int same, cudaStream_t st);
 
 // out = (k(x1, x2) [+ (diag_const + *diag_dev) I when SAME]) W without ever holding the Gram matrix in HBM as a
 // whole once it is large: row panels are generated into the workspace and consumed by the tensor-core GEMM.
@@ -623,12 +623,18 @@ extern "C" int dcgp_gram_matmul(const dcgp_kernel_spec* spec, const void* x1, in
     const int same = (flags & DCGP_GRAM_SAME) ? 1 : 0;
     if (same && n1 != n2) return -6;
     if (n2 == 0) return -6;
-    if (!workspace || workspace_bytes < dcgp_gram_matmul_workspace(n1, n2, dtype)) return -15;
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t es = dtype == DCGP_F64 ? 8 : 4, rows = gm_rows(n1, n2, dtype);
+    const int64_t es = dtype == DCGP_F64 ? 8 : 4, rows = gm_rows_for(n1, n2, m, dtype);
     const int gflags = flags & (DCGP_GEMM_TF32X3 | DCGP_GEMM_NO_TCGEN05);
     // the generated panels feed nothing but this product: single-pass TF32 gets them rounded to nearest at the source
     const int rna = (dtype == DCGP_F32 && !(flags & DCGP_GEMM_TF32X3)) ? 1 : 0;
+    // FP32 single-pass: the fused tcgen05 kernel (gram_mm.cu) generates the Gram tiles in shared memory - no panels, no
+    // workspace.  DCGP_GEMM_NO_TCGEN05 keeps the panel path (A/B runs); shapes the kernel declines fall through.
+    if (rna && !(flags & (DCGP_GEMM_NO_TCGEN05 | DCGP_GRAM_NO_FUSE))) {
+        const int rc = dcgp_gram_matmul_fused_f32(sp, x1, n1, ldx1, x2, n2, ldx2, diag_dev, diag_const, W, m, ldw, out, ldo, same, st);
+        if (rc <= 0) return rc;
+    }
+    if (!workspace || workspace_bytes < dcgp_gram_matmul_workspace(n1, n2, dtype)) return -15;
     if (rows == n1) {
         // single panel: the symmetric Gram path (nugget applied on the diagonal by the generator itself)
         int rc = dtype == DCGP_F64 ? launch_gram_fwd<double, double>(sp, x1, n1, ldx1, x2, n2, ldx2, workspace, n2, diag_dev,

@@ -69,7 +69,10 @@ def exact_cmp_phases(x, ext, y, z, xs, lbda, timer=None, k_spec=None, l_spec=Non
     k_spec = k_spec or rbf_spec(x.size(1), dt, dev)
     l_spec = l_spec or rbf_spec(ext.size(1), dt, dev)
     with timer.phase("gram_K"):
+        # the materialised Gram build of SURVEY 8d.4 (HBM-write roofline); nothing below reads it: K W and the posterior
+        # cross-covariance go through the fused Gram-times-matrix entry point, which never holds K
         K = ops.gram(k_spec, x, None)
+    del K
     with timer.phase("gram_Lambda"):
         Lam = ops.gram(l_spec, ext, None, diag_const=lbda * N)
     with timer.phase("potrf"):
@@ -79,7 +82,7 @@ def exact_cmp_phases(x, ext, y, z, xs, lbda, timer=None, k_spec=None, l_spec=Non
     with timer.phase("potrs"):
         ops.potrs_(Lam, W)                              # W = Lambda^{-1} l(y~, y)
     with timer.phase("KW"):
-        KW = ops.gemm(K, W, C=padded(N, n, dt, dev))
+        KW = ops.gram_matmul(k_spec, x, None, W)        # FP32: tcgen05 kernel generating the Gram tiles in shared memory
     with timer.phase("Q_mll"):
         Q = ops.gemm(W, KW, transa=True)
         Q.diagonal().add_(noise)
@@ -89,11 +92,8 @@ def exact_cmp_phases(x, ext, y, z, xs, lbda, timer=None, k_spec=None, l_spec=Non
         ops.potrs_(Lq, alpha)
         logdet = ops.logdet_chol(Lq)
         mll = -0.5 * ((z * alpha.squeeze(-1)).sum() + logdet + n * math.log(2 * math.pi)) / n
-    del K
     with timer.phase("posterior"):
-        Ks = ops.gram(k_spec, xs, x)                     # k(x*, x)
-        C = ops.gemm(Ks, W, C=padded(xs.size(0), n, dt, dev))   # N* x n
-        del Ks
+        C = ops.gram_matmul(k_spec, xs, x, W)            # k(x*, x) W, N* x n
         mean = ops.gemm(C, alpha).squeeze(-1)
         Vt = C.t().contiguous()
         ops.trsm_(Lq, Vt, trans=False)                  # Lq^{-1} C^T

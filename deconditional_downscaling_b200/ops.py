@@ -106,6 +106,9 @@ def _ld(t: torch.Tensor) -> int:
 # cuBLAS TF32 does inside its kernels) makes the products unbiased.  A tensor is rounded once and the copy reused
 # while the tensor object is alive and unmodified (A = Lambda^{-1} B and A~ feed half a dozen products each).
 ROUND_TF32 = os.environ.get("DCGP_ROUND_TF32", "1") != "0"
+# (k(x1, x2) + c I) W of FP32 models on the fused tcgen05 kernel of csrc/gram_mm.cu (Gram tiles generated in shared
+# memory, never written); "0" keeps the panel path: Gram rows into a workspace + GEMM
+FUSED_GRAM_MATMUL = os.environ.get("DCGP_FUSED_GRAM_MATMUL", "1") != "0"
 _RNA = {}
 
 
@@ -209,11 +212,18 @@ def gram_matmul(spec: FlatSpec, x1, x2, W, diag_dev=None, diag_const=0.0):
         raise ValueError(f"gram_matmul: W has {W.size(0)} rows, the Gram matrix {n2} columns")
     out = torch.empty(n1, m, dtype=x1.dtype, device=x1.device)
     lib = _lib.load()
-    ws = _workspace(lib.dcgp_gram_matmul_workspace(n1, n2, _dt(x1)), x1.device)
     cs = spec.c_spec()
     flags = (GRAM_SAME if same else 0) | _x3(x1, n1 * n2 * m <= X3_GEMM_LIMIT)
-    if _single_pass_tc(x1.dtype, n1, m, n2, flags):
-        W = _rna(W)      # the Gram panels are rounded by their generator (csrc/gram.cu)
+    fused = False
+    if x1.dtype == torch.float32 and USE_TCGEN05 and not (flags & (_lib.GEMM_TF32X3 | _lib.GEMM_NO_TCGEN05)):
+        if FUSED_GRAM_MATMUL and n1 >= 128 and n2 >= 64 and m >= 32 and n1 * n2 >= (1 << 22):
+            W = _tma_rows(W)   # the fused kernel (csrc/gram_mm.cu) reads W through TMA: 16-byte aligned rows
+            fused = True       # mirrors dcgp_gram_matmul_fused_f32's own conditions: no panel workspace needed
+        if fused or _single_pass_tc(x1.dtype, n1, m, n2, flags):
+            W = _rna(W)        # the Gram tiles / panels are rounded to nearest TF32 by their generator
+    if not fused:
+        flags |= _lib.GRAM_NO_FUSE
+    ws = _workspace(16 if fused else lib.dcgp_gram_matmul_workspace(n1, n2, _dt(x1)), x1.device)
     rc = lib.dcgp_gram_matmul(ctypes.byref(cs), _ptr(x1), n1, _ld(x1), _ptr(x2), n2, _ld(x2), _ptr(diag_dev), float(diag_const),
                               _ptr(W), m, _ld(W), _ptr(out), _ld(out), _ptr(ws), ws.numel(), _dt(x1), flags, _stream())
     check(rc, "dcgp_gram_matmul")

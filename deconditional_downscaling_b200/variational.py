@@ -29,6 +29,9 @@ SIDE_STREAM = os.environ.get("DCGP_SIDE_STREAM", "auto")
 _SCOPE = [0]
 # prefetch() also whitens K_Zx and forms D on the side stream (B200, captured bench step: 12.58 -> 12.20 ms, 3 of 3 runs)
 SIDE_WHITEN = os.environ.get("DCGP_SIDE_WHITEN", "1") == "1"
+# experiment: K_Zx evaluated and whitened entirely in float64 (then cast), to separate the arithmetic of the whitening
+# from the FP32 evaluation of the cross Gram in the parity of FP32 models
+WHITEN64 = os.environ.get("DCGP_WHITEN64", "0") == "1"
 
 
 def side_stream_active():
@@ -156,7 +159,7 @@ class VariationalPosterior(MultivariateNormal):
             if SIDE_WHITEN:
                 # ... and what follows from it without the CME solve: A~ = L_Z^{-1} K_Zx and D = L_S L_S^T - I.  Their
                 # backward nodes run on the side stream as well, next to the second big solve of the backward pass.
-                self._c["At"] = self._whiten(self.kops.gram(self.Z, self.x))
+                self._c["At"] = self._At64() if WHITEN64 else self._whiten(self.kops.gram(self.Z, self.x))
                 self.D
                 keys += ["At", "Ls", "D"]
         self._c["_side"], self._c["_side_keys"] = side, keys
@@ -167,9 +170,15 @@ class VariationalPosterior(MultivariateNormal):
             return F.trsm(self.Lz, K, trans=False)
         return F.split_matmul(self.Wz, K)
 
+    def _At64(self):
+        Zd, xd = self.Z.double(), self.x.double()
+        return F.matmul(self.Wz, self.kernel.ops(Zd).gram(Zd, xd)).to(self.dtype)
+
     @property
     def At(self):
         """A~ = L_Z^{-1} K_Zx (float64 factor, result in the model dtype), M x N."""
+        if WHITEN64 and self.dtype != torch.float64:
+            return self._get("At", self._At64)
         return self._get("At", lambda: self._whiten(self.kops.gram(self.Z, self.x)))
 
     @property

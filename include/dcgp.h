@@ -12,9 +12,19 @@
  * Conventions
  *   - plain C: pointers + sizes, no C++/torch types.  All data pointers are
  *     DEVICE pointers unless stated; the caller owns every buffer (inputs,
- *     outputs, workspace); the library never allocates device memory, never
- *     synchronises the stream and keeps no mutable global state (except a
- *     relaxed-atomic diagnostic launch counter).
+ *     outputs, workspace): the library never allocates device memory and
+ *     never synchronises the stream.
+ *   - host-side state the library does keep (all of it created lazily, none
+ *     of it visible in results): per calling thread and per caller stream a
+ *     set of two internal CUDA streams (high / low priority) and their events
+ *     - the "lanes" of the look-ahead factorisation and solves, forked from
+ *     and joined back into the caller's stream with events only, so calls stay
+ *     capturable in a CUDA graph; `cudaFuncSetAttribute` latches per kernel;
+ *     the SM count; tuning switches read once from the environment (DCGP_*,
+ *     DESIGN.md section 7); a relaxed-atomic diagnostic launch counter.
+ *     Calls are safe from several host threads (thread-local lanes) and from
+ *     several streams of one thread (one lane set per stream); one process
+ *     drives one device (the state is keyed by stream, not by device).
  *   - matrices are ROW-MAJOR with an explicit leading dimension (elements
  *     between consecutive rows).
  *   - dtype: DCGP_F64 computes and stores in double (FP64 tensor/vector
@@ -55,6 +65,8 @@ extern "C" {
 /* flags */
 #define DCGP_GRAM_SAME 1        /* x2 is x1 (enables +diag and the symmetric fast path)  */
 #define DCGP_GRAM_OUT_F64 2     /* dtype F32 inputs/math, store K as double (fp64 island) */
+#define DCGP_GRAM_NO_FUSE 256   /* dcgp_gram_matmul: keep the panel path (Gram rows into the workspace + GEMM) even where
+                                   the fused tcgen05 kernel would take the product (A/B runs) */
 #define DCGP_GEMM_LOWER 1       /* only tiles touching the lower triangle of C are computed/written */
 #define DCGP_GEMM_NO_SPLITK 2   /* C aliases an input (in-place): the K loop is never split across CTAs */
 #define DCGP_GEMM_INPLACE 16    /* C aliases A (then n <= 128) or B (then m <= 128): single tile along that dimension */

@@ -468,3 +468,46 @@ def test_adam_step_matches_torch_adam_and_honours_the_veto(dtype):
     ops.adam_step(p, g, m, v, step, 0.01, 0.9, 0.999, 1e-8, veto=veto, zero_grads=True)
     assert step.item() == 5 and torch.equal(p, before[0]) and torch.equal(m, before[1]) and torch.equal(v, before[2])
     assert g.abs().max().item() > 0                      # a vetoed update does not clear the gradient either
+
+
+@pytest.mark.parametrize("n1,n2,m,same,kind", [(4096, 4096, 1024, True, "rbf5"), (5000, 3000, 328, False, "rbf3"),
+                                               (8192, 8192, 100, True, "add"), (4100, 2100, 77, False, "mat"),
+                                               (2048, 2048, 32, True, "rbf3")])
+def test_fused_gram_matmul_tcgen05_matches_dense_product(n1, n2, m, same, kind):
+    """csrc/gram_mm.cu: (k(x1, x2) + c I) W with the Gram tiles generated in shared memory and fed to tcgen05.mma - against
+    the dense FP64 product (single-pass TF32 with operands rounded to nearest: 1e-3 normwise, measured ~2e-4) and against
+    the panel path (Gram rows into a workspace + GEMM), for ragged sizes, W with unaligned rows, additive / Matern
+    kernels with active dims and the diagonal terms of a self-product."""
+    from deconditional_downscaling_b200 import ops
+    torch.manual_seed(n1 + m)
+    d = {"rbf5": 5, "rbf3": 3, "add": 5, "mat": 3}[kind]
+    dev = lambda t: t.to("cuda")
+    if kind == "add":
+        spec64 = ops.FlatSpec(["matern32", "rbf"], [[0, 1], [2, 3, 4]], [dev(torch.tensor([0.9, 1.3], dtype=torch.float64)),
+                              dev(torch.tensor([1.1, 0.7, 1.5], dtype=torch.float64))],
+                              [dev(torch.tensor([0.6], dtype=torch.float64)), dev(torch.tensor([0.8], dtype=torch.float64))])
+    else:
+        spec64 = ops.FlatSpec(["matern32" if kind == "mat" else "rbf"], [list(range(d))],
+                              [dev(0.8 + 0.5 * torch.rand(d, dtype=torch.float64))], [dev(torch.tensor([0.7], dtype=torch.float64))])
+    spec32 = spec64.cast(torch.float32)
+    x1 = torch.randn(n1, d, dtype=torch.float64, device="cuda")
+    x2 = x1 if same else torch.randn(n2, d, dtype=torch.float64, device="cuda")
+    W = torch.randn(n2, m, dtype=torch.float64, device="cuda")
+    diag = 0.37 if same else 0.0
+    ref = ops.gram(spec64, x1, None if same else x2, diag_const=diag) @ W
+    x1f, x2f, Wf = x1.float(), (None if same else x2.float()), W.float()
+    assert ops.FUSED_GRAM_MATMUL
+    from deconditional_downscaling_b200 import _lib as L_
+    n0 = L_.load().dcgp_launch_count()
+    got = ops.gram_matmul(spec32, x1f, x2f, Wf, diag_const=diag)
+    launches = L_.load().dcgp_launch_count() - n0
+    assert launches <= 2, launches                # the fused kernel (+ the one-off TF32 rounding of W): no panels, no GEMM
+    ops.FUSED_GRAM_MATMUL = False
+    try:
+        panel = ops.gram_matmul(spec32, x1f, x2f, Wf, diag_const=diag)
+    finally:
+        ops.FUSED_GRAM_MATMUL = True
+    rel = lambda a, b: ((a.double() - b).norm() / b.norm()).item()
+    assert rel(got, ref) < 1e-3, rel(got, ref)
+    assert rel(got, panel.double()) < 1e-3
+    assert torch.isfinite(got).all()
