@@ -957,8 +957,11 @@ int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
     // leaf; B200: FP32 8192^2 factorisation 4.18 -> 3.81 ms, 1024^2 0.46 -> 0.36 ms, profiles/r02_link_tm.txt); 0 = the
     // shared-memory potrf_step_kernel of round 1
     static const int link_tm = getenv("DCGP_LINK_TM") ? atoi(getenv("DCGP_LINK_TM")) : 1;
+    // the TMEM link kernel also leaves the TF32 remainders of inv(L_jj) for the bulk lane's 3xTF32 panel solve: two slots
+    // alternate (link j + 2 starts only after the bulk lane has finished with panel j)
+    auto invlo_slot = [&](int64_t blk) { return rcopy + (size_t)(2 + (blk & 1)) * NB * NB; };
     if (link_tm) {
-        rc = dcgp_potrf_link_tm(c.A + j0 * c.lda + j0, c.lda, NB, c.ws + (j0 / NB) * NB * NB, nullptr, c.info, j0, nullptr, nullptr, sa);
+        rc = dcgp_potrf_link_tm(c.A + j0 * c.lda + j0, c.lda, NB, c.ws + (j0 / NB) * NB * NB, invlo_slot(0), c.info, j0, nullptr, nullptr, sa);
         if (rc) return rc;
     } else {
 #define CALL(M)                                                                                                 \
@@ -984,9 +987,11 @@ int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
         // before its epilogue overwrites them (the remainders of the panel came from the previous update)
         rc = 1;
         if (end - b1 >= NB) {
-            float* invlo = rcopy + 2 * NB * NB;
-            rc = dcgp_split_lo_impl(invj, invlo, NB, NB, NB, NB, sb);
-            if (rc) return rc;
+            float* invlo = invlo_slot(j);
+            if (!link_tm) {
+                rc = dcgp_split_lo_impl(invj, invlo, NB, NB, NB, NB, sb);
+                if (rc) return rc;
+            }
             rc = dcgp_gemm_tc_ex(0, 1, end - b1, NB, NB, 1.0, P, c.lda, invj, NB, 0.0, P, c.lda, 0, Plo, invlo, Plo, 0, 0, sb);
             if (rc < 0) return rc;
         }
@@ -1021,7 +1026,7 @@ int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
         if (j > 0) DCGP_CU(cudaStreamWaitEvent(sa, x.upd[ep], 0));
         TRACE_MARK("A.waited", j, sa);
         if (link_tm) {
-            rc = dcgp_potrf_link_tm(c.A + b1 * c.lda + b1, c.lda, (int)w1, c.ws + (b1 / NB) * NB * NB, nullptr, c.info, b1,
+            rc = dcgp_potrf_link_tm(c.A + b1 * c.lda + b1, c.lda, (int)w1, c.ws + (b1 / NB) * NB * NB, invlo_slot(j + 1), c.info, b1,
                                     rcopy + (size_t)(j & 1) * NB * NB, invj, sa);
             if (rc) return rc;
         } else {
@@ -1120,7 +1125,7 @@ int potrf_impl(T* A, int64_t n, int64_t lda, int* info, T* ws, size_t ws_bytes, 
 #undef CALL
     if (rc) return rc;
     T* lo = nullptr;
-    const size_t rcopy_bytes = 3 * NB * NB * 4;  // two block-row copies + remainders of one inverted block
+    const size_t rcopy_bytes = 4 * NB * NB * 4;  // two block-row copies + TF32 remainders of two inverted blocks
     if (sizeof(T) == 4 && xf && n > 2 * NB && ws_bytes >= inv_ws_bytes(n, dtype) + rcopy_bytes + (size_t)n * lda * 4)
         lo = ws + (inv_ws_bytes(n, dtype) + rcopy_bytes) / sizeof(T);
     Ctx<T> c{A, lda, ws, info, dtype, xf, st, lo};
@@ -1680,7 +1685,7 @@ int trtri_impl(const T* L, int64_t n, int64_t ldl, T* W, int64_t ldw, T* tmp, in
 // leading dimensions; with padded ones the drivers fall back to the mma.sync 3xTF32 kernel).
 extern "C" size_t dcgp_potrf_workspace(int64_t n, int dtype) {
     if (n <= 0) return 0;
-    return inv_ws_bytes(n, dtype) + (dtype == DCGP_F32 ? (size_t)n * n * 4 + 3 * NB * NB * 4 : 0);
+    return inv_ws_bytes(n, dtype) + (dtype == DCGP_F32 ? (size_t)n * n * 4 + 4 * NB * NB * 4 : 0);
 }
 
 extern "C" int dcgp_potrf(void* A, int64_t n, int64_t lda, int* info, void* workspace, size_t workspace_bytes,

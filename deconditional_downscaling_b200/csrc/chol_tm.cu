@@ -21,6 +21,7 @@
 #include "mma.cuh"
 #include "tc.cuh"
 #include <cstdio>
+#include <cstdlib>
 
 namespace {
 
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(NT, 1) potrf_link_tm_kernel(float* __restrict_
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef DCGP_LEAF_TIMING
-    long long tq[8] = {clock64(), 0, 0, 0, 0, 0, 0, 0}, ta = 0, tb = 0, tc = 0, tl;
+    long long tq[8] = {clock64(), 0, 0, 0, 0, 0, 0, 0}, ta = 0, tb = 0, tc = 0, tl, tb1 = 0, tb2 = 0, tb3 = 0, tb4 = 0, tc1 = 0, tc2 = 0, tm;
 #define TMARK(i) tq[i] = clock64()
 #else
 #define TMARK(i)
@@ -107,8 +108,8 @@ __global__ void __launch_bounds__(NT, 1) potrf_link_tm_kernel(float* __restrict_
 
     if (tid == 0) {
         mbar_init(&bar, 1);
-        mbar_init(&bar_u, 1);
-        mbar_init(&bar_r, 1);
+        mbar_init(&bar_u, 2);   // two issuing threads (S and Y updates) commit to each of these
+        mbar_init(&bar_r, 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -142,16 +143,18 @@ __global__ void __launch_bounds__(NT, 1) potrf_link_tm_kernel(float* __restrict_
         issue_mma(TP, a2, a1, 0, 128, 16, false, false);
         umma_commit(&bar);
     }
-    // ---- meanwhile: the diagonal tile -> TS (lane = row; identity padding outside the valid lower triangle) and I -> TY
-    if (warp < 8) {
+    // ---- meanwhile: the diagonal tile -> TS (lane = row; identity padding outside the valid lower triangle; warps 0-3
+    // fill columns 0..63 of their rows, warps 8-11 - same TMEM lane quadrants - columns 64..127) and I -> TY (warps 4-7)
+    if (warp < 12) {
         const int row = (warp & 3) * 32 + lane;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        if (warp < 4) {
+        if (warp < 4 || warp >= 8) {
             // 16-byte loads of the row's lower part (the caller guarantees lda % 4 == 0 and a 16-byte aligned A), all of a
             // 32-column chunk in flight before the first use
             const float4* arow = reinterpret_cast<const float4*>(A + (int64_t)row * lda);
+            const int cbeg = warp < 4 ? 0 : 64;
 #pragma unroll 1
-            for (int c0 = 0; c0 < NB; c0 += 32) {
+            for (int c0 = cbeg; c0 < cbeg + 64; c0 += 32) {
                 float4 q4[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
@@ -233,32 +236,54 @@ __global__ void __launch_bounds__(NT, 1) potrf_link_tm_kernel(float* __restrict_
 
     // ---- factorisation + inverse, 16 columns at a time.  Operand sets (P16 hi / lo, Y16 hi / lo: 128 rows x 128 B each)
     // alternate between B0 (+0 .. +64 KB) and B1; B0's first use (p = 0) comes after the update above has finished with it.
+    // Every row thread (S rows: warps 0-3, Y rows: warps 4-7) pulls the 16 entries of its row in the current sub-panel out
+    // of TMEM once the narrow ("urgent") update of the previous sub-panel has landed; the pivot warp factors the diagonal
+    // block out of the same registers.  (A tcgen05.ld issued behind queued MMAs waits for them - 1600 .. 2900 cycles per
+    // sub-panel behind the wide update, B200 clock64.  Loading one sub-panel ahead, before the wide update is queued,
+    // needs one more CTA barrier per sub-panel and measured slower: link 44 .. 46 us against 40 .. 42 us,
+    // profiles/r02_link_tm.txt.)
     uint32_t n_u = 0, n_r = 0;
+    const bool isY = warp >= 4;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t tm_row = (isY ? TY : TS) + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t v[16];
+    const uint64_t dbase = make_desc(0, 16, 1024, 2);
+    // six MMAs: D[:, c0 : c0 + n] -= A16 B16[c0 : c0 + n]^T as 3xTF32 (hi hi, lo hi, hi lo), K = 16 = two k-steps
+    auto issue3x = [&](uint32_t tm_d, uint32_t ahi, uint32_t alo, uint32_t bhi, uint32_t blo, int c0, int n) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t dah = dbase | (uint64_t)((ahi >> 4) & 0x3FFF), dal = dbase | (uint64_t)((alo >> 4) & 0x3FFF);
+        const uint64_t dbh = dbase | (uint64_t)(((bhi + (uint32_t)c0 * 128) >> 4) & 0x3FFF);
+        const uint64_t dbl = dbase | (uint64_t)(((blo + (uint32_t)c0 * 128) >> 4) & 0x3FFF);
+        umma_tf32(tm_d + (uint32_t)c0, dah, dbh, idesc, 1u);
+        umma_tf32(tm_d + (uint32_t)c0, dah + 2, dbh + 2, idesc, 1u);     // + 32 bytes: the second k-step
+        umma_tf32(tm_d + (uint32_t)c0, dal, dbh, idesc, 1u);
+        umma_tf32(tm_d + (uint32_t)c0, dal + 2, dbh + 2, idesc, 1u);
+        umma_tf32(tm_d + (uint32_t)c0, dah, dbl, idesc, 1u);
+        umma_tf32(tm_d + (uint32_t)c0, dah + 2, dbl + 2, idesc, 1u);
+    };
     TMARK(4);          // S = A_diag - P P^T in TMEM
     for (int p = 0; p * SB < nb; ++p) {
         const int p0 = p * SB, pw = min(SB, nb - p0), t0 = p0 + SB, set = p & 1;
 #ifdef DCGP_LEAF_TIMING
         tl = clock64();
 #endif
-        // (a) pivots: the warp owning TMEM lanes 32 (p / 2) .. factors the 16 x 16 block held by its lanes 16 (p & 1) ..
+        // (a) pivots: the warp whose rows 16 (p & 1) .. hold the 16 x 16 diagonal block factors it out of its registers
         if (warp == (p >> 1)) {
-            uint32_t v[16];
-            TM_LD16(v, TS + ((uint32_t)((p >> 1) * 32) << 16) + (uint32_t)p0);
+            TM_LD16(v, tm_row + (uint32_t)p0);
             const int off = (p & 1) * 16, r = lane - off;
             const bool act = r >= 0 && r < pw, mine = r >= 0 && r < SB;
             // the 16 lanes of the other half carry the rows of the identity: what the elimination makes of them is
             // T = L_d^{-T} (row i = e_i L_d^{-T}), with which every other row solves its 16 entries as a product
-            float row[SB];
+            float rw[SB];
 #pragma unroll
             for (int c = 0; c < SB; ++c)
-                row[c] = mine ? ((act && c <= r) ? __uint_as_float(v[c]) : ((r == c) ? 1.f : 0.f)) : (((lane & 15) == c) ? 1.f : 0.f);
-            float myinv = 0.f;
+                rw[c] = mine ? ((act && c <= r) ? __uint_as_float(v[c]) : ((r == c) ? 1.f : 0.f)) : (((lane & 15) == c) ? 1.f : 0.f);
             int bad = 0;
 #pragma unroll
             for (int c = 0; c < SB; c += 2) {
-                const float a = __shfl_sync(0xffffffffu, row[c], c + off);
-                const float b = __shfl_sync(0xffffffffu, row[c], c + 1 + off);
-                const float e = __shfl_sync(0xffffffffu, row[c + 1], c + 1 + off);
+                const float a = __shfl_sync(0xffffffffu, rw[c], c + off);
+                const float b = __shfl_sync(0xffffffffu, rw[c], c + 1 + off);
+                const float e = __shfl_sync(0xffffffffu, rw[c + 1], c + 1 + off);
                 const float det = fmaf(a, e, -(b * b));
                 if (bad == 0) {
                     if (!(a > 0.f)) bad = c + 1;
@@ -266,48 +291,41 @@ __global__ void __launch_bounds__(NT, 1) potrf_link_tm_kernel(float* __restrict_
                 }
                 const float y1 = rsqrt_ftz_nr(a), yd = rsqrt_ftz_nr(det);
                 const float sa = a * y1, y2 = sa * yd, l21 = b * y1;
-                const float l1 = (r == c) ? sa : row[c] * y1;
-                const float t = fmaf(-l1, l21, row[c + 1]);
+                const float l1 = (r == c) ? sa : rw[c] * y1;
+                const float t = fmaf(-l1, l21, rw[c + 1]);
                 const float l2 = (r == c + 1) ? (det * yd) * y1 : t * y2;
-                row[c] = l1;
-                row[c + 1] = l2;
-                if (r == c) myinv = y1;
-                if (r == c + 1) myinv = y2;
+                rw[c] = l1;
+                rw[c + 1] = l2;
 #pragma unroll
                 for (int k = c + 2; k < SB; ++k) {
                     const float lk1 = __shfl_sync(0xffffffffu, l1, k + off);
                     const float lk2 = __shfl_sync(0xffffffffu, l2, k + off);
-                    row[k] = fmaf(-l2, lk2, fmaf(-l1, lk1, row[k]));
+                    rw[k] = fmaf(-l2, lk2, fmaf(-l1, lk1, rw[k]));
                 }
             }
             if (mine) {
 #pragma unroll
-                for (int c = 0; c < SB; ++c) Ld[set][r][c] = (c <= r) ? row[c] : 0.f;
+                for (int c = 0; c < SB; ++c) Ld[set][r][c] = (c <= r) ? rw[c] : 0.f;
             } else {
 #pragma unroll
-                for (int c = 0; c < SB; ++c) Tm[set][lane & 15][c] = (c >= (lane & 15)) ? row[c] : 0.f;
+                for (int c = 0; c < SB; ++c) Tm[set][lane & 15][c] = (c >= (lane & 15)) ? rw[c] : 0.f;
             }
-            (void)myinv;
             if (lane == off && bad != 0 && bad <= pw && info && *info == 0) *info = (int)(j0 + p0 + bad);
         }
         __syncthreads();
 #ifdef DCGP_LEAF_TIMING
-        { long long t = clock64(); ta += t - tl; tl = t; }
+        { long long t = clock64(); ta += t - tl; tl = t; tm = t; }
 #endif
-        // (b) one thread per row of S (warps 0-3) and of Y (warps 4-7): solve against L_d, publish the operand tiles.
-        // The stores of the final values to global memory come AFTER the MMAs are issued: fence.proxy.async waits for the
-        // thread's outstanding memory operations, and with 16 .. 32 global stores in flight per thread this phase took
-        // 4300 cycles per sub-panel (B200, clock64) instead of a few hundred.
+        // (b) one thread per row: x = (its 16 entries) L_d^{-T}, published as the operands of the rank-16 updates.  (The
+        // stores of the final values to global memory come after the MMAs are issued: fence.proxy.async waits for the
+        // thread's outstanding memory operations.)
         float x[SB];
-        const bool isY = warp >= 4;
-        const int row = (warp & 3) * 32 + lane;
         if (warp < 8) {
-            uint32_t v[16];
-            TM_LD16(v, (isY ? TY : TS) + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)p0);
+            if (warp != (p >> 1)) { TM_LD16(v, tm_row + (uint32_t)p0); }
             const bool solve = isY ? (row < p0 + pw && row < nb) : (row >= t0 && row < nb);
             const bool diag = !isY && row >= p0 && row < p0 + pw;
             if (solve) {
-                // x = a L_d^{-T}: x[c] = sum_{i <= c} a[i] T[i][c] - 136 independent multiply-adds, T rows as 16-byte broadcasts
+                // x[c] = sum_{i <= c} a[i] T[i][c]: 136 independent multiply-adds, T rows as 16-byte broadcasts
 #pragma unroll
                 for (int c = 0; c < SB; ++c) x[c] = 0.f;
 #pragma unroll
@@ -332,7 +350,10 @@ __global__ void __launch_bounds__(NT, 1) potrf_link_tm_kernel(float* __restrict_
                     x[4 * c4] = l4.x; x[4 * c4 + 1] = l4.y; x[4 * c4 + 2] = l4.z; x[4 * c4 + 3] = l4.w;
                 }
             }
-            // operand tiles of the rank-16 updates: 16 floats = chunks 0 .. 3 of the row's 128-byte line
+#ifdef DCGP_LEAF_TIMING
+            { long long t = clock64(); tb2 += t - tm; tm = t; }
+#endif
+            // operand tiles: 16 floats = chunks 0 .. 3 of the row's 128-byte line
             unsigned char* hi = (set ? B1 : B0) + (isY ? 2 * 16384 : 0);
             unsigned char* lo = hi + 16384;
 #pragma unroll
@@ -343,6 +364,9 @@ __global__ void __launch_bounds__(NT, 1) potrf_link_tm_kernel(float* __restrict_
                 *reinterpret_cast<float4*>(lo + off) = make_float4(tf32_lo(h4.x), tf32_lo(h4.y), tf32_lo(h4.z), tf32_lo(h4.w));
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#ifdef DCGP_LEAF_TIMING
+            { long long t = clock64(); tb3 += t - tm; tm = t; }
+#endif
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -350,21 +374,29 @@ __global__ void __launch_bounds__(NT, 1) potrf_link_tm_kernel(float* __restrict_
 #ifdef DCGP_LEAF_TIMING
         { long long t = clock64(); tb += t - tl; tl = t; }
 #endif
-        // (c) rank-16 updates: the next sub-panel's 16 columns first, the remaining trailing columns behind them
-        if (tid == 0 && t0 < nb) {
-            const uint32_t sp = smem_u32(set ? B1 : B0), phi = sp, plo = sp + 16384, yhi = sp + 2 * 16384, ylo = sp + 3 * 16384;
-            for (int part = 0; part < 2; ++part) {
-                const int c0 = part ? t0 + SB : t0, n = part ? NB - t0 - SB : SB;
-                if (n <= 0) break;
-                issue_mma(TS + (uint32_t)c0, phi, phi, c0, n, 2, true, false);
-                issue_mma(TS + (uint32_t)c0, plo, phi, c0, n, 2, true, false);
-                issue_mma(TS + (uint32_t)c0, phi, plo, c0, n, 2, true, false);
-                issue_mma(TY + (uint32_t)c0, yhi, phi, c0, n, 2, true, false);
-                issue_mma(TY + (uint32_t)c0, ylo, phi, c0, n, 2, true, false);
-                issue_mma(TY + (uint32_t)c0, yhi, plo, c0, n, 2, true, false);
-                umma_commit(part ? &bar_r : &bar_u);
+        const bool more = t0 < nb;
+        const uint32_t sp = smem_u32(set ? B1 : B0);
+        // (c) rank-16 updates, the next sub-panel's 16 columns ("urgent": the only MMAs the chain waits for) ahead of the
+        // remaining trailing columns: S by thread 0, Y by thread 128 - two issuers, two arrivals per barrier
+        if (more && tid == 0) {
+            issue3x(TS, sp, sp + 16384, sp, sp + 16384, t0, SB);
+            umma_commit(&bar_u);
+            if (NB - t0 - SB > 0) {
+                issue3x(TS, sp, sp + 16384, sp, sp + 16384, t0 + SB, NB - t0 - SB);
+                umma_commit(&bar_r);
             }
         }
+        if (more && tid == 128) {
+            issue3x(TY, sp + 2 * 16384, sp + 3 * 16384, sp, sp + 16384, t0, SB);
+            umma_commit(&bar_u);
+            if (NB - t0 - SB > 0) {
+                issue3x(TY, sp + 2 * 16384, sp + 3 * 16384, sp, sp + 16384, t0 + SB, NB - t0 - SB);
+                umma_commit(&bar_r);
+            }
+        }
+#ifdef DCGP_LEAF_TIMING
+        { long long t = clock64(); tc1 += t - tl; tm = t; }
+#endif
         // final values -> global memory, under the MMAs
         if (warp < 8) {
             if (!isY) {
@@ -389,13 +421,16 @@ __global__ void __launch_bounds__(NT, 1) potrf_link_tm_kernel(float* __restrict_
                 }
             }
         }
-        if (t0 >= nb) break;
-        if (NB - t0 - SB > 0) ++n_r;
+#ifdef DCGP_LEAF_TIMING
+        { long long t = clock64(); tc2 += t - tm; tm = t; }
+#endif
+        if (!more) break;
         mbar_wait(&bar_u, n_u & 1u);
         ++n_u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (NB - t0 - SB > 0) ++n_r;
 #ifdef DCGP_LEAF_TIMING
-        { long long t = clock64(); tc += t - tl; tl = t; }
+        { long long t = clock64(); tc += t - tl; tl = t; tb4 += t - tm; }
 #endif
     }
     TMARK(5);
@@ -407,9 +442,9 @@ __global__ void __launch_bounds__(NT, 1) potrf_link_tm_kernel(float* __restrict_
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
     }
 #ifdef DCGP_LEAF_TIMING
-    if (tid == 0 && (j0 == 256 || j0 == 4096))
-        printf("link_tm j0=%lld: operands %lld  tmem-fill %lld  P %lld  update %lld  loop %lld (pivots %lld  rows %lld  mma+wait %lld)  tail %lld\n",
-               (long long)j0, tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], tq[4] - tq[3], tq[5] - tq[4], ta, tb, tc, clock64() - tq[5]);
+    if ((tid == 0 || tid == 200) && (j0 == 4096))
+        printf("link_tm tid %d j0=%lld: operands %lld  tmem-fill %lld  P %lld  update %lld  loop %lld (pivots %lld  rows %lld [wait+ld %lld compute %lld sts+fence %lld rest-issue %lld]  mma+wait %lld [issue %lld stores %lld])  tail %lld\n",
+               tid, (long long)j0, tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], tq[4] - tq[3], tq[5] - tq[4], ta, tb, tb1, tb2, tb3, tb4, tc, tc1, tc2, clock64() - tq[5]);
 #endif
 }
 

@@ -55,13 +55,19 @@ struct GmParams {
 // RBF1: a single RBF term (the common case: ScaleKernel(RBFKernel(ard))) takes the short form of the evaluation - the
 // first version spent 49 instructions per Gram entry (ncu, profiles/r02_ncu_gram_mm_v2.txt: issue slots 59 % busy,
 // tensor pipe 20 %), i.e. the generators, not the MMAs, set the pace:
-//     k = os 2^(h1 + h2 + u1 . u2),  u = x / l * sqrt(log2 e),  h = -|u|^2 / 2
-// (TD fused multiply-adds, one ex2, one multiply; the expansion's cancellation error ~1e-7 |u|^2 is far below the TF32
-// rounding of the operand), with every address of the swizzled store folded into compile-time offsets.
-template <int NC, int DPC, int TN, bool RBF1>
+//     k = 2^(h1 + h2 + u1 . u2),  u = x / l * sqrt(log2 e),  h1 = log2 os - |u1|^2 / 2,  h2 = -|u2|^2 / 2
+// (TD fused multiply-adds and one ex2; the expansion's cancellation error ~1e-7 |u|^2 is far below the TF32 rounding of
+// the operand), with every address of the swizzled store folded into compile-time offsets, the rounding to TF32 done as
+// an integer add + mask (the values are positive and finite), and - when the component has fewer dimensions than its
+// template bucket (d = 3 in a bucket of 4, d = 5 in 8: MODE 2) - h1 riding in the free coordinate slot against a 1 on the
+// x2 side, so that one 16-byte shared-memory load and TD multiply-adds produce the whole exponent.  v2 -> v4 -> v5 on
+// B200, N = 16384, m = 328, d = 3: 1.44 -> 0.81 -> see profiles/r02_gram_mm.txt ms (2490 warp instructions per k-tile in
+// v4, ncu: 620 issue cycles against 512 cycles of MMA work).
+template <int NC, int DPC, int TN, int MODE>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gram_mm_tc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ CUtensorMap mapW, const __grid_constant__ GmParams p) {
     constexpr int TD = NC * DPC;
+    constexpr bool RBF1 = MODE != 0, SLOT = MODE == 2;   // SLOT: the component has fewer dims than its bucket
     constexpr int STAGE = gm_stage_bytes<TN>();
     extern __shared__ unsigned char smem_raw[];
     // (pointer arithmetic, not an integer round trip: the compiler keeps the shared address space and emits LDS / STS)
@@ -144,6 +150,7 @@ gram_mm_tc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ CU
 #pragma unroll
             for (int k = 0; k < TD; ++k) h2 = fmaf(b[k], b[k], h2);
             h2 = (j < p.n2) ? -0.5f * h2 : -1e30f;
+            if (SLOT) b[sp.ndims[0]] = 1.f;          // meets h1 in the same slot of the x1 side
             mbar_wait(&empty[s], ((kt / GM_STAGES) & 1u) ^ 1u);
             float* dst = xc + ((size_t)s * GM_TK + lane) * XC;
 #pragma unroll
@@ -162,15 +169,17 @@ gram_mm_tc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ CU
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * GM_GEN_WARPS) : "memory");
         if (RBF1) {
+            const float lg_os = log2f(sv.os[0]);
             for (int r = threadIdx.x - 64; r < GM_TM; r += 32 * GM_GEN_WARPS) {
                 float h = 0.f;
 #pragma unroll
                 for (int k = 0; k < TD; ++k) h = fmaf(xs1[r * TD + k], xs1[r * TD + k], h);
-                hs1[r] = (i0 + r < p.n1) ? -0.5f * h : -1e30f;       // rows past the end: 2^(-huge) = 0
+                h = (i0 + r < p.n1) ? lg_os - 0.5f * h : -1e30f;       // rows past the end: 2^(-huge) = 0
+                hs1[r] = h;
+                if (SLOT) xs1[r * TD + sp.ndims[0]] = h;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(32 * GM_GEN_WARPS) : "memory");
         }
-        const float os0 = sv.os[0];
         // byte offset of (row gw + 16 i, column lane) in the canonical operand tile: (gw + 16 i) & 7 == gw & 7
         const uint32_t st_off = (uint32_t)(gw * 128 + ((((lane >> 2) ^ (gw & 7)) << 4) | ((lane & 3) << 2)));
         for (int kt = 0; kt < nkt; ++kt) {
@@ -205,17 +214,19 @@ gram_mm_tc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ CU
 #pragma unroll
                     for (int k = 0; k < TD; ++k) a[k] = xs1[r * TD + k];
                 }
-                float v;
+                uint32_t bits;
                 if (RBF1) {
-                    float arg = hs1[r] + h2;
+                    float arg = SLOT ? h2 : hs1[r] + h2;
 #pragma unroll
                     for (int k = 0; k < TD; ++k) arg = fmaf(a[k], b[k], arg);
-                    v = os0 * ex2_ftz(fminf(arg, 0.f));
+                    // round to nearest TF32 (ties away): positive finite values, so an integer add and a mask do it
+                    bits = (__float_as_uint(ex2_ftz(arg)) + 0x1000u) & 0xFFFFE000u;
                 } else {
-                    v = eval_pair<float, NC, DPC>(sp, sv.os, a, b);
+                    float v = eval_pair<float, NC, DPC>(sp, sv.os, a, b);
                     if (j >= p.n2 || i0 + r >= p.n1) v = 0.f;
+                    bits = to_tf32(v);
                 }
-                *reinterpret_cast<uint32_t*>(sa + i * (GM_GEN_WARPS * 128)) = to_tf32(v);
+                *reinterpret_cast<uint32_t*>(sa + i * (GM_GEN_WARPS * 128)) = bits;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
@@ -274,26 +285,27 @@ gram_mm_tc_kernel(const __grid_constant__ DevSpec sp, const __grid_constant__ CU
     }
 }
 
-template <int NC, int DPC, int TN, bool RBF1>
+template <int NC, int DPC, int TN, int MODE>
 int launch_gm1(const DevSpec& sp, const CUtensorMap& mapW, const GmParams& p, cudaStream_t st) {
     constexpr size_t smem = gm_smem<TN, NC * DPC>();
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(gram_mm_tc_kernel<NC, DPC, TN, RBF1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gram_mm_tc_kernel<NC, DPC, TN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
         attr = true;
     }
     dim3 grid((unsigned)((p.m + TN - 1) / TN), (unsigned)((p.n1 + GM_TM - 1) / GM_TM));
-    gram_mm_tc_kernel<NC, DPC, TN, RBF1><<<grid, GM_THREADS, smem, st>>>(sp, mapW, p);
+    gram_mm_tc_kernel<NC, DPC, TN, MODE><<<grid, GM_THREADS, smem, st>>>(sp, mapW, p);
     DCGP_CHECK_LAUNCH();
     return 0;
 }
 template <int NC, int DPC, int TN>
 int launch_gm(const DevSpec& sp, const CUtensorMap& mapW, const GmParams& p, cudaStream_t st) {
     if constexpr (NC == 1) {
-        if (sp.kind[0] == DCGP_KIND_RBF) return launch_gm1<NC, DPC, TN, true>(sp, mapW, p, st);
+        if (sp.kind[0] == DCGP_KIND_RBF)
+            return sp.ndims[0] < DPC ? launch_gm1<NC, DPC, TN, 2>(sp, mapW, p, st) : launch_gm1<NC, DPC, TN, 1>(sp, mapW, p, st);
     }
-    return launch_gm1<NC, DPC, TN, false>(sp, mapW, p, st);
+    return launch_gm1<NC, DPC, TN, 0>(sp, mapW, p, st);
 }
 
 }  // namespace
@@ -304,6 +316,10 @@ int dcgp_gram_matmul_fused_f32(const DevSpec& sp, const void* x1, int64_t n1, in
                                int64_t ldx2, const void* diag_dev, double diag_const, const void* W, int64_t m, int64_t ldw,
                                void* out, int64_t ldo, int same, cudaStream_t st) {
     if (n1 < 128 || n2 < 64 || m < 32) return 1;                       // not worth a 128-row tensor-core tile
+    // every 256-column block of the result regenerates the Gram tiles: up to two blocks the fused kernel matches or beats
+    // panel generation + GEMM (B200, profiles/r02_gram_mm.txt: N = 32768, m = 328: 2.75 vs 2.97 ms; N = 16384: 0.74 vs 0.72),
+    // at four (m = 1024, d = 5) it loses (0.48 vs 0.36 ms) - wider products keep the panel path
+    if (m > 512) return 1;
     if ((ldw & 3) || (reinterpret_cast<uintptr_t>(W) & 15)) return 1;  // TMA needs 16-byte aligned rows of W
     if (n2 > 0x7fffffff || m > 0x7fffffff) return 1;
     if ((int64_t)n1 * n2 < ((int64_t)1 << 22)) return 1;

@@ -216,7 +216,7 @@ def gram_matmul(spec: FlatSpec, x1, x2, W, diag_dev=None, diag_const=0.0):
     flags = (GRAM_SAME if same else 0) | _x3(x1, n1 * n2 * m <= X3_GEMM_LIMIT)
     fused = False
     if x1.dtype == torch.float32 and USE_TCGEN05 and not (flags & (_lib.GEMM_TF32X3 | _lib.GEMM_NO_TCGEN05)):
-        if FUSED_GRAM_MATMUL and n1 >= 128 and n2 >= 64 and m >= 32 and n1 * n2 >= (1 << 22):
+        if FUSED_GRAM_MATMUL and n1 >= 128 and n2 >= 64 and 32 <= m <= 512 and n1 * n2 >= (1 << 22):
             W = _tma_rows(W)   # the fused kernel (csrc/gram_mm.cu) reads W through TMA: 16-byte aligned rows
             fused = True       # mirrors dcgp_gram_matmul_fused_f32's own conditions: no panel workspace needed
         if fused or _single_pass_tc(x1.dtype, n1, m, n2, flags):

@@ -29,8 +29,13 @@ SIDE_STREAM = os.environ.get("DCGP_SIDE_STREAM", "auto")
 _SCOPE = [0]
 # prefetch() also whitens K_Zx and forms D on the side stream (B200, captured bench step: 12.58 -> 12.20 ms, 3 of 3 runs)
 SIDE_WHITEN = os.environ.get("DCGP_SIDE_WHITEN", "1") == "1"
-# experiment: K_Zx evaluated and whitened entirely in float64 (then cast), to separate the arithmetic of the whitening
-# from the FP32 evaluation of the cross Gram in the parity of FP32 models
+# FP32 models whiten K_Zx with L_Z^{-1} as an FP32 hi / lo pair on 3xTF32 products (functional.split_matmul).  The rows of
+# L_Z^{-1} are long alternating sums (|L_Z^{-1}| ~ cond(K_ZZ + 1e-3 I)^(1/2) ~ 30 - 100), so the ~5e-7 product error
+# becomes ~2e-4 on A~: q(f).mean of the config-5 minibatch is 2.8e-4 off the FP64 oracle (inside the 1e-3 gate) and
+# the gradients of Z and of the variational mean, which feel the residual z - A^T mu_q, 3.5e-3.  WHITEN64 ("DCGP_WHITEN64=1")
+# evaluates K_Zx and the whitening product in float64 instead: 3e-6 / 6e-4 / 1.6e-3, at 1.6 ms per step (92.8 -> 80.7
+# steps/s on B200) - an accuracy option, not the default (profiles/r02_parity.txt).  Adding only the image of the part
+# of K_Zx that FP32 storage drops was tried and changes nothing: the product, not the storage, is where the error is.
 WHITEN64 = os.environ.get("DCGP_WHITEN64", "0") == "1"
 
 
@@ -159,7 +164,7 @@ class VariationalPosterior(MultivariateNormal):
             if SIDE_WHITEN:
                 # ... and what follows from it without the CME solve: A~ = L_Z^{-1} K_Zx and D = L_S L_S^T - I.  Their
                 # backward nodes run on the side stream as well, next to the second big solve of the backward pass.
-                self._c["At"] = self._At64() if WHITEN64 else self._whiten(self.kops.gram(self.Z, self.x))
+                self._c["At"] = self._whiten_kzx()
                 self.D
                 keys += ["At", "Ls", "D"]
         self._c["_side"], self._c["_side_keys"] = side, keys
@@ -170,16 +175,17 @@ class VariationalPosterior(MultivariateNormal):
             return F.trsm(self.Lz, K, trans=False)
         return F.split_matmul(self.Wz, K)
 
-    def _At64(self):
-        Zd, xd = self.Z.double(), self.x.double()
-        return F.matmul(self.Wz, self.kernel.ops(Zd).gram(Zd, xd)).to(self.dtype)
+    def _whiten_kzx(self):
+        """A~ = L_Z^{-1} K_Zx for the model's own x (see WHITEN64)."""
+        if WHITEN64 and self.dtype != torch.float64:
+            Zd, xd = self.Z.double(), self.x.double()
+            return F.matmul(self.Wz, self.kernel.ops(Zd).gram(Zd, xd)).to(self.dtype)
+        return self._whiten(self.kops.gram(self.Z, self.x))
 
     @property
     def At(self):
         """A~ = L_Z^{-1} K_Zx (float64 factor, result in the model dtype), M x N."""
-        if WHITEN64 and self.dtype != torch.float64:
-            return self._get("At", self._At64)
-        return self._get("At", lambda: self._whiten(self.kops.gram(self.Z, self.x)))
+        return self._get("At", self._whiten_kzx)
 
     @property
     def loc(self):

