@@ -1210,10 +1210,15 @@ int trsm128_impl(int trans, const T* L, int64_t n, int64_t ldl, T* B, int64_t m,
 // n = 8192, m = 1024: sweeps 0.82 -> 0.72 ms, plan build 0.38 -> 0.59 ms, errors 2x larger).
 // Chosen at every public entry point, so plans, workspaces and solves always agree.
 constexpr int NBI_MIN = 512;
+constexpr int64_t NBI_DEFAULT = 512;   // see pick_nbi
 thread_local int64_t NBI = NBI_MIN;
 inline void pick_nbi(int64_t n) {
+    // DCGP_NBI = 512 | 1024 | 2048 forces the width where the matrix has at least four such blocks
     static const int64_t forced = getenv("DCGP_NBI") ? atoll(getenv("DCGP_NBI")) : 0;
-    NBI = (forced == 1024 && n >= 4096) ? 1024 : NBI_MIN;
+    int64_t w = forced ? forced : NBI_DEFAULT;
+    if (w != 512 && w != 1024 && w != 2048) w = 512;
+    while (w > NBI_MIN && n < 4 * w) w >>= 1;
+    NBI = w;
 }
 
 template <typename T>
@@ -1248,7 +1253,7 @@ int build_inv512(const T* L, int64_t n, int64_t ldl, T* inv, T* tmp, int dtype, 
     trtri_blocks_kernel<T><<<(unsigned)nblk, NTHREADS, leaf_smem<T>(), st>>>(L, ldl, n, inv, NBI / NB);
     DCGP_CHECK_LAUNCH();
     const int64_t sL = (int64_t)NBI * (ldl + 1), sX = (int64_t)NBI * NBI;
-    for (int b = NB; b < NBI; b *= 2) {
+    for (int b = NB; b < NBI && b < 512; b *= 2) {   // wider levels: build_inv_wide
         for (int j = 0; j < NBI / (2 * b); ++j) {
             const int64_t o1 = (int64_t)j * 2 * b, o2 = o1 + b;  // first / second half inside the 512 block
             // full blocks, batched:  T = L21 X11 ;  X21 = -X22 T
@@ -1275,6 +1280,49 @@ int build_inv512(const T* L, int64_t n, int64_t ldl, T* inv, T* tmp, int dtype, 
                 if (rc) return rc;
             }
         }
+    }
+    return 0;
+}
+
+// Doubling levels b >= 512 of the inverted diagonal blocks (NBI = 1024, 2048) as individual tensor-core products on the two
+// lanes: the batched mma.sync kernel above runs 3xTF32 at ~30 TF/s, which made wide blocks a loss in round 1 (NBI = 1024:
+// sweeps 0.82 -> 0.72 ms, plan 0.38 -> 0.59 ms).  T = L21 X11 and X21 = -X22 T with hi / lo operands: the remainders of L
+// (Llo), of the blocks inverted so far (invlo, kept up to date through the epilogues) and of T.
+template <typename T>
+int build_inv_wide(const T* L, const T* Llo, int64_t n, int64_t ldl, T* inv, T* invlo, T* Tb, T* Tblo, int dtype, int xf,
+                   cudaStream_t st) {
+    LookAhead& x = lanes_for(st);
+    int rc = x.init();
+    if (rc) return rc;
+    const int64_t nbig = (n + NBI - 1) / NBI, sX = (int64_t)NBI * NBI;
+    const bool lo = Llo && invlo && Tblo;
+    for (int64_t b = 512; b < NBI; b *= 2) {
+        DCGP_CU(cudaEventRecord(x.fork, st));
+        DCGP_CU(cudaStreamWaitEvent(x.sh, x.fork, 0));
+        DCGP_CU(cudaStreamWaitEvent(x.sb, x.fork, 0));
+        int turn = 0;
+        for (int64_t kb = 0; kb < nbig; ++kb) {
+            const int64_t row0 = kb * NBI, rows = (n - row0 < NBI) ? n - row0 : NBI;
+            for (int64_t j = 0; j < NBI / (2 * b); ++j) {
+                const int64_t o1 = j * 2 * b, o2 = o1 + b;
+                if (rows <= o2) break;
+                const int64_t r2 = (rows - o2 < b) ? rows - o2 : b;
+                cudaStream_t ls = (turn++ & 1) ? x.sb : x.sh;
+                const int64_t oL = (row0 + o2) * ldl + row0 + o1, o11 = kb * sX + o1 * NBI + o1, o22 = kb * sX + o2 * NBI + o2,
+                              o21 = kb * sX + o2 * NBI + o1;
+                rc = dcgp_gemm_impl(0, 0, r2, b, b, 1.0, L + oL, ldl, inv + o11, NBI, 0.0, Tb + o21, NBI, dtype, xf, ls,
+                                    lo ? Llo + oL : nullptr, lo ? invlo + o11 : nullptr, lo ? Tblo + o21 : nullptr);
+                if (rc) return rc;
+                rc = dcgp_gemm_impl(0, 0, r2, b, r2, -1.0, inv + o22, NBI, Tb + o21, NBI, 0.0, inv + o21, NBI, dtype,
+                                    xf | DCGP_GEMM_A_LOWER, ls, lo ? invlo + o22 : nullptr, lo ? Tblo + o21 : nullptr,
+                                    lo ? invlo + o21 : nullptr);
+                if (rc) return rc;
+            }
+        }
+        DCGP_CU(cudaEventRecord(x.join, x.sh));
+        DCGP_CU(cudaStreamWaitEvent(st, x.join, 0));
+        DCGP_CU(cudaEventRecord(x.fork, x.sb));
+        DCGP_CU(cudaStreamWaitEvent(st, x.fork, 0));
     }
     return 0;
 }
@@ -1534,12 +1582,18 @@ size_t plan_bytes_impl(int64_t n, int64_t ldl, int dtype) {
     const size_t es = dtype == DCGP_F64 ? 8 : 4;
     const size_t nbig = (size_t)(n + NBI - 1) / NBI;
     return 2 * nbig * NBI * NBI * es + (dtype == DCGP_F32 ? (size_t)n * ldl * 4 : 0) +
-           (trsm_la_mode() >= 2 ? (dtype == DCGP_F32 ? 2 : 1) * 2 * nbig * 2 * NBI * NBI * es : 0);
+           (trsm_la_mode() >= 2 ? (dtype == DCGP_F32 ? 2 : 1) * 2 * nbig * 2 * NBI * NBI * es : 0) +
+           (NBI > 512 ? 2 * nbig * NBI * NBI * es : 0);   // wide blocks: scratch of build_inv_wide (T and its remainders)
 }
 template <typename T>
 inline T* plan_la2(const T* plan, int64_t n, int64_t ldl, int dtype) {
     const size_t nbig = (size_t)(n + NBI - 1) / NBI;
     return const_cast<T*>(plan) + 2 * nbig * NBI * NBI + (dtype == DCGP_F32 ? (size_t)n * ldl : 0);
+}
+template <typename T>
+inline T* plan_wide_scratch(const T* plan, int64_t n, int64_t ldl, int dtype) {
+    const size_t nbig = (size_t)(n + NBI - 1) / NBI;
+    return plan_la2<T>(plan, n, ldl, dtype) + (trsm_la_mode() >= 2 ? (dtype == DCGP_F32 ? 2 : 1) * 2 * nbig * 2 * NBI * NBI : 0);
 }
 
 // X (+ FP32: remainders of X and of B, and a copy of B with a TMA-compatible leading dimension - a multiple of
@@ -1558,13 +1612,20 @@ int plan_build(const T* L, int64_t n, int64_t ldl, T* plan, int dtype, int xf, c
     const int64_t nbig = (n + NBI - 1) / NBI;
     T* inv = plan;
     T* tmp = inv + nbig * NBI * NBI;
-    int rc = build_inv512<T>(L, n, ldl, inv, tmp, dtype, xf, st);
+    int rc = build_inv512<T>(L, n, ldl, inv, tmp, dtype, xf, st);   // levels below 512 (scratch: tmp)
     if (rc) return rc;
-    if (sizeof(T) == 4 && xf) {
-        // the doubling scratch is dead once the inverted blocks exist: it receives their remainders
+    const bool lo = sizeof(T) == 4 && xf;
+    if (lo) {
+        // the doubling scratch is dead once the 512-wide inverses exist: it receives their remainders
         rc = dcgp_split_lo_impl(inv, tmp, nbig * NBI, NBI, NBI, NBI, st);
         if (rc) return rc;
         rc = dcgp_split_lo_impl(L, tmp + nbig * NBI * NBI, n, n, ldl, ldl, st);
+        if (rc) return rc;
+    }
+    if (NBI > 512) {
+        T* Tb = plan_wide_scratch<T>(plan, n, ldl, dtype);
+        rc = build_inv_wide<T>(L, lo ? tmp + nbig * NBI * NBI : nullptr, n, ldl, inv, lo ? tmp : nullptr, Tb,
+                               lo ? Tb + nbig * NBI * NBI : nullptr, dtype, xf, st);
         if (rc) return rc;
     }
     if (nbig >= 4 && trsm_la_mode() >= 2) {   // the sweeps that use them (trsm_impl)

@@ -582,12 +582,16 @@ int dcgp_gemm_tc_ex(int transa, int transb, int64_t m, int64_t n, int64_t k, dou
     // narrow tiles when the wide ones would not fill one wave of SMs
     const int64_t wide = ((m + TM - 1) / TM) * ((n + 255) / 256);
     const int tn = (2 * wide <= num_sms()) ? 128 : 256;
+    // (64-wide tiles for products whose 128-wide tiles cover less than half of the SMs were measured: 512 x 1024 x 512
+    // 15.9 -> 14.6 us per launch, but planned potrs and the ELBO step did not move - not kept.)
     // multicast pairs (two CTAs share every B tile) once there is more than a wave of wide tiles
     static const int cl_on = getenv("DCGP_TC_CLUSTER") ? atoi(getenv("DCGP_TC_CLUSTER")) : 2;
     // (measured on B200 at 8192^3: NN 650 -> 675, TN 597 -> 648 TF/s, but NT 692 -> 670: mode 1 = always, 2 = only when
     // B is MN-major, i.e. not transposed)
     const int cl = (cl_on && (cl_on == 1 || !transb) && tn == 256 && wide >= num_sms() && m >= 2 * TM &&
-                    !(flags & (DCGP_GEMM_A_LOWER | DCGP_GEMM_A_UPPER))) ? 2 : 1;  // pairs must share their k-range
+              !(flags & (DCGP_GEMM_A_LOWER | DCGP_GEMM_A_UPPER))) ? 2 : 1;  // pairs must share their k-range
+    // (Multicast pairs on the 128-wide 3xTF32 tiles of the small products of the triangular sweeps were measured too:
+    // 512 x 1024 x 512 stays at 16.0 us per launch, planned potrs 8192 x 1024 1.48 -> 1.60 ms - not kept.)
     CUtensorMap mapA, mapB, mapAlo, mapBlo;
     // op(A)[m, k]: notrans -> A is m x k (K-major); trans -> A is k x m (MN-major)
     // op(B)[k, n]: trans -> B is n x k (K-major); notrans -> B is k x n (MN-major)
@@ -618,9 +622,10 @@ int dcgp_gemm_tc_ex(int transa, int transb, int64_t m, int64_t n, int64_t k, dou
     p.clo_cols = clo_cols;
     p.a_tri = (flags & DCGP_GEMM_A_LOWER) ? 1 : ((flags & DCGP_GEMM_A_UPPER) ? 2 : 0);
     static const int fat = getenv("DCGP_TC_FAT") ? atoi(getenv("DCGP_TC_FAT")) : 2;  // 0: off, 1: narrow tiles, 2: all
-    if (tn == 128)
+    if (tn == 128) {
         return (x3 && fat) ? launch_tc<128, true, 1>(mapA, mapB, mapAlo, mapBlo, p, st)
                            : launch_tc<128, false, 1>(mapA, mapB, mapAlo, mapBlo, p, st);
+    }
     if (cl == 2)
         return (x3 && fat >= 2) ? launch_tc<256, true, 2>(mapA, mapB, mapAlo, mapBlo, p, st)
                                 : launch_tc<256, false, 2>(mapA, mapB, mapAlo, mapBlo, p, st);
