@@ -468,6 +468,8 @@ __global__ void __launch_bounds__(256) whitened_kl_kernel(const T* __restrict__ 
     }
 }
 
+#include "gram_rbf.cuh"   // single-component RBF fast path (namespace rbf)
+
 // ------------------------------------------------------------------------- launchers
 template <typename T, typename TO>
 int launch_gram_fwd(const DevSpec& sp, const void* x1, int64_t n1, int64_t ldx1, const void* x2, int64_t n2,
@@ -481,6 +483,13 @@ int launch_gram_fwd(const DevSpec& sp, const void* x1, int64_t n1, int64_t ldx1,
     while (rt > 1 && gx * ((tiles_y + rt - 1) / rt) < (int64_t)num_sms() * 8) rt >>= 1;
     dim3 grid((unsigned)gx, (unsigned)((tiles_y + rt - 1) / rt));
     int vec_ok = ((reinterpret_cast<uintptr_t>(K) % 16) == 0) && ((ldk * sizeof(TO)) % 16 == 0);
+    if constexpr (sizeof(T) == sizeof(TO)) {
+        if (rbf::applies(sp)) {
+            rbf::launch_fwd<T>(sp, x1, n1, ldx1, x2, n2, ldx2, K, ldk, diag_dev, diag_const, same, grid, vec_ok, (int)rt, rna, st);
+            DCGP_CHECK_LAUNCH();
+            return 0;
+        }
+    }
 #define CALL(NCV, DPCV)                                                                                      \
     gram_fwd_kernel<T, TO, NCV, DPCV><<<grid, 256, 0, st>>>(sp, (const T*)x1, n1, ldx1, (const T*)x2, n2, ldx2, \
                                                             (TO*)K, ldk, (const T*)diag_dev, (T)diag_const, same, \
@@ -522,6 +531,11 @@ template <typename T>
 int launch_gram_bwd(const DevSpec& sp, const void* x1, int64_t n1, int64_t ldx1, const void* x2, int64_t n2,
                     int64_t ldx2, const void* G, int64_t ldg, void* dls, void* dos, void* dx1, int64_t lddx1,
                     int same, cudaStream_t st) {
+    if (!dx1 && rbf::applies(sp)) {   // hyper-parameter adjoints only (coordinate adjoints: the generic kernel)
+        rbf::launch_bwd<T>(sp, x1, n1, ldx1, x2, n2, ldx2, G, ldg, dls, dos, st);
+        DCGP_CHECK_LAUNCH();
+        return 0;
+    }
 #define CALL(NCV, DPCV)                                                                                             \
     launch_gram_bwd_one<T, NCV, DPCV, (NCV * DPCV <= 4 ? 4 : (NCV * DPCV <= 8 ? 2 : 1))>(sp, x1, n1, ldx1, x2, n2,  \
                                                                                          ldx2, G, ldg, dls, dos,   \

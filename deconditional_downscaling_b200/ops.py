@@ -244,6 +244,12 @@ def syrk(A, trans=False, alpha=1.0, beta=0.0, C=None):
     return C
 
 
+def _zero_theta(nc, dtype, device):
+    """Adjoint accumulators of the hyper-parameters, (dls [nc, MAX_DIMS], dos [nc]), zeroed by ONE fill."""
+    buf = torch.zeros(nc * (MAX_DIMS + 1), dtype=dtype, device=device)
+    return buf[:nc * MAX_DIMS].view(nc, MAX_DIMS), buf[nc * MAX_DIMS:]
+
+
 def gram_bwd(spec: FlatSpec, x1, x2, G, need_dx1=False):
     """Returns (dls [ncomp, MAX_DIMS], dos [ncomp], dx1 or None)."""
     same = x2 is None
@@ -252,8 +258,7 @@ def gram_bwd(spec: FlatSpec, x1, x2, G, need_dx1=False):
     G = _rowmajor(G)
     _req(x1, x2, G)
     nc = len(spec.kinds)
-    dls = torch.zeros(nc, MAX_DIMS, dtype=x1.dtype, device=x1.device)
-    dos = torch.zeros(nc, dtype=x1.dtype, device=x1.device)
+    dls, dos = _zero_theta(nc, x1.dtype, x1.device)
     dx1 = torch.zeros_like(x1) if need_dx1 else None
     cs = spec.c_spec()
     rc = _lib.load().dcgp_gram_bwd(ctypes.byref(cs), _ptr(x1), x1.size(0), _ld(x1), _ptr(x2), x2.size(0), _ld(x2),
@@ -442,8 +447,7 @@ def gram_bagsum_bwd(spec, z, x, offsets, G, need_dz=True):
     _req(z, x, offsets, G)
     nb = offsets.numel() - 1
     nc = len(spec.kinds)
-    dls = torch.zeros(nc, MAX_DIMS, dtype=z.dtype, device=z.device)
-    dos = torch.zeros(nc, dtype=z.dtype, device=z.device)
+    dls, dos = _zero_theta(nc, z.dtype, z.device)
     dz = torch.zeros_like(z) if need_dz else None
     cs = spec.c_spec()
     check(_lib.load().dcgp_gram_bagsum_bwd(ctypes.byref(cs), _ptr(z), z.size(0), _ld(z), _ptr(x), _ld(x),
@@ -469,8 +473,7 @@ def gram_bag_blocksum_bwd(spec, x, offsets, g):
     _req(x, offsets, g)
     nb = offsets.numel() - 1
     nc = len(spec.kinds)
-    dls = torch.zeros(nc, MAX_DIMS, dtype=x.dtype, device=x.device)
-    dos = torch.zeros(nc, dtype=x.dtype, device=x.device)
+    dls, dos = _zero_theta(nc, x.dtype, x.device)
     cs = spec.c_spec()
     check(_lib.load().dcgp_gram_bag_blocksum_bwd(ctypes.byref(cs), _ptr(x), _ld(x), _ptr(offsets), nb, _ptr(g),
                                                  _ptr(dls), _ptr(dos), _dt(x), 0, _stream()),
