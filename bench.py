@@ -201,7 +201,7 @@ def roofline_entry(by_call, n_calls, t_calls, fl_calls, n_tc, t_tc, fl_tc, t_eag
     peak_src = f"{pk['source']}: sustained bf16 cuBLAS rate / 2 (TF32 issues at half the bf16 MMA rate)"
     return {
         "bound": "tensor",
-        "kernel": "dcgp_potrf = potrf_step_kernel (single-CTA chain: tcgen05 3xTF32 products + 128-wide leaf) beside "
+        "kernel": "dcgp_potrf = potrf_link_tm_kernel (single-CTA chain link: tcgen05 3xTF32 products, 128-wide factor and its inverse on TMEM) beside "
                   "gemm_tc_kernel (tcgen05 rank-128 bulk updates) on two prioritised lanes",
         "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak if ach else None,
         "issued_frac": 3.0 * ach / tf32_peak if ach else None,
@@ -382,7 +382,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": batch_bytes(host[0]), "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "final_loss": final_loss,
         "value_eager": world * K_ / t_eager,
-        # The dominant CALL of the step is the factorisation of Lambda (dcgp_potrf: the potrf_step_kernel chain +
+        # The dominant CALL of the step is the factorisation of Lambda (dcgp_potrf: the potrf_link_tm_kernel chain +
         # gemm_tc_kernel bulk updates, ~37 % of a step): `roofline` describes it.  Algorithmic flops n^3/3 per call
         #  over the CUDA-event time of each call in the eagerly issued copy of the timed steps; the kernels
         # inside issue 3xTF32, i.e. three MMAs per algorithmic product, which `issued_frac` accounts for.
@@ -544,7 +544,7 @@ def run_exact(device, N, dt=torch.float64, cpu_sample_n=0):
                         "frac": fl["potrf"] / ph["potrf"] / 1e12 / peak, "peak_source": peak_src,
                         "composite_frac": tot_fl / total / 1e12 / peak},
            # the Gram build is bound by the N^2 * s bytes it writes; in FP64 exp (~25 DFMA per entry) is the co-bound
-           "gram_roofline": {"bound": "hbm", "kernel": f"gram_fwd_kernel<{'double' if f64 else 'float'}>",
+           "gram_roofline": {"bound": "hbm", "kernel": f"rbf::gram_rbf_fwd_kernel<{'double' if f64 else 'float'}, 3> (csrc/gram_rbf.cuh; ncu: profiles/r02_gram_rbf_ncu.txt)",
                              "achieved": N * N * es / ph["gram_K"] / 1e9, "peak": peaks()["hbm_gbs"], "unit": "GB/s",
                              "frac": N * N * es / ph["gram_K"] / 1e9 / peaks()["hbm_gbs"], "peak_source": peaks()["source"]},
            "potrf_info": int(res["info"].item()), "mll": float(res["mll"].item())}
