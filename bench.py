@@ -685,7 +685,29 @@ def run_vbagg(device, steps=10, warmup=3):
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / steps
     evals = float(Mz) * nb * per
-    return {"metric": "vbagg_elbo_steps_per_s", "value": 1e3 / ms, "ms_per_step": ms, "bags_per_step": nb,
+    # the same minibatches through the two-call C composite (dcgp_vbagg_elbo_fwd / _bwd: value + every gradient)
+    from deconditional_downscaling_b200 import ops
+    from deconditional_downscaling_b200 import _lib as dl
+    spec = ops.FlatSpec(["rbf"], [list(range(d))], [torch.full((d,), 0.6931, device=device)], [torch.full((1,), 0.6931, device=device)])
+    Zc, mc, Lc = torch.randn(Mz, d, generator=g).to(device), torch.zeros(Mz, device=device), torch.eye(Mz, device=device)
+    off = torch.arange(0, nb * per + 1, per, dtype=torch.int64, device=device)
+    noise = torch.full((1,), 0.6932, device=device)
+    comp = lambda i: ops.vbagg_elbo(spec, Zc, batches[i][0], off, batches[i][1], mc, Lc, noise, 10240.0)
+    for i in range(warmup):
+        comp(i)
+    torch.cuda.synchronize()
+    l0 = dl.load().dcgp_launch_count()
+    s.record()
+    for i in range(warmup, warmup + steps):
+        elbo_c, _, info_c = comp(i)
+    e.record()
+    torch.cuda.synchronize()
+    ms_c = s.elapsed_time(e) / steps
+    composite = {"what": "dcgp_vbagg_elbo_fwd + dcgp_vbagg_elbo_bwd (include/dcgp.h): ELBO and every gradient, FP32 with 3xTF32 "
+                         "products, no FP64 island, no optimiser update", "ms_fwd_bwd": ms_c,
+                 "launches_per_call_pair": (dl.load().dcgp_launch_count() - l0) / steps, "elbo": float(elbo_c.item()),
+                 "info": int(info_c.item())}
+    return {"metric": "vbagg_elbo_steps_per_s", "value": 1e3 / ms, "ms_per_step": ms, "bags_per_step": nb, "c_abi_composite": composite,
             "individuals_per_step": nb * per, "inducing_points": Mz, "dtype": "f32 (f64 K_ZZ factor)",
             "cross_gram_kernel_evals_per_step": evals, "final_loss": float(loss.item()),
             "note": "bag-summed cross Gram forward + backward = 2 x M x N_b kernel evaluations per step, K_Zx never stored"}

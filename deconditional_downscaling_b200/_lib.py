@@ -27,6 +27,20 @@ class KernelSpec(Structure):
     _fields_ = [("n_components", c_int32), ("reserved", c_int32), ("comp", Component * MAX_COMPONENTS)]
 
 
+class VbaggProblem(Structure):
+    """dcgp_vbagg_problem (include/dcgp.h)."""
+    _fields_ = [("spec", POINTER(KernelSpec)), ("Z", c_void_p), ("M", c_int64), ("ldz", c_int64), ("x", c_void_p),
+                ("ldx", c_int64), ("offsets", c_void_p), ("n_bags", c_int64), ("z", c_void_p), ("var_mean", c_void_p),
+                ("chol_var", c_void_p), ("ldc", c_int64), ("noise", c_void_p), ("mean_const", c_void_p),
+                ("num_data", c_double), ("beta", c_double), ("jitter", c_double), ("var_jitter", c_double)]
+
+
+class VbaggGrads(Structure):
+    """dcgp_vbagg_grads (include/dcgp.h)."""
+    _fields_ = [("dZ", c_void_p), ("lddz", c_int64), ("dls", c_void_p), ("dos", c_void_p), ("dvar_mean", c_void_p),
+                ("dchol_var", c_void_p), ("lddc", c_int64), ("dnoise", c_void_p), ("dmean_const", c_void_p)]
+
+
 class DcgpError(RuntimeError):
     pass
 
@@ -85,6 +99,10 @@ _SIGNATURES = {
                                  c_void_p]),
     "dcgp_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double,
                                c_double, c_double, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "dcgp_vbagg_elbo_workspace": (c_size_t, [c_int64, c_int64, c_int]),
+    "dcgp_vbagg_elbo_fwd": (c_int, [POINTER(VbaggProblem), c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "dcgp_vbagg_elbo_bwd": (c_int, [POINTER(VbaggProblem), c_double, POINTER(VbaggGrads), c_void_p, c_size_t, c_int, c_int,
+                                    c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -599,3 +599,50 @@ def whitened_kl(variational_mean, chol_variational_covar):
     """KL(N(m, tril(Ls) tril(Ls)^T) || N(0, I)) in one pass; the lower mask of
     CholeskyVariationalDistribution is applied inside the kernel."""
     return _WhitenedKLFn.apply(variational_mean, chol_variational_covar)
+
+
+# ---------------------------------------------------------------------- whole VBagg ELBO (C composite)
+class _VbaggElboFn(Function):
+    """ELBO of one VBagg minibatch through dcgp_vbagg_elbo_fwd / _bwd (csrc/vbagg.cu): the forward call also runs the
+    backward one (the gradients of a scalar do not depend on the upstream value except as a factor), so autograd's
+    backward is a handful of scalar multiplications.  Inputs: Z, x, offsets, z, var_mean, chol_var, noise, mean_const,
+    then the kernel hyper-parameter VALUES [ls_0, os_0, ...]."""
+
+    @staticmethod
+    def forward(ctx, meta, num_data, beta, Z, x, offsets, z, var_mean, chol_var, noise, mean_const, *hyp):
+        spec = _spec(meta, hyp)
+        need = any(ctx.needs_input_grad)
+        elbo, g, info = ops.vbagg_elbo(spec, Z.detach(), x, offsets, z, var_mean.detach(), chol_var.detach(),
+                                       noise.detach(), num_data, beta=beta,
+                                       mean_const=None if mean_const is None else mean_const.detach().reshape(1),
+                                       scale=1.0, need_grads=need, info=_info_slot())
+        _raise_if_not_pd(info)
+        ctx.meta, ctx.g = meta, g
+        ctx.shapes = (noise.shape, None if mean_const is None else mean_const.shape, [h.shape for h in hyp])
+        ctx.hyp_dtypes = [h.dtype for h in hyp]
+        return elbo
+
+    @staticmethod
+    def backward(ctx, go):
+        g, need = ctx.g, ctx.needs_input_grad
+        noise_shape, mc_shape, hyp_shapes = ctx.shapes
+        out = [None, None, None,
+               go * g["Z"] if need[3] else None, None, None, None,
+               go * g["var_mean"] if need[7] else None,
+               go * g["chol_var"] if need[8] else None,
+               (go * g["noise"]).reshape(noise_shape) if need[9] else None,
+               (go * g["mean_const"]).reshape(mc_shape) if (mc_shape is not None and need[10]) else None]
+        for c in range(len(ctx.meta.kinds)):
+            ls_shape, os_shape = hyp_shapes[2 * c], hyp_shapes[2 * c + 1]
+            n = 1
+            for d in ls_shape:
+                n *= d
+            out.append((go * g["dls"][c, :n]).reshape(ls_shape) if need[11 + 2 * c] else None)
+            out.append((go * g["dos"][c]).reshape(os_shape) if need[12 + 2 * c] else None)
+        return tuple(out)
+
+
+def vbagg_elbo(meta: KernelMeta, hyp, Z, x, offsets, z, var_mean, chol_var, noise, num_data, beta=1.0, mean_const=None):
+    """Differentiable ELBO (not its negative) of a VBagg minibatch; see _VbaggElboFn."""
+    return _VbaggElboFn.apply(meta, float(num_data), float(beta), Z, x, offsets, z, var_mean, chol_var, noise, mean_const,
+                              *hyp)

@@ -548,3 +548,40 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, g
                                         0 if veto is None else veto.numel(), 1 if zero_grads else 0, _dt(params),
                                         _stream(params.device))
     check(rc, "dcgp_adam_step")
+
+
+def vbagg_elbo(spec: FlatSpec, Z, x, offsets, z, var_mean, chol_var, noise, num_data, beta=1.0, mean_const=None,
+               scale=-1.0, need_grads=True, jitter=1e-3, var_jitter=1e-4, info=None):
+    """Whole VBagg minibatch ELBO through dcgp_vbagg_elbo_fwd / _bwd: returns (elbo [device scalar], grads dict or None,
+    info).  grads = scale * d ELBO / d {Z, lengthscales, outputscales, var_mean, chol_var, noise, mean_const}, with
+    respect to the hyper-parameter VALUES (the softplus chain of the raw parameters is the caller's)."""
+    Z, x = _rowmajor(Z), _rowmajor(x)
+    z, var_mean, chol_var = z.contiguous(), var_mean.contiguous(), _rowmajor(chol_var)
+    noise = noise.reshape(1).contiguous()
+    _req(Z, x, offsets, z, var_mean, chol_var, noise, mean_const)
+    _same_dtype("vbagg_elbo", Z, x, z, var_mean, chol_var, noise)
+    lib = _lib.load()
+    M, nb, dt, dev = Z.size(0), offsets.numel() - 1, Z.dtype, Z.device
+    cs = spec.c_spec()
+    p = _lib.VbaggProblem(ctypes.pointer(cs), _ptr(Z), M, _ld(Z), _ptr(x), _ld(x), _ptr(offsets), nb, _ptr(z),
+                          _ptr(var_mean), _ptr(chol_var), _ld(chol_var), _ptr(noise), _ptr(mean_const), float(num_data),
+                          float(beta), float(jitter), float(var_jitter))
+    nbytes = lib.dcgp_vbagg_elbo_workspace(M, nb, _dt(Z))
+    ws = _workspace(nbytes, dev)
+    elbo = torch.empty(1, dtype=dt, device=dev)
+    if info is None:
+        info = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(lib.dcgp_vbagg_elbo_fwd(ctypes.byref(p), _ptr(elbo), _ptr(info), _ptr(ws), nbytes, _dt(Z), 0, _stream()),
+          "dcgp_vbagg_elbo_fwd")
+    if not need_grads:
+        return elbo[0], None, info
+    nc = len(spec.kinds)
+    g = {"Z": torch.empty_like(Z), "dls": torch.empty(nc, MAX_DIMS, dtype=dt, device=dev),
+         "dos": torch.empty(nc, dtype=dt, device=dev), "var_mean": torch.empty_like(var_mean),
+         "chol_var": torch.empty(M, M, dtype=dt, device=dev), "noise": torch.empty(1, dtype=dt, device=dev),
+         "mean_const": torch.empty(1, dtype=dt, device=dev) if mean_const is not None else None}
+    cg = _lib.VbaggGrads(_ptr(g["Z"]), _ld(g["Z"]), _ptr(g["dls"]), _ptr(g["dos"]), _ptr(g["var_mean"]),
+                         _ptr(g["chol_var"]), M, _ptr(g["noise"]), _ptr(g["mean_const"]))
+    check(lib.dcgp_vbagg_elbo_bwd(ctypes.byref(p), float(scale), ctypes.byref(cg), _ptr(ws), nbytes, _dt(Z), 0, _stream()),
+          "dcgp_vbagg_elbo_bwd")
+    return elbo[0], g, info

@@ -18,6 +18,7 @@ Step protocol (`DataParallelStepper`, the same on every rank, no rank-local cont
      all-reduce and all ranks raise NotPSDError together).
 Steps 1-4 are what `cuda_graph=True` captures and replays.
 """
+import os
 from typing import Dict, Iterable, List, Optional
 
 import torch
@@ -267,7 +268,41 @@ class ElboTrainer(DataParallelStepper):
         self._graphs, self._graph_calls, self._capture_stream = {}, {}, None
         self.launches_replayed = 0   # libdcgp kernel launches executed through graph replays (host counters do not see them)
 
+    def _fused_vbagg_loss(self, x, z, bags_sizes):
+        """-ELBO of a VBagg minibatch through the two-call C composite (dcgp_vbagg_elbo_fwd / _bwd), or None when the
+        model is outside its scope: additive stationary kernel terms only, zero or constant mean.  FP64 models take it
+        by default (same arithmetic as the layered path); FP32 models only with DCGP_VBAGG_FUSED=1, because the
+        composite keeps K_ZZ in FP32 where the layered path has the reference's FP64 island."""
+        from .likelihoods import bag_offsets
+        from .means import ConstantMean, ZeroMean
+        vs = getattr(self.model, "variational_strategy", None)
+        if vs is None or not hasattr(vs, "_prior_modules"):
+            return None
+        if x.dtype != torch.float64 and os.environ.get("DCGP_VBAGG_FUSED", "0") != "1":
+            return None
+        if os.environ.get("DCGP_VBAGG_FUSED", "1") == "0":
+            return None
+        kernel, mean = vs._prior_modules()
+        x2 = x if x.dim() == 2 else x.unsqueeze(-1)
+        kops = kernel.ops(x2)
+        if not kops.is_flat or not isinstance(mean, (ConstantMean, ZeroMean)):
+            return None
+        vs.ensure_initialized()
+        vd = vs._variational_distribution
+        mc = mean.constant.to(x.dtype) if isinstance(mean, ConstantMean) else None
+        elbo = F.vbagg_elbo(kops.meta, kops.hyp, vs.inducing_points.to(x.dtype), x2, bag_offsets(bags_sizes, x.device), z,
+                            vd.variational_mean.to(x.dtype), vd.chol_variational_covar.to(x.dtype),
+                            self.likelihood.noise.to(x.dtype), self.elbo.num_data, self.elbo.beta, mean_const=mc)
+        return -elbo
+
     def loss(self, x, z, **kw):
+        if isinstance(self.likelihood, VBaggGaussianLikelihood) and set(kw) == {"bags_sizes"}:
+            try:
+                fused = self._fused_vbagg_loss(x, z, kw["bags_sizes"])
+            except F.NotPSDError:
+                fused = None      # checked pass after a failed factorisation: the layered path retries with jitter
+            if fused is not None:
+                return fused
         q = self.model(x)
         if isinstance(self.likelihood, CMPLikelihood):
             kw = self.model.get_elbo_computation_parameters(bags_values=kw["bags_values"],

@@ -255,7 +255,8 @@ DCGP_API int dcgp_vbagg_ell(const void* z, const void* S, const void* T, const i
                    const void* noise, void* ell, void* dS, void* dT, void* dnoise, int dtype, void* stream);
 
 /* ---- whitened KL ---------------------------------------------------------------
- * out[0] = 0.5 * (||tril(Ls)||_F^2 + ||m||^2 - M - sum_i log Ls_ii^2) in one pass over Ls
+ * out[0] += 0.5 * (||tril(Ls)||_F^2 + ||m||^2 - M - sum_i log Ls_ii^2) in one pass over Ls (out is ACCUMULATED
+ * with atomics: the caller zeroes it)
  * (src/mlls/bag_variational_elbo.py:49 -> variational_strategy.kl_divergence()).
  * dLs (M x M, optional) = tril(Ls) - diag(1/Ls_ii), dm (optional) = m. */
 DCGP_API int dcgp_whitened_kl(const void* m, const void* Ls, int64_t M, int64_t ldls, void* out, void* dm, void* dLs,
@@ -272,6 +273,59 @@ DCGP_API int dcgp_whitened_kl(const void* m, const void* Ls, int64_t M, int64_t 
 DCGP_API int dcgp_adam_step(void* params, void* grads, void* exp_avg, void* exp_avg_sq, void* step, int64_t n, double lr,
                             double beta1, double beta2, double eps, double grad_scale, const int* veto, int n_veto,
                             int zero_grads, int dtype, void* stream);
+
+/* ---- whole VBagg minibatch ELBO: value and every gradient behind two calls ---------------------------
+ * SURVEY.md section 8b `vbagg_elbo_fwd/bwd`.  Replaces, for one optimiser step of the VBagg model
+ * (experiments/swiss_roll/models/vbagg.py, experiments/downscaling/models/vbagg.py): q(f) of the whitened SVGP
+ * (src/variational/variational_strategy.py:14-68), its per-bag aggregation and the expected log-likelihood
+ * (src/likelihoods/vbagg_gaussian_likelihood.py:54-111), the ELBO combination ELL / n_bags - beta KL / num_data
+ * (src/mlls/bag_variational_elbo.py:47-69) and torch's .backward() over all of them.  K_Zx, Sigma_q and the
+ * aggregation matrix are never formed; the algebra is written out at the top of csrc/vbagg.cu.
+ *
+ * All pointers are device pointers of the compute dtype unless noted; hyper-parameters are VALUES (lengthscale,
+ * outputscale, noise after their constraint), as in dcgp_kernel_spec; gradients are with respect to those values.
+ * dcgp_vbagg_elbo_fwd writes the ELBO (device scalar) and leaves its intermediates in the workspace;
+ * dcgp_vbagg_elbo_bwd must follow on the same stream with the same problem and workspace and writes
+ * scale * d ELBO / d(.) into every non-NULL field of `grads` (scale = -1 for the loss the trainers minimise).
+ * `info`: device int, LAPACK-style status of the K_ZZ factorisation (0 = ok), as for dcgp_potrf.
+ * F32 runs every product error-compensated (3xTF32); no FP64 island - callers that need the reference's double
+ * precision K_ZZ factor (variational_strategy.py:35-44) use dtype F64. */
+typedef struct dcgp_vbagg_problem {
+    const dcgp_kernel_spec* spec; /* individuals kernel k                                              */
+    const void* Z;                /* inducing points, M x d row-major (d = columns the spec addresses)  */
+    int64_t M, ldz;
+    const void* x;                /* individuals of the minibatch, bag after bag, N x d                 */
+    int64_t ldx;
+    const int64_t* offsets;       /* n_bags + 1 row offsets (device int64)                              */
+    int64_t n_bags;
+    const void* z;                /* bag observations, n_bags                                           */
+    const void* var_mean;         /* variational mean m, M                                              */
+    const void* chol_var;         /* variational factor L_S, M x M; only its lower triangle is read     */
+    int64_t ldc;
+    const void* noise;            /* device scalar sigma^2                                              */
+    const void* mean_const;       /* device scalar of a ConstantMean, NULL for ZeroMean                 */
+    double num_data, beta;        /* BagVariationalELBO(num_data, beta)                                 */
+    double jitter;                /* added to diag K_ZZ: 1e-3 in the reference                          */
+    double var_jitter;            /* added to diag K_xx: 1e-4 in the reference                          */
+} dcgp_vbagg_problem;
+
+typedef struct dcgp_vbagg_grads {   /* any field may be NULL */
+    void* dZ;                       /* M x d, row stride lddz (overwritten)               */
+    int64_t lddz;
+    void* dls;                      /* [n_components][DCGP_MAX_DIMS] (overwritten)        */
+    void* dos;                      /* [n_components] (overwritten)                       */
+    void* dvar_mean;                /* M                                                  */
+    void* dchol_var;                /* M x M, row stride lddc, zero above the diagonal    */
+    int64_t lddc;
+    void* dnoise;                   /* scalar                                             */
+    void* dmean_const;              /* scalar                                             */
+} dcgp_vbagg_grads;
+
+DCGP_API size_t dcgp_vbagg_elbo_workspace(int64_t M, int64_t n_bags, int dtype);
+DCGP_API int dcgp_vbagg_elbo_fwd(const dcgp_vbagg_problem* problem, void* elbo, int* info, void* workspace,
+                                 size_t workspace_bytes, int dtype, int flags, void* stream);
+DCGP_API int dcgp_vbagg_elbo_bwd(const dcgp_vbagg_problem* problem, double scale, const dcgp_vbagg_grads* grads,
+                                 void* workspace, size_t workspace_bytes, int dtype, int flags, void* stream);
 
 #ifdef __cplusplus
 }
