@@ -20,7 +20,7 @@ from oracle.ref_loader import load_reference_src  # noqa: E402
 
 load_reference_src()
 import gpytorch  # noqa: E402  (the shim)
-from src.models import ExactCMP, VariationalCMP, VariationalGP  # noqa: E402
+from src.models import BaggedGP, ExactCMP, VariationalCMP, VariationalGP  # noqa: E402
 from src.likelihoods import CMPLikelihood, VBaggGaussianLikelihood  # noqa: E402
 from src.mlls import BagVariationalELBO  # noqa: E402
 from src.kernels import RFFKernel  # noqa: E402
@@ -269,6 +269,37 @@ def golden_vbagg():
     save("vbagg", **out)
 
 
+def golden_bagged_gp():
+    """BaggedGP baseline (src/models/bagged_gp.py, prediction_strategies/bagged_gp_prediction_strategy.py) driven as
+    experiments/swiss_roll/models/bagged_gp.py:52-79 drives it: aggregate prior, exact MLL with the bag-size scaled
+    noise of VBaggGaussianLikelihood.marginal, every gradient, posterior on the training individuals."""
+    bag_sizes = [5, 9, 1, 12, 13, 4]
+    d = 3
+    x, _, _, z = toy_bags(21, bag_sizes, d=d, r=1)
+    k = scale_rbf(3, [0.4, -0.2, 0.1], 0.25)
+    lik = VBaggGaussianLikelihood()
+    lik.initialize(**{"noise_covar.raw_noise": torch.tensor([-0.3])})
+    model = BaggedGP(train_individuals=x, bags_sizes=bag_sizes, train_aggregate_targets=z,
+                     individuals_mean=gpytorch.means.ZeroMean(), individuals_kernel=k, likelihood=lik)
+    model.train()
+    lik.train()
+    mll = gpytorch.mlls.ExactMarginalLogLikelihood(lik, model)
+    named = [("model." + n, p) for n, p in model.named_parameters()]
+    output = model(model.train_individuals, model.bags_sizes)
+    loss = -mll(output, model.train_aggregate_targets, model.bags_sizes)
+    loss.backward()
+    out = {"x": x, "z": z, "bag_sizes": np.array(bag_sizes), "prior_mean": output.mean,
+           "prior_var": output.covariance_matrix.diagonal(), "loss": loss}
+    out.update(params_of(named))
+    out.update(grads_of(named))
+    model.eval()
+    lik.eval()
+    with torch.no_grad():
+        post = model.predict(x, bag_sizes)
+        out.update(post_mean=post.mean, post_covar=post.covariance_matrix)
+    save("bagged_gp", **out)
+
+
 if __name__ == "__main__":
     golden_gram()
     golden_exact_cmp(noise=False)
@@ -279,3 +310,4 @@ if __name__ == "__main__":
     golden_variational_cmp(noise=False, additive=True)
     golden_variational_cmp_rff()
     golden_vbagg()
+    golden_bagged_gp()

@@ -374,3 +374,34 @@ def test_cuda_graph_trainer_matches_eager(kind):
     assert all(abs(a - b) <= 2e-4 * max(1.0, abs(a)) for a, b in zip(le, lg)), (le, lg)
     for p, q in zip(te.params, tg.params):
         assert torch.allclose(p, q, rtol=2e-3, atol=2e-4)
+
+
+# ----------------------------------------------------------------------------- BaggedGP baseline
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-6), (torch.float32, 1e-3)])
+def test_bagged_gp_matches_reference_golden(dtype, tol):
+    """src/models/bagged_gp.py + prediction_strategies/bagged_gp_prediction_strategy.py driven as the swiss-roll trainer
+    drives them (experiments/swiss_roll/models/bagged_gp.py:52-79): aggregate prior, exact MLL, every gradient and the
+    posterior on the training individuals against vectors produced by the reference's own code
+    (tests/golden/make_golden.py::golden_bagged_gp)."""
+    _, K, L, Mn, E, M = pkg()
+    g = G.load("bagged_gp")
+    to = lambda t: t.to(device=DEV, dtype=dtype)
+    sizes = [int(s) for s in g["bag_sizes"]]
+    model = M.BaggedGP(train_individuals=to(g["x"]), bags_sizes=sizes, train_aggregate_targets=to(g["z"]),
+                       individuals_mean=Mn.ZeroMean(), individuals_kernel=rbf_scale(K, 3),
+                       likelihood=L.VBaggGaussianLikelihood()).to(DEV).to(dtype)
+    load_params(model, g, "model__", dtype)
+    model.train(); model.likelihood.train()
+    mll = E.ExactMarginalLogLikelihood(model.likelihood, model)
+    out = model(model.train_individuals, model.bags_sizes)
+    assert rel(out.mean, g["prior_mean"]) < tol or g["prior_mean"].abs().max() == 0
+    assert rel(out.covariance_matrix.diagonal(), g["prior_var"]) < tol
+    loss = -mll(out, model.train_aggregate_targets, model.bags_sizes)
+    assert rel(loss, g["loss"]) < tol
+    loss.backward()
+    check_grads(model, g, "model__", tol * 5 if dtype == torch.float32 else tol)
+    model.eval(); model.likelihood.eval()
+    with torch.no_grad():
+        post = model.predict(to(g["x"]), sizes)
+    assert rel(post.mean, g["post_mean"]) < tol
+    assert rel(post.covariance_matrix, g["post_covar"]) < tol
