@@ -210,7 +210,7 @@ def roofline_entry(by_call, n_calls, t_calls, fl_calls, n_tc, t_tc, fl_tc, t_eag
         "peak_source": peak_src,
         "calls": potrf["calls"] if potrf else 0, "avg_call_ms": potrf["ms"] / potrf["calls"] if potrf else None,
         "share_of_step": (potrf["ms"] * 1e-3) / t_eager if potrf and t_eager > 0 else None,
-        "measured_on": "the eager issue of the same steps (value_eager): CUDA events cannot bracket kernels inside a graph replay",
+        "measured_on": "the layered composition of the same step issued eagerly from Python (value_eager_layered; same kernels and shapes as the C composite): CUDA events cannot bracket kernels inside a graph replay or inside a C call",
         # the whole step against the same peak: all contraction flops of a step / the step time of the timed (graph) run
         "whole_step": {"algorithmic_flops_per_step": fl_calls / steps,
                        "achieved": fl_calls / steps / (t_dev / steps) / 1e12,
@@ -305,8 +305,13 @@ def run_ours(args):
 
     # ---- eager pass with CUDA events around every tensor-core contraction call: the roofline numbers.  (Events cannot
     # be recorded around individual kernels of a graph replay, so the same steps are issued eagerly once.)
+    # The product path runs the step below the C ABI (dcgp_cmp_elbo_fwd / _bwd), where Python-level probes see one call;
+    # the per-call numbers therefore come from the LAYERED composition of the same step (DCGP_CMP_FUSED=0: the same
+    # kernels on the same shapes, issued from Python), and `value_eager` from the product path issued eagerly.
     probe = GemmProbe(ops)
     probe.install()
+    fused_env = os.environ.get("DCGP_CMP_FUSED")
+    os.environ["DCGP_CMP_FUSED"] = "0"
     eager = build_trainer(wl, device)
 
     def eager_step(i):
@@ -315,6 +320,14 @@ def run_ours(args):
         return eager.step(b.pop("x"), b.pop("z"), **b)
     t_eager, _, _ = timed(eager_step)
     probe.on = False
+    del eager
+    if fused_env is None:
+        os.environ.pop("DCGP_CMP_FUSED")
+    else:
+        os.environ["DCGP_CMP_FUSED"] = fused_env
+    torch.cuda.empty_cache()
+    eager = build_trainer(wl, device)
+    t_eager_product, _, _ = timed(lambda i: (lambda b: eager.step(b.pop("x"), b.pop("z"), **b))(dict(devb[i])))
     del eager
     torch.cuda.empty_cache()
 
@@ -381,7 +394,10 @@ def run_ours(args):
         "e2e": {"value": world * K_ / t_e2e, "unit": "minibatch ELBO steps/s (whole job)",
                 "h2d_bytes_per_step": batch_bytes(host[0]), "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "final_loss": final_loss,
-        "value_eager": world * K_ / t_eager,
+        "value_eager": world * K_ / t_eager_product, "value_eager_layered": world * K_ / t_eager,
+        "composition": ("layered Python path (DCGP_CMP_FUSED=0)" if os.environ.get("DCGP_CMP_FUSED", "1") == "0" else
+                        "C composite dcgp_cmp_elbo_fwd / dcgp_cmp_elbo_bwd (csrc/cmp.cu) behind autograd + softplus chain + "
+                        "device-side Adam"),
         # The dominant CALL of the step is the factorisation of Lambda (dcgp_potrf: the potrf_link_tm_kernel chain +
         # gemm_tc_kernel bulk updates, ~37 % of a step): `roofline` describes it.  Algorithmic flops n^3/3 per call
         #  over the CUDA-event time of each call in the eagerly issued copy of the timed steps; the kernels

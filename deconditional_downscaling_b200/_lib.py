@@ -41,6 +41,23 @@ class VbaggGrads(Structure):
                 ("dchol_var", c_void_p), ("lddc", c_int64), ("dnoise", c_void_p), ("dmean_const", c_void_p)]
 
 
+class CmpProblem(Structure):
+    """dcgp_cmp_problem (include/dcgp.h)."""
+    _fields_ = [("k_spec", POINTER(KernelSpec)), ("l_spec", POINTER(KernelSpec)), ("Z", c_void_p), ("M", c_int64),
+                ("ldz", c_int64), ("x", c_void_p), ("N", c_int64), ("ldx", c_int64), ("ext", c_void_p), ("ldext", c_int64),
+                ("y", c_void_p), ("n", c_int64), ("ldy", c_int64), ("z", c_void_p), ("var_mean", c_void_p),
+                ("chol_var", c_void_p), ("ldc", c_int64), ("noise", c_void_p), ("ind_noise", c_void_p),
+                ("mean_const", c_void_p), ("lbda", c_double), ("num_data", c_double), ("beta", c_double),
+                ("jitter", c_double), ("var_jitter", c_double)]
+
+
+class CmpGrads(Structure):
+    """dcgp_cmp_grads (include/dcgp.h)."""
+    _fields_ = [("dZ", c_void_p), ("lddz", c_int64), ("dk_ls", c_void_p), ("dk_os", c_void_p), ("dl_ls", c_void_p),
+                ("dl_os", c_void_p), ("dvar_mean", c_void_p), ("dchol_var", c_void_p), ("lddc", c_int64),
+                ("dnoise", c_void_p), ("dind_noise", c_void_p), ("dmean_const", c_void_p)]
+
+
 class DcgpError(RuntimeError):
     pass
 
@@ -99,6 +116,10 @@ _SIGNATURES = {
                                  c_void_p]),
     "dcgp_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double,
                                c_double, c_double, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "dcgp_cmp_elbo_workspace": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int]),
+    "dcgp_cmp_elbo_fwd": (c_int, [POINTER(CmpProblem), c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "dcgp_cmp_elbo_bwd": (c_int, [POINTER(CmpProblem), c_double, POINTER(CmpGrads), c_void_p, c_size_t, c_int, c_int,
+                                  c_void_p]),
     "dcgp_vbagg_elbo_workspace": (c_size_t, [c_int64, c_int64, c_int]),
     "dcgp_vbagg_elbo_fwd": (c_int, [POINTER(VbaggProblem), c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "dcgp_vbagg_elbo_bwd": (c_int, [POINTER(VbaggProblem), c_double, POINTER(VbaggGrads), c_void_p, c_size_t, c_int, c_int,

@@ -1,0 +1,119 @@
+// Shared pieces of the composite entry points (vbagg.cu, cmp.cu): small dense-matrix kernels, the 3xTF32 product helper and
+// error macros.  Include after common.cuh.
+#pragma once
+
+// internal entries of gemm.cu (3xTF32 on the tcgen05 kernel needs the TF32 remainders of both operands)
+int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
+                   const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype, int flags,
+                   cudaStream_t st, const void* Alo, const void* Blo, void* Clo);
+int dcgp_split_lo_impl(const void* src, void* dst, int64_t rows, int64_t cols, int64_t lds, int64_t ldd, cudaStream_t st);
+
+namespace composite {
+
+
+template <typename T>
+__global__ void tril_copy_kernel(const T* __restrict__ src, int64_t lds, T* __restrict__ dst, int64_t n) {
+    const int64_t i = blockIdx.y, j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) dst[i * n + j] = (j <= i) ? src[i * lds + j] : T(0);
+}
+
+template <typename T>
+__global__ void add_diag_kernel(T* __restrict__ A, int64_t n, T c) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[i * n + i] += c;
+}
+
+// dst = alpha * tril(src) (+ beta * add on the lower triangle), zero above;  halve_diag: diagonal times 1/2
+template <typename T>
+__global__ void tril_axpby_kernel(const T* __restrict__ src, int64_t n, T alpha, const T* __restrict__ add, int64_t lda,
+                                  T beta, int halve_diag, T* __restrict__ dst, int64_t ldd) {
+    const int64_t i = blockIdx.y, j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    T v = T(0);
+    if (j <= i) {
+        v = alpha * src[i * n + j];
+        if (halve_diag && i == j) v *= T(0.5);
+        if (add) v += beta * add[i * lda + j];
+    }
+    dst[i * ldd + j] = v;
+}
+
+// dst = (src + src^T) / 2
+template <typename T>
+__global__ void symmetrize_kernel(const T* __restrict__ src, int64_t n, T* __restrict__ dst) {
+    const int64_t i = blockIdx.y, j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) dst[i * n + j] = T(0.5) * (src[i * n + j] + src[j * n + i]);
+}
+
+
+inline size_t up(size_t v) { return (v + 31) & ~(size_t)31; }
+
+#define DCGP_CU_RC(x)                                     \
+    do {                                                 \
+        cudaError_t e_ = (x);                            \
+        if (e_ != cudaSuccess) return DCGP_CUDA_ERR(e_); \
+    } while (0)
+
+#define RC(x)               \
+    do {                    \
+        int rc_ = (x);      \
+        if (rc_) return rc_; \
+    } while (0)
+
+// C = alpha op(A) op(B) + beta C with packed operands.  FP32: 3xTF32; the remainders of A / B are taken from Alo / Blo
+// when the caller keeps them, else split here into the scratch slots s1 / s2 (the product then runs on the tcgen05
+// kernel; dcgp_gemm_impl falls back to the mma.sync 3xTF32 kernel for shapes that kernel declines).
+template <typename T>
+int gemm3(int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha, const T* A, int64_t lda, const T* Alo, const T* B,
+          int64_t ldb, const T* Blo, double beta, T* C, int64_t ldc, T* s1, T* s2, int dtype, int flags, cudaStream_t st) {
+    if constexpr (sizeof(T) == 4) {
+        if (m >= 128 && n >= 32 && k >= 64) {
+            if (!Alo) {
+                RC(dcgp_split_lo_impl(A, s1, ta ? k : m, ta ? m : k, lda, lda, st));
+                Alo = s1;
+            }
+            if (!Blo) {
+                RC(dcgp_split_lo_impl(B, s2, tb ? n : k, tb ? k : n, ldb, ldb, st));
+                Blo = s2;
+            }
+        } else {
+            Alo = Blo = nullptr;
+        }
+    } else {
+        Alo = Blo = nullptr;
+    }
+    return dcgp_gemm_impl(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, dtype, flags, st, Alo, Blo, nullptr);
+}
+
+// Single-pass TF32 product for the large (individuals-sized) contractions: tcgen05 reads FP32 operands by truncation, so
+// both operands are first rounded to nearest TF32 (Ar / Br: copies the caller keeps, else made here in s1 / s2) - the
+// policy of the Python layer (ops._rna).  FP64, and shapes the tcgen05 kernel does not take, go to gemm3.
+template <typename T>
+int gemm1(int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha, const T* A, int64_t lda, const T* Ar, const T* B,
+          int64_t ldb, const T* Br, double beta, T* C, int64_t ldc, T* s1, T* s2, int dtype, int flags, cudaStream_t st) {
+    if constexpr (sizeof(T) == 4) {
+        const int64_t tiles = ((m + 127) / 128) * ((n + 127) / 128);
+        if (m >= 128 && n >= 128 && k >= 64 && tiles >= 32 && (lda % 4) == 0 && (ldb % 4) == 0 && (ldc % 4) == 0) {
+            if (!Ar) {
+                RC(dcgp_round_tf32(A, s1, ta ? k : m, ta ? m : k, lda, lda, st));
+                Ar = s1;
+            }
+            if (!Br) {
+                RC(dcgp_round_tf32(B, s2, tb ? n : k, tb ? k : n, ldb, ldb, st));
+                Br = s2;
+            }
+            return dcgp_gemm_impl(ta, tb, m, n, k, alpha, Ar, lda, Br, ldb, beta, C, ldc, dtype, flags & ~DCGP_GEMM_TF32X3, st,
+                                  nullptr, nullptr, nullptr);
+        }
+    }
+    return gemm3<T>(ta, tb, m, n, k, alpha, A, lda, nullptr, B, ldb, nullptr, beta, C, ldc, s1, s2, dtype, flags, st);
+}
+
+template <typename T>
+int split_keep(const T* src, T* dst, int64_t rows, int64_t cols, cudaStream_t st) {
+    if constexpr (sizeof(T) == 4) return dcgp_split_lo_impl(src, dst, rows, cols, cols, cols, st);
+    return 0;
+}
+
+
+}  // namespace composite

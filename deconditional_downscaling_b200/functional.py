@@ -125,11 +125,11 @@ class InfoPool:
     def reset(self):
         self.used = 0
 
-    def next(self):
-        if self.used >= self.buf.numel():
+    def next(self, words=1):
+        if self.used + words > self.buf.numel():
             raise RuntimeError("InfoPool exhausted: more factorisations in one step than slots")
-        slot = self.buf[self.used:self.used + 1]
-        self.used += 1
+        slot = self.buf[self.used:self.used + words]
+        self.used += words
         return slot
 
     def words(self):
@@ -140,9 +140,9 @@ class InfoPool:
         return self.used > 0 and bool(self.words().cpu().any())
 
 
-def _info_slot():
+def _info_slot(words=1):
     """Where the next factorisation reports: a pool slot inside a pooled deferred region, else a fresh word."""
-    return _POOL.next() if _POOL is not None else None
+    return _POOL.next(words) if _POOL is not None else None
 
 
 def _raise_if_not_pd(info):
@@ -151,9 +151,9 @@ def _raise_if_not_pd(info):
     if _DEFERRED is not None:
         _DEFERRED.append(info)
         return
-    i = int(info.item())
-    if i != 0:
-        raise NotPSDError(f"Cholesky failed: leading minor {i} is not positive definite")
+    for i in info.reshape(-1).tolist():
+        if i != 0:
+            raise NotPSDError(f"Cholesky failed: leading minor {i} is not positive definite")
 
 
 class deferred_pd_checks:
@@ -646,3 +646,54 @@ def vbagg_elbo(meta: KernelMeta, hyp, Z, x, offsets, z, var_mean, chol_var, nois
     """Differentiable ELBO (not its negative) of a VBagg minibatch; see _VbaggElboFn."""
     return _VbaggElboFn.apply(meta, float(num_data), float(beta), Z, x, offsets, z, var_mean, chol_var, noise, mean_const,
                               *hyp)
+
+
+# ---------------------------------------------------------------------- whole VariationalCMP ELBO (C composite)
+class _CmpElboFn(Function):
+    """ELBO of one VariationalCMP minibatch (with individuals noise) through dcgp_cmp_elbo_fwd / _bwd (csrc/cmp.cu).
+    As in _VbaggElboFn the forward call runs both C calls and autograd's backward only scales the cached gradients.
+    Inputs: Z, x, ext, y, z, var_mean, chol_var, noise, ind_noise, mean_const, then the hyper-parameter VALUES of the
+    individuals kernel and of the bag kernel [ls_0, os_0, ...]."""
+
+    @staticmethod
+    def forward(ctx, meta_k, meta_l, lbda, num_data, beta, Z, x, ext, y, z, var_mean, chol_var, noise, ind_noise, mean_const,
+                *hyp):
+        nk = 2 * len(meta_k.kinds)
+        hk, hl = hyp[:nk], hyp[nk:]
+        need = any(ctx.needs_input_grad)
+        elbo, g, info = ops.cmp_elbo(_spec(meta_k, hk), _spec(meta_l, hl), Z.detach(), x, ext, y, z, var_mean.detach(),
+                                     chol_var.detach(), noise.detach(), ind_noise.detach(), lbda, num_data, beta=beta,
+                                     mean_const=None if mean_const is None else mean_const.detach().reshape(1), scale=1.0,
+                                     need_grads=need, info=_info_slot(3))
+        _raise_if_not_pd(info)
+        ctx.metas, ctx.g = (meta_k, meta_l), g
+        ctx.shapes = (noise.shape, ind_noise.shape, None if mean_const is None else mean_const.shape, [h.shape for h in hyp])
+        return elbo
+
+    @staticmethod
+    def backward(ctx, go):
+        g, need = ctx.g, ctx.needs_input_grad
+        noise_shape, ind_shape, mc_shape, hyp_shapes = ctx.shapes
+        out = [None] * 5 + [go * g["Z"] if need[5] else None, None, None, None, None,
+                            go * g["var_mean"] if need[10] else None, go * g["chol_var"] if need[11] else None,
+                            (go * g["noise"]).reshape(noise_shape) if need[12] else None,
+                            (go * g["ind_noise"]).reshape(ind_shape) if need[13] else None,
+                            (go * g["mean_const"]).reshape(mc_shape) if (mc_shape is not None and need[14]) else None]
+        pos = 15
+        for meta, dls, dos in ((ctx.metas[0], g["dk_ls"], g["dk_os"]), (ctx.metas[1], g["dl_ls"], g["dl_os"])):
+            for c in range(len(meta.kinds)):
+                ls_shape, os_shape = hyp_shapes[pos - 15], hyp_shapes[pos - 14]
+                n = 1
+                for d in ls_shape:
+                    n *= d
+                out.append((go * dls[c, :n]).reshape(ls_shape) if need[pos] else None)
+                out.append((go * dos[c]).reshape(os_shape) if need[pos + 1] else None)
+                pos += 2
+        return tuple(out)
+
+
+def cmp_elbo(meta_k: KernelMeta, hyp_k, meta_l: KernelMeta, hyp_l, Z, x, ext, y, z, var_mean, chol_var, noise, ind_noise, lbda,
+             num_data, beta=1.0, mean_const=None):
+    """Differentiable ELBO (not its negative) of a VariationalCMP minibatch; see _CmpElboFn."""
+    return _CmpElboFn.apply(meta_k, meta_l, float(lbda), float(num_data), float(beta), Z, x, ext, y, z, var_mean, chol_var,
+                            noise, ind_noise, mean_const, *hyp_k, *hyp_l)

@@ -585,3 +585,46 @@ def vbagg_elbo(spec: FlatSpec, Z, x, offsets, z, var_mean, chol_var, noise, num_
     check(lib.dcgp_vbagg_elbo_bwd(ctypes.byref(p), float(scale), ctypes.byref(cg), _ptr(ws), nbytes, _dt(Z), 0, _stream()),
           "dcgp_vbagg_elbo_bwd")
     return elbo[0], g, info
+
+
+def cmp_elbo(k_spec: FlatSpec, l_spec: FlatSpec, Z, x, ext, y, z, var_mean, chol_var, noise, ind_noise, lbda, num_data,
+             beta=1.0, mean_const=None, scale=-1.0, need_grads=True, jitter=1e-3, var_jitter=1e-4, info=None):
+    """Whole VariationalCMP minibatch ELBO (with individuals noise) through dcgp_cmp_elbo_fwd / _bwd: returns
+    (elbo [device scalar], grads dict or None, info [3 ints: Lambda, K_ZZ, C]).  grads = scale * d ELBO / d {Z, k and l
+    lengthscales / outputscales, var_mean, chol_var, noise, ind_noise, mean_const} with respect to the VALUES."""
+    Z, x, ext, y = _rowmajor(Z), _rowmajor(x), _rowmajor(ext), _rowmajor(y)
+    z, var_mean, chol_var = z.contiguous(), var_mean.contiguous(), _rowmajor(chol_var)
+    noise, ind_noise = noise.reshape(1).contiguous(), ind_noise.reshape(1).contiguous()
+    _req(Z, x, ext, y, z, var_mean, chol_var, noise, ind_noise, mean_const)
+    _same_dtype("cmp_elbo", Z, x, ext, y, z, var_mean, chol_var, noise, ind_noise)
+    lib = _lib.load()
+    M, N, n, dt, dev = Z.size(0), x.size(0), y.size(0), Z.dtype, Z.device
+    if ext.size(0) != N or z.numel() != n:
+        raise ValueError("ext must have one row per individual and z one entry per bag")
+    ck, cl = k_spec.c_spec(), l_spec.c_spec()
+    p = _lib.CmpProblem(ctypes.pointer(ck), ctypes.pointer(cl), _ptr(Z), M, _ld(Z), _ptr(x), N, _ld(x), _ptr(ext), _ld(ext),
+                        _ptr(y), n, _ld(y), _ptr(z), _ptr(var_mean), _ptr(chol_var), _ld(chol_var), _ptr(noise),
+                        _ptr(ind_noise), _ptr(mean_const), float(lbda), float(num_data), float(beta), float(jitter),
+                        float(var_jitter))
+    nbytes = lib.dcgp_cmp_elbo_workspace(N, n, M, _ld(Z), _dt(Z))
+    ws = _workspace(nbytes, dev)
+    elbo = torch.empty(1, dtype=dt, device=dev)
+    if info is None:
+        info = torch.zeros(3, dtype=torch.int32, device=dev)
+    check(lib.dcgp_cmp_elbo_fwd(ctypes.byref(p), _ptr(elbo), _ptr(info), _ptr(ws), nbytes, _dt(Z), 0, _stream()),
+          "dcgp_cmp_elbo_fwd")
+    if not need_grads:
+        return elbo[0], None, info
+    nk, nl = len(k_spec.kinds), len(l_spec.kinds)
+    g = {"Z": torch.empty_like(Z), "dk_ls": torch.empty(nk, MAX_DIMS, dtype=dt, device=dev),
+         "dk_os": torch.empty(nk, dtype=dt, device=dev), "dl_ls": torch.empty(nl, MAX_DIMS, dtype=dt, device=dev),
+         "dl_os": torch.empty(nl, dtype=dt, device=dev), "var_mean": torch.empty_like(var_mean),
+         "chol_var": torch.empty(M, M, dtype=dt, device=dev), "noise": torch.empty(1, dtype=dt, device=dev),
+         "ind_noise": torch.empty(1, dtype=dt, device=dev),
+         "mean_const": torch.empty(1, dtype=dt, device=dev) if mean_const is not None else None}
+    cg = _lib.CmpGrads(_ptr(g["Z"]), _ld(g["Z"]), _ptr(g["dk_ls"]), _ptr(g["dk_os"]), _ptr(g["dl_ls"]), _ptr(g["dl_os"]),
+                       _ptr(g["var_mean"]), _ptr(g["chol_var"]), M, _ptr(g["noise"]), _ptr(g["ind_noise"]),
+                       _ptr(g["mean_const"]))
+    check(lib.dcgp_cmp_elbo_bwd(ctypes.byref(p), float(scale), ctypes.byref(cg), _ptr(ws), nbytes, _dt(Z), 0, _stream()),
+          "dcgp_cmp_elbo_bwd")
+    return elbo[0], g, info

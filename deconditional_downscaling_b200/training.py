@@ -295,7 +295,44 @@ class ElboTrainer(DataParallelStepper):
                             self.likelihood.noise.to(x.dtype), self.elbo.num_data, self.elbo.beta, mean_const=mc)
         return -elbo
 
+    def _fused_cmp_loss(self, x, z, bags_values, extended_bags_values):
+        """-ELBO of a VariationalCMP minibatch through the two-call C composite (dcgp_cmp_elbo_fwd / _bwd: the FP64 K_ZZ
+        island, the Lambda factorisation and both solves, the bag-level Gaussian terms and the whole backward pass below
+        the C ABI), or None when the model is outside its scope: stationary additive kernel terms only, zero or constant
+        individuals mean, individuals noise.  DCGP_CMP_FUSED=0 keeps the layered path."""
+        from .means import ConstantMean, ZeroMean
+        if os.environ.get("DCGP_CMP_FUSED", "1") == "0":
+            return None
+        m = self.model
+        if not (hasattr(m, "bag_kernel") and hasattr(m, "individuals_kernel")) or getattr(m, "noise_kernel", None) is None:
+            return None
+        if not getattr(self.likelihood, "use_individuals_noise", False):
+            return None
+        mean = m.individuals_mean
+        x2 = x if x.dim() == 2 else x.unsqueeze(-1)
+        y2 = bags_values if bags_values.dim() == 2 else bags_values.unsqueeze(-1)
+        e2 = extended_bags_values if extended_bags_values.dim() == 2 else extended_bags_values.unsqueeze(-1)
+        kk, kl = m.individuals_kernel.ops(x2), m.bag_kernel.ops(e2)
+        if not (kk.is_flat and kl.is_flat) or not isinstance(mean, (ConstantMean, ZeroMean)):
+            return None
+        vs = m.variational_strategy
+        vs.ensure_initialized()
+        vd = vs._variational_distribution
+        dt = x.dtype
+        mc = mean.constant.to(dt) if isinstance(mean, ConstantMean) else None
+        elbo = F.cmp_elbo(kk.meta, kk.hyp, kl.meta, kl.hyp, vs.inducing_points.to(dt), x2, e2, y2, z, vd.variational_mean.to(dt),
+                          vd.chol_variational_covar.to(dt), self.likelihood.noise.to(dt), m.noise_kernel.outputscale.to(dt),
+                          m.lbda, self.elbo.num_data, self.elbo.beta, mean_const=mc)
+        return -elbo
+
     def loss(self, x, z, **kw):
+        if isinstance(self.likelihood, CMPLikelihood) and set(kw) == {"bags_values", "extended_bags_values"}:
+            try:
+                fused = self._fused_cmp_loss(x, z, kw["bags_values"], kw["extended_bags_values"])
+            except F.NotPSDError:
+                fused = None      # checked pass after a failed factorisation: the layered path retries with jitter
+            if fused is not None:
+                return fused
         if isinstance(self.likelihood, VBaggGaussianLikelihood) and set(kw) == {"bags_sizes"}:
             try:
                 fused = self._fused_vbagg_loss(x, z, kw["bags_sizes"])

@@ -327,6 +327,64 @@ DCGP_API int dcgp_vbagg_elbo_fwd(const dcgp_vbagg_problem* problem, void* elbo, 
 DCGP_API int dcgp_vbagg_elbo_bwd(const dcgp_vbagg_problem* problem, double scale, const dcgp_vbagg_grads* grads,
                                  void* workspace, size_t workspace_bytes, int dtype, int flags, void* stream);
 
+/* ---- whole VariationalCMP minibatch ELBO (with individuals noise): value and every gradient behind two calls --------
+ * SURVEY.md section 8b `cmp_elbo_fwd/bwd`.  Replaces, for one optimiser step of
+ * experiments/downscaling/models/variational_cmp.py:163-186 (and experiments/swiss_roll/models/variational_cmp.py):
+ * model(x) (src/variational/variational_strategy.py:14-68), get_elbo_computation_parameters
+ * (src/models/variational_cmp.py:86-113), CMPLikelihood._compute_expected_log_prob_with_individuals_noise
+ * (src/likelihoods/cmp_likelihood.py:41-78), BagVariationalELBO (src/mlls/bag_variational_elbo.py:47-69) and
+ * .backward().  The algebra (no root of Lambda^{-1}, no Sigma_q) is written out at the top of csrc/cmp.cu.
+ * Conventions as for dcgp_vbagg_elbo_*: device pointers of the compute dtype, hyper-parameter VALUES, gradients with
+ * respect to those values scaled by `scale`, the workspace carries the forward intermediates to the backward call.
+ * `info`: THREE device ints - status of the factorisations of Lambda, K_ZZ and the bag-level matrix C (0 = ok).
+ * F32 problems keep the reference's FP64 island (variational_strategy.py:35-44): K_ZZ is evaluated, factored and inverted
+ * in double, its inverse factor applied as an FP32 hi + lo pair, its adjoint taken in double again - on a side lane beside
+ * the Lambda factorisation, so it costs no wall-clock (DCGP_CMP_ISLAND=0 keeps K_ZZ in FP32 / 3xTF32). */
+typedef struct dcgp_cmp_problem {
+    const dcgp_kernel_spec* k_spec; /* individuals kernel k                                                  */
+    const dcgp_kernel_spec* l_spec; /* bag kernel l                                                          */
+    const void* Z;                  /* inducing points, M x d                                                */
+    int64_t M, ldz;
+    const void* x;                  /* individuals of the CME sample, N x d                                  */
+    int64_t N, ldx;
+    const void* ext;                /* their bag values y~ (extended_bags_values), N x r                     */
+    int64_t ldext;
+    const void* y;                  /* bag values of the minibatch, n x r                                    */
+    int64_t n, ldy;
+    const void* z;                  /* aggregate observations, n                                             */
+    const void* var_mean;           /* variational mean m, M                                                 */
+    const void* chol_var;           /* variational factor L_S, M x M; only its lower triangle is read        */
+    int64_t ldc;
+    const void* noise;              /* device scalar: aggregate noise sigma^2 (likelihood.noise)             */
+    const void* ind_noise;          /* device scalar: individuals noise (noise_kernel.outputscale)           */
+    const void* mean_const;         /* device scalar of a ConstantMean, NULL for ZeroMean                    */
+    double lbda;                    /* CME regulariser: Lambda = l(y~, y~) + lbda N I                         */
+    double num_data, beta;
+    double jitter, var_jitter;      /* 1e-3 on K_ZZ, 1e-4 on K_xx in the reference                           */
+} dcgp_cmp_problem;
+
+typedef struct dcgp_cmp_grads {     /* any field may be NULL; all are overwritten */
+    void* dZ;                       /* M x d, row stride lddz                              */
+    int64_t lddz;
+    void* dk_ls;                    /* [k components][DCGP_MAX_DIMS]                       */
+    void* dk_os;                    /* [k components]                                      */
+    void* dl_ls;                    /* [l components][DCGP_MAX_DIMS]                       */
+    void* dl_os;                    /* [l components]                                      */
+    void* dvar_mean;                /* M                                                   */
+    void* dchol_var;                /* M x M, row stride lddc, zero above the diagonal     */
+    int64_t lddc;
+    void* dnoise;                   /* scalar                                              */
+    void* dind_noise;               /* scalar                                              */
+    void* dmean_const;              /* scalar                                              */
+} dcgp_cmp_grads;
+
+/* ldz: the row stride of Z that will be passed (the FP64 island of F32 problems keeps double copies of Z and dZ) */
+DCGP_API size_t dcgp_cmp_elbo_workspace(int64_t N, int64_t n, int64_t M, int64_t ldz, int dtype);
+DCGP_API int dcgp_cmp_elbo_fwd(const dcgp_cmp_problem* problem, void* elbo, int* info, void* workspace,
+                               size_t workspace_bytes, int dtype, int flags, void* stream);
+DCGP_API int dcgp_cmp_elbo_bwd(const dcgp_cmp_problem* problem, double scale, const dcgp_cmp_grads* grads, void* workspace,
+                               size_t workspace_bytes, int dtype, int flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

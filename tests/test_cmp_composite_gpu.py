@@ -1,0 +1,131 @@
+"""dcgp_cmp_elbo_fwd / dcgp_cmp_elbo_bwd (the whole VariationalCMP minibatch ELBO with individuals noise and all its
+gradients behind two C calls) against the CPU oracle port of the reference step (oracle/port.py::vcmp_loss: explicit root
+of Lambda^{-1}, chol(Sigma_q), dense q(f) covariance - the reference's own algorithm,
+src/likelihoods/cmp_likelihood.py:41-78), differentiated by torch autograd in FP64."""
+import pytest
+import torch
+from torch.nn.functional import softplus
+
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _problem(M, N, n, d, r, seed, additive):
+    g = torch.Generator().manual_seed(seed)
+    p = port.make_vcmp_params(M, d, r, dtype=torch.float64, seed=seed, additive_bag_kernel=additive)
+    p["var_mean"] = 0.2 * torch.randn(M, generator=g, dtype=torch.float64)
+    p["chol_var"] = torch.eye(M, dtype=torch.float64) + 0.05 * torch.randn(M, M, generator=g, dtype=torch.float64)
+    p["k_raw_ls"] = p["k_raw_ls"] + 0.3 * torch.randn(d, generator=g, dtype=torch.float64)
+    p["raw_noise"] = torch.tensor([0.2], dtype=torch.float64)
+    p["noise_kernel_raw_os"] = torch.tensor(-0.4, dtype=torch.float64)
+    x = torch.randn(N, d, generator=g, dtype=torch.float64)
+    ext = torch.randn(N, r, generator=g, dtype=torch.float64)
+    y = torch.randn(n, r, generator=g, dtype=torch.float64)
+    z = torch.randn(n, generator=g, dtype=torch.float64)
+    return p, x, ext, y, z
+
+
+def _oracle(p, x, ext, y, z, lbda, num_data, beta):
+    q = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    loss = port.vcmp_loss(q, x, ext, y, z, lbda, num_data, beta, True)
+    loss.backward()
+    return loss.detach(), {k: v.grad for k, v in q.items()}
+
+
+def _gpu(p, x, ext, y, z, lbda, num_data, beta, dtype):
+    from deconditional_downscaling_b200 import ops
+    d, r = x.shape[1], ext.shape[1]
+    t = lambda v: v.to(device=DEV, dtype=dtype)
+    k_spec = ops.FlatSpec(["rbf"], [list(range(d))], [t(softplus(p["k_raw_ls"]))], [t(softplus(p["k_raw_os"]))])
+    if "l1_raw_ls" in p:
+        l_spec = ops.FlatSpec(["matern32", "rbf"], [[0, 1], list(range(2, r))],
+                              [t(softplus(p["l0_raw_ls"])), t(softplus(p["l1_raw_ls"]))],
+                              [t(softplus(p["l0_raw_os"])), t(softplus(p["l1_raw_os"]))])
+        lraws = [("l0_raw_ls", "l0_raw_os"), ("l1_raw_ls", "l1_raw_os")]
+    else:
+        l_spec = ops.FlatSpec(["rbf"], [list(range(r))], [t(softplus(p["l0_raw_ls"]))], [t(softplus(p["l0_raw_os"]))])
+        lraws = [("l0_raw_ls", "l0_raw_os")]
+    noise = t(softplus(p["raw_noise"]) + 1e-4)
+    ind = t(softplus(p["noise_kernel_raw_os"]))
+    elbo, g, info = ops.cmp_elbo(k_spec, l_spec, t(p["Z"]), t(x), t(ext), t(y), t(z), t(p["var_mean"]), t(p["chol_var"]),
+                                 noise, ind, lbda, num_data, beta=beta, scale=-1.0)
+    assert info.tolist() == [0, 0, 0]
+    sg = lambda name: torch.sigmoid(t(p[name]))
+    out = {"Z": g["Z"], "var_mean": g["var_mean"], "chol_var": g["chol_var"], "raw_noise": g["noise"] * sg("raw_noise"),
+           "noise_kernel_raw_os": g["ind_noise"] * sg("noise_kernel_raw_os"),
+           "k_raw_ls": g["dk_ls"][0, :d] * sg("k_raw_ls"), "k_raw_os": g["dk_os"][0] * sg("k_raw_os")}
+    for c, (a, b) in enumerate(lraws):
+        out[a] = g["dl_ls"][c, :p[a].numel()] * sg(a)
+        out[b] = g["dl_os"][c] * sg(b)
+    return -elbo, out
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-7), (torch.float32, 3e-3)])
+@pytest.mark.parametrize("M,N,n,d,r,additive", [(48, 300, 40, 3, 3, True), (130, 700, 150, 5, 3, True), (33, 257, 19, 2, 2, False)])
+def test_loss_and_every_gradient_match_the_oracle(dtype, tol, M, N, n, d, r, additive):
+    p, x, ext, y, z = _problem(M, N, n, d, r, seed=M + n, additive=additive)
+    lbda, num_data, beta = 1e-3, 10.0 * n, 0.8
+    ref, gref = _oracle(p, x, ext, y, z, lbda, num_data, beta)
+    loss, g = _gpu(p, x, ext, y, z, lbda, num_data, beta, dtype)
+    assert abs(loss.item() - ref.item()) <= tol * max(1.0, abs(ref.item())), (loss.item(), ref.item())
+    for name, gr in gref.items():
+        got = g[name].double().cpu().reshape(gr.shape)
+        if name == "chol_var":
+            gr = gr.tril()
+            assert got.triu(1).abs().max().item() == 0.0
+        err = (got - gr).norm().item() / max(gr.norm().item(), 1e-12)
+        # bag-kernel hyper-parameters: sums of two opposing parts (through l(y~, y) and through Lambda^{-1})
+        lim = tol * (40 if (dtype == torch.float32 and name.startswith("l")) else 5)
+        assert err <= lim, (name, err)
+
+
+def test_failed_lambda_factorisation_is_reported():
+    """Two identical individuals' bag values and lbda = 0: Lambda is singular, info[0] must say so."""
+    from deconditional_downscaling_b200 import ops
+    p, x, ext, y, z = _problem(16, 140, 12, 2, 2, seed=4, additive=False)
+    ext[5] = ext[4]
+    t = lambda v: v.to(device=DEV, dtype=torch.float64)
+    k_spec = ops.FlatSpec(["rbf"], [[0, 1]], [t(softplus(p["k_raw_ls"]))], [t(softplus(p["k_raw_os"]))])
+    l_spec = ops.FlatSpec(["rbf"], [[0, 1]], [t(softplus(p["l0_raw_ls"]))], [t(softplus(p["l0_raw_os"]))])
+    _, _, info = ops.cmp_elbo(k_spec, l_spec, t(p["Z"]), t(x), t(ext), t(y), t(z), t(p["var_mean"]), t(p["chol_var"]),
+                              t(softplus(p["raw_noise"])), t(softplus(p["noise_kernel_raw_os"])), 0.0, 100.0,
+                              need_grads=False)
+    assert info[0].item() != 0
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-8), (torch.float32, 2e-3)])
+def test_trainer_takes_the_composite_and_follows_the_layered_path(dtype, tol, monkeypatch):
+    """ElboTrainer on a VariationalCMP (additive bag kernel, constant mean, individuals noise): three Adam steps through the
+    C composite (default) and through the layered Python path (DCGP_CMP_FUSED=0) give the same losses and parameters."""
+    from deconditional_downscaling_b200 import kernels as K, likelihoods as L, means as Mn, models as Md
+    from deconditional_downscaling_b200 import _lib
+    from deconditional_downscaling_b200.training import ElboTrainer
+    g = torch.Generator().manual_seed(17)
+    N, n, M, d, r = 600, 64, 40, 3, 3
+    x = torch.randn(N, d, generator=g).to(DEV, dtype)
+    ext = torch.randn(N, r, generator=g).to(DEV, dtype)
+    y = torch.randn(n, r, generator=g).to(DEV, dtype)
+    z = torch.randn(n, generator=g).to(DEV, dtype)
+    Z0 = torch.randn(M, d, generator=g)
+    runs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("DCGP_CMP_FUSED", flag)
+        torch.manual_seed(5)
+        k = K.ScaleKernel(K.RBFKernel(ard_num_dims=d))
+        l = K.ScaleKernel(K.MaternKernel(nu=1.5, ard_num_dims=2, active_dims=[0, 1])) + \
+            K.ScaleKernel(K.RBFKernel(ard_num_dims=1, active_dims=[2]))
+        model = Md.VariationalCMP(inducing_points=Z0.clone(), individuals_mean=Mn.ConstantMean(), individuals_kernel=k,
+                                  bag_kernel=l, lbda=1e-3, use_individuals_noise=True).to(DEV).to(dtype)
+        lik = L.CMPLikelihood(use_individuals_noise=True).to(DEV).to(dtype)
+        tr = ElboTrainer(model, lik, num_data=640, beta=1.0, lr=0.05, cuda_graph=False)
+        l0 = _lib.load().dcgp_launch_count()
+        losses = [tr.step(x, z, bags_values=y, extended_bags_values=ext).item() for _ in range(3)]
+        runs[flag] = (losses, {nm: p.detach().clone() for nm, p in list(model.named_parameters()) + list(lik.named_parameters())},
+                      _lib.load().dcgp_launch_count() - l0)
+    for a, b in zip(runs["1"][0], runs["0"][0]):
+        assert abs(a - b) <= tol * max(1.0, abs(b)), (runs["1"][0], runs["0"][0])
+    for nm, p in runs["0"][1].items():
+        assert (runs["1"][1][nm] - p).abs().max().item() <= (1e-6 if dtype == torch.float64 else 5e-3), nm
+    assert runs["1"][2] != runs["0"][2]          # the two runs really took different paths

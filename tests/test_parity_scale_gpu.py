@@ -194,6 +194,50 @@ def test_variational_cmp_config5_minibatch_matches_fp64_oracle(config5, dtype):
         assert grad_error(got, ref, key) < gtol, f"gradient of {key}: {grad_error(got, ref, key):.3e}"
 
 
+def composite_vcmp(inp, p, lbda, num_data, dtype, beta=1.0):
+    """The same minibatch through the two-call C composite (dcgp_cmp_elbo_fwd / _bwd, csrc/cmp.cu); gradients mapped to
+    the raw parameters with the softplus chain rule."""
+    from deconditional_downscaling_b200 import ops
+    d, r = inp["x"].shape[1], inp["ext"].shape[1]
+    t = lambda v: v.to(device=DEV, dtype=dtype)
+    k_spec = ops.FlatSpec(["rbf"], [list(range(d))], [t(softplus(p["k_raw_ls"]))], [t(softplus(p["k_raw_os"]))])
+    l_spec = ops.FlatSpec(["matern32", "rbf"], [[0, 1], list(range(2, r))],
+                          [t(softplus(p["l0_raw_ls"])), t(softplus(p["l1_raw_ls"]))],
+                          [t(softplus(p["l0_raw_os"])), t(softplus(p["l1_raw_os"]))])
+    elbo, g, info = ops.cmp_elbo(k_spec, l_spec, t(p["Z"]), t(inp["x"]), t(inp["ext"]), t(inp["y"]), t(inp["z"]),
+                                 t(p["var_mean"]), t(p["chol_var"]), t(softplus(p["raw_noise"]) + 1e-4),
+                                 t(softplus(p["noise_kernel_raw_os"])), lbda, num_data, beta=beta, scale=-1.0)
+    assert info.tolist() == [0, 0, 0]
+    sg = lambda name: torch.sigmoid(t(p[name]))
+    grads = {"Z": g["Z"], "var_mean": g["var_mean"], "chol_var": g["chol_var"], "raw_noise": g["noise"] * sg("raw_noise"),
+             "noise_kernel_raw_os": g["ind_noise"] * sg("noise_kernel_raw_os"),
+             "k_raw_ls": g["dk_ls"][0, :d] * sg("k_raw_ls"), "k_raw_os": g["dk_os"][0] * sg("k_raw_os"),
+             "l0_raw_ls": g["dl_ls"][0, :2] * sg("l0_raw_ls"), "l0_raw_os": g["dl_os"][0] * sg("l0_raw_os"),
+             "l1_raw_ls": g["dl_ls"][1, :r - 2] * sg("l1_raw_ls"), "l1_raw_os": g["dl_os"][1] * sg("l1_raw_os")}
+    torch.cuda.synchronize()
+    return dict(loss=-elbo, grads=grads)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_cmp_composite_config5_minibatch_matches_fp64_oracle(config5, dtype):
+    """dcgp_cmp_elbo_fwd / _bwd at the bench minibatch shape: loss and every gradient against the FP64 oracle, same
+    bounds as the layered path above (the FP32 composite keeps K_ZZ in FP32 / 3xTF32: no FP64 island)."""
+    inp, p, ref = config5
+    got = composite_vcmp(inp, p, lbda=1e-4, num_data=10240, dtype=dtype)
+    lines = [f"composite config5 {dtype}: loss {rel(got['loss'], ref['loss']):.2e}"]
+    for key in sorted(ref["grads"]):
+        g_ = got["grads"][key].detach().double().cpu().reshape(ref["grads"][key].shape)
+        if key == "chol_var":
+            g_ = g_.tril()
+        got["grads"][key] = g_
+        lines.append(f"    grad {key:22s} {grad_error(got, ref, key):.2e}")
+    print("\n".join(lines))
+    assert rel(got["loss"], ref["loss"]) < (1e-6 if dtype == torch.float64 else 1e-3)
+    gtol = 1e-6 if dtype == torch.float64 else GRAD_TOL_F32
+    for key in ref["grads"]:
+        assert grad_error(got, ref, key) < gtol, f"gradient of {key}: {grad_error(got, ref, key):.3e}"
+
+
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_variational_cmp_with_constant_mean_matches_fp64_oracle(dtype):
     """individuals_mean = ConstantMean(0.3): mu(x) enters q(f).mean (variational_strategy.py:47-52) and the
