@@ -221,10 +221,13 @@ inline dcgp_kernel_spec spec_f64(const dcgp_kernel_spec* sp, const double* hyp) 
     return s;
 }
 
-inline bool island_enabled() {
-    static const bool on = !(getenv("DCGP_CMP_ISLAND") && atoi(getenv("DCGP_CMP_ISLAND")) == 0);
-    return on;
+// DCGP_CMP_ISLAND: 1 (default) = forward and adjoint of the K_ZZ factor in FP64; 2 = forward in FP64, adjoint chain in
+// FP32 / 3xTF32 on the rounded factor; 0 = no island
+inline int island_mode() {
+    static const int m = getenv("DCGP_CMP_ISLAND") ? atoi(getenv("DCGP_CMP_ISLAND")) : 1;
+    return m;
 }
+inline bool island_enabled() { return island_mode() != 0; }
 
 struct Layout {
     size_t Lam, NN, A, Ar, KA, dA, P, Kzx, At, dAt, dKzx, U, DU, dU, tU, H, G, C, Wc, Cinv, T1, dC, S2, Gd, Gd2, Lz, W, Wlo, D, Ls, t1, t2,
@@ -358,6 +361,11 @@ int fwd_impl(const dcgp_cmp_problem* p, void* elbo, int* info, void* ws, size_t 
             f64_to_hilo_kernel<<<(unsigned)(((int64_t)M * M + 255) / 256), 256, 0, ss>>>(W64, (float*)(w + l.W), (float*)(w + l.Wlo),
                                                                                    (int64_t)M * M);
             DCGP_CHECK_LAUNCH();
+            if (island_mode() == 2) {
+                f64_to_hilo_kernel<<<(unsigned)(((int64_t)M * M + 255) / 256), 256, 0, ss>>>(L64, (float*)(w + l.Lz), (float*)(w + l.t1),
+                                                                                       (int64_t)M * M);
+                DCGP_CHECK_LAUNCH();
+            }
             RC(gemm3<T>(0, 0, M, N, M, 1.0, w + l.W, M, nullptr, w + l.Kzx, N, nullptr, 0.0, w + l.At, N, q3, q4, dtype, gf, ss));
             RC(gemm3<T>(0, 0, M, N, M, 1.0, w + l.Wlo, M, nullptr, w + l.Kzx, N, nullptr, 1.0, w + l.At, N, q3, q4, dtype, gf, ss));
         }
@@ -507,13 +515,16 @@ int bwd_impl(const dcgp_cmp_problem* p, double scale, const dcgp_cmp_grads* g, v
     bool island = false;
     if constexpr (sizeof(T) == 4) island = island_enabled();
     RC(gemm3<T>(1, 0, M, N, M, 1.0, w + l.W, M, nullptr, w + l.dAt, N, nullptr, 0.0, w + l.dKzx, N, q3, q4, dtype, gf, ss));
-    if (island)
+    if (island)   // (still true in mode 2 here: W is a hi + lo pair whenever the forward island ran)
         RC(gemm3<T>(1, 0, M, N, M, 1.0, w + l.Wlo, M, nullptr, w + l.dAt, N, nullptr, 1.0, w + l.dKzx, N, q3, q4, dtype, gf, ss));
     RC(dcgp_gram_bwd(p->k_spec, p->Z, M, p->ldz, p->x, N, p->ldx, w + l.dKzx, N, g->dk_ls, g->dk_os, g->dZ, g->lddz, dtype, 0,
                      ss));
     RC(gemm3<T>(0, 1, M, M, N, 1.0, w + l.dAt, N, nullptr, w + l.Kzx, N, nullptr, 0.0, w + l.t3, M, q3, q4, dtype, gf, ss));
     tril_axpby_kernel<T><<<gM, 256, 0, ss>>>(w + l.t3, M, T(1), nullptr, 0, T(0), 0, w + l.t2, M);
     DCGP_CHECK_LAUNCH();
+    if constexpr (sizeof(T) == 4) {
+        if (island_mode() == 2) island = false;    // adjoint chain below in FP32 / 3xTF32 on the rounded factor
+    }
     if constexpr (sizeof(T) == 4) {
         if (island) {
             // the adjoint of W = chol(K_ZZ)^{-1} in FP64, as products with W (functional._CholInverseFn)
