@@ -129,3 +129,63 @@ def test_trainer_takes_the_composite_and_follows_the_layered_path(dtype, tol, mo
     for nm, p in runs["0"][1].items():
         assert (runs["1"][1][nm] - p).abs().max().item() <= (1e-6 if dtype == torch.float64 else 5e-3), nm
     assert runs["1"][2] != runs["0"][2]          # the two runs really took different paths
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-7), (torch.float32, 3e-3)])
+def test_constant_individuals_mean_and_its_gradient(dtype, tol):
+    """individuals_mean = ConstantMean(c): mu(x) enters q(f).mean (variational_strategy.py:47-52) and the residual
+    z - A^T mu_q (cmp_likelihood.py:70)."""
+    from oracle import restate as R
+    from deconditional_downscaling_b200 import ops
+    p, x, ext, y, z = _problem(40, 260, 30, 3, 3, seed=9, additive=True)
+    lbda, num_data, beta, c0 = 1e-3, 300.0, 1.0, 0.35
+    q = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    q["mean_const"] = torch.tensor([c0], dtype=torch.float64, requires_grad=True)
+    k, l = port.vcmp_specs(q, 3)
+    mu_q, Sigma_q = R.svgp_q(k, q["Z"], x, q["var_mean"], q["chol_var"], mu_x=q["mean_const"].expand(x.shape[0]))
+    Rt, B = R.elbo_computation_parameters(l, y, ext, lbda)
+    ell = R.cmp_ell_with_noise(z, mu_q, Sigma_q, Rt, B, softplus(q["noise_kernel_raw_os"]), q["raw_noise"])
+    ref = -R.bag_elbo(ell, R.whitened_kl(q["var_mean"], q["chol_var"]), z.numel(), num_data, beta)
+    ref.backward()
+    t = lambda v: v.to(device=DEV, dtype=dtype)
+    k_spec = ops.FlatSpec(["rbf"], [[0, 1, 2]], [t(softplus(p["k_raw_ls"]))], [t(softplus(p["k_raw_os"]))])
+    l_spec = ops.FlatSpec(["matern32", "rbf"], [[0, 1], [2]], [t(softplus(p["l0_raw_ls"])), t(softplus(p["l1_raw_ls"]))],
+                          [t(softplus(p["l0_raw_os"])), t(softplus(p["l1_raw_os"]))])
+    elbo, g, info = ops.cmp_elbo(k_spec, l_spec, t(p["Z"]), t(x), t(ext), t(y), t(z), t(p["var_mean"]), t(p["chol_var"]),
+                                 t(softplus(p["raw_noise"]) + 1e-4), t(softplus(p["noise_kernel_raw_os"])), lbda, num_data,
+                                 beta=beta, mean_const=t(torch.tensor([c0])), scale=-1.0)
+    assert info.tolist() == [0, 0, 0]
+    assert abs(-elbo.item() - ref.item()) <= tol * max(1.0, abs(ref.item()))
+    assert abs(g["mean_const"].item() - q["mean_const"].grad.item()) <= 5 * tol * max(abs(q["mean_const"].grad.item()), 1e-3)
+    err = (g["var_mean"].double().cpu() - q["var_mean"].grad).norm() / q["var_mean"].grad.norm()
+    assert err.item() <= 5 * tol
+
+
+def test_argument_errors_are_reported_as_negative_codes():
+    """C-ABI error convention: -k for a bad argument, no CUDA work issued."""
+    import ctypes
+    from deconditional_downscaling_b200 import _lib
+    lib = _lib.load()
+    assert lib.dcgp_cmp_elbo_workspace(0, 4, 4, 2, 0) == 0
+    assert lib.dcgp_vbagg_elbo_workspace(4, 0, 0) == 0
+    empty = _lib.CmpProblem()
+    assert lib.dcgp_cmp_elbo_fwd(ctypes.byref(empty), None, None, None, 0, 0, 0, None) == -1
+    empty_v = _lib.VbaggProblem()
+    assert lib.dcgp_vbagg_elbo_fwd(ctypes.byref(empty_v), None, None, None, 0, 0, 0, None) == -1
+    # a workspace that is too small is refused before anything is launched
+    from deconditional_downscaling_b200 import ops
+    p, x, ext, y, z = _problem(16, 140, 12, 2, 2, seed=4, additive=False)
+    t = lambda v: v.to(device=DEV, dtype=torch.float64)
+    k_spec = ops.FlatSpec(["rbf"], [[0, 1]], [t(softplus(p["k_raw_ls"]))], [t(softplus(p["k_raw_os"]))]).c_spec()
+    l_spec = ops.FlatSpec(["rbf"], [[0, 1]], [t(softplus(p["l0_raw_ls"]))], [t(softplus(p["l0_raw_os"]))]).c_spec()
+    Z, xd, ed, yd, zd, m, Ls = t(p["Z"]), t(x), t(ext), t(y), t(z), t(p["var_mean"]), t(p["chol_var"])
+    noise, ind = t(torch.ones(1)), t(torch.ones(1))
+    prob = _lib.CmpProblem(ctypes.pointer(k_spec), ctypes.pointer(l_spec), Z.data_ptr(), 16, 2, xd.data_ptr(), 140, 2,
+                           ed.data_ptr(), 2, yd.data_ptr(), 12, 2, zd.data_ptr(), m.data_ptr(), Ls.data_ptr(), 16,
+                           noise.data_ptr(), ind.data_ptr(), None, 1e-3, 100.0, 1.0, 1e-3, 1e-4)
+    ws = torch.empty(1024, dtype=torch.uint8, device=DEV)
+    out = torch.empty(1, dtype=torch.float64, device=DEV)
+    info = torch.zeros(3, dtype=torch.int32, device=DEV)
+    l0 = lib.dcgp_launch_count()
+    rc = lib.dcgp_cmp_elbo_fwd(ctypes.byref(prob), out.data_ptr(), info.data_ptr(), ws.data_ptr(), 1024, 0, 0, None)
+    assert rc == -5 and lib.dcgp_launch_count() == l0
