@@ -53,24 +53,13 @@ __device__ __forceinline__ T block_sum(T v, T* red) {
     return t;
 }
 
-// sc[0] = ell, sc[3] = mean term, sc[4] = covar term;  out = ell / n - kl * klw      (one block)
+// sc[3] = e^T C^{-1} e and sc[4] = tr(C^{-1} G) come from dot();  sc[0] = ell;  out = ell / n - kl * klw
 template <typename T>
-__global__ void ell_kernel(const T* __restrict__ Cinv, const T* __restrict__ G, const T* __restrict__ u,
-                           const T* __restrict__ e, int64_t n, const T* __restrict__ logdet, const T* __restrict__ kl,
-                           T klw, T* __restrict__ sc, T* __restrict__ out) {
-    __shared__ T red[32];
-    T m = T(0), c = T(0);
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fma(u[i], e[i], m);
-    for (int64_t i = threadIdx.x; i < n * n; i += blockDim.x) c = fma(Cinv[i], G[i], c);
-    m = block_sum(m, red);
-    c = block_sum(c, red);
-    if (threadIdx.x == 0) {
-        const T ell = T(-0.5) * ((T)n * T(1.8378770664093453) + logdet[0] + m + c);
-        sc[0] = ell;
-        sc[3] = m;
-        sc[4] = c;
-        out[0] = ell / (T)n - kl[0] * klw;
-    }
+__global__ void ell_kernel(int64_t n, const T* __restrict__ logdet, const T* __restrict__ kl, T klw, T* __restrict__ sc,
+                           T* __restrict__ out) {
+    const T ell = T(-0.5) * ((T)n * T(1.8378770664093453) + logdet[0] + sc[3] + sc[4]);
+    sc[0] = ell;
+    out[0] = ell / (T)n - kl[0] * klw;
 }
 
 // dC = c0 (Cinv - u u^T - T1);  S2 = 2 s_ind dC;  Gd = c0 Cinv (= dG);  Gd2 = 2 Gd
@@ -88,23 +77,24 @@ __global__ void dc_kernel(const T* __restrict__ Cinv, const T* __restrict__ T1, 
     Gd2[i * n + j] = T(2) * c0 * ci;
 }
 
-// dnoise = tr(dC), dind = <dC, H>, da = -2 c0 u      (one block)
+// da = -2 c0 u;  sc[8] += tr(dC)   (<dC, H> comes from dot() into sc[9])
 template <typename T>
-__global__ void dscal_kernel(const T* __restrict__ dC, const T* __restrict__ H, const T* __restrict__ u, int64_t n, T c0,
-                             T* __restrict__ dnoise, T* __restrict__ dind, T* __restrict__ da) {
+__global__ void dscal_kernel(const T* __restrict__ dC, const T* __restrict__ u, int64_t n, T c0, T* __restrict__ da,
+                             T* __restrict__ sc) {
     __shared__ T red[32];
-    T t = T(0), h = T(0);
+    T t = T(0);
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
         t += dC[i * n + i];
         da[i] = T(-2) * c0 * u[i];
     }
-    for (int64_t i = threadIdx.x; i < n * n; i += blockDim.x) h = fma(dC[i], H[i], h);
     t = block_sum(t, red);
-    h = block_sum(h, red);
-    if (threadIdx.x == 0) {
-        if (dnoise) dnoise[0] = t;
-        if (dind) dind[0] = h;
-    }
+    if (threadIdx.x == 0) sc[8] = t;
+}
+
+template <typename T>
+__global__ void dscal_out_kernel(const T* __restrict__ sc, T* __restrict__ dnoise, T* __restrict__ dind) {
+    if (dnoise) dnoise[0] = sc[8];
+    if (dind) dind[0] = sc[9];
 }
 
 // Mx[i, j] += a_i b_j
@@ -230,7 +220,7 @@ inline int island_mode() {
 inline bool island_enabled() { return island_mode() != 0; }
 
 struct Layout {
-    size_t Lam, NN, A, Ar, KA, dA, P, Kzx, At, dAt, dKzx, U, DU, dU, tU, H, G, C, Wc, Cinv, T1, dC, S2, Gd, Gd2, Lz, W, Wlo, D, Ls, t1, t2,
+    size_t Lam, NN, A, Ar, KA, dA, P, Kzx, Kzxlo, At, dAt, dAtlo, dKzx, U, DU, dU, tU, H, G, C, Wc, Cinv, T1, dC, S2, Gd, Gd2, Lz, W, Wlo, D, Ls, t1, t2,
         t3, t4, mu, dmu, a, e, u, da, v, sc, q1, q2, q3, q4, end;
 };
 
@@ -245,7 +235,7 @@ inline Layout layout(int64_t N, int64_t n, int64_t M) {
 #define TAKE(f, s) l.f = o; o += (s)
     TAKE(Lam, NNs); TAKE(NN, NNs);
     TAKE(A, Nn); TAKE(Ar, Nn); TAKE(KA, Nn); TAKE(dA, Nn); TAKE(P, Nn);
-    TAKE(Kzx, MN); TAKE(At, MN); TAKE(dAt, MN); TAKE(dKzx, MN);
+    TAKE(Kzx, MN); TAKE(Kzxlo, MN); TAKE(At, MN); TAKE(dAt, MN); TAKE(dAtlo, MN); TAKE(dKzx, MN);
     TAKE(U, Mn); TAKE(DU, Mn); TAKE(dU, Mn); TAKE(tU, Mn);
     TAKE(H, nn); TAKE(G, nn); TAKE(C, nn); TAKE(Wc, nn); TAKE(Cinv, nn); TAKE(T1, nn); TAKE(dC, nn); TAKE(S2, nn); TAKE(Gd, nn);
     TAKE(Gd2, nn);
@@ -302,12 +292,6 @@ inline Scratch scratch(const Layout& l, size_t es, int64_t N, int64_t n, int64_t
     return s;
 }
 
-// plain (non-compensated) product for the vector-shaped contractions
-template <typename T>
-int gemv(int ta, int64_t m, int64_t k, const T* A, int64_t lda, const T* x, T* y, int dtype, int flags, cudaStream_t st) {
-    return dcgp_gemm(ta, 0, m, 1, k, 1.0, A, lda, x, 1, 0.0, y, 1, dtype, flags, st);
-}
-
 template <typename T>
 int fwd_impl(const dcgp_cmp_problem* p, void* elbo, int* info, void* ws, size_t ws_bytes, int dtype, int flags,
              cudaStream_t st) {
@@ -339,6 +323,8 @@ int fwd_impl(const dcgp_cmp_problem* p, void* elbo, int* info, void* ws, size_t 
     }
     // --- K_ZZ + jitter I -> L_Z -> W;  A~ = W k(Z, x);  D
     RC(dcgp_gram(p->k_spec, p->Z, M, p->ldz, p->x, N, p->ldx, w + l.Kzx, N, nullptr, 0.0, dtype, 0, ss));
+    T* const Kzxlo = f32 ? w + l.Kzxlo : nullptr;      // TF32 remainders of K_Zx: operand of three 3xTF32 products
+    RC(split_keep<T>(w + l.Kzx, Kzxlo, M, N, ss));
     bool island = false;
     if constexpr (sizeof(T) == 4) {
         island = island_enabled();
@@ -366,8 +352,8 @@ int fwd_impl(const dcgp_cmp_problem* p, void* elbo, int* info, void* ws, size_t 
                                                                                        (int64_t)M * M);
                 DCGP_CHECK_LAUNCH();
             }
-            RC(gemm3<T>(0, 0, M, N, M, 1.0, w + l.W, M, nullptr, w + l.Kzx, N, nullptr, 0.0, w + l.At, N, q3, q4, dtype, gf, ss));
-            RC(gemm3<T>(0, 0, M, N, M, 1.0, w + l.Wlo, M, nullptr, w + l.Kzx, N, nullptr, 1.0, w + l.At, N, q3, q4, dtype, gf, ss));
+            RC(gemm3<T>(0, 0, M, N, M, 1.0, w + l.W, M, nullptr, w + l.Kzx, N, Kzxlo, 0.0, w + l.At, N, q3, q4, dtype, gf, ss));
+            RC(gemm3<T>(0, 0, M, N, M, 1.0, w + l.Wlo, M, nullptr, w + l.Kzx, N, Kzxlo, 1.0, w + l.At, N, q3, q4, dtype, gf, ss));
         }
     }
     if (!island) {
@@ -377,7 +363,7 @@ int fwd_impl(const dcgp_cmp_problem* p, void* elbo, int* info, void* ws, size_t 
         DCGP_CHECK_LAUNCH();
         DCGP_CU_RC(cudaMemcpyAsync(w + l.Lz, w + l.t1, (size_t)M * M * sizeof(T), cudaMemcpyDeviceToDevice, ss));
         RC(dcgp_trtri(w + l.Lz, M, M, w + l.W, M, wb + s.solver2, s.solver2_bytes, dtype, gf, ss));
-        RC(gemm3<T>(0, 0, M, N, M, 1.0, w + l.W, M, nullptr, w + l.Kzx, N, nullptr, 0.0, w + l.At, N, q3, q4, dtype, gf, ss));
+        RC(gemm3<T>(0, 0, M, N, M, 1.0, w + l.W, M, nullptr, w + l.Kzx, N, Kzxlo, 0.0, w + l.At, N, q3, q4, dtype, gf, ss));
     }
     tril_copy_kernel<T><<<gM, 256, 0, ss>>>((const T*)p->chol_var, p->ldc, w + l.Ls, M);
     DCGP_CHECK_LAUNCH();
@@ -397,12 +383,12 @@ int fwd_impl(const dcgp_cmp_problem* p, void* elbo, int* info, void* ws, size_t 
         DCGP_CU_RC(cudaStreamWaitEvent(st, lane->join, 0));
     }
     // --- mu_q, a, H, K A, U, G
-    RC(gemv<T>(1, N, M, w + l.At, N, (const T*)p->var_mean, w + l.mu, dtype, gf, st));
+    RC(gemv<T>(1, N, M, w + l.At, N, (const T*)p->var_mean, w + l.mu, st));
     if (p->mean_const) {
         add_scalar_kernel<T><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(w + l.mu, N, (const T*)p->mean_const);
         DCGP_CHECK_LAUNCH();
     }
-    RC(gemv<T>(1, n, N, w + l.A, n, w + l.mu, w + l.a, dtype, gf, st));
+    RC(gemv<T>(1, n, N, w + l.A, n, w + l.mu, w + l.a, st));
     if (f32) RC(dcgp_round_tf32(w + l.A, w + l.Ar, N, n, n, n, st));   // A is an operand of ten products
     RC(gemm1<T>(1, 0, n, n, N, 1.0, w + l.A, n, Ar, w + l.A, n, Ar, 0.0, w + l.H, n, q1, q2, dtype, gf, st));
     RC(dcgp_gram_matmul(p->k_spec, p->x, N, p->ldx, p->x, N, p->ldx, nullptr, p->var_jitter, w + l.A, n, n, w + l.KA, n,
@@ -421,10 +407,11 @@ int fwd_impl(const dcgp_cmp_problem* p, void* elbo, int* info, void* ws, size_t 
     RC(dcgp_logdet_chol(w + l.t1, n, n, w + l.sc + 2, dtype, st));
     RC(dcgp_trtri(w + l.t1, n, n, w + l.Wc, n, wb + s.solver, s.solver_bytes, dtype, gf, st));
     RC(gemm3<T>(1, 0, n, n, n, 1.0, w + l.Wc, n, nullptr, w + l.Wc, n, nullptr, 0.0, w + l.Cinv, n, q1, q2, dtype, gf, st));
-    RC(gemv<T>(0, n, n, w + l.Cinv, n, w + l.e, w + l.u, dtype, gf, st));
+    RC(gemv<T>(0, n, n, w + l.Cinv, n, w + l.e, w + l.u, st));
     RC(dcgp_whitened_kl(p->var_mean, w + l.Ls, M, M, w + l.sc + 1, w + l.t4 + (size_t)M * M, w + l.t4, M, dtype, st));
-    ell_kernel<T><<<1, 1024, 0, st>>>(w + l.Cinv, w + l.G, w + l.u, w + l.e, n, w + l.sc + 2, w + l.sc + 1,
-                                      (T)(p->beta / p->num_data), w + l.sc, (T*)elbo);
+    RC(dot<T>(w + l.u, w + l.e, n, w + l.sc + 3, st));
+    RC(dot<T>(w + l.Cinv, w + l.G, n * n, w + l.sc + 4, st));
+    ell_kernel<T><<<1, 1, 0, st>>>(n, w + l.sc + 2, w + l.sc + 1, (T)(p->beta / p->num_data), w + l.sc, (T*)elbo);
     DCGP_CHECK_LAUNCH();
     return 0;
 }
@@ -462,7 +449,11 @@ int bwd_impl(const dcgp_cmp_problem* p, double scale, const dcgp_cmp_grads* g, v
     dc_kernel<T><<<gn, 256, 0, st>>>(w + l.Cinv, w + l.T1, w + l.u, n, c0, (const T*)p->ind_noise, w + l.dC, w + l.S2,
                                      w + l.Gd, w + l.Gd2);
     DCGP_CHECK_LAUNCH();
-    dscal_kernel<T><<<1, 1024, 0, st>>>(w + l.dC, w + l.H, w + l.u, n, c0, (T*)g->dnoise, (T*)g->dind_noise, w + l.da);
+    DCGP_CU_RC(cudaMemsetAsync(w + l.sc + 8, 0, 2 * sizeof(T), st));
+    dscal_kernel<T><<<1, 1024, 0, st>>>(w + l.dC, w + l.u, n, c0, w + l.da, w + l.sc);
+    DCGP_CHECK_LAUNCH();
+    RC(dot<T>(w + l.dC, w + l.H, n * n, w + l.sc + 9, st));
+    dscal_out_kernel<T><<<1, 1, 0, st>>>(w + l.sc, (T*)g->dnoise, (T*)g->dind_noise);
     DCGP_CHECK_LAUNCH();
     // --- dU = D U (2 dG), dD = U dG U^T -> dL_S
     RC(gemm3<T>(0, 0, M, n, n, 1.0, w + l.DU, n, nullptr, w + l.Gd2, n, nullptr, 0.0, w + l.dU, n, q1, q2, dtype, gf, st));
@@ -490,14 +481,14 @@ int bwd_impl(const dcgp_cmp_problem* p, double scale, const dcgp_cmp_grads* g, v
         DCGP_CHECK_LAUNCH();
     }
     // --- dmu = A da;  dA~ = dU A^T + m dmu^T;  dm;  mean constant
-    RC(gemv<T>(0, N, n, w + l.A, n, w + l.da, w + l.dmu, dtype, gf, st));
+    RC(gemv<T>(0, N, n, w + l.A, n, w + l.da, w + l.dmu, st));
     RC(gemm1<T>(0, 1, M, N, n, 1.0, w + l.dU, n, nullptr, w + l.A, n, Ar, 0.0, w + l.dAt, N, q1, q2, dtype, gf, st));
     {
         const dim3 gr((unsigned)((N + 255) / 256), (unsigned)M);
         rank1_kernel<T><<<gr, 256, 0, st>>>(w + l.dAt, M, N, (const T*)p->var_mean, w + l.dmu);
         DCGP_CHECK_LAUNCH();
     }
-    RC(gemv<T>(0, M, N, w + l.At, N, w + l.dmu, w + l.v, dtype, gf, st));
+    RC(gemv<T>(0, M, N, w + l.At, N, w + l.dmu, w + l.v, st));
     tail_kernel<T><<<1, 1024, 0, st>>>(w + l.v, w + l.t4 + (size_t)M * M, M, s2, (T*)g->dvar_mean, w + l.dmu, N,
                                        (T*)g->dmean_const);
     DCGP_CHECK_LAUNCH();
@@ -514,12 +505,15 @@ int bwd_impl(const dcgp_cmp_problem* p, double scale, const dcgp_cmp_grads* g, v
     // --- dK_Zx = W^T dA~;  dW = tril(dA~ K_Zx^T) -> dK_ZZ
     bool island = false;
     if constexpr (sizeof(T) == 4) island = island_enabled();
-    RC(gemm3<T>(1, 0, M, N, M, 1.0, w + l.W, M, nullptr, w + l.dAt, N, nullptr, 0.0, w + l.dKzx, N, q3, q4, dtype, gf, ss));
+    T* const dAtlo = f32 ? w + l.dAtlo : nullptr;      // remainders of dA~: operand of three 3xTF32 products
+    const T* const Kzxlo = f32 ? w + l.Kzxlo : nullptr;
+    RC(split_keep<T>(w + l.dAt, dAtlo, M, N, ss));
+    RC(gemm3<T>(1, 0, M, N, M, 1.0, w + l.W, M, nullptr, w + l.dAt, N, dAtlo, 0.0, w + l.dKzx, N, q3, q4, dtype, gf, ss));
     if (island)   // (still true in mode 2 here: W is a hi + lo pair whenever the forward island ran)
-        RC(gemm3<T>(1, 0, M, N, M, 1.0, w + l.Wlo, M, nullptr, w + l.dAt, N, nullptr, 1.0, w + l.dKzx, N, q3, q4, dtype, gf, ss));
+        RC(gemm3<T>(1, 0, M, N, M, 1.0, w + l.Wlo, M, nullptr, w + l.dAt, N, dAtlo, 1.0, w + l.dKzx, N, q3, q4, dtype, gf, ss));
     RC(dcgp_gram_bwd(p->k_spec, p->Z, M, p->ldz, p->x, N, p->ldx, w + l.dKzx, N, g->dk_ls, g->dk_os, g->dZ, g->lddz, dtype, 0,
                      ss));
-    RC(gemm3<T>(0, 1, M, M, N, 1.0, w + l.dAt, N, nullptr, w + l.Kzx, N, nullptr, 0.0, w + l.t3, M, q3, q4, dtype, gf, ss));
+    RC(gemm3<T>(0, 1, M, M, N, 1.0, w + l.dAt, N, dAtlo, w + l.Kzx, N, Kzxlo, 0.0, w + l.t3, M, q3, q4, dtype, gf, ss));
     tril_axpby_kernel<T><<<gM, 256, 0, ss>>>(w + l.t3, M, T(1), nullptr, 0, T(0), 0, w + l.t2, M);
     DCGP_CHECK_LAUNCH();
     if constexpr (sizeof(T) == 4) {

@@ -116,4 +116,74 @@ int split_keep(const T* src, T* dst, int64_t rows, int64_t cols, cudaStream_t st
 }
 
 
+// ---- bandwidth-bound helpers (the GEMM kernels are the wrong tool for one right-hand side or for a dot product) ----
+// out[0] += sum_i a[i] * b[i]   (grid-stride, one atomic per block; out zeroed by the caller)
+template <typename T>
+__global__ void __launch_bounds__(256) dot_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t n, T* __restrict__ out) {
+    T acc = T(0);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        acc = fma(a[i], b[i], acc);
+    acc = warp_sum(acc);
+    __shared__ T red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T t = T(0);
+        for (int w = 0; w < 8; ++w) t += red[w];
+        atomicAdd(out, t);
+    }
+}
+
+template <typename T>
+int dot(const T* a, const T* b, int64_t n, T* out, cudaStream_t st) {
+    int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+    if (blocks > 592) blocks = 592;
+    if (blocks < 1) blocks = 1;
+    dot_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(a, b, n, out);
+    DCGP_CHECK_LAUNCH();
+    return 0;
+}
+
+// y = A x for row-major A (m x k, row stride lda): one warp per row
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_n_kernel(const T* __restrict__ A, int64_t lda, int64_t m, int64_t k,
+                                                     const T* __restrict__ x, T* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= m) return;
+    T acc = T(0);
+    for (int64_t j = lane; j < k; j += 32) acc = fma(A[row * lda + j], x[j], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) y[row] = acc;
+}
+
+// y += A^T x for row-major A (k x m): a thread owns a column, a block row-chunk of 256 rows; y zeroed by the caller
+template <typename T>
+__global__ void __launch_bounds__(128) gemv_t_kernel(const T* __restrict__ A, int64_t lda, int64_t k, int64_t m,
+                                                     const T* __restrict__ x, T* __restrict__ y) {
+    const int64_t col = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * 256, r1 = r0 + 256 < k ? r0 + 256 : k;
+    __shared__ T xs[256];
+    for (int i = threadIdx.x; i < 256; i += 128) xs[i] = (r0 + i < k) ? x[r0 + i] : T(0);
+    __syncthreads();
+    if (col >= m) return;
+    T acc = T(0);
+    for (int64_t i = r0; i < r1; ++i) acc = fma(A[i * lda + col], xs[i - r0], acc);
+    atomicAdd(&y[col], acc);
+}
+
+// y = op(A) x: ta = 0: A is m x k; ta = 1: A is k x m (stored), y has m entries
+template <typename T>
+int gemv(int ta, int64_t m, int64_t k, const T* A, int64_t lda, const T* x, T* y, cudaStream_t st) {
+    if (ta == 0) {
+        gemv_n_kernel<T><<<(unsigned)((m + 7) / 8), 256, 0, st>>>(A, lda, m, k, x, y);
+    } else {
+        DCGP_CU_RC(cudaMemsetAsync(y, 0, (size_t)m * sizeof(T), st));
+        const dim3 grid((unsigned)((m + 127) / 128), (unsigned)((k + 255) / 256));
+        gemv_t_kernel<T><<<grid, 128, 0, st>>>(A, lda, k, m, x, y);
+    }
+    DCGP_CHECK_LAUNCH();
+    return 0;
+}
+
 }  // namespace composite
