@@ -36,6 +36,7 @@ int dcgp_gemm_tc_ex(int transa, int transb, int64_t m, int64_t n, int64_t k, dou
                     const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int flags, const void* Alo, const void* Blo,
                     void* Clo, int64_t lower_off, int64_t clo_cols, cudaStream_t st);
 
+void dcgp_tc_cap(int ctas);
 int dcgp_potrf_link_tm(float* A, int64_t lda, int nb, float* inv, float* invlo, int* info, int64_t j0, const float* R,
                        const float* invp, cudaStream_t st);
 
@@ -840,8 +841,8 @@ int chol_rec(const Ctx<T>& c, int64_t j0, int64_t nb) {
 // so the rank-128 trailing update of panel j overlaps leaf j+1.  Both lanes are forked from and joined back
 // into the caller's stream with events only, which keeps the call capturable in a CUDA graph.
 struct LookAhead {
-    cudaStream_t sh = nullptr, sb = nullptr;  // chain (highest priority) and bulk (lowest) lanes
-    cudaEvent_t leaf[4] = {}, row[4] = {}, upd[4] = {}, fork = nullptr, join = nullptr;
+    cudaStream_t sh = nullptr, sb = nullptr, sc = nullptr;  // chain (highest priority), bulk (lowest) and helper lanes
+    cudaEvent_t leaf[4] = {}, row[4] = {}, upd[4] = {}, tr[4] = {}, hc[4] = {}, fork = nullptr, join = nullptr;
     int dev = -1;
     int init() {
         int d = 0;
@@ -853,10 +854,14 @@ struct LookAhead {
         if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
         e = cudaStreamCreateWithPriority(&sb, cudaStreamNonBlocking, lo);
         if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
+        e = cudaStreamCreateWithPriority(&sc, cudaStreamNonBlocking, hi + 1 <= lo ? hi + 1 : lo);
+        if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
         for (int i = 0; i < 4; ++i) {
             cudaEventCreateWithFlags(&leaf[i], cudaEventDisableTiming);
             cudaEventCreateWithFlags(&row[i], cudaEventDisableTiming);
             cudaEventCreateWithFlags(&upd[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&tr[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&hc[i], cudaEventDisableTiming);
         }
         cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
         e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
@@ -970,6 +975,104 @@ int chol_la_fused(const Ctx<float>& c, int64_t j0, int64_t nb, float* rcopy) {
         DCGP_LEAF_DISPATCH(CALL);
 #undef CALL
         DCGP_CHECK_LAUNCH();
+    }
+    // DCGP_POTRF_H = h > 0: a helper lane takes the panel solve of panel j and the update of the NEXT panel's column
+    // ("strip": rows below x 128 columns) on h SMs, the bulk lane keeps only the trailing square on the other SMs.  The
+    // first half of an 8192^2 factorisation is bound by the bulk lane (panel solve 18 us + trailing update up to 86 us per
+    // link against 40 us for the link itself); with the helper lane the panel solve and the strip run beside the
+    // trailing update of the previous panel instead of in front of the current one.  Measured on B200 (h = 14 .. 18): 8192^2
+    // 3.51 -> 3.31 ms stand-alone, but the trailing square on 132 SMs takes as long as the whole update took on 146 (it is
+    // bound by the bytes crossing L2, not by SMs), and inside the ELBO step - where the K_ZZ lane runs beside the
+    // factorisation - alternating A/B runs show no gain (101.2 vs 100.0 .. 101.6 steps/s): opt-in.
+    static const int hsm = getenv("DCGP_POTRF_H") ? atoi(getenv("DCGP_POTRF_H")) : 0;
+    if (hsm > 0 && link_tm && nb >= 48 * NB) {   // (4096: 1.25 -> 1.28 ms, 8192: 3.51 -> 3.32 ms)
+        const cudaStream_t sc = x.sc;
+        DCGP_CU(cudaStreamWaitEvent(sc, x.fork, 0));
+        const int bulk_cap = num_sms() - 2 - hsm;
+        for (int64_t j = 0; j + 1 < q; ++j) {
+            const int64_t bj = j0 + j * NB;
+            const int64_t b1 = bj + NB, w1 = (end - b1 < NB) ? end - b1 : NB, r0 = b1 + w1, nr = end - r0;
+            const int e = (int)(j & 3), ep = (int)((j + 3) & 3);
+            float* invj = c.ws + (bj / NB) * NB * NB;
+            TRACE_MARK("A.leaf", j, sa);
+            DCGP_CU(cudaEventRecord(x.leaf[e], sa));
+            // ---- helper lane: panel solve of panel j (its column was completed by strip(j-1), issued on this lane)
+            DCGP_CU(cudaStreamWaitEvent(sc, x.leaf[e], 0));
+            float* P = c.A + b1 * c.lda + bj;
+            float* Plo = c.Alo + b1 * c.lda + bj;
+            rc = 1;
+            dcgp_tc_cap(hsm);
+            if (end - b1 >= NB) {
+                rc = dcgp_gemm_tc_ex(0, 1, end - b1, NB, NB, 1.0, P, c.lda, invj, NB, 0.0, P, c.lda, 0, Plo, invlo_slot(j), Plo, 0, 0, sc);
+                if (rc < 0) { dcgp_tc_cap(0); return rc; }
+            }
+            dcgp_tc_cap(0);
+            if (rc == 1) {
+                rc = dcgp_gemm_impl(0, 1, end - b1, NB, NB, 1.0, P, c.lda, invj, NB, 0.0, P, c.lda, c.dtype, DCGP_GEMM_INPLACE | c.xf,
+                                    sc, nullptr, nullptr, Plo);
+                if (rc) return rc;
+            }
+            TRACE_MARK("B.trsm", j, sc);
+            DCGP_CU(cudaEventRecord(x.tr[e], sc));
+            if (nr > 0) {
+                float* P2 = c.A + r0 * c.lda + bj;
+                const float* P2lo = c.Alo + r0 * c.lda + bj;
+                // ---- bulk lane: trailing square, rows and columns from r0
+                DCGP_CU(cudaStreamWaitEvent(sb, x.tr[e], 0));
+                rc = 1;
+                if (nr >= NB) {
+                    dcgp_tc_cap(bulk_cap);
+                    rc = dcgp_gemm_tc_ex(0, 1, nr, nr, NB, -1.0, P2, c.lda, P2, c.lda, 1.0, c.A + r0 * c.lda + r0, c.lda, DCGP_GEMM_LOWER,
+                                         P2lo, P2lo, nullptr, 0, 0, sb);
+                    dcgp_tc_cap(0);
+                    if (rc < 0) return rc;
+                }
+                if (rc == 1) {
+                    rc = dcgp_gemm_impl(0, 1, nr, nr, NB, -1.0, P2, c.lda, P2, c.lda, 1.0, c.A + r0 * c.lda + r0, c.lda, c.dtype,
+                                        DCGP_GEMM_LOWER | c.xf, sb, P2lo, P2lo, nullptr);
+                    if (rc) return rc;
+                }
+                TRACE_MARK("B.trail", j, sb);
+                DCGP_CU(cudaEventRecord(x.upd[e], sb));
+                // ---- helper lane: strip = column of panel j+1 below its diagonal block (last written by the trailing
+                // square of panel j-1), then the private copy of block row j+2 for the chain lane
+                if (j > 0) DCGP_CU(cudaStreamWaitEvent(sc, x.upd[ep], 0));
+                rc = 1;
+                if (nr >= NB) {
+                    dcgp_tc_cap(hsm);
+                    rc = dcgp_gemm_tc_ex(0, 1, nr, w1, NB, -1.0, P2, c.lda, P, c.lda, 1.0, c.A + r0 * c.lda + b1, c.lda, 0, P2lo, Plo,
+                                         c.Alo + r0 * c.lda + b1, 0, 0, sc);
+                    dcgp_tc_cap(0);
+                    if (rc < 0) return rc;
+                }
+                if (rc == 1) {
+                    rc = dcgp_gemm_impl(0, 1, nr, w1, NB, -1.0, P2, c.lda, P, c.lda, 1.0, c.A + r0 * c.lda + b1, c.lda, c.dtype, c.xf, sc,
+                                        P2lo, Plo, c.Alo + r0 * c.lda + b1);
+                    if (rc) return rc;
+                }
+                const int64_t w2 = (end - r0 < NB) ? end - r0 : NB;
+                DCGP_CU(copy_row(r0, b1, w2, (int)((j + 1) & 1), sc));
+                TRACE_MARK("B.col", j, sc);
+                DCGP_CU(cudaEventRecord(x.hc[e], sc));
+            }
+            // ---- chain lane: block j+1 (diagonal block from the trailing square of panel j-1, block row from the helper)
+            if (j > 0) {
+                DCGP_CU(cudaStreamWaitEvent(sa, x.upd[ep], 0));
+                DCGP_CU(cudaStreamWaitEvent(sa, x.hc[ep], 0));
+            }
+            TRACE_MARK("A.waited", j, sa);
+            rc = dcgp_potrf_link_tm(c.A + b1 * c.lda + b1, c.lda, (int)w1, c.ws + (b1 / NB) * NB * NB, invlo_slot(j + 1), c.info, b1,
+                                    rcopy + (size_t)(j & 1) * NB * NB, invj, sa);
+            if (rc) return rc;
+        }
+        DCGP_CU(cudaEventRecord(x.join, sa));
+        DCGP_CU(cudaStreamWaitEvent(c.st, x.join, 0));
+        DCGP_CU(cudaEventRecord(x.fork, sb));
+        DCGP_CU(cudaStreamWaitEvent(c.st, x.fork, 0));
+        DCGP_CU(cudaEventRecord(x.row[0], sc));
+        DCGP_CU(cudaStreamWaitEvent(c.st, x.row[0], 0));
+        TRACE_DUMP();
+        return 0;
     }
     for (int64_t j = 0; j + 1 < q; ++j) {
         const int64_t bj = j0 + j * NB;

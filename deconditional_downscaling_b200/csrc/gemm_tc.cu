@@ -525,6 +525,11 @@ extern "C" int dcgp_round_tf32(const void* src, void* dst, int64_t rows, int64_t
     return 0;
 }
 
+// Optional cap on the persistent grid of the calling thread's next launches (0 = none): the look-ahead factorisation runs
+// its panel solves / strip updates on a helper lane beside the trailing update and gives each side its own share of the SMs.
+thread_local int g_tc_cap = 0;
+void dcgp_tc_cap(int ctas) { g_tc_cap = ctas; }
+
 template <int TN, bool FAT, int CL>
 int launch_tc(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapAlo, const CUtensorMap& mapBlo,
               TcParams& p, cudaStream_t st) {
@@ -543,7 +548,8 @@ int launch_tc(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMa
     // K_ZZ chain a captured ELBO step runs beside it): their kernels must not queue behind a persistent grid
     // occupying every SM
     static const int reserve = getenv("DCGP_TC_RESERVE") ? atoi(getenv("DCGP_TC_RESERVE")) : 2;
-    const int64_t cap = (num_sms() > 8 + reserve ? num_sms() - reserve : num_sms()) / CL;
+    int64_t cap = (num_sms() > 8 + reserve ? num_sms() - reserve : num_sms()) / CL;
+    if (g_tc_cap > 0 && g_tc_cap / CL >= 1 && g_tc_cap / CL < cap) cap = g_tc_cap / CL;
     const unsigned grid = (unsigned)(items < cap ? items : cap) * CL;
     if constexpr (CL == 1) {
         gemm_tc_kernel<TN, FAT, CL><<<grid, NTHREADS_TC, smem_tc<TN, FAT>(), st>>>(mapA, mapB, mapAlo, mapBlo, p);
