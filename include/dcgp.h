@@ -16,10 +16,11 @@
  *     never synchronises the stream.
  *   - host-side state the library does keep (all of it created lazily, none
  *     of it visible in results): per calling thread and per caller stream a
- *     set of two internal CUDA streams (high / low priority) and their events
- *     - the "lanes" of the look-ahead factorisation and solves, forked from
- *     and joined back into the caller's stream with events only, so calls stay
- *     capturable in a CUDA graph; `cudaFuncSetAttribute` latches per kernel;
+ *     set of three internal CUDA streams (high / middle / low priority) and
+ *     their events - the "lanes" of the look-ahead factorisation and solves -
+ *     plus one side lane (a stream and two events) of dcgp_cmp_elbo_fwd/bwd,
+ *     all forked from and joined back into the caller's stream with events
+ *     only, so calls stay capturable in a CUDA graph; `cudaFuncSetAttribute` latches per kernel;
  *     the SM count; tuning switches read once from the environment (DCGP_*,
  *     DESIGN.md section 7); a relaxed-atomic diagnostic launch counter.
  *     Calls are safe from several host threads (thread-local lanes) and from
