@@ -46,6 +46,11 @@ constexpr int GROUP_M = 16;
 // tile crosses L2 -> shared memory once instead of twice (3 stages of 64 KB for 128-wide tiles, 2 of 96 KB for
 // 256-wide ones).  3xTF32 products are bound by the per-SM operand streaming rate, not by the tensor pipe:
 // measured on B200, potrs 8192 x 1024 1.98 -> 1.73 ms, 8192 x 8192 7.58 -> 6.96 ms.
+// (Round 2 also tried making the A_lo / B_lo tiles of a stage in shared memory from the FP32 tiles - one or two extra warps
+// computing x - trunc_tf32(x) behind the TMA - to halve the operand bytes of the rank-128 updates of the factorisation:
+// correct, but slower everywhere (8192^2 potrf 3.52 -> 3.97 ms, planned potrs 1.25 -> 1.47 ms, the update itself 149 -> 175 us).
+// ncu on that update: DRAM 49 %, L2 43 %, tensor pipe 43 % of peak, long-scoreboard stalls in the epilogue's reads of C -
+// it is a latency-bound pipeline, not an operand-bandwidth-bound one.  Removed.)
 template <int TN, bool FAT> constexpr int n_stages() { return FAT ? (TN == 128 ? 3 : 2) : STAGES; }
 template <int TN, bool FAT> constexpr int stage_bytes() { return (FAT ? 2 : 1) * (A_BYTES + TN * TK * 4); }
 template <int TN, bool FAT> constexpr size_t smem_tc() {
@@ -123,7 +128,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     constexpr int B_BYTES = TN * TK * 4;
     constexpr int TMEM_COLS = 2 * TN;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // aligned by pointer arithmetic, not through an integer cast: the compiler then keeps every access below in the shared
+    // state space (LDS / STS); with the cast the epilogue's transpose went through generic LD.E / ST.E (ncu source page of the
+    // 3xTF32 rank-128 update, round 2: 149 -> 145 us at 8192^2, planned potrs 1.25 -> 1.21 ms)
+    unsigned char* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* stg_all = reinterpret_cast<float*>(tiles + (size_t)STAGES * STAGE_BYTES);
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)STAGES * STAGE_BYTES + (size_t)EPI_WARPS * STG_BYTES);
     uint64_t* empty = full + STAGES;
