@@ -720,11 +720,11 @@ def run_vbagg(device, steps=10, warmup=3):
     torch.cuda.synchronize()
     ms_c = s.elapsed_time(e) / steps
     composite = {"what": "dcgp_vbagg_elbo_fwd + dcgp_vbagg_elbo_bwd (include/dcgp.h): ELBO and every gradient, FP32 with 3xTF32 "
-                         "products, no FP64 island, no optimiser update", "ms_fwd_bwd": ms_c,
+                         "products and the FP64 K_ZZ island, no optimiser update", "ms_fwd_bwd": ms_c,
                  "launches_per_call_pair": (dl.load().dcgp_launch_count() - l0) / steps, "elbo": float(elbo_c.item()),
                  "info": int(info_c.item())}
     return {"metric": "vbagg_elbo_steps_per_s", "value": 1e3 / ms, "ms_per_step": ms, "bags_per_step": nb, "c_abi_composite": composite,
-            "individuals_per_step": nb * per, "inducing_points": Mz, "dtype": "f32 (f64 K_ZZ factor)",
+            "individuals_per_step": nb * per, "inducing_points": Mz, "dtype": "f32 (f64 K_ZZ factor)", "composition": "ElboTrainer on the C composite (DCGP_VBAGG_FUSED=0: layered path)",
             "cross_gram_kernel_evals_per_step": evals, "final_loss": float(loss.item()),
             "note": "bag-summed cross Gram forward + backward = 2 x M x N_b kernel evaluations per step, K_Zx never stored"}
 

@@ -120,7 +120,7 @@ _SIGNATURES = {
     "dcgp_cmp_elbo_fwd": (c_int, [POINTER(CmpProblem), c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "dcgp_cmp_elbo_bwd": (c_int, [POINTER(CmpProblem), c_double, POINTER(CmpGrads), c_void_p, c_size_t, c_int, c_int,
                                   c_void_p]),
-    "dcgp_vbagg_elbo_workspace": (c_size_t, [c_int64, c_int64, c_int]),
+    "dcgp_vbagg_elbo_workspace": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
     "dcgp_vbagg_elbo_fwd": (c_int, [POINTER(VbaggProblem), c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "dcgp_vbagg_elbo_bwd": (c_int, [POINTER(VbaggProblem), c_double, POINTER(VbaggGrads), c_void_p, c_size_t, c_int, c_int,
                                     c_void_p]),

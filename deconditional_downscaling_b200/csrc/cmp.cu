@@ -146,71 +146,6 @@ inline bool side_enabled() {
     return on;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// FP64 island of FP32 problems (src/variational/variational_strategy.py:35-44: the reference factors K_ZZ in double):
-// K_ZZ + jitter I is evaluated, factored and inverted in FP64 on the side lane (off the critical path), W = L_Z^{-1}
-// is handed to the FP32 products as an exact hi + lo pair, and the adjoint of the factor runs in FP64 again.
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void f32_to_f64_kernel(const float* __restrict__ src, double* __restrict__ dst, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = (double)src[i];
-}
-
-// hyper-parameter values of a spec, FP32 -> FP64: slot c * 9 + j (lengthscales), c * 9 + 8 (outputscale)
-__global__ void spec_to_f64_kernel(const __grid_constant__ dcgp_kernel_spec sp, double* __restrict__ dst) {
-    const int c = blockIdx.x, j = threadIdx.x;
-    if (c >= sp.n_components) return;
-    if (j < sp.comp[c].ndims) dst[c * 9 + j] = (double)((const float*)sp.comp[c].lengthscale)[j];
-    if (j == 8) dst[c * 9 + 8] = (double)((const float*)sp.comp[c].outputscale)[0];
-}
-
-// hi = float(x), lo = float(x - hi)
-__global__ void f64_to_hilo_kernel(const double* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double x = src[i];
-    const float h = (float)x;
-    hi[i] = h;
-    lo[i] = (float)(x - (double)h);
-}
-
-// dst (rows x cols, row stride ldd, FP32) += src (FP64, row stride lds); dst may be NULL
-__global__ void acc_f64_kernel(const double* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int64_t rows,
-                               int64_t cols) {
-    const int64_t i = blockIdx.y, j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (dst && i < rows && j < cols) dst[i * ldd + j] += (float)src[i * lds + j];
-}
-
-struct Island {   // byte offsets of the FP64 region
-    size_t Z, hyp, L, W, t1, t2, t3, dZ, dth, end;
-};
-
-inline Island island_layout(size_t base, int64_t M, int64_t ldz) {
-    Island a;
-    size_t o = (base + 255) & ~(size_t)255;
-    const size_t mm = (((size_t)M * M * 8) + 255) & ~(size_t)255, mz = (((size_t)M * ldz * 8) + 255) & ~(size_t)255;
-    a.Z = o; o += mz;
-    a.hyp = o; o += 512;
-    a.L = o; o += mm;
-    a.W = o; o += mm;
-    a.t1 = o; o += mm;
-    a.t2 = o; o += mm;
-    a.t3 = o; o += mm;
-    a.dZ = o; o += mz;
-    a.dth = o; o += 512;      // dls64 [4][8], dos64 [4]
-    a.end = o;
-    return a;
-}
-
-inline dcgp_kernel_spec spec_f64(const dcgp_kernel_spec* sp, const double* hyp) {
-    dcgp_kernel_spec s = *sp;
-    for (int c = 0; c < s.n_components; ++c) {
-        s.comp[c].lengthscale = hyp + c * 9;
-        s.comp[c].outputscale = hyp + c * 9 + 8;
-    }
-    return s;
-}
-
 // DCGP_CMP_ISLAND: 1 (default) = forward and adjoint of the K_ZZ factor in FP64; 2 = forward in FP64, adjoint chain in
 // FP32 / 3xTF32 on the rounded factor; 0 = no island
 inline int island_mode() {

@@ -90,7 +90,7 @@ __global__ void tail_kernel(const T* __restrict__ v, const T* __restrict__ dmkl,
 }
 
 struct Layout {   // element offsets into the workspace (all of type T), then the byte offset of the solver scratch
-    size_t L, W, D, Ls, Kb, U, DU, S, T, dS, dT, bs, sc, t1, t2, t3, t4, Llo, Wlo, Dlo, Lslo, Kblo, Ulo, lt1, lt2, end;
+    size_t L, W, D, Ls, Kb, U, DU, S, T, dS, dT, bs, sc, t1, t2, t3, t4, Llo, Wlo, Wl2, Dlo, Lslo, Kblo, Ulo, lt1, lt2, end;
 };
 
 inline Layout layout(int64_t M, int64_t nb, bool f32) {
@@ -116,10 +116,11 @@ inline Layout layout(int64_t M, int64_t nb, bool f32) {
     l.t4 = o; o += up((size_t)M * (M + 1));   // dKL / dm_kl
     // FP32: TF32 remainders (x - trunc_tf32(x)) of the operands that several products share, and two slots for the
     // remainders of scratch operands - with them every product runs 3xTF32 on the tcgen05 kernel (unused in FP64)
-    l.Llo = l.Wlo = l.Dlo = l.Lslo = l.Kblo = l.Ulo = l.lt1 = l.lt2 = 0;
+    l.Llo = l.Wlo = l.Wl2 = l.Dlo = l.Lslo = l.Kblo = l.Ulo = l.lt1 = l.lt2 = 0;
     if (f32) {
         l.Llo = o; o += mm;
         l.Wlo = o; o += mm;
+        l.Wl2 = o; o += mm;    // FP32 low part of the FP64 inverse factor (island)
         l.Dlo = o; o += mm;
         l.Lslo = o; o += mm;
         l.Kblo = o; o += mn;
@@ -132,8 +133,23 @@ inline Layout layout(int64_t M, int64_t nb, bool f32) {
 }
 
 inline size_t solver_bytes(int64_t M, int dtype) {
-    const size_t a = dcgp_potrf_workspace(M, dtype), b = dcgp_trtri_workspace(M, dtype);
+    size_t a = dcgp_potrf_workspace(M, dtype), b = dcgp_trtri_workspace(M, dtype);
+    if (dtype == DCGP_F32) {   // FP64 island of FP32 problems
+        const size_t a2 = dcgp_potrf_workspace(M, DCGP_F64), b2 = dcgp_trtri_workspace(M, DCGP_F64);
+        if (a2 > a) a = a2;
+        if (b2 > b) b = b2;
+    }
     return ((a > b ? a : b) + 255) & ~(size_t)255;
+}
+
+// DCGP_VBAGG_ISLAND (default 1): F32 problems evaluate, factor and invert K_ZZ in FP64 and take the adjoint of the factor in
+// FP64 (src/variational/variational_strategy.py:35-44), as dcgp_cmp_elbo_* does; 0 = K_ZZ in FP32 / 3xTF32
+inline bool island_enabled() {
+    static const bool on = !(getenv("DCGP_VBAGG_ISLAND") && atoi(getenv("DCGP_VBAGG_ISLAND")) == 0);
+    return on;
+}
+inline size_t island_base(const Layout& l, size_t es, int64_t M, int dtype) {
+    return ((l.end * es + 255) & ~(size_t)255) + solver_bytes(M, dtype);
 }
 
 template <typename T>
@@ -141,7 +157,8 @@ int fwd_impl(const dcgp_vbagg_problem* p, void* elbo, int* info, void* ws, size_
              cudaStream_t st) {
     const int64_t M = p->M, nb = p->n_bags;
     const Layout l = layout(M, nb, sizeof(T) == 4);
-    const size_t need = l.end * sizeof(T) + 256 + solver_bytes(M, dtype);
+    const size_t need = sizeof(T) == 4 ? island_layout(island_base(l, 4, M, dtype), M, p->ldz).end
+                                       : l.end * sizeof(T) + 256 + solver_bytes(M, dtype);
     if (ws_bytes < need) return -5;
     T* w = reinterpret_cast<T*>(ws);
     const bool f32 = sizeof(T) == 4;
@@ -155,18 +172,47 @@ int fwd_impl(const dcgp_vbagg_problem* p, void* elbo, int* info, void* ws, size_
     const dim3 g2((unsigned)((M + 255) / 256), (unsigned)M);
     DCGP_CU_RC(cudaMemsetAsync(w + l.sc, 0, 32 * sizeof(T), st));   // dcgp_whitened_kl accumulates into its output
     // K_ZZ + jitter I -> L_Z -> W
-    RC(dcgp_gram(p->spec, p->Z, M, p->ldz, p->Z, M, p->ldz, w + l.L, M, nullptr, p->jitter, dtype, DCGP_GRAM_SAME, st));
-    RC(dcgp_potrf(w + l.L, M, M, info, solver, sbytes, dtype, gf, st));
-    tril_copy_kernel<T><<<g2, 256, 0, st>>>(w + l.L, M, w + l.t1, M);
-    DCGP_CHECK_LAUNCH();
-    DCGP_CU_RC(cudaMemcpyAsync(w + l.L, w + l.t1, (size_t)M * M * sizeof(T), cudaMemcpyDeviceToDevice, st));
-    RC(split_keep<T>(w + l.L, Llo, M, M, st));
-    RC(dcgp_trtri(w + l.L, M, M, w + l.W, M, solver, sbytes, dtype, gf, st));
+    bool island = false;
+    unsigned char* wb = reinterpret_cast<unsigned char*>(ws);
+    if constexpr (sizeof(T) == 4) {
+        island = island_enabled();
+        if (island) {
+            const Island a = island_layout(island_base(l, 4, M, dtype), M, p->ldz);
+            double *Z64 = (double*)(wb + a.Z), *hyp = (double*)(wb + a.hyp), *L64 = (double*)(wb + a.L), *W64 = (double*)(wb + a.W),
+                   *t64 = (double*)(wb + a.t1);
+            const int64_t nz = M * p->ldz;
+            f32_to_f64_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, st>>>((const float*)p->Z, Z64, nz);
+            DCGP_CHECK_LAUNCH();
+            spec_to_f64_kernel<<<DCGP_MAX_COMPONENTS, 32, 0, st>>>(*p->spec, hyp);
+            DCGP_CHECK_LAUNCH();
+            const dcgp_kernel_spec k64 = spec_f64(p->spec, hyp);
+            RC(dcgp_gram(&k64, Z64, M, p->ldz, Z64, M, p->ldz, L64, M, nullptr, p->jitter, DCGP_F64, DCGP_GRAM_SAME, st));
+            RC(dcgp_potrf(L64, M, M, info, solver, sbytes, DCGP_F64, flags, st));
+            tril_copy_kernel<double><<<g2, 256, 0, st>>>(L64, M, t64, M);
+            DCGP_CHECK_LAUNCH();
+            DCGP_CU_RC(cudaMemcpyAsync(L64, t64, (size_t)M * M * 8, cudaMemcpyDeviceToDevice, st));
+            RC(dcgp_trtri(L64, M, M, W64, M, solver, sbytes, DCGP_F64, flags, st));
+            f64_to_hilo_kernel<<<(unsigned)(((int64_t)M * M + 255) / 256), 256, 0, st>>>(W64, (float*)(w + l.W), (float*)(w + l.Wl2),
+                                                                                   (int64_t)M * M);
+            DCGP_CHECK_LAUNCH();
+        }
+    }
+    if (!island) {
+        RC(dcgp_gram(p->spec, p->Z, M, p->ldz, p->Z, M, p->ldz, w + l.L, M, nullptr, p->jitter, dtype, DCGP_GRAM_SAME, st));
+        RC(dcgp_potrf(w + l.L, M, M, info, solver, sbytes, dtype, gf, st));
+        tril_copy_kernel<T><<<g2, 256, 0, st>>>(w + l.L, M, w + l.t1, M);
+        DCGP_CHECK_LAUNCH();
+        DCGP_CU_RC(cudaMemcpyAsync(w + l.L, w + l.t1, (size_t)M * M * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        RC(split_keep<T>(w + l.L, Llo, M, M, st));
+        RC(dcgp_trtri(w + l.L, M, M, w + l.W, M, solver, sbytes, dtype, gf, st));
+    }
     // bag-summed cross Gram and its whitening
     RC(dcgp_gram_bagsum(p->spec, p->Z, M, p->ldz, p->x, p->ldx, p->offsets, nb, w + l.Kb, M, dtype, 0, st));
     RC(split_keep<T>(w + l.W, Wlo, M, M, st));
     RC(split_keep<T>(w + l.Kb, Kblo, nb, M, st));
     RC(gemm3<T>(0, 1, M, nb, M, 1.0, w + l.W, M, Wlo, w + l.Kb, M, Kblo, 0.0, w + l.U, nb, q1, q2, dtype, gf, st));
+    if (island)   // W = hi + lo of the FP64 inverse factor
+        RC(gemm3<T>(0, 1, M, nb, M, 1.0, w + l.Wl2, M, nullptr, w + l.Kb, M, Kblo, 1.0, w + l.U, nb, q1, q2, dtype, gf, st));
     RC(split_keep<T>(w + l.U, Ulo, M, nb, st));
     // D = L_S L_S^T - I on the masked factor
     tril_copy_kernel<T><<<g2, 256, 0, st>>>((const T*)p->chol_var, p->ldc, w + l.Ls, M);
@@ -197,7 +243,9 @@ int bwd_impl(const dcgp_vbagg_problem* p, double scale, const dcgp_vbagg_grads* 
              int flags, cudaStream_t st) {
     const int64_t M = p->M, nb = p->n_bags;
     const Layout l = layout(M, nb, sizeof(T) == 4);
-    if (ws_bytes < l.end * sizeof(T) + 256 + solver_bytes(M, dtype)) return -5;
+    if (ws_bytes < (sizeof(T) == 4 ? island_layout(island_base(l, 4, M, dtype), M, p->ldz).end
+                                   : l.end * sizeof(T) + 256 + solver_bytes(M, dtype)))
+        return -5;
     T* w = reinterpret_cast<T*>(ws);
     const bool f32 = sizeof(T) == 4;
     T* const Llo = f32 ? w + l.Llo : nullptr; T* const Wlo = f32 ? w + l.Wlo : nullptr; T* const Dlo = f32 ? w + l.Dlo : nullptr;
@@ -235,13 +283,56 @@ int bwd_impl(const dcgp_vbagg_problem* p, double scale, const dcgp_vbagg_grads* 
         RC(dcgp_gram_bag_blocksum_bwd(p->spec, p->x, p->ldx, p->offsets, nb, w + l.bs, g->dls, g->dos, dtype, 0, st));
     // dKb = dU^T W (n_bags x M) -> bag-summed cross Gram adjoint
     RC(split_keep<T>(w + l.t1, q1, M, nb, st));   // dU is an operand twice
+    bool island = false;
+    if constexpr (sizeof(T) == 4) island = island_enabled();
     RC(gemm3<T>(1, 0, nb, M, M, 1.0, w + l.t1, nb, q1, w + l.W, M, Wlo, 0.0, w + l.t2, M, q1, q2, dtype, gf, st));
+    if (island)
+        RC(gemm3<T>(1, 0, nb, M, M, 1.0, w + l.t1, nb, q1, w + l.Wl2, M, nullptr, 1.0, w + l.t2, M, q1, q2, dtype, gf, st));
     RC(dcgp_gram_bagsum_bwd(p->spec, p->Z, M, p->ldz, p->x, p->ldx, p->offsets, nb, w + l.t2, M, g->dls, g->dos, g->dZ,
                             g->lddz, dtype, 0, st));
     // dW = tril(dU Kb);  dL_Z = -tril(W^T dW W^T);  Phi;  dK_ZZ = sym(W^T Phi W)
     RC(gemm3<T>(0, 0, M, M, nb, 1.0, w + l.t1, nb, q1, w + l.Kb, M, Kblo, 0.0, w + l.t3, M, q1, q2, dtype, gf, st));
     tril_axpby_kernel<T><<<g2, 256, 0, st>>>(w + l.t3, M, T(1), nullptr, 0, T(0), 0, w + l.t2, M);
     DCGP_CHECK_LAUNCH();
+    if constexpr (sizeof(T) == 4) {
+        if (island) {
+            // the adjoint of W = chol(K_ZZ)^{-1} in FP64 (as in cmp.cu)
+            unsigned char* wb = reinterpret_cast<unsigned char*>(ws);
+            const Island a = island_layout(island_base(l, 4, M, dtype), M, p->ldz);
+            double *Z64 = (double*)(wb + a.Z), *hyp = (double*)(wb + a.hyp), *L64 = (double*)(wb + a.L), *W64 = (double*)(wb + a.W),
+                   *u1 = (double*)(wb + a.t1), *u2 = (double*)(wb + a.t2), *u3 = (double*)(wb + a.t3), *dZ64 = (double*)(wb + a.dZ),
+                   *dth = (double*)(wb + a.dth);
+            const int64_t mm = (int64_t)M * M;
+            f32_to_f64_kernel<<<(unsigned)((mm + 255) / 256), 256, 0, st>>>((const float*)(w + l.t2), u2, mm);
+            DCGP_CHECK_LAUNCH();
+            RC(dcgp_gemm(1, 0, M, M, M, 1.0, W64, M, u2, M, 0.0, u1, M, DCGP_F64, flags, st));
+            RC(dcgp_gemm(0, 1, M, M, M, -1.0, u1, M, W64, M, 0.0, u3, M, DCGP_F64, flags, st));
+            tril_axpby_kernel<double><<<g2, 256, 0, st>>>(u3, M, 1.0, nullptr, 0, 0.0, 0, u2, M);
+            DCGP_CHECK_LAUNCH();
+            RC(dcgp_gemm(1, 0, M, M, M, 1.0, L64, M, u2, M, 0.0, u1, M, DCGP_F64, flags, st));
+            tril_axpby_kernel<double><<<g2, 256, 0, st>>>(u1, M, 1.0, nullptr, 0, 0.0, 1, u2, M);
+            DCGP_CHECK_LAUNCH();
+            RC(dcgp_gemm(1, 0, M, M, M, 1.0, W64, M, u2, M, 0.0, u1, M, DCGP_F64, flags, st));
+            RC(dcgp_gemm(0, 0, M, M, M, 1.0, u1, M, W64, M, 0.0, u3, M, DCGP_F64, flags, st));
+            symmetrize_kernel<double><<<g2, 256, 0, st>>>(u3, M, u2);
+            DCGP_CHECK_LAUNCH();
+            const dcgp_kernel_spec k64 = spec_f64(p->spec, hyp);
+            DCGP_CU_RC(cudaMemsetAsync(dth, 0, 512, st));
+            DCGP_CU_RC(cudaMemsetAsync(dZ64, 0, (size_t)M * p->ldz * 8, st));
+            RC(dcgp_gram_bwd(&k64, Z64, M, p->ldz, Z64, M, p->ldz, u2, M, g->dls ? dth : nullptr, g->dos ? dth + 32 : nullptr,
+                             g->dZ ? dZ64 : nullptr, p->ldz, DCGP_F64, DCGP_GRAM_SAME, st));
+            acc_f64_kernel<<<dim3(1, (unsigned)nc), 32, 0, st>>>(dth, DCGP_MAX_DIMS, (float*)g->dls, DCGP_MAX_DIMS, nc, DCGP_MAX_DIMS);
+            DCGP_CHECK_LAUNCH();
+            acc_f64_kernel<<<dim3(1, 1), 32, 0, st>>>(dth + 32, nc, (float*)g->dos, nc, 1, nc);
+            DCGP_CHECK_LAUNCH();
+            if (g->dZ) {
+                acc_f64_kernel<<<dim3((unsigned)((p->ldz + 31) / 32), (unsigned)M), 32, 0, st>>>(
+                    dZ64, p->ldz, (float*)g->dZ, g->lddz, M, p->ldz < g->lddz ? p->ldz : g->lddz);
+                DCGP_CHECK_LAUNCH();
+            }
+            return 0;
+        }
+    }
     RC(gemm3<T>(1, 0, M, M, M, 1.0, w + l.W, M, Wlo, w + l.t2, M, nullptr, 0.0, w + l.t1, M, q1, q2, dtype, gf, st));
     RC(gemm3<T>(0, 1, M, M, M, -1.0, w + l.t1, M, nullptr, w + l.W, M, Wlo, 0.0, w + l.t3, M, q1, q2, dtype, gf, st));
     tril_axpby_kernel<T><<<g2, 256, 0, st>>>(w + l.t3, M, T(1), nullptr, 0, T(0), 0, w + l.t2, M);
@@ -267,10 +358,11 @@ inline int check(const dcgp_vbagg_problem* p) {
 
 }  // namespace
 
-extern "C" size_t dcgp_vbagg_elbo_workspace(int64_t M, int64_t n_bags, int dtype) {
-    if (M < 1 || n_bags < 1) return 0;
-    const size_t es = dtype == DCGP_F64 ? 8 : 4;
-    return layout(M, n_bags, dtype == DCGP_F32).end * es + 256 + solver_bytes(M, dtype);
+extern "C" size_t dcgp_vbagg_elbo_workspace(int64_t M, int64_t n_bags, int64_t ldz, int dtype) {
+    if (M < 1 || n_bags < 1 || ldz < 1) return 0;
+    const Layout l = layout(M, n_bags, dtype == DCGP_F32);
+    if (dtype == DCGP_F32) return island_layout(island_base(l, 4, M, dtype), M, ldz).end;
+    return l.end * 8 + 256 + solver_bytes(M, dtype);
 }
 
 extern "C" int dcgp_vbagg_elbo_fwd(const dcgp_vbagg_problem* p, void* elbo, int* info, void* workspace,

@@ -566,7 +566,7 @@ def vbagg_elbo(spec: FlatSpec, Z, x, offsets, z, var_mean, chol_var, noise, num_
     p = _lib.VbaggProblem(ctypes.pointer(cs), _ptr(Z), M, _ld(Z), _ptr(x), _ld(x), _ptr(offsets), nb, _ptr(z),
                           _ptr(var_mean), _ptr(chol_var), _ld(chol_var), _ptr(noise), _ptr(mean_const), float(num_data),
                           float(beta), float(jitter), float(var_jitter))
-    nbytes = lib.dcgp_vbagg_elbo_workspace(M, nb, _dt(Z))
+    nbytes = lib.dcgp_vbagg_elbo_workspace(M, nb, _ld(Z), _dt(Z))
     ws = _workspace(nbytes, dev)
     elbo = torch.empty(1, dtype=dt, device=dev)
     if info is None:

@@ -270,15 +270,12 @@ class ElboTrainer(DataParallelStepper):
 
     def _fused_vbagg_loss(self, x, z, bags_sizes):
         """-ELBO of a VBagg minibatch through the two-call C composite (dcgp_vbagg_elbo_fwd / _bwd), or None when the
-        model is outside its scope: additive stationary kernel terms only, zero or constant mean.  FP64 models take it
-        by default (same arithmetic as the layered path); FP32 models only with DCGP_VBAGG_FUSED=1, because the
-        composite keeps K_ZZ in FP32 where the layered path has the reference's FP64 island."""
+        model is outside its scope: additive stationary kernel terms only, zero or constant mean.  FP32 models keep the
+        reference's FP64 K_ZZ island inside the composite.  DCGP_VBAGG_FUSED=0 keeps the layered path."""
         from .likelihoods import bag_offsets
         from .means import ConstantMean, ZeroMean
         vs = getattr(self.model, "variational_strategy", None)
         if vs is None or not hasattr(vs, "_prior_modules"):
-            return None
-        if x.dtype != torch.float64 and os.environ.get("DCGP_VBAGG_FUSED", "0") != "1":
             return None
         if os.environ.get("DCGP_VBAGG_FUSED", "1") == "0":
             return None

@@ -289,8 +289,9 @@ DCGP_API int dcgp_adam_step(void* params, void* grads, void* exp_avg, void* exp_
  * dcgp_vbagg_elbo_bwd must follow on the same stream with the same problem and workspace and writes
  * scale * d ELBO / d(.) into every non-NULL field of `grads` (scale = -1 for the loss the trainers minimise).
  * `info`: device int, LAPACK-style status of the K_ZZ factorisation (0 = ok), as for dcgp_potrf.
- * F32 runs every product error-compensated (3xTF32); no FP64 island - callers that need the reference's double
- * precision K_ZZ factor (variational_strategy.py:35-44) use dtype F64. */
+ * F32 runs every product error-compensated (3xTF32) and keeps the reference's FP64 island (variational_strategy.py:35-44):
+ * K_ZZ is evaluated, factored and inverted in double, its inverse factor applied as an FP32 hi + lo pair, its adjoint
+ * taken in double again (DCGP_VBAGG_ISLAND=0: K_ZZ in FP32 / 3xTF32). */
 typedef struct dcgp_vbagg_problem {
     const dcgp_kernel_spec* spec; /* individuals kernel k                                              */
     const void* Z;                /* inducing points, M x d row-major (d = columns the spec addresses)  */
@@ -322,7 +323,8 @@ typedef struct dcgp_vbagg_grads {   /* any field may be NULL */
     void* dmean_const;              /* scalar                                             */
 } dcgp_vbagg_grads;
 
-DCGP_API size_t dcgp_vbagg_elbo_workspace(int64_t M, int64_t n_bags, int dtype);
+/* ldz: the row stride of Z that will be passed (F32 problems keep double copies of Z and dZ for the FP64 island) */
+DCGP_API size_t dcgp_vbagg_elbo_workspace(int64_t M, int64_t n_bags, int64_t ldz, int dtype);
 DCGP_API int dcgp_vbagg_elbo_fwd(const dcgp_vbagg_problem* problem, void* elbo, int* info, void* workspace,
                                  size_t workspace_bytes, int dtype, int flags, void* stream);
 DCGP_API int dcgp_vbagg_elbo_bwd(const dcgp_vbagg_problem* problem, double scale, const dcgp_vbagg_grads* grads,

@@ -167,7 +167,7 @@ def test_argument_errors_are_reported_as_negative_codes():
     from deconditional_downscaling_b200 import _lib
     lib = _lib.load()
     assert lib.dcgp_cmp_elbo_workspace(0, 4, 4, 2, 0) == 0
-    assert lib.dcgp_vbagg_elbo_workspace(4, 0, 0) == 0
+    assert lib.dcgp_vbagg_elbo_workspace(4, 0, 2, 0) == 0
     empty = _lib.CmpProblem()
     assert lib.dcgp_cmp_elbo_fwd(ctypes.byref(empty), None, None, None, 0, 0, 0, None) == -1
     empty_v = _lib.VbaggProblem()

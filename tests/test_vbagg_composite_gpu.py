@@ -132,7 +132,7 @@ def test_failed_factorisation_is_reported_not_raised():
 
 
 @pytest.mark.parametrize("mean", ["zero", "constant"])
-def test_trainer_takes_the_composite_for_fp64_models_and_follows_the_layered_path(mean, monkeypatch):
+def test_trainer_takes_the_composite_and_follows_the_layered_path(mean, monkeypatch):
     """ElboTrainer on a VariationalGP + VBaggGaussianLikelihood in FP64: three Adam steps through the C composite
     (default) and through the layered Python path (DCGP_VBAGG_FUSED=0) give the same losses and parameters."""
     from deconditional_downscaling_b200 import kernels as K, likelihoods as L, means as Mn, models as Md
@@ -164,3 +164,25 @@ def test_trainer_takes_the_composite_for_fp64_models_and_follows_the_layered_pat
         assert runs["1"][2] != runs["0"][2]          # the two runs really took different paths
     finally:
         torch.set_default_dtype(torch.float32)
+
+
+def test_fp32_trainer_with_the_fp64_island_follows_the_layered_path(monkeypatch):
+    """FP32 model: the composite (FP64 K_ZZ island inside, default) against the layered path (FP64 island in Python)."""
+    from deconditional_downscaling_b200 import kernels as K, likelihoods as L, means as Mn, models as Md
+    from deconditional_downscaling_b200.training import ElboTrainer
+    g = torch.Generator().manual_seed(12)
+    sizes = torch.randint(2, 9, (200,), generator=g).tolist()
+    x = torch.randn(sum(sizes), 3, generator=g).to(DEV)
+    z = torch.randn(200, generator=g).to(DEV)
+    Z0 = torch.randn(160, 3, generator=g)
+    runs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("DCGP_VBAGG_FUSED", flag)
+        torch.manual_seed(321)
+        model = Md.VariationalGP(inducing_points=Z0.clone(), mean_module=Mn.ZeroMean(),
+                                 covar_module=K.ScaleKernel(K.RBFKernel(ard_num_dims=3))).to(DEV)
+        lik = L.VBaggGaussianLikelihood().to(DEV)
+        tr = ElboTrainer(model, lik, num_data=2000, beta=1.0, lr=0.02, cuda_graph=False)
+        runs[flag] = [tr.step(x, z, bags_sizes=sizes).item() for _ in range(3)]
+    for a, b in zip(runs["1"], runs["0"]):
+        assert abs(a - b) <= 2e-3 * max(1.0, abs(b)), runs
