@@ -50,7 +50,10 @@ constexpr int GROUP_M = 16;
 // computing x - trunc_tf32(x) behind the TMA - to halve the operand bytes of the rank-128 updates of the factorisation:
 // correct, but slower everywhere (8192^2 potrf 3.52 -> 3.97 ms, planned potrs 1.25 -> 1.47 ms, the update itself 149 -> 175 us).
 // ncu on that update: DRAM 49 %, L2 43 %, tensor pipe 43 % of peak, long-scoreboard stalls in the epilogue's reads of C -
-// it is a latency-bound pipeline, not an operand-bandwidth-bound one.  Removed.)
+// it is a latency-bound pipeline, not an operand-bandwidth-bound one.  Removed.  So was software-pipelining the epilogue's
+// tcgen05.ld one chunk ahead (the load of chunk ch + 1 issued right after chunk ch left its registers): 147 -> 152 us.
+// Reference points for that update (8192^2, K = 128): beta = 1 147 us single-pass and 3xTF32 alike, beta = 0 90 / 116 us;
+// a plain in-place scale of the same matrix takes 83 us (tools/inplace_bw.py).)
 template <int TN, bool FAT> constexpr int n_stages() { return FAT ? (TN == 128 ? 3 : 2) : STAGES; }
 template <int TN, bool FAT> constexpr int stage_bytes() { return (FAT ? 2 : 1) * (A_BYTES + TN * TK * 4); }
 template <int TN, bool FAT> constexpr size_t smem_tc() {
