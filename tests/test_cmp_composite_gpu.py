@@ -189,3 +189,37 @@ def test_argument_errors_are_reported_as_negative_codes():
     l0 = lib.dcgp_launch_count()
     rc = lib.dcgp_cmp_elbo_fwd(ctypes.byref(prob), out.data_ptr(), info.data_ptr(), ws.data_ptr(), 1024, 0, 0, None)
     assert rc == -5 and lib.dcgp_launch_count() == l0
+
+
+def test_trainer_step_with_a_singular_lambda_never_corrupts_the_parameters():
+    """lbda = 0 and duplicated bag values make Lambda singular: the composite reports it through `info`, the device-side
+    update is vetoed, and the trainer's checked pass (layered path, psd_safe_cholesky-style jitter retries) either
+    completes the step or raises NotPSDError - in both cases no parameter may turn NaN."""
+    from deconditional_downscaling_b200 import kernels as K, likelihoods as L, means as Mn, models as Md
+    from deconditional_downscaling_b200.functional import NotPSDError
+    from deconditional_downscaling_b200.training import ElboTrainer
+    g = torch.Generator().manual_seed(3)
+    N, n, M, d, r = 400, 32, 24, 2, 2
+    x = torch.randn(N, d, generator=g, dtype=torch.float64).to(DEV)
+    ext = torch.randn(N, r, generator=g, dtype=torch.float64)
+    ext[N // 2:] = ext[: N // 2]                      # every bag value twice: rank-deficient Gram
+    ext = ext.to(DEV)
+    y = torch.randn(n, r, generator=g, dtype=torch.float64).to(DEV)
+    z = torch.randn(n, generator=g, dtype=torch.float64).to(DEV)
+    torch.manual_seed(7)
+    model = Md.VariationalCMP(inducing_points=torch.randn(M, d, generator=g, dtype=torch.float64), individuals_mean=Mn.ZeroMean(),
+                              individuals_kernel=K.ScaleKernel(K.RBFKernel(ard_num_dims=d)),
+                              bag_kernel=K.ScaleKernel(K.RBFKernel(ard_num_dims=r)), lbda=0.0,
+                              use_individuals_noise=True).to(DEV).double()
+    lik = L.CMPLikelihood(use_individuals_noise=True).to(DEV).double()
+    tr = ElboTrainer(model, lik, num_data=320, beta=1.0, lr=0.05, cuda_graph=False)
+    before = {nm: p.detach().clone() for nm, p in model.named_parameters()}
+    try:
+        loss = tr.step(x, z, bags_values=y, extended_bags_values=ext)
+        assert torch.isfinite(loss).item()
+    except NotPSDError:
+        for nm, p in model.named_parameters():      # a failed step leaves the parameters as they were
+            if nm in before and before[nm].shape == p.shape and "variational" not in nm:
+                assert torch.equal(p.detach(), before[nm]), nm
+    for nm, p in model.named_parameters():
+        assert torch.isfinite(p).all().item(), nm
