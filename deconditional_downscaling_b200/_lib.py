@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("DCGP_LIB") or os.path.join(_HERE, "lib", "libdcgp.so"
 F64, F32 = 0, 1
 KIND_RBF, KIND_MATERN32, KIND_MATERN12, KIND_MATERN52 = 0, 1, 2, 3
 MAX_COMPONENTS, MAX_DIMS = 4, 8
-GRAM_SAME, GRAM_OUT_F64, GRAM_NO_FUSE = 1, 2, 256
+GRAM_SAME, GRAM_OUT_F64, GRAM_NO_FUSE, GRAM_BWD_FUSE = 1, 2, 256, 512
 GEMM_LOWER, GEMM_NO_SPLITK, GEMM_TF32X3, GEMM_NO_TCGEN05 = 1, 2, 4, 8
 
 
@@ -70,6 +70,10 @@ _SIGNATURES = {
                           c_int64, c_void_p, c_double, c_int, c_int, c_void_p]),
     "dcgp_gram_bwd": (c_int, [POINTER(KernelSpec), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
                               c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "dcgp_gram_bwd_lowrank_workspace": (c_size_t, [c_int64, c_int64, c_int]),
+    "dcgp_gram_bwd_lowrank": (c_int, [POINTER(KernelSpec), c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
+                                      c_int64, c_void_p, c_int64, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_size_t, c_int,
+                                      c_int, c_void_p]),
     "dcgp_gemm": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_double, c_void_p, c_int64, c_void_p, c_int64,
                           c_double, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "dcgp_split_lo": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),

@@ -201,6 +201,34 @@ __device__ __forceinline__ void kernel_phi_w_fast<float>(int kind, float r2, flo
     }
 }
 
+// accumulate the adjoints of one pair: g multiplies dK/dtheta, gs multiplies dK/da (only when DX)
+template <typename T, int NC, int DPC, bool DX = true, bool FAST = false>
+__device__ __forceinline__ void accum_pair(const DevSpec& sp, const T* os, const T (&a)[NC * DPC],
+                                           const T (&b)[NC * DPC], T g, T gs, T (&gl)[NC * DPC], T (&go)[NC],
+                                           T (&ga)[NC * DPC]) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        T acc = T(0);
+        T u[DPC];
+#pragma unroll
+        for (int j = 0; j < DPC; ++j) {
+            u[j] = a[c * DPC + j] - b[c * DPC + j];
+            acc = fma(u[j], u[j], acc);
+        }
+        T phi, w;
+        if (FAST) kernel_phi_w_fast<T>(sp.kind[c], acc, phi, w);
+        else kernel_phi_w<T>(sp.kind[c], acc, phi, w);
+        go[c] = fma(g, phi, go[c]);
+        const T ow = os[c] * w;
+        const T gow = g * ow, gsow = -gs * ow;
+#pragma unroll
+        for (int j = 0; j < DPC; ++j) {
+            gl[c * DPC + j] = fma(gow * u[j], u[j], gl[c * DPC + j]);
+            if (DX) ga[c * DPC + j] = fma(gsow, u[j], ga[c * DPC + j]);
+        }
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

@@ -73,6 +73,14 @@ struct TcParams {
     int64_t lower_off;  // lower: keep tiles with col0 <= row0 + TM - 1 + lower_off
     int64_t clo_cols;   // Clo is written for columns < clo_cols only (0 = all)
     int a_tri;          // op(A) triangular: 1 lower (k <= row), 2 upper (k >= row) - k-tiles of zeros are skipped
+    // Gram-adjoint epilogue (NC > 0): the product is an upstream gradient G = alpha op(A) op(B) of a Gram matrix
+    // k(x1, x2) that is contracted with d k / d theta tile by tile and never stored
+    const float* gx1;
+    const float* gx2;
+    int64_t gldx1, gldx2;
+    float* gdls;        // [n_comp][DCGP_MAX_DIMS], accumulated
+    float* gdos;        // [n_comp], accumulated
+    DevSpec gsp;
 };
 
 // index -> (row, column) over a rows x cols grid, in groups of `group` rows (column-major inside a group) so that
@@ -121,7 +129,7 @@ __device__ __forceinline__ void k_range(const TcParams& p, int tm, int nkt, int&
     if (p.a_tri == 2) kt0 = min(nkt - 1, (tm * TM) / TK);
 }
 
-template <int TN, bool FAT, int CL>
+template <int TN, bool FAT, int CL, int NC = 0, int DPC = 0>
 __global__ void __launch_bounds__(NTHREADS_TC, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapBlo,
@@ -159,6 +167,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __shared__ SpecVals<float> gsv;   // Gram-adjoint epilogue only (68 bytes)
+    if constexpr (NC > 0) load_spec_vals<float>(p.gsp, &gsv);
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "n"(TMEM_COLS));
@@ -283,7 +293,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     } else if (warp == 2 + EPI_WARPS) {
         // ===== with beta != 0: pull the C tile of the tile whose MMAs are starting into L2, one tile ahead of the
         // epilogue, which cannot keep enough loads in flight by itself to cover DRAM latency =====
-        if (p.beta != 0.f) {
+        if (NC == 0 && p.beta != 0.f) {
             constexpr int LPR = TN * 4 / 128;  // 128-byte lines per tile row
             uint32_t lt = 0;
             for (int i = 0;; ++i) {
@@ -313,6 +323,86 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // epilogue warps per scheduler the loop is bound by its instruction count, not by bandwidth.
         const int q = warp & 3, h = (warp - 2) >> 2;
         float4* stg4 = reinterpret_cast<float4*>(stg_all + (size_t)(warp - 2) * 32 * STG_PITCH);
+        if constexpr (NC > 0) {
+            // ===== Gram-adjoint epilogue: thread = row.  The scaled coordinates of this warp's TN / 2 columns sit in its
+            // 4 KB staging buffer and are read as broadcasts; the D + 1 sums per component stay in registers over all
+            // tiles of the CTA and reach memory as one atomic per value and warp. =====
+            constexpr int TD = NC * DPC;
+            static_assert(TD <= 8 && TN == 256, "the staging buffer holds 128 columns x 8 coordinates");
+            float* cols = reinterpret_cast<float*>(stg4);
+            float gl[TD], go[NC], ga[TD];
+#pragma unroll
+            for (int k = 0; k < TD; ++k) gl[k] = 0.f;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) go[c] = 0.f;
+            uint32_t lt = 0;
+            for (int i = 0;; ++i) {
+                int tm, tn;
+                bool store;
+                const int st = work_item<TN, CL>(p, i, rank, tm, tn, store);
+                if (st == 0) break;
+                if (st == 2) continue;
+                const int64_t m0 = (int64_t)tm * TM, n0 = (int64_t)tn * TN;
+                const uint32_t buf = lt & 1u;
+                const int64_t row = m0 + q * 32 + lane;
+                float a[TD];
+#pragma unroll
+                for (int k = 0; k < TD; ++k) a[k] = (row < p.m) ? p.gx1[row * p.gldx1 + p.gsp.col[k]] * gsv.inv_ls[k] : 0.f;
+                __syncwarp();   // the previous tile's reads of `cols` are over
+                for (int c = lane; c < TN / 2; c += 32) {
+                    const int64_t col = n0 + h * (TN / 2) + c;
+#pragma unroll
+                    for (int k = 0; k < TD; ++k)
+                        cols[c * TD + k] = (col < p.n) ? p.gx2[col * p.gldx2 + p.gsp.col[k]] * gsv.inv_ls[k] : 0.f;
+                }
+                __syncwarp();
+                mbar_wait(&tmem_full[buf], (lt >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (int ch = 0; ch < TN / 64; ++ch) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * TN + (uint32_t)(h * (TN / 2) + ch * 32);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+                          "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+                          "=r"(r[30]), "=r"(r[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (ch == TN / 64 - 1) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+                    }
+                    // rows / columns outside the matrix carry G = 0 (zero-filled operand tiles) and zero coordinates
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float b[TD];
+#pragma unroll
+                        for (int k = 0; k < TD; ++k) b[k] = cols[(ch * 32 + j) * TD + k];
+                        const float g = p.alpha * __uint_as_float(r[j]);
+                        accum_pair<float, NC, DPC, false, true>(p.gsp, gsv.os, a, b, g, g, gl, go, ga);
+                    }
+                }
+                ++lt;
+            }
+#pragma unroll
+            for (int k = 0; k < TD; ++k) {
+                const float v = warp_sum(gl[k]);
+                const int c = k / DPC, j = k % DPC;
+                if (lane == 0 && p.gdls && c < p.gsp.n_comp && j < p.gsp.ndims[c])
+                    atomicAdd(&p.gdls[c * DCGP_MAX_DIMS + j], v * gsv.inv_ls[k]);
+            }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const float v = warp_sum(go[c]);
+                if (lane == 0 && p.gdos && c < p.gsp.n_comp) atomicAdd(&p.gdos[c], v);
+            }
+        } else {
         const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                          (!p.Clo || (reinterpret_cast<uintptr_t>(p.Clo) & 15) == 0);
         const int rsub = lane >> 3, c4 = (lane & 7) * 4;  // coalesced phase: 4 rows x 128 B per instruction
@@ -440,6 +530,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
             ++lt;
         }
+        }   // store epilogue
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -541,12 +632,12 @@ extern "C" int dcgp_round_tf32(const void* src, void* dst, int64_t rows, int64_t
 thread_local int g_tc_cap = 0;
 void dcgp_tc_cap(int ctas) { g_tc_cap = ctas; }
 
-template <int TN, bool FAT, int CL>
+template <int TN, bool FAT, int CL, int NC = 0, int DPC = 0>
 int launch_tc(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapAlo, const CUtensorMap& mapBlo,
               TcParams& p, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<TN, FAT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<TN, FAT, CL, NC, DPC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem_tc<TN, FAT>());
         if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
         attr = true;
@@ -563,7 +654,7 @@ int launch_tc(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMa
     if (g_tc_cap > 0 && g_tc_cap / CL >= 1 && g_tc_cap / CL < cap) cap = g_tc_cap / CL;
     const unsigned grid = (unsigned)(items < cap ? items : cap) * CL;
     if constexpr (CL == 1) {
-        gemm_tc_kernel<TN, FAT, CL><<<grid, NTHREADS_TC, smem_tc<TN, FAT>(), st>>>(mapA, mapB, mapAlo, mapBlo, p);
+        gemm_tc_kernel<TN, FAT, CL, NC, DPC><<<grid, NTHREADS_TC, smem_tc<TN, FAT>(), st>>>(mapA, mapB, mapAlo, mapBlo, p);
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
@@ -577,7 +668,7 @@ int launch_tc(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMa
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<TN, FAT, CL>, mapA, mapB, mapAlo, mapBlo, p);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<TN, FAT, CL, NC, DPC>, mapA, mapB, mapAlo, mapBlo, p);
         if (e != cudaSuccess) return DCGP_CUDA_ERR(e);
     }
     DCGP_CHECK_LAUNCH();
@@ -638,6 +729,7 @@ int dcgp_gemm_tc_ex(int transa, int transb, int64_t m, int64_t n, int64_t k, dou
     p.lower_off = lower_off;
     p.clo_cols = clo_cols;
     p.a_tri = (flags & DCGP_GEMM_A_LOWER) ? 1 : ((flags & DCGP_GEMM_A_UPPER) ? 2 : 0);
+    p.gx1 = p.gx2 = nullptr; p.gldx1 = p.gldx2 = 0; p.gdls = p.gdos = nullptr; p.gsp = DevSpec{};
     static const int fat = getenv("DCGP_TC_FAT") ? atoi(getenv("DCGP_TC_FAT")) : 2;  // 0: off, 1: narrow tiles, 2: all
     if (tn == 128) {
         return (x3 && fat) ? launch_tc<128, true, 1>(mapA, mapB, mapAlo, mapBlo, p, st)
@@ -648,6 +740,40 @@ int dcgp_gemm_tc_ex(int transa, int transb, int64_t m, int64_t n, int64_t k, dou
                                 : launch_tc<256, false, 2>(mapA, mapB, mapAlo, mapBlo, p, st);
     return (x3 && fat >= 2) ? launch_tc<256, true, 1>(mapA, mapB, mapAlo, mapBlo, p, st)
                             : launch_tc<256, false, 1>(mapA, mapB, mapAlo, mapBlo, p, st);
+}
+
+// Gram adjoint for a low-rank upstream gradient: d theta += sum_ij G_ij d k(x1_i, x2_j) / d theta with G = alpha P Q^T
+// (P: n1 x k, Q: n2 x k, row-major FP32, single-pass TF32: pass operands rounded to nearest).  G exists only as TMEM
+// accumulator tiles: the epilogue of the tcgen05 kernel contracts every tile with the kernel derivatives on the spot.
+// In the ELBO step the adjoints of Lambda and of K_xx are such products (dLambda = -X A^T, dK_xx = (A dG) A^T): this
+// replaces an N x N x n product that wrote 268 MB and a Gram-adjoint kernel that read them back.
+// Returns 0, 1 (shape / alignment / kernel layout not taken: more than 8 coordinate slots), < 0 on CUDA errors.
+int dcgp_gram_bwd_lowrank_tc(const DevSpec& sp, const float* x1, int64_t n1, int64_t ldx1, const float* x2, int64_t n2,
+                             int64_t ldx2, const float* P, int64_t ldp, const float* Q, int64_t ldq, int64_t k, double alpha,
+                             float* dls, float* dos, cudaStream_t st) {
+    if (sp.ncb * sp.dpc > 8 || k < 32 || n1 < 128 || n2 < 128) return 1;
+    if ((reinterpret_cast<uintptr_t>(P) & 15) || (reinterpret_cast<uintptr_t>(Q) & 15) || (ldp & 3) || (ldq & 3)) return 1;
+    if (n1 > 0x7fffffff || n2 > 0x7fffffff || k > 0x7fffffff) return 1;
+    CUtensorMap mapA, mapB;
+    if (make_map(&mapA, P, n1, k, ldp, TK, TM, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (make_map(&mapB, Q, n2, k, ldq, TK, 256, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    TcParams p;
+    p.m = n1; p.n = n2; p.k = k;
+    p.C = nullptr; p.Clo = nullptr; p.ldc = 0;
+    p.alpha = (float)alpha; p.beta = 0.f;
+    p.lower = 0; p.a_mn = 0; p.b_mn = 0; p.x3 = 0;
+    p.lower_off = 0; p.clo_cols = 0; p.a_tri = 0;
+    p.gx1 = x1; p.gx2 = x2; p.gldx1 = ldx1; p.gldx2 = ldx2;
+    p.gdls = dls; p.gdos = dos; p.gsp = sp;
+#define CALL(NCV, DPCV) return launch_tc<256, false, 1, NCV, DPCV>(mapA, mapB, mapA, mapB, p, st)
+    if (sp.ncb == 1 && sp.dpc == 2) CALL(1, 2);
+    if (sp.ncb == 1 && sp.dpc == 4) CALL(1, 4);
+    if (sp.ncb == 1 && sp.dpc == 8) CALL(1, 8);
+    if (sp.ncb == 2 && sp.dpc == 2) CALL(2, 2);
+    if (sp.ncb == 2 && sp.dpc == 4) CALL(2, 4);
+    if (sp.ncb == 4 && sp.dpc == 2) CALL(4, 2);
+#undef CALL
+    return 1;
 }
 
 int dcgp_gemm_tc_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,

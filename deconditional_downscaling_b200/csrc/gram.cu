@@ -17,34 +17,6 @@
 
 namespace {
 
-// accumulate the adjoints of one pair: g multiplies dK/dtheta, gs multiplies dK/da (only when DX)
-template <typename T, int NC, int DPC, bool DX = true, bool FAST = false>
-__device__ __forceinline__ void accum_pair(const DevSpec& sp, const T* os, const T (&a)[NC * DPC],
-                                           const T (&b)[NC * DPC], T g, T gs, T (&gl)[NC * DPC], T (&go)[NC],
-                                           T (&ga)[NC * DPC]) {
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        T acc = T(0);
-        T u[DPC];
-#pragma unroll
-        for (int j = 0; j < DPC; ++j) {
-            u[j] = a[c * DPC + j] - b[c * DPC + j];
-            acc = fma(u[j], u[j], acc);
-        }
-        T phi, w;
-        if (FAST) kernel_phi_w_fast<T>(sp.kind[c], acc, phi, w);
-        else kernel_phi_w<T>(sp.kind[c], acc, phi, w);
-        go[c] = fma(g, phi, go[c]);
-        const T ow = os[c] * w;
-        const T gow = g * ow, gsow = -gs * ow;
-#pragma unroll
-        for (int j = 0; j < DPC; ++j) {
-            gl[c * DPC + j] = fma(gow * u[j], u[j], gl[c * DPC + j]);
-            if (DX) ga[c * DPC + j] = fma(gsow, u[j], ga[c * DPC + j]);
-        }
-    }
-}
-
 // commit warp-reduced hyper-parameter adjoints: d/dl_k = sum g*os*w*u_k^2 / l_k
 template <typename T, int NC, int DPC>
 __device__ __forceinline__ void commit_theta(const DevSpec& sp, const SpecVals<T>& sv, T (&gl)[NC * DPC], T (&go)[NC],
@@ -573,6 +545,9 @@ extern "C" int dcgp_gram(const dcgp_kernel_spec* spec, const void* x1, int64_t n
 int dcgp_gemm_impl(int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const void* A, int64_t lda,
                    const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int dtype, int flags,
                    cudaStream_t st, const void* Alo, const void* Blo, void* Clo);
+int dcgp_gram_bwd_lowrank_tc(const DevSpec& sp, const float* x1, int64_t n1, int64_t ldx1, const float* x2, int64_t n2,
+                             int64_t ldx2, const float* P, int64_t ldp, const float* Q, int64_t ldq, int64_t k, double alpha,
+                             float* dls, float* dos, cudaStream_t st);
 
 namespace {
 // out[r, :] += (diag_const + diag_dev[0]) * W[r, :]: the nugget term of (K + c I) W for a row chunk
@@ -886,4 +861,40 @@ extern "C" int dcgp_vbagg_ell(const void* z, const void* S, const void* T, const
         return -11;
     DCGP_CHECK_LAUNCH();
     return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gram adjoint for a low-rank upstream gradient G = alpha P Q^T (see dcgp.h)
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" size_t dcgp_gram_bwd_lowrank_workspace(int64_t n1, int64_t n2, int dtype) {
+    if (n1 < 1 || n2 < 1) return 0;
+    return (size_t)n1 * n2 * (dtype == DCGP_F64 ? 8 : 4);   // the fallback forms G; the fused F32 path uses none of it
+}
+
+extern "C" int dcgp_gram_bwd_lowrank(const dcgp_kernel_spec* spec, const void* x1, int64_t n1, int64_t ldx1, const void* x2,
+                                     int64_t n2, int64_t ldx2, const void* P, int64_t ldp, const void* Q, int64_t ldq, int64_t k,
+                                     double alpha, void* dls, void* dos, void* workspace, size_t workspace_bytes, int dtype,
+                                     int flags, void* stream) {
+    DevSpec sp;
+    if (make_dev_spec(spec, &sp)) return -1;
+    if (!x1 || n1 < 0 || ldx1 < 1) return -2;
+    if (!x2 || n2 < 0 || ldx2 < 1) return -5;
+    if (!P || ldp < k) return -8;
+    if (!Q || ldq < k) return -10;
+    if (k < 1) return -12;
+    if (dtype != DCGP_F64 && dtype != DCGP_F32) return -19;
+    if (n1 == 0 || n2 == 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == DCGP_F32 && (flags & DCGP_GRAM_BWD_FUSE) && !(flags & DCGP_GEMM_TF32X3)) {
+        const int rc = dcgp_gram_bwd_lowrank_tc(sp, (const float*)x1, n1, ldx1, (const float*)x2, n2, ldx2, (const float*)P, ldp,
+                                                (const float*)Q, ldq, k, alpha, (float*)dls, (float*)dos, st);
+        if (rc <= 0) return rc;
+    }
+    // fallback: G into the workspace, then the dense adjoint kernel
+    if (!workspace || workspace_bytes < dcgp_gram_bwd_lowrank_workspace(n1, n2, dtype)) return -16;
+    int rc = dcgp_gemm_impl(0, 1, n1, n2, k, alpha, P, ldp, Q, ldq, 0.0, workspace, n2, dtype, flags & DCGP_GEMM_TF32X3, st,
+                            nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    return dcgp_gram_bwd(spec, x1, n1, ldx1, x2, n2, ldx2, workspace, n2, dls, dos, nullptr, 0, dtype, 0, stream);
 }

@@ -628,3 +628,31 @@ def cmp_elbo(k_spec: FlatSpec, l_spec: FlatSpec, Z, x, ext, y, z, var_mean, chol
     check(lib.dcgp_cmp_elbo_bwd(ctypes.byref(p), float(scale), ctypes.byref(cg), _ptr(ws), nbytes, _dt(Z), 0, _stream()),
           "dcgp_cmp_elbo_bwd")
     return elbo[0], g, info
+
+
+def gram_bwd_lowrank(spec: FlatSpec, x1, x2, P, Q, alpha=1.0, fused=False):
+    """(dls [ncomp, MAX_DIMS], dos [ncomp]) = sum_ij G_ij d k(x1_i, x2_j) / d theta for G = alpha P Q^T (dcgp_gram_bwd_lowrank);
+    x2 None means x1.  fused=True (FP32): G is contracted inside the tcgen05 product and never stored - pass TF32-rounded
+    operands (round_tf32); shapes / kernels the fused kernel does not take fall back to the two-call route."""
+    x1 = _rowmajor(x1)
+    x2 = x1 if x2 is None else _rowmajor(x2)
+    P, Q = _rowmajor(P), _rowmajor(Q)
+    _req(x1, x2, P, Q)
+    _same_dtype("gram_bwd_lowrank", x1, x2, P, Q)
+    lib = _lib.load()
+    n1, n2, k = x1.size(0), x2.size(0), P.size(1)
+    if P.size(0) != n1 or Q.size(0) != n2 or Q.size(1) != k:
+        raise ValueError("P must be n1 x k and Q n2 x k")
+    nc = len(spec.kinds)
+    dls, dos = _zero_theta(nc, x1.dtype, x1.device)
+    cs = spec.c_spec()
+    nbytes = lib.dcgp_gram_bwd_lowrank_workspace(n1, n2, _dt(x1))
+    flags = _lib.GRAM_BWD_FUSE if (fused and x1.dtype == torch.float32) else 0
+    call = lambda ws: lib.dcgp_gram_bwd_lowrank(ctypes.byref(cs), _ptr(x1), n1, _ld(x1), _ptr(x2), n2, _ld(x2), _ptr(P), _ld(P),
+                                                _ptr(Q), _ld(Q), k, float(alpha), _ptr(dls), _ptr(dos), _ptr(ws), ws.numel(),
+                                                _dt(x1), flags, _stream())
+    rc = call(_workspace(16, x1.device)) if flags else -16
+    if rc == -16:      # two-call route (or the fused kernel declined the shape): it needs room for G
+        rc = call(_workspace(nbytes, x1.device))
+    check(rc, "dcgp_gram_bwd_lowrank")
+    return dls, dos

@@ -66,6 +66,7 @@ extern "C" {
 /* flags */
 #define DCGP_GRAM_SAME 1        /* x2 is x1 (enables +diag and the symmetric fast path)  */
 #define DCGP_GRAM_OUT_F64 2     /* dtype F32 inputs/math, store K as double (fp64 island) */
+#define DCGP_GRAM_BWD_FUSE 512  /* dcgp_gram_bwd_lowrank: contract G tile by tile inside the tcgen05 product (G never stored) */
 #define DCGP_GRAM_NO_FUSE 256   /* dcgp_gram_matmul: keep the panel path (Gram rows into the workspace + GEMM) even where
                                    the fused tcgen05 kernel would take the product (A/B runs) */
 #define DCGP_GEMM_LOWER 1       /* only tiles touching the lower triangle of C are computed/written */
@@ -110,6 +111,21 @@ DCGP_API unsigned long long dcgp_launch_count(void);
 DCGP_API int dcgp_gram(const dcgp_kernel_spec* spec, const void* x1, int64_t n1, int64_t ldx1, const void* x2, int64_t n2,
               int64_t ldx2, void* K, int64_t ldk, const void* diag_dev, double diag_const, int dtype, int flags,
               void* stream);
+
+/* Gram adjoint for a LOW-RANK upstream gradient: dls / dos += sum_ij G_ij d k(x1_i, x2_j) / d theta with
+ * G = alpha P Q^T (P: n1 x k, Q: n2 x k).  In the ELBO step the adjoints of Lambda = l(y~, y~) + lbda N I and of K_xx
+ * arrive in exactly this form (torch autograd forms them densely: the backward of src/models/variational_cmp.py:99-103 and
+ * of src/likelihoods/cmp_likelihood.py:58-61).  Default: G goes into the workspace (dcgp_gram_bwd_lowrank_workspace bytes)
+ * by one product and dcgp_gram_bwd contracts it.  With DCGP_GRAM_BWD_FUSE (F32, single-pass TF32 on operands rounded to
+ * nearest, at most 8 coordinate slots, n1, n2 >= 128): one tcgen05 launch whose epilogue contracts each accumulator tile
+ * with the kernel derivatives - G is never stored and the workspace is not touched (536 MB less at N = 8192 x 2), but
+ * the eight epilogue warps make it slower than the two-call route on B200 (8192^2, k = 1024: 368 vs 328 us for an RBF
+ * kernel, 462 vs 431 us for Matern + RBF), so it is a memory option, not the default. */
+DCGP_API size_t dcgp_gram_bwd_lowrank_workspace(int64_t n1, int64_t n2, int dtype);
+DCGP_API int dcgp_gram_bwd_lowrank(const dcgp_kernel_spec* spec, const void* x1, int64_t n1, int64_t ldx1, const void* x2,
+                                   int64_t n2, int64_t ldx2, const void* P, int64_t ldp, const void* Q, int64_t ldq,
+                                   int64_t k, double alpha, void* dls, void* dos, void* workspace, size_t workspace_bytes,
+                                   int dtype, int flags, void* stream);
 
 /* out = (k(x1, x2) [+ (diag_const + *diag_dev) I with DCGP_GRAM_SAME]) W, W is n2 x m: the fused K W of
  * SURVEY.md section 8a row 6 (src/kernels/cme_aggregate_kernel.py:58-70 forms K R by materialising K).  The
