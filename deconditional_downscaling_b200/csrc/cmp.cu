@@ -325,12 +325,20 @@ int fwd_impl(const dcgp_cmp_problem* p, void* elbo, int* info, void* ws, size_t 
     }
     RC(gemv<T>(1, n, N, w + l.A, n, w + l.mu, w + l.a, st));
     if (f32) RC(dcgp_round_tf32(w + l.A, w + l.Ar, N, n, n, n, st));   // A is an operand of ten products
+    // U = A~ A and D U on the side lane again: these tall-K products have 64 output tiles each, less than half a wave of
+    // SMs, and run beside H / K_xx A / A^T (K_xx A) on the main lane
+    if (lane) {
+        DCGP_CU_RC(cudaEventRecord(lane->fork, st));      // A (rounded) and A~ are ready
+        DCGP_CU_RC(cudaStreamWaitEvent(ss, lane->fork, 0));
+    }
+    RC(gemm1<T>(0, 0, M, n, N, 1.0, w + l.At, N, nullptr, w + l.A, n, Ar, 0.0, w + l.U, n, q3, q4, dtype, gf, ss));
+    RC(gemm3<T>(0, 0, M, n, M, 1.0, w + l.D, M, nullptr, w + l.U, n, nullptr, 0.0, w + l.DU, n, q3, q4, dtype, gf, ss));
+    if (lane) DCGP_CU_RC(cudaEventRecord(lane->join, ss));
     RC(gemm1<T>(1, 0, n, n, N, 1.0, w + l.A, n, Ar, w + l.A, n, Ar, 0.0, w + l.H, n, q1, q2, dtype, gf, st));
     RC(dcgp_gram_matmul(p->k_spec, p->x, N, p->ldx, p->x, N, p->ldx, nullptr, p->var_jitter, w + l.A, n, n, w + l.KA, n,
                         wb + s.gm, s.gm_bytes, dtype, DCGP_GRAM_SAME | flags, st));
-    RC(gemm1<T>(0, 0, M, n, N, 1.0, w + l.At, N, nullptr, w + l.A, n, Ar, 0.0, w + l.U, n, q1, q2, dtype, gf, st));
-    RC(gemm3<T>(0, 0, M, n, M, 1.0, w + l.D, M, nullptr, w + l.U, n, nullptr, 0.0, w + l.DU, n, q1, q2, dtype, gf, st));
     RC(gemm1<T>(1, 0, n, n, N, 1.0, w + l.A, n, Ar, w + l.KA, n, nullptr, 0.0, w + l.G, n, q1, q2, dtype, gf, st));
+    if (lane) DCGP_CU_RC(cudaStreamWaitEvent(st, lane->join, 0));
     RC(gemm3<T>(1, 0, n, n, M, 1.0, w + l.U, n, nullptr, w + l.DU, n, nullptr, 1.0, w + l.G, n, q1, q2, dtype, gf, st));
     // --- C, e, the Gaussian terms through C^{-1} = Wc^T Wc
     build_c_kernel<T><<<gn, 256, 0, st>>>(w + l.H, n, (const T*)p->ind_noise, (const T*)p->noise, w + l.C, (const T*)p->z,
