@@ -155,7 +155,7 @@ inline int island_mode() {
 inline bool island_enabled() { return island_mode() != 0; }
 
 struct Layout {
-    size_t Lam, NN, A, Ar, KA, dA, P, Kzx, Kzxlo, At, dAt, dAtlo, dKzx, U, DU, dU, tU, H, G, C, Wc, Cinv, T1, dC, S2, Gd, Gd2, Lz, W, Wlo, D, Ls, t1, t2,
+    size_t Lam, NN, NN2, A, Ar, KA, dA, P, Kzx, Kzxlo, At, dAt, dAtlo, dKzx, U, DU, dU, tU, H, G, C, Wc, Cinv, T1, dC, S2, Gd, Gd2, Lz, W, Wlo, D, Ls, t1, t2,
         t3, t4, mu, dmu, a, e, u, da, v, sc, q1, q2, q3, q4, end;
 };
 
@@ -168,7 +168,7 @@ inline Layout layout(int64_t N, int64_t n, int64_t M) {
     size_t big = Nn > MN ? Nn : MN;
     if (sq > big) big = sq;
 #define TAKE(f, s) l.f = o; o += (s)
-    TAKE(Lam, NNs); TAKE(NN, NNs);
+    TAKE(Lam, NNs); TAKE(NN, NNs); TAKE(NN2, NNs);
     TAKE(A, Nn); TAKE(Ar, Nn); TAKE(KA, Nn); TAKE(dA, Nn); TAKE(P, Nn);
     TAKE(Kzx, MN); TAKE(Kzxlo, MN); TAKE(At, MN); TAKE(dAt, MN); TAKE(dAtlo, MN); TAKE(dKzx, MN);
     TAKE(U, Mn); TAKE(DU, Mn); TAKE(dU, Mn); TAKE(tU, Mn);
@@ -325,21 +325,21 @@ int fwd_impl(const dcgp_cmp_problem* p, void* elbo, int* info, void* ws, size_t 
     }
     RC(gemv<T>(1, n, N, w + l.A, n, w + l.mu, w + l.a, st));
     if (f32) RC(dcgp_round_tf32(w + l.A, w + l.Ar, N, n, n, n, st));   // A is an operand of ten products
-    // U = A~ A and D U on the side lane again: these tall-K products have 64 output tiles each, less than half a wave of
-    // SMs, and run beside H / K_xx A / A^T (K_xx A) on the main lane
+    // Second fork: G = A^T (K_xx + vj I) A + U^T D U (needed only by the trace term and by the backward pass) is built on the
+    // side lane - U = A~ A, D U, K_xx A, two tall-K products - while the main lane goes from H straight to C and its factor,
+    // a chain of single-CTA links that leaves the SMs to those products (serial: ~1.1 ms, overlapped: ~0.7 ms)
     if (lane) {
-        DCGP_CU_RC(cudaEventRecord(lane->fork, st));      // A (rounded) and A~ are ready
+        DCGP_CU_RC(cudaEventRecord(lane->fork, st));      // A (rounded), A~, D are ready
         DCGP_CU_RC(cudaStreamWaitEvent(ss, lane->fork, 0));
     }
     RC(gemm1<T>(0, 0, M, n, N, 1.0, w + l.At, N, nullptr, w + l.A, n, Ar, 0.0, w + l.U, n, q3, q4, dtype, gf, ss));
     RC(gemm3<T>(0, 0, M, n, M, 1.0, w + l.D, M, nullptr, w + l.U, n, nullptr, 0.0, w + l.DU, n, q3, q4, dtype, gf, ss));
+    RC(dcgp_gram_matmul(p->k_spec, p->x, N, p->ldx, p->x, N, p->ldx, nullptr, p->var_jitter, w + l.A, n, n, w + l.KA, n,
+                        wb + s.gm, s.gm_bytes, dtype, DCGP_GRAM_SAME | flags, ss));
+    RC(gemm1<T>(1, 0, n, n, N, 1.0, w + l.A, n, Ar, w + l.KA, n, nullptr, 0.0, w + l.G, n, q3, q4, dtype, gf, ss));
+    RC(gemm3<T>(1, 0, n, n, M, 1.0, w + l.U, n, nullptr, w + l.DU, n, nullptr, 1.0, w + l.G, n, q3, q4, dtype, gf, ss));
     if (lane) DCGP_CU_RC(cudaEventRecord(lane->join, ss));
     RC(gemm1<T>(1, 0, n, n, N, 1.0, w + l.A, n, Ar, w + l.A, n, Ar, 0.0, w + l.H, n, q1, q2, dtype, gf, st));
-    RC(dcgp_gram_matmul(p->k_spec, p->x, N, p->ldx, p->x, N, p->ldx, nullptr, p->var_jitter, w + l.A, n, n, w + l.KA, n,
-                        wb + s.gm, s.gm_bytes, dtype, DCGP_GRAM_SAME | flags, st));
-    RC(gemm1<T>(1, 0, n, n, N, 1.0, w + l.A, n, Ar, w + l.KA, n, nullptr, 0.0, w + l.G, n, q1, q2, dtype, gf, st));
-    if (lane) DCGP_CU_RC(cudaStreamWaitEvent(st, lane->join, 0));
-    RC(gemm3<T>(1, 0, n, n, M, 1.0, w + l.U, n, nullptr, w + l.DU, n, nullptr, 1.0, w + l.G, n, q1, q2, dtype, gf, st));
     // --- C, e, the Gaussian terms through C^{-1} = Wc^T Wc
     build_c_kernel<T><<<gn, 256, 0, st>>>(w + l.H, n, (const T*)p->ind_noise, (const T*)p->noise, w + l.C, (const T*)p->z,
                                           w + l.a, w + l.e);
@@ -352,6 +352,7 @@ int fwd_impl(const dcgp_cmp_problem* p, void* elbo, int* info, void* ws, size_t 
     RC(gemm3<T>(1, 0, n, n, n, 1.0, w + l.Wc, n, nullptr, w + l.Wc, n, nullptr, 0.0, w + l.Cinv, n, q1, q2, dtype, gf, st));
     RC(gemv<T>(0, n, n, w + l.Cinv, n, w + l.e, w + l.u, st));
     RC(dcgp_whitened_kl(p->var_mean, w + l.Ls, M, M, w + l.sc + 1, w + l.t4 + (size_t)M * M, w + l.t4, M, dtype, st));
+    if (lane) DCGP_CU_RC(cudaStreamWaitEvent(st, lane->join, 0));
     RC(dot<T>(w + l.u, w + l.e, n, w + l.sc + 3, st));
     RC(dot<T>(w + l.Cinv, w + l.G, n * n, w + l.sc + 4, st));
     ell_kernel<T><<<1, 1, 0, st>>>(n, w + l.sc + 2, w + l.sc + 1, (T)(p->beta / p->num_data), w + l.sc, (T*)elbo);
@@ -398,22 +399,34 @@ int bwd_impl(const dcgp_cmp_problem* p, double scale, const dcgp_cmp_grads* g, v
     RC(dot<T>(w + l.dC, w + l.H, n * n, w + l.sc + 9, st));
     dscal_out_kernel<T><<<1, 1, 0, st>>>(w + l.sc, (T*)g->dnoise, (T*)g->dind_noise);
     DCGP_CHECK_LAUNCH();
-    // --- dU = D U (2 dG), dD = U dG U^T -> dL_S
-    RC(gemm3<T>(0, 0, M, n, n, 1.0, w + l.DU, n, nullptr, w + l.Gd2, n, nullptr, 0.0, w + l.dU, n, q1, q2, dtype, gf, st));
+    // --- early fork: the adjoints of L_S and of K_xx need only dG - they go to the side lane at once and run beside the
+    // critical path dU -> dA -> Lambda^{-1} dA (the sweeps of that solve leave SMs idle between their dependent products)
+    cudaStream_t ss = st;
+    SideLane* lane = nullptr;
+    if (side_enabled()) {
+        lane = &g_side[st];
+        RC(lane->init());
+        ss = lane->s;
+        DCGP_CU_RC(cudaEventRecord(lane->fork, st));
+        DCGP_CU_RC(cudaStreamWaitEvent(ss, lane->fork, 0));
+    }
+    // dD = U dG U^T -> dL_S
     if (g->dchol_var) {
-        RC(gemm3<T>(0, 0, M, n, n, 1.0, w + l.U, n, nullptr, w + l.Gd, n, nullptr, 0.0, w + l.tU, n, q1, q2, dtype, gf, st));
-        RC(gemm3<T>(0, 1, M, M, n, 1.0, w + l.tU, n, nullptr, w + l.U, n, nullptr, 0.0, w + l.t1, M, q1, q2, dtype, gf, st));
-        RC(gemm3<T>(0, 0, M, M, M, 1.0, w + l.t1, M, nullptr, w + l.Ls, M, nullptr, 0.0, w + l.t2, M, q1, q2, dtype, gf, st));
-        tril_axpby_kernel<T><<<gM, 256, 0, st>>>(w + l.t2, M, T(2), w + l.t4, M, s2, 0, (T*)g->dchol_var, g->lddc);
+        RC(gemm3<T>(0, 0, M, n, n, 1.0, w + l.U, n, nullptr, w + l.Gd, n, nullptr, 0.0, w + l.tU, n, q3, q4, dtype, gf, ss));
+        RC(gemm3<T>(0, 1, M, M, n, 1.0, w + l.tU, n, nullptr, w + l.U, n, nullptr, 0.0, w + l.t1, M, q3, q4, dtype, gf, ss));
+        RC(gemm3<T>(0, 0, M, M, M, 1.0, w + l.t1, M, nullptr, w + l.Ls, M, nullptr, 0.0, w + l.t2, M, q3, q4, dtype, gf, ss));
+        tril_axpby_kernel<T><<<gM, 256, 0, ss>>>(w + l.t2, M, T(2), w + l.t4, M, s2, 0, (T*)g->dchol_var, g->lddc);
         DCGP_CHECK_LAUNCH();
     }
-    // --- dK_xx = (A dG) A^T -> individuals-kernel hyper-parameters
-    RC(gemm1<T>(0, 0, N, n, n, 1.0, w + l.A, n, Ar, w + l.Gd, n, nullptr, 0.0, w + l.P, n, q1, q2, dtype, gf, st));
+    // dK_xx = (A dG) A^T -> individuals-kernel hyper-parameters (its own N x N buffer: the main lane forms dLambda meanwhile)
     if (g->dk_ls || g->dk_os) {
-        RC(gemm1<T>(0, 1, N, N, n, 1.0, w + l.P, n, nullptr, w + l.A, n, Ar, 0.0, w + l.NN, N, q1, q2, dtype, gf, st));
-        RC(dcgp_gram_bwd(p->k_spec, p->x, N, p->ldx, p->x, N, p->ldx, w + l.NN, N, g->dk_ls, g->dk_os, nullptr, 0, dtype,
-                         DCGP_GRAM_SAME, st));
+        RC(gemm1<T>(0, 0, N, n, n, 1.0, w + l.A, n, Ar, w + l.Gd, n, nullptr, 0.0, w + l.P, n, q3, q4, dtype, gf, ss));
+        RC(gemm1<T>(0, 1, N, N, n, 1.0, w + l.P, n, nullptr, w + l.A, n, Ar, 0.0, w + l.NN2, N, q3, q4, dtype, gf, ss));
+        RC(dcgp_gram_bwd(p->k_spec, p->x, N, p->ldx, p->x, N, p->ldx, w + l.NN2, N, g->dk_ls, g->dk_os, nullptr, 0, dtype,
+                         DCGP_GRAM_SAME, ss));
     }
+    // --- main lane: dU = D U (2 dG)
+    RC(gemm3<T>(0, 0, M, n, n, 1.0, w + l.DU, n, nullptr, w + l.Gd2, n, nullptr, 0.0, w + l.dU, n, q1, q2, dtype, gf, st));
     // --- dA = A (2 s_ind dC) + K A (2 dG) + mu da^T + A~^T dU
     RC(gemm1<T>(0, 0, N, n, n, 1.0, w + l.A, n, Ar, w + l.S2, n, nullptr, 0.0, w + l.dA, n, q1, q2, dtype, gf, st));
     RC(gemm1<T>(0, 0, N, n, n, 1.0, w + l.KA, n, nullptr, w + l.Gd2, n, nullptr, 1.0, w + l.dA, n, q1, q2, dtype, gf, st));
@@ -435,13 +448,9 @@ int bwd_impl(const dcgp_cmp_problem* p, double scale, const dcgp_cmp_grads* g, v
     tail_kernel<T><<<1, 1024, 0, st>>>(w + l.v, w + l.t4 + (size_t)M * M, M, s2, (T*)g->dvar_mean, w + l.dmu, N,
                                        (T*)g->dmean_const);
     DCGP_CHECK_LAUNCH();
-    // --- fork: the adjoint of the inducing-point chain runs beside the adjoint solve with Lambda
-    cudaStream_t ss = st;
-    SideLane* lane = nullptr;
-    if (side_enabled()) {
-        lane = &g_side[st];
-        RC(lane->init());
-        ss = lane->s;
+    // --- second fork point: dA~ is complete - the adjoint of the inducing-point chain follows on the side lane, beside the
+    // adjoint solve with Lambda
+    if (lane) {
         DCGP_CU_RC(cudaEventRecord(lane->fork, st));
         DCGP_CU_RC(cudaStreamWaitEvent(ss, lane->fork, 0));
     }
