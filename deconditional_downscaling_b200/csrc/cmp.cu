@@ -482,10 +482,10 @@ int bwd_impl(const dcgp_cmp_problem* p, double scale, const dcgp_cmp_grads* g, v
             f32_to_f64_kernel<<<(unsigned)((mm + 255) / 256), 256, 0, ss>>>((const float*)(w + l.t2), u2, mm);
             DCGP_CHECK_LAUNCH();
             RC(dcgp_gemm(1, 0, M, M, M, 1.0, W64, M, u2, M, 0.0, u1, M, DCGP_F64, flags, ss));
-            RC(dcgp_gemm(0, 1, M, M, M, -1.0, u1, M, W64, M, 0.0, u3, M, DCGP_F64, flags, ss));
+            RC(dcgp_gemm(0, 1, M, M, M, -1.0, u1, M, W64, M, 0.0, u3, M, DCGP_F64, flags | DCGP_GEMM_LOWER, ss));   // only its lower triangle is read
             tril_axpby_kernel<double><<<gM, 256, 0, ss>>>(u3, M, 1.0, nullptr, 0, 0.0, 0, u2, M);
             DCGP_CHECK_LAUNCH();
-            RC(dcgp_gemm(1, 0, M, M, M, 1.0, L64, M, u2, M, 0.0, u1, M, DCGP_F64, flags, ss));
+            RC(dcgp_gemm(1, 0, M, M, M, 1.0, L64, M, u2, M, 0.0, u1, M, DCGP_F64, flags | DCGP_GEMM_LOWER, ss));    // likewise
             tril_axpby_kernel<double><<<gM, 256, 0, ss>>>(u1, M, 1.0, nullptr, 0, 0.0, 1, u2, M);
             DCGP_CHECK_LAUNCH();
             RC(dcgp_gemm(1, 0, M, M, M, 1.0, W64, M, u2, M, 0.0, u1, M, DCGP_F64, flags, ss));
