@@ -427,7 +427,14 @@ int bwd_impl(const dcgp_cmp_problem* p, double scale, const dcgp_cmp_grads* g, v
     }
     // --- main lane: dU = D U (2 dG)
     RC(gemm3<T>(0, 0, M, n, n, 1.0, w + l.DU, n, nullptr, w + l.Gd2, n, nullptr, 0.0, w + l.dU, n, q1, q2, dtype, gf, st));
-    // --- dA = A (2 s_ind dC) + K A (2 dG) + mu da^T + A~^T dU
+    // --- second fork point: dU is complete.  Everything that feeds the inducing-point side of the graph (dmu, dA~, dm, the
+    // mean constant, then the adjoint of the K_ZZ chain) follows on the side lane; the main lane keeps only dA and the
+    // adjoint solve with Lambda
+    if (lane) {
+        DCGP_CU_RC(cudaEventRecord(lane->fork, st));
+        DCGP_CU_RC(cudaStreamWaitEvent(ss, lane->fork, 0));
+    }
+    // --- main lane: dA = A (2 s_ind dC) + K A (2 dG) + mu da^T + A~^T dU
     RC(gemm1<T>(0, 0, N, n, n, 1.0, w + l.A, n, Ar, w + l.S2, n, nullptr, 0.0, w + l.dA, n, q1, q2, dtype, gf, st));
     RC(gemm1<T>(0, 0, N, n, n, 1.0, w + l.KA, n, nullptr, w + l.Gd2, n, nullptr, 1.0, w + l.dA, n, q1, q2, dtype, gf, st));
     RC(gemm1<T>(1, 0, N, n, M, 1.0, w + l.At, N, nullptr, w + l.dU, n, nullptr, 1.0, w + l.dA, n, q1, q2, dtype, gf, st));
@@ -436,24 +443,18 @@ int bwd_impl(const dcgp_cmp_problem* p, double scale, const dcgp_cmp_grads* g, v
         rank1_kernel<T><<<gr, 256, 0, st>>>(w + l.dA, N, n, w + l.mu, w + l.da);
         DCGP_CHECK_LAUNCH();
     }
-    // --- dmu = A da;  dA~ = dU A^T + m dmu^T;  dm;  mean constant
-    RC(gemv<T>(0, N, n, w + l.A, n, w + l.da, w + l.dmu, st));
-    RC(gemm1<T>(0, 1, M, N, n, 1.0, w + l.dU, n, nullptr, w + l.A, n, Ar, 0.0, w + l.dAt, N, q1, q2, dtype, gf, st));
+    // --- side lane: dmu = A da;  dA~ = dU A^T + m dmu^T;  dm;  mean constant
+    RC(gemv<T>(0, N, n, w + l.A, n, w + l.da, w + l.dmu, ss));
+    RC(gemm1<T>(0, 1, M, N, n, 1.0, w + l.dU, n, nullptr, w + l.A, n, Ar, 0.0, w + l.dAt, N, q3, q4, dtype, gf, ss));
     {
         const dim3 gr((unsigned)((N + 255) / 256), (unsigned)M);
-        rank1_kernel<T><<<gr, 256, 0, st>>>(w + l.dAt, M, N, (const T*)p->var_mean, w + l.dmu);
+        rank1_kernel<T><<<gr, 256, 0, ss>>>(w + l.dAt, M, N, (const T*)p->var_mean, w + l.dmu);
         DCGP_CHECK_LAUNCH();
     }
-    RC(gemv<T>(0, M, N, w + l.At, N, w + l.dmu, w + l.v, st));
-    tail_kernel<T><<<1, 1024, 0, st>>>(w + l.v, w + l.t4 + (size_t)M * M, M, s2, (T*)g->dvar_mean, w + l.dmu, N,
+    RC(gemv<T>(0, M, N, w + l.At, N, w + l.dmu, w + l.v, ss));
+    tail_kernel<T><<<1, 1024, 0, ss>>>(w + l.v, w + l.t4 + (size_t)M * M, M, s2, (T*)g->dvar_mean, w + l.dmu, N,
                                        (T*)g->dmean_const);
     DCGP_CHECK_LAUNCH();
-    // --- second fork point: dA~ is complete - the adjoint of the inducing-point chain follows on the side lane, beside the
-    // adjoint solve with Lambda
-    if (lane) {
-        DCGP_CU_RC(cudaEventRecord(lane->fork, st));
-        DCGP_CU_RC(cudaStreamWaitEvent(ss, lane->fork, 0));
-    }
     // --- dK_Zx = W^T dA~;  dW = tril(dA~ K_Zx^T) -> dK_ZZ
     bool island = false;
     if constexpr (sizeof(T) == 4) island = island_enabled();
