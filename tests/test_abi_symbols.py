@@ -51,3 +51,27 @@ def test_ops_refuse_cpu_tensors():
     spec = ops.FlatSpec(["rbf"], [[0]], [torch.ones(1)], [torch.ones(1)])
     with pytest.raises(_lib.DcgpError):
         ops.gram(spec, torch.zeros(4, 1))
+
+
+def test_ctypes_structures_match_the_header_layout(tmp_path):
+    """The ctypes mirrors in _lib.py (KernelSpec, CmpProblem, CmpGrads, VbaggProblem, VbaggGrads) have the size and the
+    field offsets of the C structs in include/dcgp.h - checked by compiling a C program that prints them."""
+    from deconditional_downscaling_b200 import _lib
+    pairs = [("dcgp_kernel_spec", _lib.KernelSpec), ("dcgp_component", _lib.Component), ("dcgp_cmp_problem", _lib.CmpProblem),
+             ("dcgp_cmp_grads", _lib.CmpGrads), ("dcgp_vbagg_problem", _lib.VbaggProblem), ("dcgp_vbagg_grads", _lib.VbaggGrads)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dcgp.h"', 'int main(void){']
+    for cname, ct in pairs:
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines.append('return 0;}')
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, ct in pairs:
+        assert int(out[cname]) == ctypes.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
