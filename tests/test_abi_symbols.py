@@ -75,3 +75,24 @@ def test_ctypes_structures_match_the_header_layout(tmp_path):
         assert int(out[cname]) == ctypes.sizeof(ct), cname
         for fname, _ in ct._fields_:
             assert int(out[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
+
+
+def test_workspace_queries_are_host_only_and_monotone():
+    """Workspace sizes of the composites are plain host arithmetic (no GPU needed): positive, growing with every
+    dimension, zero for degenerate shapes, and large enough for the buffers the headers promise."""
+    from deconditional_downscaling_b200 import _lib
+    lib = _lib.load()
+    for dt, es in ((_lib.F32, 4), (_lib.F64, 8)):
+        base = lib.dcgp_cmp_elbo_workspace(2048, 256, 128, 3, dt)
+        assert base >= (2 * 2048 * 2048 + 5 * 2048 * 256 + 4 * 128 * 2048) * es
+        assert lib.dcgp_cmp_elbo_workspace(4096, 256, 128, 3, dt) > base
+        assert lib.dcgp_cmp_elbo_workspace(2048, 512, 128, 3, dt) > base
+        assert lib.dcgp_cmp_elbo_workspace(2048, 256, 256, 3, dt) > base
+        assert lib.dcgp_cmp_elbo_workspace(0, 256, 128, 3, dt) == 0
+        vb = lib.dcgp_vbagg_elbo_workspace(256, 100, 3, dt)
+        assert vb >= (4 * 256 * 256 + 3 * 256 * 100) * es
+        assert lib.dcgp_vbagg_elbo_workspace(512, 100, 3, dt) > vb
+        assert lib.dcgp_vbagg_elbo_workspace(256, 0, 3, dt) == 0
+        assert lib.dcgp_gram_bwd_lowrank_workspace(300, 200, dt) == 300 * 200 * es
+    # the FP32 composites carry the FP64 island: double copies of Z and of M x M matrices
+    assert lib.dcgp_vbagg_elbo_workspace(256, 100, 8, _lib.F32) > lib.dcgp_vbagg_elbo_workspace(256, 100, 3, _lib.F32)
