@@ -1,7 +1,7 @@
-"""gpytorch.settings stand-ins.  The reference toggles these around prediction / NLL code
-(experiments/swiss_roll/core/metrics.py:24, src/models/exact_cmp.py:141-143); this implementation has one
-numerical path (Cholesky on the GPU, never Lanczos / CG), so they only have to exist, nest and report
-their state."""
+"""gpytorch.settings stand-ins for the four switches the reference touches: `fast_pred_var` and
+`fast_computations` around prediction / NLL code (experiments/swiss_roll/core/metrics.py:24),
+`detach_test_caches` (src/models/exact_cmp.py:141-143) and `trace_mode` (src/variational/variational_strategy.py:4,56).  This implementation has one numerical path (Cholesky on the
+GPU, never Lanczos / CG), so they only have to exist, nest and report their state."""
 import contextlib
 
 
@@ -12,25 +12,17 @@ class _Flag(contextlib.ContextDecorator):
         self.state, self._prev = bool(state), None
 
     def __enter__(self):
-        self._prev = type(self)._state()
-        type(self)._set(self.state)
+        self._prev = type(self).on()
+        type(self)._value = self.state
         return self
 
     def __exit__(self, *exc):
-        type(self)._set(self._prev)
+        type(self)._value = self._prev
         return False
 
     @classmethod
-    def _state(cls):
-        return cls.__dict__.get("_value", cls._default)
-
-    @classmethod
-    def _set(cls, v):
-        cls._value = v
-
-    @classmethod
     def on(cls):
-        return bool(cls._state())
+        return bool(cls.__dict__.get("_value", cls._default))
 
     @classmethod
     def off(cls):
@@ -41,24 +33,12 @@ class fast_pred_var(_Flag):
     pass
 
 
-class fast_pred_samples(_Flag):
-    pass
-
-
 class detach_test_caches(_Flag):
     _default = True
 
 
 class trace_mode(_Flag):
     pass
-
-
-class skip_posterior_variances(_Flag):
-    pass
-
-
-class debug(_Flag):
-    _default = True
 
 
 class fast_computations(contextlib.ContextDecorator):
@@ -72,35 +52,3 @@ class fast_computations(contextlib.ContextDecorator):
 
     def __exit__(self, *exc):
         return False
-
-
-class _Value(contextlib.ContextDecorator):
-    _default = None
-
-    def __init__(self, value):
-        self.v, self._prev = value, None
-
-    def __enter__(self):
-        self._prev = type(self).value()
-        type(self)._value = self.v
-        return self
-
-    def __exit__(self, *exc):
-        type(self)._value = self._prev
-        return False
-
-    @classmethod
-    def value(cls):
-        return cls.__dict__.get("_value", cls._default)
-
-
-class max_cholesky_size(_Value):
-    _default = 800
-
-
-class cholesky_jitter(_Value):
-    _default = None
-
-
-class max_root_decomposition_size(_Value):
-    _default = 100
